@@ -1,0 +1,182 @@
+/*
+ * pnerf_b200.h — C ABI of libpnerf_b200.so: the B200 (sm_100a) implementation of PaletteNeRF's
+ * volumetric-rendering hot path.
+ *
+ * Conventions (all entry points)
+ *   - plain device pointers + sizes, no torch types; caller allocates every buffer (SURVEY §8b "Ownership");
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - never throws, never allocates device memory, keeps no pointer after return;
+ *   - returns PNERF_OK (0) or a negative pnerf_status; pnerf_status_string() explains it;
+ *   - "ref:" names the reference interface the function replaces (path:line under the reference repo).
+ *
+ * The Python packages raymarching/, gridencoder/, shencoder/, freqencoder/ and palette.backend bind exactly
+ * these symbols through ctypes (palettenerf_b200/_lib.py); INTEGRATION.md shows the stub.
+ */
+#ifndef PNERF_B200_H_
+#define PNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PNERF_API __attribute__((visibility("default")))
+#else
+#define PNERF_API
+#endif
+
+typedef enum pnerf_status {
+    PNERF_OK = 0,
+    PNERF_ERR_INVALID_ARG = -1,  /* null pointer, negative size, bad enum */
+    PNERF_ERR_UNSUPPORTED = -2,  /* configuration outside what the kernels implement (e.g. n_channel > 128) */
+    PNERF_ERR_CUDA = -3          /* a CUDA runtime call / launch failed; see pnerf_last_cuda_error() */
+} pnerf_status;
+
+typedef enum pnerf_dtype { PNERF_F16 = 0, PNERF_F32 = 1, PNERF_F64 = 2 } pnerf_dtype;
+
+/* output layout of the grid encoder: the reference kernel writes [L,B,C] and the wrapper permutes
+ * (ref: gridencoder/grid.py:41-52); the native layout writes the final [B, L*C] rows directly. */
+typedef enum pnerf_grid_layout { PNERF_LAYOUT_LBC = 0, PNERF_LAYOUT_BLC = 1 } pnerf_grid_layout;
+
+PNERF_API const char* pnerf_status_string(int status);
+PNERF_API const char* pnerf_last_cuda_error(void);
+PNERF_API int pnerf_abi_version(void);
+/* compiled gencode string, e.g. "sm_100a" */
+PNERF_API const char* pnerf_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * raymarching  (ref: raymarching/src/raymarching.h:7-23, bindings.cpp:5-23)
+ * all float buffers are fp32, index buffers int32, bitfield uint8
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ref: raymarching.cu:95-159 near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars) */
+PNERF_API int pnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                                       uint32_t N, float min_near, float* nears, float* fars, void* stream);
+
+/* ref: raymarching.cu:166-211 sph_from_ray(rays_o, rays_d, radius, N, coords[N,2]) */
+PNERF_API int pnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                                 float* coords, void* stream);
+
+/* ref: raymarching.cu:217-235 morton3D(coords[N,3], N, indices[N]) */
+PNERF_API int pnerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+
+/* ref: raymarching.cu:240-263 morton3D_invert(indices[N], N, coords[N,3]) */
+PNERF_API int pnerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+
+/* ref: raymarching.cu:271-303 packbits(grid, N = C*H^3/8 bytes, density_thresh, bitfield[N]) */
+PNERF_API int pnerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                             void* stream);
+
+/* ref: raymarching.cu:315-493 march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+ *      nears, fars, xyzs, dirs, deltas, rays, counter, noises)
+ * xyzs/dirs [M,3], deltas [M,2] must be zero-initialised by the caller (only occupied slots are written);
+ * rays [N,3] = (ray id, sample offset, sample count); counter[2] += (total samples, N).
+ * Slot assignment is a deterministic exclusive scan in ray order (one of the orders the reference's
+ * atomicAdd race can produce); rays that would overflow M are skipped exactly like raymarching.cu:419.
+ * `order` : 0 = deterministic scan (default), 1 = reserved. */
+PNERF_API int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                                     uint32_t H, uint32_t M, const float* nears, const float* fars,
+                                     float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                                     const float* noises, void* stream);
+
+/* ref: raymarching.cu:504-580,647-655 */
+PNERF_API int pnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                                 const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                                 float* weights_sum, float* depth, float* image, void* stream);
+
+/* ref: raymarching.cu:681-761,821-829; grad_sigmas/grad_rgbs must be zero-initialised */
+PNERF_API int pnerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                  const float* sigmas, const float* rgbs, const float* deltas,
+                                                  const int32_t* rays, const float* weights_sum,
+                                                  const float* image, uint32_t M, uint32_t N, float T_thresh,
+                                                  float* grad_sigmas, float* grad_rgbs, void* stream);
+
+/* ref: raymarching.cu:583-645,657-668 (n_channel <= 128, else PNERF_ERR_UNSUPPORTED) */
+PNERF_API int pnerf_composite_rays_flex_train_forward(const float* sigmas, const float* input,
+                                                      const float* deltas, const int32_t* rays, uint32_t M,
+                                                      uint32_t N, uint32_t n_channel, float T_thresh,
+                                                      float* output, void* stream);
+
+/* ref: raymarching.cu:764-819,831-844; grad_input must be zero-initialised */
+PNERF_API int pnerf_composite_rays_flex_train_backward(const float* grad_output, const float* sigmas,
+                                                       const float* input, const float* deltas,
+                                                       const int32_t* rays, const float* output, uint32_t M,
+                                                       uint32_t N, uint32_t n_channel, float T_thresh,
+                                                       float* grad_input, void* stream);
+
+/* ref: raymarching.cu:848-894 spread_ray_to_sample(input[N,c], rays, M, N, n_channel, output[M,c]) */
+PNERF_API int pnerf_spread_ray_to_sample(const float* input, const int32_t* rays, uint32_t M, uint32_t N,
+                                         uint32_t n_channel, float* output, void* stream);
+
+/* ref: raymarching.cu:907-1021 march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+ *      max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises); outputs zero-initialised by caller */
+PNERF_API int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                               const float* rays_t, const float* rays_o, const float* rays_d, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                               const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                               const float* noises, void* stream);
+
+/* ref: raymarching.cu:1025-1111,1187-1193 (in-place on rays_alive, rays_t, weights_sum, depth, image) */
+PNERF_API int pnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                                   float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                                   float* weights_sum, float* depth, float* image, void* stream);
+
+/* ref: raymarching.cu:1114-1185,1195-1205 (in-place on output; reads weights_sum) */
+PNERF_API int pnerf_composite_rays_flex(uint32_t n_alive, uint32_t n_step, uint32_t n_channel, float T_thresh,
+                                        const int32_t* rays_alive, const float* rays_t, const float* sigmas,
+                                        const float* input, const float* deltas, const float* weights_sum,
+                                        float* output, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gridencoder  (ref: gridencoder/src/gridencoder.h:12-13)
+ * inputs fp32 [B,D] in [0,1]; embeddings/outputs/grad of `dtype`; offsets int32 [L+1]
+ * S = log2(per_level_scale) as fp32, H = base resolution, gridtype 0 = hash, 1 = tiled
+ * dy_dx (optional, may be NULL): [B, L, D, C] of `dtype`
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                                        void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                        uint32_t H, void* dy_dx, uint32_t gridtype, int align_corners,
+                                        int dtype, int out_layout, void* stream);
+
+/* grad_embeddings must be zero-initialised (or hold a running sum to accumulate into);
+ * grad_inputs (optional, with dy_dx) is overwritten; grad layout follows `grad_layout`. */
+PNERF_API int pnerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                         const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                                         uint32_t C, uint32_t L, float S, uint32_t H, const void* dy_dx,
+                                         void* grad_inputs, uint32_t gridtype, int align_corners, int dtype,
+                                         int grad_layout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * shencoder  (ref: shencoder/src/shencoder.h:9-10)  fp32, D must be 3, degree C in [1,8]
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t C,
+                                      float* dy_dx, void* stream);
+/* grad_inputs is accumulated into (+=), as shencoder.cu:377-380 does */
+PNERF_API int pnerf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D,
+                                       uint32_t C, const float* dy_dx, float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * freqencoder  (ref: freqencoder/src/freqencoder.h:7-10)  fp32
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                                        float* outputs, void* stream);
+PNERF_API int pnerf_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D,
+                                         uint32_t deg, uint32_t C, float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * palette ops  (ref: palette/src/palette_func.h:7-8, palette/src/bindings.cpp:40-104)
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_rgb_to_hsv(uint32_t n, const float* input, float* output, void* stream);
+PNERF_API int pnerf_hsv_to_rgb(uint32_t n, const float* input, float* output, void* stream);
+/* host function (CPU pointers): colors_rgb [n,3] f32, weights [n] f32 ->
+ * bin_weights [2^(3b)] f64, bin_centers_rgb [2^(3b),3] f32; ref: bindings.cpp:52-91 */
+PNERF_API int pnerf_compute_rgb_histogram(const float* colors_rgb, const float* weights, uint64_t n,
+                                          int bits_per_channel, double* bin_weights, float* bin_centers_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNERF_B200_H_ */

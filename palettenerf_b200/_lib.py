@@ -1,0 +1,113 @@
+"""ctypes binding of libpnerf_b200.so (the C ABI declared in include/pnerf_b200.h).
+
+There is NO CPU fallback: if the library is missing it is built once with nvcc (palettenerf_b200/build.py);
+if that fails, importing raises. Every wrapper passes raw device pointers + the current CUDA stream and turns a
+non-zero status into RuntimeError (the reference surfaces TORCH_CHECK failures the same way).
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_uint32, c_uint64, c_void_p
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "libpnerf_b200.so")
+
+F16, F32, F64 = 0, 1, 2
+LAYOUT_LBC, LAYOUT_BLC = 0, 1
+_DTYPE_ID = {torch.float16: F16, torch.float32: F32, torch.float64: F64}
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing and could not be built; pnerf_b200 has no CPU fallback")
+    return ctypes.CDLL(_LIB_PATH)
+
+
+lib = _load()
+
+P, U, F, I = c_void_p, c_uint32, c_float, c_int
+_SIGS = {
+    "pnerf_near_far_from_aabb": [P, P, P, U, F, P, P, P],
+    "pnerf_sph_from_ray": [P, P, F, U, P, P],
+    "pnerf_morton3D": [P, U, P, P],
+    "pnerf_morton3D_invert": [P, U, P, P],
+    "pnerf_packbits": [P, U, F, P, P],
+    "pnerf_march_rays_train": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P],
+    "pnerf_composite_rays_train_forward": [P, P, P, P, U, U, F, P, P, P, P],
+    "pnerf_composite_rays_train_backward": [P, P, P, P, P, P, P, P, U, U, F, P, P, P],
+    "pnerf_composite_rays_flex_train_forward": [P, P, P, P, U, U, U, F, P, P],
+    "pnerf_composite_rays_flex_train_backward": [P, P, P, P, P, P, U, U, U, F, P, P],
+    "pnerf_spread_ray_to_sample": [P, P, U, U, U, P, P],
+    "pnerf_march_rays": [U, U, P, P, P, P, F, F, U, U, U, P, P, P, P, P, P, P, P],
+    "pnerf_composite_rays": [U, U, F, P, P, P, P, P, P, P, P, P],
+    "pnerf_composite_rays_flex": [U, U, U, F, P, P, P, P, P, P, P, P],
+    "pnerf_grid_encode_forward": [P, P, P, P, U, U, U, U, F, U, P, U, I, I, I, P],
+    "pnerf_grid_encode_backward": [P, P, P, P, P, U, U, U, U, F, U, P, P, U, I, I, I, P],
+    "pnerf_sh_encode_forward": [P, P, U, U, U, P, P],
+    "pnerf_sh_encode_backward": [P, P, U, U, U, P, P, P],
+    "pnerf_freq_encode_forward": [P, U, U, U, U, P, P],
+    "pnerf_freq_encode_backward": [P, P, U, U, U, U, P, P],
+    "pnerf_rgb_to_hsv": [U, P, P, P],
+    "pnerf_hsv_to_rgb": [U, P, P, P],
+    "pnerf_compute_rgb_histogram": [P, P, c_uint64, I, P, P],
+}
+EXPORTS = sorted(list(_SIGS) + ["pnerf_status_string", "pnerf_last_cuda_error", "pnerf_abi_version", "pnerf_build_arch"])
+
+for _name, _args in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = c_int
+lib.pnerf_status_string.argtypes = [c_int]
+lib.pnerf_status_string.restype = c_char_p
+lib.pnerf_last_cuda_error.restype = c_char_p
+lib.pnerf_abi_version.restype = c_int
+lib.pnerf_build_arch.restype = c_char_p
+
+
+def register(name, argtypes):
+    """declare a further entry point (used by the fused-kernel modules)"""
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = c_int
+    _SIGS[name] = argtypes
+    return fn
+
+
+def ptr(t):
+    """device (or host) address of a tensor / None -> NULL"""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib.pnerf_status_string(status).decode()
+        if status == -3:
+            msg += ": " + lib.pnerf_last_cuda_error().decode()
+        raise RuntimeError(f"pnerf_b200.{what} failed: {msg}")
+
+
+def call(name, *args):
+    check(getattr(lib, name)(*args), name)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pnerf_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def dtype_id(dt):
+    try:
+        return _DTYPE_ID[dt]
+    except KeyError:
+        raise RuntimeError(f"pnerf_b200: unsupported dtype {dt}")

@@ -1,0 +1,32 @@
+// core.cu — status / error plumbing of the C ABI.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pnerf {
+static thread_local char g_last_err[256] = "";
+void set_last_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace pnerf
+
+extern "C" {
+
+const char* pnerf_status_string(int status) {
+    switch (status) {
+        case PNERF_OK: return "ok";
+        case PNERF_ERR_INVALID_ARG: return "invalid argument (null pointer / bad size / bad enum)";
+        case PNERF_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PNERF_ERR_CUDA: return "CUDA error";
+        default: return "unknown status";
+    }
+}
+
+const char* pnerf_last_cuda_error(void) { return pnerf::g_last_err; }
+
+int pnerf_abi_version(void) { return 1; }
+
+const char* pnerf_build_arch(void) { return "sm_100a"; }
+
+}  // extern "C"

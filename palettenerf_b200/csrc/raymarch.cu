@@ -1,0 +1,525 @@
+// raymarch.cu — occupancy-grid ray marching for B200 (sm_100a).
+//
+// Replaces raymarching/src/raymarching.cu:95-493,848-1021 of the reference (near/far, sphere coords, Morton,
+// packbits, training march, inference march, spread). The float arithmetic of one marching step mirrors the
+// reference expression by expression so that sample positions, counts and offsets are
+// bit-identical; the *schedule* is new:
+//   - training march = count kernel -> single-CTA exclusive scan in ray order -> write kernel, instead of two
+//     global atomics per ray; slot order is deterministic (ray order), which is one of the orders the
+//     reference's atomic race may produce;
+//   - the write kernel is warp-cooperative per ray group: samples are staged through shared memory and
+//     leave the SM as coalesced runs;
+//   - packbits reads 2x float4 per byte, morton/near-far read and write through coalesced vector accesses.
+#include "common.cuh"
+
+namespace pnerf {
+
+// ------------------------------------------------------------------------------------------------
+// bit tricks (ref: raymarching.cu:59-84)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    // 10 input bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton_encode(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// exponent e with v = m * 2^e, m in [0.5, 1) — frexpf semantics for the values that matter here
+// (normal floats; zero/denormals give e <= 0 which every caller clamps to 0, as frexpf's would be).
+__device__ __forceinline__ int frexp_exponent(float v) {
+    return (int)((__float_as_uint(v) >> 23) & 0xffu) - 126;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-ray marcher. One instance per thread; `probe(t)` evaluates the lattice point t and either reports an
+// occupied sample or advances t past the empty voxel. Arithmetic follows raymarching.cu:364-403 exactly.
+// ------------------------------------------------------------------------------------------------
+struct Marcher {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float bound, dt_gamma, dt_min, dt_max;
+    float rH, Hf, halfH, Hm1, H3f, Cm1;
+    const uint8_t* __restrict__ grid;
+
+    __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d, float bound_,
+                                         float dt_gamma_, uint32_t max_steps, uint32_t C, uint32_t H,
+                                         const uint8_t* __restrict__ grid_) {
+        ox = o[0]; oy = o[1]; oz = o[2];
+        dx = d[0]; dy = d[1]; dz = d[2];
+        rdx = 1 / dx; rdy = 1 / dy; rdz = 1 / dz;
+        bound = bound_;
+        dt_gamma = dt_gamma_;
+        const float two_sqrt3 = 2 * 1.7320508075688772f;
+        dt_min = two_sqrt3 / max_steps;
+        dt_max = two_sqrt3 * (1u << (C - 1)) / H;
+        Hf = (float)H;
+        rH = 1 / Hf;
+        halfH = 0.5f * Hf;  // exact; (0.5 * v * H) in double rounds once, same as v * halfH in float
+        Hm1 = (float)(H - 1);
+        H3f = (float)(H * H * H);
+        Cm1 = (float)C - 1.0f;
+        grid = grid_;
+    }
+
+    __device__ __forceinline__ float step_size(float t) const { return clampf(t * dt_gamma, dt_min, dt_max); }
+
+    // Evaluate lattice point t. Returns true if (x,y,z) is an occupied sample (t is NOT advanced; caller adds dt).
+    // Otherwise advances t to the first lattice point at/after the voxel exit and returns false.
+    __device__ __forceinline__ bool probe(float& t, float& x, float& y, float& z, float& dt) const {
+        x = clampf(ox + t * dx, -bound, bound);
+        y = clampf(oy + t * dy, -bound, bound);
+        z = clampf(oz + t * dz, -bound, bound);
+        dt = step_size(t);
+
+        // cascade from position and from step size (ref: raymarching.cu:45-57)
+        const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        const int lp = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(mx)));
+        const int ld = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(dt * Hf * 0.5f)));
+        const int level = max(lp, ld);
+
+        const float mip_bound = fminf(scalbnf(1.0f, level), bound);
+        const float mip_rbound = 1 / mip_bound;
+
+        const int nx = (int)clampf((x * mip_rbound + 1) * halfH, 0.0f, Hm1);
+        const int ny = (int)clampf((y * mip_rbound + 1) * halfH, 0.0f, Hm1);
+        const int nz = (int)clampf((z * mip_rbound + 1) * halfH, 0.0f, Hm1);
+
+        // the reference forms this index in fp32 (level * H3 + morton); keep its rounding behaviour
+        const uint32_t index = (uint32_t)((float)level * H3f + (float)morton_encode(nx, ny, nz));
+        const bool occ = grid[index >> 3] & (1u << (index & 7u));
+        if (occ) return true;
+
+        // distance to the exit face of this voxel along each axis
+        const float sx = copysignf(1.0f, dx), sy = copysignf(1.0f, dy), sz = copysignf(1.0f, dz);
+        const float tx = (((nx + 0.5f + 0.5f * sx) * rH * 2 - 1) * mip_bound - x) * rdx;
+        const float ty = (((ny + 0.5f + 0.5f * sy) * rH * 2 - 1) * mip_bound - y) * rdy;
+        const float tz = (((nz + 0.5f + 0.5f * sz) * rH * 2 - 1) * mip_bound - z) * rdz;
+        const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+        do {
+            t += step_size(t);
+        } while (t < tt);
+        return false;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// near / far  (ref: raymarching.cu:95-148)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                  const float* __restrict__ aabb, uint32_t N, float min_near,
+                                                  float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3 + 0], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3 + 0], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+    const float flt_max = 3.402823466e+38f;
+
+    float near = (aabb[0] - ox) * rdx, far = (aabb[3] - ox) * rdx;
+    if (near > far) { float s = near; near = far; far = s; }
+    float near_y = (aabb[1] - oy) * rdy, far_y = (aabb[4] - oy) * rdy;
+    if (near_y > far_y) { float s = near_y; near_y = far_y; far_y = s; }
+    bool miss = (near > far_y) || (near_y > far);
+    if (!miss) {
+        if (near_y > near) near = near_y;
+        if (far_y < far) far = far_y;
+        float near_z = (aabb[2] - oz) * rdz, far_z = (aabb[5] - oz) * rdz;
+        if (near_z > far_z) { float s = near_z; near_z = far_z; far_z = s; }
+        miss = (near > far_z) || (near_z > far);
+        if (!miss) {
+            if (near_z > near) near = near_z;
+            if (far_z < far) far = far_z;
+            if (near < min_near) near = min_near;
+        }
+    }
+    nears[n] = miss ? flt_max : near;
+    fars[n] = miss ? flt_max : far;
+}
+
+// ------------------------------------------------------------------------------------------------
+// background sphere coordinates (ref: raymarching.cu:166-201)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sph_from_ray(const float* __restrict__ rays_o,
+                                                      const float* __restrict__ rays_d, float radius, uint32_t N,
+                                                      float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3 + 0], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3 + 0], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ox * dx + oy * dy + oz * dz;  // half of the linear coefficient
+    const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bh + sqrtf(Bh * Bh - A * Cc)) / A;  // far intersection
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    const float rpi = 0.3183098861837907f;
+    reinterpret_cast<float2*>(coords)[n] = make_float2(2 * theta * rpi - 1, phi * rpi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Morton (ref: raymarching.cu:217-257)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_morton3D(const int32_t* __restrict__ coords, uint32_t N,
+                                                  int32_t* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int32_t)morton_encode((uint32_t)coords[n * 3 + 0], (uint32_t)coords[n * 3 + 1],
+                                        (uint32_t)coords[n * 3 + 2]);
+}
+
+__global__ void __launch_bounds__(256) k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N,
+                                                         int32_t* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int32_t ind = indices[n];  // arithmetic shifts of the signed value, like the reference
+    coords[n * 3 + 0] = (int32_t)compact3((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int32_t)compact3((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int32_t)compact3((uint32_t)(ind >> 2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// packbits (ref: raymarching.cu:271-292): one thread packs 4 bytes = 32 cells = 8 x float4 loads,
+// coalesced 128-bit streaming reads, 32-bit stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid, uint32_t N, float thresh,
+                                                  uint8_t* __restrict__ bitfield) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit word index
+    const uint32_t n0 = w * 4;
+    if (n0 >= N) return;
+    if (n0 + 4 <= N && ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) &&
+        ((reinterpret_cast<uintptr_t>(bitfield) & 3u) == 0)) {
+        const float4* g4 = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 v = ld_stream4(g4 + i);
+            bits |= (v.x > thresh ? 1u : 0u) << (4 * i + 0);
+            bits |= (v.y > thresh ? 1u : 0u) << (4 * i + 1);
+            bits |= (v.z > thresh ? 1u : 0u) << (4 * i + 2);
+            bits |= (v.w > thresh ? 1u : 0u) << (4 * i + 3);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+    } else {
+        for (uint32_t n = n0; n < N && n < n0 + 4; n++) {
+            uint8_t bits = 0;
+            for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (uint8_t)(1u << i) : 0;
+            bitfield[n] = bits;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// training march (ref: raymarching.cu:315-483)
+// ------------------------------------------------------------------------------------------------
+
+// pass 1: count occupied steps per ray; rays[n] = (n, <offset later>, count)
+__global__ void __launch_bounds__(128) k_march_train_count(const float* __restrict__ rays_o,
+                                                           const float* __restrict__ rays_d,
+                                                           const uint8_t* __restrict__ grid, float bound,
+                                                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                                                           uint32_t H, const float* __restrict__ nears,
+                                                           const float* __restrict__ fars,
+                                                           const float* __restrict__ noises,
+                                                           int32_t* __restrict__ rays) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    Marcher m;
+    m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
+    const float far = fars[n];
+    float t = nears[n];
+    t += m.step_size(t) * noises[n];
+    uint32_t num_steps = 0;
+    float x, y, z, dt;
+    while (t < far && num_steps < max_steps) {
+        if (m.probe(t, x, y, z, dt)) {
+            num_steps++;
+            t += dt;
+        }
+    }
+    rays[n * 3 + 0] = (int32_t)n;
+    rays[n * 3 + 2] = (int32_t)num_steps;
+}
+
+// pass 2: single-CTA exclusive scan of the counts in ray order. 1024 threads, each owns a contiguous run.
+__global__ void __launch_bounds__(1024) k_march_train_scan(int32_t* __restrict__ rays, uint32_t N,
+                                                           int32_t* __restrict__ counter) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t base_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t per = ceil_div(N, 1024u);
+    const uint32_t lo = min(N, tid * per), hi = min(N, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += (uint32_t)rays[i * 3 + 2];
+    // inclusive warp scan
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += v;
+        }
+        warp_tot[lane] = winc - w;  // exclusive
+        if (lane == 31) {
+            // counter[0] accumulates the grand total, counter[1] the ray count (ref: raymarching.cu:408-409)
+            base_s = (uint32_t)counter[0];
+            counter[0] = (int32_t)(base_s + winc);
+            counter[1] += (int32_t)N;
+        }
+    }
+    __syncthreads();
+    uint32_t off = base_s + warp_tot[wid] + (inc - sum);
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = (uint32_t)rays[i * 3 + 2];
+        rays[i * 3 + 1] = (int32_t)off;
+        off += c;
+    }
+}
+
+// pass 3: re-march and write. One thread per ray marches; every time the warp has produced samples they are
+// staged in shared memory and flushed by the whole warp so that global stores are coalesced runs per ray.
+constexpr int kStage = 8;  // samples staged per ray before a cooperative flush
+
+__global__ void __launch_bounds__(128) k_march_train_write(const float* __restrict__ rays_o,
+                                                           const float* __restrict__ rays_d,
+                                                           const uint8_t* __restrict__ grid, float bound,
+                                                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                                                           uint32_t H, uint32_t M, const float* __restrict__ nears,
+                                                           const float* __restrict__ fars,
+                                                           const float* __restrict__ noises,
+                                                           const int32_t* __restrict__ rays, float* __restrict__ xyzs,
+                                                           float* __restrict__ dirs, float* __restrict__ deltas) {
+    // per warp: 32 rays x kStage samples x (xyz 3 + delta 2) floats
+    __shared__ float s_xyz[4][32][kStage * 3 + 1];
+    __shared__ float s_dl[4][32][kStage * 2 + 1];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+
+    Marcher m;
+    uint32_t num_steps = 0, offset = 0;
+    float far = 0.f, t = 0.f;
+    bool active = false;
+    if (n < N) {
+        num_steps = (uint32_t)rays[n * 3 + 2];
+        offset = (uint32_t)rays[n * 3 + 1];
+        active = (num_steps != 0) && (offset + num_steps <= M);
+    }
+    if (active) {
+        m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
+        far = fars[n];
+        t = nears[n];
+        t += m.step_size(t) * noises[n];
+    }
+    float last_t = t;
+    uint32_t step = 0;     // samples produced so far
+    uint32_t flushed = 0;  // samples already written to global
+
+    while (__any_sync(0xffffffffu, active)) {
+        // each active lane produces up to kStage samples into its staging row
+        uint32_t staged = 0;
+        if (active) {
+            float x, y, z, dt;
+            while (staged < kStage && t < far && step < num_steps) {
+                if (m.probe(t, x, y, z, dt)) {
+                    t += dt;
+                    s_xyz[wid][lane][staged * 3 + 0] = x;
+                    s_xyz[wid][lane][staged * 3 + 1] = y;
+                    s_xyz[wid][lane][staged * 3 + 2] = z;
+                    s_dl[wid][lane][staged * 2 + 0] = dt;
+                    s_dl[wid][lane][staged * 2 + 1] = t - last_t;
+                    last_t = t;
+                    staged++;
+                    step++;
+                }
+            }
+            if (!(t < far && step < num_steps)) active = false;
+        }
+        __syncwarp();
+        // cooperative flush: for each ray r of the warp, lanes write its staged run contiguously
+#pragma unroll 1
+        for (uint32_t r = 0; r < 32; r++) {
+            const uint32_t cnt = __shfl_sync(0xffffffffu, staged, r);
+            if (cnt == 0) continue;
+            const uint32_t base = __shfl_sync(0xffffffffu, offset + flushed, r);
+            const float ddx = __shfl_sync(0xffffffffu, m.dx, r);
+            const float ddy = __shfl_sync(0xffffffffu, m.dy, r);
+            const float ddz = __shfl_sync(0xffffffffu, m.dz, r);
+            if (lane < cnt * 3) {
+                xyzs[(size_t)base * 3 + lane] = s_xyz[wid][r][lane];
+                const uint32_t c = lane % 3;
+                dirs[(size_t)base * 3 + lane] = (c == 0) ? ddx : ((c == 1) ? ddy : ddz);
+            }
+            if (lane < cnt * 2) deltas[(size_t)base * 2 + lane] = s_dl[wid][r][lane];
+        }
+        flushed += staged;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference march (ref: raymarching.cu:907-1011)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_march_rays(uint32_t n_alive, uint32_t n_step,
+                                                    const int32_t* __restrict__ rays_alive,
+                                                    const float* __restrict__ rays_t,
+                                                    const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                    float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                                                    uint32_t H, const uint8_t* __restrict__ grid,
+                                                    const float* __restrict__ nears, const float* __restrict__ fars,
+                                                    float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                    float* __restrict__ deltas, const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    Marcher m;
+    m.init(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, bound, dt_gamma, max_steps, C, H, grid);
+    const float far = fars[index];
+    float t = rays_t[index];
+    t += m.step_size(t) * noises[n];
+    float last_t = t;
+    uint32_t step = 0;
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float* pl = deltas + (size_t)n * n_step * 2;
+    float x, y, z, dt;
+    while (t < far && step < n_step) {
+        if (m.probe(t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = m.dx; pd[1] = m.dy; pd[2] = m.dz;
+            t += dt;
+            pl[0] = dt;
+            pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            step++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// spread per-ray values to the ray's samples (ref: raymarching.cu:848-882); warp per ray, coalesced writes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_spread(const float* __restrict__ input, const int32_t* __restrict__ rays,
+                                                uint32_t M, uint32_t N, uint32_t n_channel,
+                                                float* __restrict__ output) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= N) return;
+    const uint32_t index = (uint32_t)rays[warp * 3], offset = (uint32_t)rays[warp * 3 + 1];
+    uint32_t num_steps = (uint32_t)rays[warp * 3 + 2];
+    if (num_steps == 0 || offset >= M) return;
+    num_steps = min(num_steps, M - offset);
+    const float* in = input + (size_t)index * n_channel;
+    float* out = output + (size_t)offset * n_channel;
+    const uint32_t total = num_steps * n_channel;
+    for (uint32_t i = lane; i < total; i += 32) out[i] = in[i % n_channel];
+}
+
+}  // namespace pnerf
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace pnerf;
+
+extern "C" {
+
+int pnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                             float* nears, float* fars, void* stream) {
+    PNERF_REQUIRE(rays_o && rays_d && aabb && nears && fars);
+    if (N == 0) return PNERF_OK;
+    k_near_far<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return check_launch("near_far_from_aabb");
+}
+
+int pnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                       void* stream) {
+    PNERF_REQUIRE(rays_o && rays_d && coords);
+    if (N == 0) return PNERF_OK;
+    k_sph_from_ray<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    return check_launch("sph_from_ray");
+}
+
+int pnerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
+    PNERF_REQUIRE(coords && indices);
+    if (N == 0) return PNERF_OK;
+    k_morton3D<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    return check_launch("morton3D");
+}
+
+int pnerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
+    PNERF_REQUIRE(coords && indices);
+    if (N == 0) return PNERF_OK;
+    k_morton3D_invert<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    return check_launch("morton3D_invert");
+}
+
+int pnerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    PNERF_REQUIRE(grid && bitfield);
+    if (N == 0) return PNERF_OK;
+    const uint32_t words = ceil_div(N, 4u);
+    k_packbits<<<ceil_div(words, 256u), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+    return check_launch("packbits");
+}
+
+int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                           const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                           const float* noises, void* stream) {
+    PNERF_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter && noises);
+    PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
+    if (H > 1024) return PNERF_ERR_UNSUPPORTED;  // 10-bit Morton coordinates
+    if (N == 0) return PNERF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_march_train_count<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                          nears, fars, noises, rays);
+    k_march_train_scan<<<1, 1024, 0, s>>>(rays, N, counter);
+    k_march_train_write<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                          nears, fars, noises, rays, xyzs, dirs, deltas);
+    return check_launch("march_rays_train");
+}
+
+int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                     float* dirs, float* deltas, const float* noises, void* stream) {
+    PNERF_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && noises);
+    PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
+    if (H > 1024) return PNERF_ERR_UNSUPPORTED;
+    if (n_alive == 0 || n_step == 0) return PNERF_OK;
+    k_march_rays<<<ceil_div(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs,
+        dirs, deltas, noises);
+    return check_launch("march_rays");
+}
+
+int pnerf_spread_ray_to_sample(const float* input, const int32_t* rays, uint32_t M, uint32_t N, uint32_t n_channel,
+                               float* output, void* stream) {
+    PNERF_REQUIRE(input && rays && output);
+    if (n_channel > 128) return PNERF_ERR_UNSUPPORTED;
+    if (N == 0 || n_channel == 0) return PNERF_OK;
+    k_spread<<<ceil_div(N * 32u, 256u), 256, 0, (cudaStream_t)stream>>>(input, rays, M, N, n_channel, output);
+    return check_launch("spread_ray_to_sample");
+}
+
+}  // extern "C"
