@@ -1,0 +1,240 @@
+"""CPU restatement (plain torch fp32) of the reference's PyTorch-level path. TEST INFRASTRUCTURE / CPU BASELINE ONLY.
+
+  * torch_grid_encode      — torch transliteration of gridencoder.cu:54-72,97-175 (multi-threaded via torch ops)
+  * torch_sh               — SH basis via the shared derivation in tools/gen_sh.py (cf. testing/test_shencoder.py:8-89)
+  * palette_forward        — PaletteNetwork.forward / color / density, palette/network.py:156-280
+  * nerf_forward           — NeRFNetwork.forward, nerf/network.py:95-124
+  * blend                  — the palette blend of palette/renderer.py:470-494 (inference) / :333-352,357-359 (train)
+  * render_sampler         — the pure-torch renderer of NeRFRenderer.run, nerf/renderer.py:127-255, with num_steps=512,
+                             upsample_steps=0 (main_palette.py:33-34) — BASELINE config 1 (the "reference PyTorch path")
+  * render_cuda_ray        — the cuda_ray inference schedule of palette/renderer.py:430-552 driven by the C oracle kernels
+  * train_forward_cuda_ray — the cuda_ray training branch of palette/renderer.py:322-429 on the C oracle kernels
+All take a `params` dict = the model's state_dict (numpy or torch CPU tensors, fp32).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import cpu_oracle as O
+
+_PRIMES = [1, 2654435761, 805459861]
+
+
+def _t(a):
+    return a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a))
+
+
+def torch_grid_encode(x01, emb, offsets, per_level_scale, H=16):
+    """x01 [B,3] in [0,1] fp32; emb [n,2] fp32; hash gridtype, align_corners False -> [B, L*2] fp32"""
+    x01, emb = _t(x01).float(), _t(emb).float()
+    offsets = [int(v) for v in offsets]
+    L = len(offsets) - 1
+    S = np.float32(np.log2(per_level_scale))
+    B = x01.shape[0]
+    outs = []
+    oob = ((x01 < 0) | (x01 > 1)).any(dim=1)
+    for level in range(L):
+        size = offsets[level + 1] - offsets[level]
+        e = np.exp2(np.float32(np.float32(level) * S)).astype(np.float32)
+        scale = np.float32(np.float64(e) * float(H) - 1.0)
+        res = int(np.ceil(scale)) + 1
+        pos = x01 * float(scale) + 0.5
+        pg = torch.floor(pos)
+        fr = pos - pg
+        pg = pg.long()
+        dense = (res + 1) ** 3 <= size
+        acc = torch.zeros(B, emb.shape[1])
+        for c in range(8):
+            w = torch.ones(B)
+            loc = []
+            for dd in range(3):
+                bit = (c >> dd) & 1
+                w = w * (fr[:, dd] if bit else (1 - fr[:, dd]))
+                loc.append(pg[:, dd] + bit)
+            if dense:
+                idx = loc[0] + loc[1] * (res + 1) + loc[2] * (res + 1) ** 2
+            else:
+                idx = (loc[0] * _PRIMES[0]) ^ ((loc[1] * _PRIMES[1]) & 0xFFFFFFFF) ^ ((loc[2] * _PRIMES[2]) & 0xFFFFFFFF)
+            idx = (idx % size) + offsets[level]
+            acc = acc + w[:, None] * emb[idx]
+        outs.append(acc)
+    out = torch.cat(outs, dim=1)
+    out[oob] = 0
+    return out
+
+
+def torch_sh(d, degree=4):
+    return torch.from_numpy(O.sh_encode(_t(d).double().numpy(), degree)).float()
+
+
+def _mlp(params, prefix, n, h, act=F.relu):
+    for i in range(n):
+        h = F.linear(h, _t(params[f"{prefix}.{i}.weight"]).float())
+        if i != n - 1:
+            h = act(h)
+    return h
+
+
+def _encode(params, name, x, bound, per_level_scale):
+    return torch_grid_encode((x + bound) / (2 * bound), params[f"{name}.embeddings"], _t(params[f"{name}.offsets"]).tolist(),
+                             per_level_scale)
+
+
+def palette_forward(params, x, d, bound, per_level_scale, pred_clip, clip_dim=16):
+    """-> (sigma, clip_feat, omega, offsets_radiance, view_dep, diffuse); palette/network.py:156-185,223-280"""
+    x, d = _t(x).float(), _t(d).float()
+    h = _mlp(params, "sigma_net", 2, _encode(params, "encoder", x, bound, per_level_scale))
+    sigma = torch.exp(h[..., 0])
+    geo = h[..., 1:]
+    if pred_clip:
+        clip = _mlp(params, "clip_net", 2, _encode(params, "encoder_clip", x, bound, per_level_scale))
+    else:
+        clip = torch.zeros(x.shape[0], clip_dim)
+    diffuse = torch.sigmoid(_mlp(params, "diff_net", 3, geo))
+    view_dep = torch.sigmoid(_mlp(params, "color_net", 3, torch.cat([torch_sh(d, 4), geo], dim=-1)))
+    hp = torch.cat([_encode(params, "encoder_palette", x, bound, per_level_scale), diffuse], dim=-1)
+    hp = _mlp(params, "basis_net", 2, hp, act=F.elu)
+    offsets_radiance = F.linear(hp, _t(params["offsets_radiance_net.weight"]).float(), _t(params["offsets_radiance_net.bias"]).float())
+    omega = F.softplus(F.linear(hp, _t(params["omega_net.0.weight"]).float())) + 0.05
+    omega = omega / omega.sum(dim=-1, keepdim=True)
+    return sigma, clip, omega, offsets_radiance, view_dep, diffuse
+
+
+def nerf_forward(params, x, d, bound, per_level_scale):
+    """-> (sigma, rgb); nerf/network.py:95-124"""
+    x, d = _t(x).float(), _t(d).float()
+    h = _mlp(params, "sigma_net", 2, _encode(params, "encoder", x, bound, per_level_scale))
+    sigma = torch.exp(h[..., 0])
+    rgb = torch.sigmoid(_mlp(params, "color_net", 3, torch.cat([torch_sh(d, 4), h[..., 1:]], dim=-1)))
+    return sigma, rgb
+
+
+def blend(params, omega, offsets_radiance, view_dep, num_basis=4):
+    """palette/renderer.py:470-494: -> rgbs [M,3], basis_rgb [M,Nb,3], unscaled_basis_rgb [M,Nb,3]"""
+    M = omega.shape[0]
+    offsets = offsets_radiance[..., :-1].reshape(M, num_basis, 3)
+    radiance = offsets_radiance[..., -1:].reshape(M, 1, 1)
+    palette = _t(params["basis_color"]).float()[None].clamp(0, 1)
+    final = F.softplus(radiance) * (palette + offsets)
+    basis_rgb = omega.reshape(M, num_basis, 1) * final
+    return basis_rgb.sum(dim=-2) + view_dep, basis_rgb, (palette + offsets)
+
+
+def render_sampler(params, rays_o, rays_d, bound=2.0, min_near=0.2, per_level_scale=2 ** (8 / 15), num_steps=512,
+                   pred_clip=False, bg_color=1.0, chunk=4096, density_scale=1.0):
+    """BASELINE config 1: uniform sampler + full field + weights compositing (nerf/renderer.py:127-255, staged in
+    max_ray_batch=4096 chunks like :564-599), palette field + blend instead of NeRFNetwork.color."""
+    rays_o, rays_d = _t(rays_o).float().reshape(-1, 3), _t(rays_d).float().reshape(-1, 3)
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    image_all, depth_all, ws_all = [], [], []
+    for h0 in range(0, rays_o.shape[0], chunk):
+        o, d = rays_o[h0:h0 + chunk], rays_d[h0:h0 + chunk]
+        N = o.shape[0]
+        nears, fars = O.near_far_from_aabb(o.numpy(), d.numpy(), aabb, min_near)
+        nears, fars = torch.from_numpy(nears)[:, None], torch.from_numpy(fars)[:, None]
+        z = nears + (fars - nears) * torch.linspace(0.0, 1.0, num_steps)[None]
+        sample_dist = (fars - nears) / num_steps
+        xyz = o[:, None, :] + d[:, None, :] * z[..., None]
+        xyz = torch.min(torch.max(xyz, torch.from_numpy(aabb[:3])), torch.from_numpy(aabb[3:]))
+        dirs = d[:, None, :].expand_as(xyz)
+        sigma, _, omega, off_rad, view_dep, _ = palette_forward(params, xyz.reshape(-1, 3), dirs.reshape(-1, 3), bound,
+                                                               per_level_scale, pred_clip)
+        rgbs, _, _ = blend(params, omega, off_rad, view_dep)
+        deltas = torch.cat([z[:, 1:] - z[:, :-1], sample_dist], dim=-1)
+        alphas = 1 - torch.exp(-deltas * density_scale * sigma.view(N, num_steps))
+        trans = torch.cumprod(torch.cat([torch.ones(N, 1), 1 - alphas + 1e-15], dim=-1), dim=-1)[:, :-1]
+        w = alphas * trans
+        ws = w.sum(-1)
+        depth = (w * ((z - nears) / (fars - nears)).clamp(0, 1)).sum(-1)
+        image = (w[..., None] * rgbs.view(N, num_steps, 3)).sum(-2) + (1 - ws)[:, None] * bg_color
+        image_all.append(image); depth_all.append(depth); ws_all.append(ws)
+    return torch.cat(image_all), torch.cat(depth_all), torch.cat(ws_all)
+
+
+def render_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min_near=0.2, per_level_scale=2 ** (8 / 15),
+                    dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, pred_clip=False, bg_color=1.0, gui_mode=False,
+                    density_scale=1.0, num_basis=4, clip_dim=16):
+    """palette/renderer.py:430-552 (inference schedule incl. n_step growth and alive-list compaction), oracle kernels"""
+    rays_o = np.ascontiguousarray(_t(rays_o).float().reshape(-1, 3).numpy())
+    rays_d = np.ascontiguousarray(_t(rays_d).float().reshape(-1, 3).numpy())
+    N = rays_o.shape[0]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o, rays_d, aabb, min_near)
+    bitfield = _t(bitfield).numpy()
+    z = lambda *s: np.zeros(s, np.float32)  # noqa: E731
+    acc = dict(weights_sum=z(N), depth=z(N), image=z(N, 3), clip_feat=z(N, clip_dim), direct_rgb=z(N, 3),
+               view_dep_rgb=z(N, 3), basis_acc=z(N, num_basis), basis_rgb=z(N, 3 * num_basis),
+               unscaled_basis_rgb=z(N, 3 * num_basis))
+    alive = np.arange(N, dtype=np.int32)
+    rays_t = nears.copy()
+    step = 0
+    n_samples = 0
+    while step < max_steps:
+        n_alive = alive.shape[0]
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        M = n_alive * n_step
+        M += 128 - (M % 128)
+        xyzs, dirs, deltas = O.march_rays(n_alive, n_step, alive, rays_t, rays_o, rays_d, bound, bitfield, C, H, nears, fars,
+                                          np.zeros(n_alive, np.float32), dt_gamma, max_steps, M=M)
+        n_samples += int((deltas[:, 0] > 0).sum())
+        sigma, clip, omega, off_rad, view_dep, diffuse = palette_forward(params, xyzs, dirs, bound, per_level_scale, pred_clip,
+                                                                         clip_dim)
+        rgbs, basis_rgb, unscaled = blend(params, omega, off_rad, view_dep, num_basis)
+        sig = (density_scale * sigma).numpy()
+        if not gui_mode:
+            for name, val in (("direct_rgb", diffuse + view_dep), ("view_dep_rgb", view_dep), ("basis_acc", omega),
+                              ("basis_rgb", basis_rgb.reshape(M, -1)),
+                              ("unscaled_basis_rgb", unscaled.expand(M, num_basis, 3).reshape(M, -1))):
+                acc[name] = O.composite_rays_flex(n_alive, n_step, alive, sig, val.numpy(), deltas, acc["weights_sum"], acc[name],
+                                                  T_thresh)
+        acc["clip_feat"] = O.composite_rays_flex(n_alive, n_step, alive, sig, clip.numpy(), deltas, acc["weights_sum"],
+                                                 acc["clip_feat"], T_thresh)
+        alive, rays_t, acc["weights_sum"], acc["depth"], acc["image"] = O.composite_rays(
+            n_alive, n_step, alive, rays_t, sig, rgbs.numpy(), deltas, acc["weights_sum"], acc["depth"], acc["image"], T_thresh)
+        alive = alive[alive >= 0]
+        step += n_step
+    ws = acc["weights_sum"]
+    out = dict(acc)
+    out["depth_origin"] = acc["depth"].copy()
+    out["image"] = acc["image"] + (1 - ws)[:, None] * bg_color
+    out["direct_rgb"] = acc["direct_rgb"] + (1 - ws)[:, None] * bg_color
+    out["depth"] = np.clip(acc["depth"] - nears, 0, None) / (fars - nears)
+    out["n_samples"] = n_samples
+    return out
+
+
+def train_forward_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min_near=0.2,
+                           per_level_scale=2 ** (8 / 15), dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, pred_clip=False,
+                           bg_color=1.0, density_scale=1.0, num_basis=4, clip_dim=16, noises=None):
+    """palette/renderer.py:322-429 forward (no smooth loss), oracle kernels; returns the result maps + sample count"""
+    rays_o = np.ascontiguousarray(_t(rays_o).float().reshape(-1, 3).numpy())
+    rays_d = np.ascontiguousarray(_t(rays_d).float().reshape(-1, 3).numpy())
+    N = rays_o.shape[0]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o, rays_d, aabb, min_near)
+    noises = np.zeros(N, np.float32) if noises is None else noises
+    # first call sizes M like raymarching.py:196-226 does (N*max_steps, then slice to m + pad)
+    xyzs, dirs, deltas, rays, counter = O.march_rays_train(rays_o, rays_d, _t(bitfield).numpy(), bound, dt_gamma, max_steps, C,
+                                                           H, N * max_steps if N * max_steps < (1 << 24) else (1 << 24),
+                                                           nears, fars, noises)
+    m = int(counter[0])
+    m += 128 - m % 128
+    xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+    sigma, clip, omega, off_rad, view_dep, diffuse = palette_forward(params, xyzs, dirs, bound, per_level_scale, pred_clip,
+                                                                     clip_dim)
+    rgbs, _, _ = blend(params, omega, off_rad, view_dep, num_basis)
+    sig = (density_scale * sigma).numpy()
+    ws, depth, image = O.composite_rays_train_forward(sig, rgbs.numpy(), deltas, rays, T_thresh)
+    offsets = off_rad[..., :-1].reshape(m, num_basis, 3)
+    sparsity = omega.sum(-1, keepdim=True) / ((omega ** 2).sum(-1, keepdim=True) + 1e-6) - 1
+    offsets_norm = (offsets ** 2).sum(-1).sum(-1, keepdim=True)
+    view_dep_norm = (view_dep ** 2).sum(-1, keepdim=True)
+    buf = torch.cat([sparsity, view_dep_norm, offsets_norm, torch.zeros_like(sparsity), view_dep, diffuse + view_dep, diffuse,
+                     clip, omega], dim=-1)
+    maps = O.composite_rays_flex_train_forward(sig, buf.numpy(), deltas, rays, T_thresh)
+    return dict(image=image + (1 - ws)[:, None] * bg_color, depth=np.clip(depth - nears, 0, None) / (fars - nears),
+                weights_sum=ws, maps=maps, n_samples=int(counter[0]))

@@ -331,8 +331,8 @@ extern "C" {
 int pnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
                                        uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
                                        float* image, void* stream) {
-    PNERF_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image);
     k_comp_train_fwd<<<ceil_div(N, 8u), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
                                                                         weights_sum, depth, image);
     return check_launch("composite_rays_train_forward");
@@ -342,9 +342,9 @@ int pnerf_composite_rays_train_backward(const float* grad_weights_sum, const flo
                                         const float* rgbs, const float* deltas, const int32_t* rays,
                                         const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                         float T_thresh, float* grad_sigmas, float* grad_rgbs, void* stream) {
+    if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image &&
                   grad_sigmas && grad_rgbs);
-    if (N == 0) return PNERF_OK;
     k_comp_train_bwd<<<ceil_div(N, 8u), 256, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs,
                                                                         deltas, rays, weights_sum, image, M, N,
                                                                         T_thresh, grad_sigmas, grad_rgbs);
@@ -354,9 +354,9 @@ int pnerf_composite_rays_train_backward(const float* grad_weights_sum, const flo
 int pnerf_composite_rays_flex_train_forward(const float* sigmas, const float* input, const float* deltas,
                                             const int32_t* rays, uint32_t M, uint32_t N, uint32_t n_channel,
                                             float T_thresh, float* output, void* stream) {
+    if (N == 0 || n_channel == 0) return PNERF_OK;
     PNERF_REQUIRE(sigmas && input && deltas && rays && output);
     if (n_channel > 128) return PNERF_ERR_UNSUPPORTED;
-    if (N == 0 || n_channel == 0) return PNERF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t grid = ceil_div(N, 8u);
     switch ((n_channel + 31) / 32) {
@@ -372,10 +372,10 @@ int pnerf_composite_rays_flex_train_backward(const float* grad_output, const flo
                                              const float* deltas, const int32_t* rays, const float* output, uint32_t M,
                                              uint32_t N, uint32_t n_channel, float T_thresh, float* grad_input,
                                              void* stream) {
+    if (N == 0 || n_channel == 0) return PNERF_OK;
     (void)input; (void)output;  // the reference kernel takes but never reads them (raymarching.cu:764-819)
     PNERF_REQUIRE(grad_output && sigmas && deltas && rays && grad_input);
     if (n_channel > 128) return PNERF_ERR_UNSUPPORTED;
-    if (N == 0 || n_channel == 0) return PNERF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t grid = ceil_div(N, 8u);
     switch ((n_channel + 31) / 32) {
@@ -390,8 +390,8 @@ int pnerf_composite_rays_flex_train_backward(const float* grad_output, const flo
 int pnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
                          const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
                          float* image, void* stream) {
-    PNERF_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image);
     if (n_alive == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image);
     k_comp_rays<<<ceil_div(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, T_thresh, rays_alive, rays_t,
                                                                           sigmas, rgbs, deltas, weights_sum, depth,
                                                                           image);
@@ -401,10 +401,10 @@ int pnerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
 int pnerf_composite_rays_flex(uint32_t n_alive, uint32_t n_step, uint32_t n_channel, float T_thresh,
                               const int32_t* rays_alive, const float* rays_t, const float* sigmas, const float* input,
                               const float* deltas, const float* weights_sum, float* output, void* stream) {
+    if (n_alive == 0 || n_channel == 0) return PNERF_OK;
     (void)rays_t;
     PNERF_REQUIRE(rays_alive && sigmas && input && deltas && weights_sum && output);
     if (n_channel > 128) return PNERF_ERR_UNSUPPORTED;
-    if (n_alive == 0 || n_channel == 0) return PNERF_OK;
     const uint64_t threads = (uint64_t)n_alive * n_channel;
     k_comp_rays_flex<<<(uint32_t)ceil_div<uint64_t>(threads, 256), 256, 0, (cudaStream_t)stream>>>(
         n_alive, n_step, n_channel, T_thresh, rays_alive, sigmas, input, deltas, weights_sum, output);

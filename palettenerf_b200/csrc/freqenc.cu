@@ -47,18 +47,18 @@ extern "C" {
 
 int pnerf_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float* outputs,
                               void* stream) {
+    if (B == 0 || D == 0) return PNERF_OK;
     PNERF_REQUIRE(inputs && outputs);
     PNERF_REQUIRE(C == D + 2 * D * deg);
-    if (B == 0 || D == 0) return PNERF_OK;
     k_freq_fwd<<<ceil_div(B * D, 256u), 256, 0, (cudaStream_t)stream>>>(inputs, B, D, deg, C, outputs);
     return check_launch("freq_encode_forward");
 }
 
 int pnerf_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg,
                                uint32_t C, float* grad_inputs, void* stream) {
+    if (B == 0 || D == 0) return PNERF_OK;
     PNERF_REQUIRE(grad && outputs && grad_inputs);
     PNERF_REQUIRE(C == D + 2 * D * deg);
-    if (B == 0 || D == 0) return PNERF_OK;
     k_freq_bwd<<<ceil_div(B * D, 256u), 256, 0, (cudaStream_t)stream>>>(grad, outputs, B, D, deg, C, grad_inputs);
     return check_launch("freq_encode_backward");
 }

@@ -491,11 +491,11 @@ extern "C" {
 int pnerf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void* dy_dx,
                               uint32_t gridtype, int align_corners, int dtype, int out_layout, void* stream) {
+    if (B == 0) return PNERF_OK;
     PNERF_REQUIRE(inputs && embeddings && offsets && outputs);
     PNERF_REQUIRE(gridtype <= 1 && (out_layout == PNERF_LAYOUT_LBC || out_layout == PNERF_LAYOUT_BLC));
     if (D < 1 || D > 5 || !(C == 1 || C == 2 || C == 4 || C == 8) || L < 1 || L > (uint32_t)kMaxLevels)
         return PNERF_ERR_UNSUPPORTED;  // ref: gridencoder.cu:354,372 throws for the same shapes
-    if (B == 0) return PNERF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const bool blc = out_layout == PNERF_LAYOUT_BLC, al = align_corners != 0;
     switch (dtype) {
@@ -510,12 +510,12 @@ int pnerf_grid_encode_backward(const void* grad, const float* inputs, const void
                                void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                                uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype, int align_corners,
                                int dtype, int grad_layout, void* stream) {
+    if (B == 0) return PNERF_OK;
     (void)embeddings;  // the gradient does not depend on the table values (ref kernel takes but never reads them)
     PNERF_REQUIRE(grad && inputs && offsets && grad_embeddings);
     PNERF_REQUIRE(gridtype <= 1 && (grad_layout == PNERF_LAYOUT_LBC || grad_layout == PNERF_LAYOUT_BLC));
     if (D < 1 || D > 5 || !(C == 1 || C == 2 || C == 4 || C == 8) || L < 1 || L > (uint32_t)kMaxLevels)
         return PNERF_ERR_UNSUPPORTED;
-    if (B == 0) return PNERF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const bool blc = grad_layout == PNERF_LAYOUT_BLC, al = align_corners != 0;
     switch (dtype) {

@@ -54,15 +54,15 @@ using namespace pnerf;
 extern "C" {
 
 int pnerf_rgb_to_hsv(uint32_t n, const float* input, float* output, void* stream) {
-    PNERF_REQUIRE(input && output);
     if (n == 0) return PNERF_OK;
+    PNERF_REQUIRE(input && output);
     k_rgb_to_hsv<<<ceil_div(n, 256u), 256, 0, (cudaStream_t)stream>>>(n, input, output);
     return check_launch("rgb_to_hsv");
 }
 
 int pnerf_hsv_to_rgb(uint32_t n, const float* input, float* output, void* stream) {
-    PNERF_REQUIRE(input && output);
     if (n == 0) return PNERF_OK;
+    PNERF_REQUIRE(input && output);
     k_hsv_to_rgb<<<ceil_div(n, 256u), 256, 0, (cudaStream_t)stream>>>(n, input, output);
     return check_launch("hsv_to_rgb");
 }

@@ -446,37 +446,37 @@ extern "C" {
 
 int pnerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
                              float* nears, float* fars, void* stream) {
-    PNERF_REQUIRE(rays_o && rays_d && aabb && nears && fars);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_o && rays_d && aabb && nears && fars);
     k_near_far<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
     return check_launch("near_far_from_aabb");
 }
 
 int pnerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
                        void* stream) {
-    PNERF_REQUIRE(rays_o && rays_d && coords);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_o && rays_d && coords);
     k_sph_from_ray<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
     return check_launch("sph_from_ray");
 }
 
 int pnerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
-    PNERF_REQUIRE(coords && indices);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(coords && indices);
     k_morton3D<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
     return check_launch("morton3D");
 }
 
 int pnerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
-    PNERF_REQUIRE(coords && indices);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(coords && indices);
     k_morton3D_invert<<<ceil_div(N, 256u), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
     return check_launch("morton3D_invert");
 }
 
 int pnerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
-    PNERF_REQUIRE(grid && bitfield);
     if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(grid && bitfield);
     const uint32_t words = ceil_div(N, 4u);
     k_packbits<<<ceil_div(words, 256u), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
     return check_launch("packbits");
@@ -486,10 +486,10 @@ int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8
                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                            const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
                            const float* noises, void* stream) {
+    if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter && noises);
     PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
     if (H > 1024) return PNERF_ERR_UNSUPPORTED;  // 10-bit Morton coordinates
-    if (N == 0) return PNERF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     k_march_train_count<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
                                                           nears, fars, noises, rays);
@@ -503,10 +503,10 @@ int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_aliv
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                      uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
                      float* dirs, float* deltas, const float* noises, void* stream) {
+    if (n_alive == 0 || n_step == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && noises);
     PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
     if (H > 1024) return PNERF_ERR_UNSUPPORTED;
-    if (n_alive == 0 || n_step == 0) return PNERF_OK;
     k_march_rays<<<ceil_div(n_alive, 128u), 128, 0, (cudaStream_t)stream>>>(
         n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs,
         dirs, deltas, noises);
@@ -515,9 +515,9 @@ int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_aliv
 
 int pnerf_spread_ray_to_sample(const float* input, const int32_t* rays, uint32_t M, uint32_t N, uint32_t n_channel,
                                float* output, void* stream) {
+    if (N == 0 || n_channel == 0) return PNERF_OK;
     PNERF_REQUIRE(input && rays && output);
     if (n_channel > 128) return PNERF_ERR_UNSUPPORTED;
-    if (N == 0 || n_channel == 0) return PNERF_OK;
     k_spread<<<ceil_div(N * 32u, 256u), 256, 0, (cudaStream_t)stream>>>(input, rays, M, N, n_channel, output);
     return check_launch("spread_ray_to_sample");
 }

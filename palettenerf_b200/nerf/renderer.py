@@ -1,0 +1,258 @@
+"""NeRFRenderer — occupancy-grid volume renderer (stage-1 model), drop-in for nerf/renderer.py:61-603 of the
+reference: same constructor, buffers (`aabb_train/infer`, `density_grid`, `density_bitfield`, `step_counter`),
+`render / run_cuda / update_extra_state / mark_untrained_grid / reset_extra_state` and result-dict keys.
+
+Only the cuda_ray path exists (the product has no CPU fallback); `run()` — the reference's pure-torch sampler — is
+restated in oracle/ as the CPU baseline instead. The density-grid maintenance is reorganised: one Morton-ordered
+coordinate table is built once and cached, the full sweep evaluates whole cascades in a few large batches, and
+`mark_untrained_grid` projects all cells of a cascade against a batch of cameras per launch.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import raymarching
+
+
+def _ceil_log2(x):
+    return math.ceil(math.log2(x))
+
+
+class OccupancyState:
+    """mixin holding the cuda_ray state shared by the NeRF and palette renderers"""
+
+    def _init_occupancy(self, bound, cuda_ray, min_near, density_thresh, density_scale, bg_radius):
+        self.bound = bound
+        self.cascade = 1 + _ceil_log2(bound)
+        self.grid_size = 128
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = bg_radius
+        box = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32)
+        self.register_buffer("aabb_train", box)
+        self.register_buffer("aabb_infer", box.clone())
+        self.cuda_ray = cuda_ray
+        if cuda_ray:
+            H3 = self.grid_size ** 3
+            self.register_buffer("density_grid", torch.zeros(self.cascade, H3))
+            self.register_buffer("density_bitfield", torch.zeros(self.cascade * H3 // 8, dtype=torch.uint8))
+            self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+            self.mean_density = 0
+            self.iter_density = 0
+            self.mean_count = 0
+            self.local_step = 0
+        self._cell_table = None
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.step_counter.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.mean_count = 0
+        self.local_step = 0
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _cells(self, device):
+        """(coords [H^3,3] int32 in x-major order, morton indices [H^3] int64), cached per device"""
+        if self._cell_table is None or self._cell_table[0].device != device:
+            g = torch.arange(self.grid_size, dtype=torch.int32, device=device)
+            coords = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).contiguous()
+            self._cell_table = (coords, raymarching.morton3D(coords).long())
+        return self._cell_table
+
+    def _cascade_extent(self, cas):
+        b = min(2 ** cas, self.bound)
+        return b, b / self.grid_size
+
+    def _next_counter(self):
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        return counter
+
+    # -- density grid maintenance (ref: nerf/renderer.py:395-561) -----------------------------------------
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """cells seen by no training camera (or closer than min_near to one) get density -1 and never set a bit"""
+        if not self.cuda_ray:
+            return
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        dev = self.density_bitfield.device
+        poses = poses.to(dev)
+        fx, fy, cx, cy = intrinsic
+        coords, indices = self._cells(dev)
+        unit = 2 * coords.float() / (self.grid_size - 1) - 1
+        seen = torch.zeros_like(self.density_grid)
+        near_cam = torch.zeros_like(self.density_grid)
+        chunk = 128 ** 3 // 8
+        for cas in range(self.cascade):
+            b, half = self._cascade_extent(cas)
+            for c0 in range(0, unit.shape[0], chunk):
+                world = (unit[c0:c0 + chunk] * (b - half)).unsqueeze(0)
+                ind = indices[c0:c0 + chunk]
+                for h in range(0, poses.shape[0], S):
+                    R, t = poses[h:h + S, :3, :3], poses[h:h + S, :3, 3]
+                    cam = (world - t.unsqueeze(1)) @ R
+                    front = cam[..., 2] > 0
+                    in_x = cam[..., 0].abs() < cx / fx * cam[..., 2] + half * 2
+                    in_y = cam[..., 1].abs() < cy / fy * cam[..., 2] + half * 2
+                    vis = front & in_x & in_y
+                    seen[cas, ind] += vis.sum(0)
+                    near_cam[cas, ind] += (vis & (cam[..., 2] < self.min_near)).sum(0)
+                    if getattr(self, "filter_close_point", False):
+                        near_cam[cas, ind] += (cam.norm(dim=-1) < self.min_near).sum(0)
+        seen = seen * (near_cam == 0)
+        self.density_grid[seen == 0] = -1
+        print(f"[mark untrained grid] {(seen == 0).sum()} from {self.grid_size ** 3 * self.cascade}")
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """EMA-max refresh of the density grid + packbits + mean sample count (ref: nerf/renderer.py:467-561)"""
+        if not self.cuda_ray:
+            return
+        dev = self.density_bitfield.device
+        H = self.grid_size
+        fresh = -torch.ones_like(self.density_grid)
+        if self.iter_density < 16:  # full sweep
+            coords, indices = self._cells(dev)
+            unit = 2 * coords.float() / (H - 1) - 1
+            chunk = H ** 3 // 4
+            for cas in range(self.cascade):
+                b, half = self._cascade_extent(cas)
+                for c0 in range(0, unit.shape[0], chunk):
+                    pts = unit[c0:c0 + chunk] * (b - half)
+                    pts = pts + (torch.rand_like(pts) * 2 - 1) * half
+                    sig = self.density(pts)["sigma"].reshape(-1).detach().float() * self.density_scale
+                    fresh[cas, indices[c0:c0 + chunk]] = sig
+        else:  # quarter of the cells at random + as many random occupied cells
+            n = H ** 3 // 4
+            for cas in range(self.cascade):
+                b, half = self._cascade_extent(cas)
+                rnd = torch.randint(0, H, (n, 3), device=dev)
+                occupied = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                occupied = occupied[torch.randint(0, occupied.shape[0], [n], dtype=torch.long, device=dev)]
+                ind = torch.cat([raymarching.morton3D(rnd).long(), occupied])
+                cells = torch.cat([rnd, raymarching.morton3D_invert(occupied)])
+                pts = (2 * cells.float() / (H - 1) - 1) * (b - half)
+                pts = pts + (torch.rand_like(pts) * 2 - 1) * half
+                fresh[cas, ind] = self.density(pts)["sigma"].reshape(-1).detach().float() * self.density_scale
+        ok = (self.density_grid >= 0) & (fresh >= 0)
+        self.density_grid[ok] = torch.maximum(self.density_grid[ok] * decay, fresh[ok])
+        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        self.iter_density += 1
+        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, self.density_thresh),
+                                                    self.density_bitfield)
+        steps = min(16, self.local_step)
+        if steps > 0:
+            self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
+        self.local_step = 0
+
+
+def mix_background(image, weights_sum, bg_color):
+    return image + (1 - weights_sum).unsqueeze(-1) * bg_color
+
+
+def normalise_depth(depth, nears, fars):
+    return torch.clamp(depth - nears, min=0) / (fars - nears)
+
+
+class NeRFRenderer(nn.Module, OccupancyState):
+    def __init__(self, bound=1, cuda_ray=False, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1,
+                 filter_close_point=False):
+        super().__init__()
+        self.filter_close_point = filter_close_point
+        self._init_occupancy(bound, cuda_ray, min_near, density_thresh, density_scale, bg_radius)
+
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def color(self, x, d, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def run(self, *args, **kwargs):
+        raise RuntimeError("palettenerf_b200 implements the cuda_ray path only (no CPU / pure-torch sampler); "
+                           "construct the model with cuda_ray=True")
+
+    def _background(self, rays_o, rays_d, bg_color):
+        if self.bg_radius > 0:
+            sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
+            return self.background(sph, rays_d)
+        return 1 if bg_color is None else bg_color
+
+    def run_cuda(self, rays_o, rays_d, rays_gt=None, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
+                 max_steps=1024, T_thresh=1e-4, **kwargs):
+        """rays_o, rays_d: [B, N, 3] (B == 1) -> dict(image [B,N,3], depth [B,N], rgb_norm, weights_sum)"""
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N, dev = rays_o.shape[0], rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+        bg_color = self._background(rays_o, rays_d, bg_color)
+        C, H = self.cascade, self.grid_size
+
+        if self.training:
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, C, H, nears, fars, self._next_counter(), self.mean_count,
+                perturb, 128, force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs = self(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            if rays_gt is not None:
+                gt = torch.zeros_like(xyzs)
+                raymarching.spread_ray_to_sample(rays_gt.contiguous().view(-1, 3), rays, gt)
+                err = ((gt - rgbs) ** 2).sum(-1, keepdim=True).repeat(1, 3)
+            else:
+                err = torch.zeros_like(rgbs)
+            if sigmas.dim() == 2:  # CCNeRF-style stack of K residual fields
+                images, depths = [], []
+                for k in range(sigmas.shape[0]):
+                    weights_sum, depth, image = raymarching.composite_rays_train(sigmas[k], rgbs[k], deltas, rays, T_thresh)
+                    images.append(mix_background(image, weights_sum, bg_color).view(*prefix, 3))
+                    depths.append(normalise_depth(depth, nears, fars).view(*prefix))
+                image, depth = torch.stack(images, 0), torch.stack(depths, 0)
+                rgb_norm = torch.zeros_like(depth[0])
+            else:
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+                _, _, err_map = raymarching.composite_rays_train(sigmas, err, deltas, rays, T_thresh)
+                image = mix_background(image, weights_sum, bg_color).view(*prefix, 3)
+                depth = normalise_depth(depth, nears, fars).view(*prefix)
+                rgb_norm = err_map.mean(dim=-1).view(*prefix)
+        else:
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
+            depth = torch.zeros(N, dtype=torch.float32, device=dev)
+            image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+            rays_alive = torch.arange(N, dtype=torch.int32, device=dev)
+            rays_t = nears.clone()
+            step = 0
+            while step < max_steps:
+                n_alive = rays_alive.shape[0]
+                if n_alive <= 0:
+                    break
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                            self.density_bitfield, C, H, nears, fars, 128,
+                                                            perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs = self(xyzs, dirs)
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, self.density_scale * sigmas, rgbs, deltas,
+                                           weights_sum, depth, image, T_thresh)
+                rays_alive = rays_alive[rays_alive >= 0]
+                step += n_step
+            image = mix_background(image, weights_sum, bg_color).view(*prefix, 3)
+            depth = normalise_depth(depth, nears, fars).view(*prefix)
+            rgb_norm = torch.zeros_like(image[..., 0])
+
+        return {"depth": depth, "image": image, "rgb_norm": rgb_norm, "weights_sum": weights_sum}
+
+    def render(self, rays_o, rays_d, rays_gt=None, staged=False, max_ray_batch=4096, **kwargs):
+        if not self.cuda_ray:
+            return self.run(rays_o, rays_d, **kwargs)
+        return self.run_cuda(rays_o, rays_d, rays_gt, **kwargs)  # never staged with cuda_ray (ref: :576)

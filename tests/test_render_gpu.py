@@ -1,0 +1,91 @@
+"""End-to-end GPU checks of the renderers on the synthetic lego-shaped scene: result-dict contract, train-mode
+forward/backward, and inference/training consistency (the two schedules composite the same samples)."""
+import pytest
+import torch
+
+from palettenerf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model(cuda):
+    return S.build_palette_model(cuda, seed=0, pred_clip=True, table_scale=0.5)
+
+
+def test_inference_contract_and_training_consistency(cuda, model):
+    o, d = S.camera_rays(64, 64)
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        out = model.render(o, d, staged=True, bg_color=1, perturb=False, gui_mode=False, fused=False)
+    for k, shape in dict(image=(1, 4096, 3), depth=(1, 4096), depth_origin=(1, 4096), weights_sum=(4096,),
+                         clip_feat=(1, 4096, 16), direct_rgb=(1, 4096, 3), view_dep_rgb=(1, 4096, 3), basis_rgb=(1, 4096, 12),
+                         unscaled_basis_rgb=(1, 4096, 12), basis_acc=(1, 4096, 4)).items():
+        assert tuple(out[k].shape) == shape, k
+        assert torch.isfinite(out[k]).all(), k
+    hit = out["weights_sum"] > 1e-3
+    assert 0.05 < hit.float().mean().item() < 0.9
+    assert (out["image"][0][~hit] - 1).abs().max().item() < 2e-3         # white background where nothing is hit
+    # basis_acc composites omega, which sums to one per sample -> sums to weights_sum per ray
+    torch.testing.assert_close(out["basis_acc"][0].sum(-1), out["weights_sum"], rtol=2e-3, atol=2e-3)
+    # basis_rgb channels sum to (image - view_dep) before background
+    recon = out["basis_rgb"][0].view(-1, 4, 3).sum(1) + out["view_dep_rgb"][0] + (1 - out["weights_sum"])[:, None]
+    torch.testing.assert_close(recon, out["image"][0], rtol=5e-3, atol=5e-3)
+
+    model.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        tr = model.render(o, d, staged=False, bg_color=1, perturb=False, force_all_rays=True)
+    for k in ["image", "depth", "weights_sum", "direct_rgb", "view_dep_rgb", "diffuse_rgb", "clip_feat", "basis_acc",
+              "omega_sparsity", "view_dep_norm", "offsets_norm", "smooth_norm"]:
+        assert k in tr and torch.isfinite(tr[k]).all(), k
+    # same samples, same field: train-mode image == inference image (T_thresh is never reached at random init)
+    torch.testing.assert_close(tr["image"].float(), out["image"], rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(tr["weights_sum"], out["weights_sum"], rtol=5e-3, atol=5e-3)
+    loss = ((tr["image"] - 0.5) ** 2).mean() + 1e-3 * tr["omega_sparsity"].mean() + 1e-3 * tr["offsets_norm"].mean() \
+        + ((tr["direct_rgb"] - 0.5) ** 2).mean() + 1e-2 * (tr["clip_feat"] ** 2).mean()
+    (loss * 4096.0).backward()   # static loss scale, standing in for the trainer's GradScaler under fp16 autocast
+    g = model.encoder_palette.embeddings.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum().item() > 0
+    assert model.encoder.embeddings.grad is None or model.encoder.embeddings.grad.abs().sum().item() == 0  # sigma path detached
+    assert model.color_net[0].weight.grad.abs().sum().item() > 0
+    assert model.offsets_radiance_net.bias.grad.abs().sum().item() > 0
+    assert model.encoder_clip.embeddings.grad.abs().sum().item() > 0
+    model.zero_grad(set_to_none=True)
+
+
+def test_nerf_stage_model_and_density_grid_update(cuda):
+    from palettenerf_b200.nerf.network import NeRFNetwork
+    torch.manual_seed(0)
+    m = NeRFNetwork(bound=2, cuda_ray=True, min_near=0.2, density_thresh=10).to(cuda)
+    m.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    with torch.autocast("cuda", dtype=torch.float16):
+        m.update_extra_state()
+    assert m.iter_density == 1 and m.mean_density > 0
+    assert m.density_bitfield.any()
+    from palettenerf_b200 import raymarching
+    thresh = min(m.mean_density, m.density_thresh)
+    assert torch.equal(m.density_bitfield, raymarching.packbits(m.density_grid, thresh))
+    o, d = S.camera_rays(32, 32)
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    m.train()
+    gt = torch.rand(1, 1024, 3, device=cuda)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = m.render(o, d, rays_gt=gt, bg_color=1, perturb=True, force_all_rays=False)
+    (((out["image"] - gt) ** 2).mean() * 4096.0).backward()   # loss scale (GradScaler stand-in)
+    assert m.encoder.embeddings.grad.abs().sum().item() > 0
+    assert out["rgb_norm"].shape == (1, 1024)
+    m.iter_density = 16  # partial-update branch
+    with torch.autocast("cuda", dtype=torch.float16):
+        m.update_extra_state()
+    assert m.mean_count > 0 and m.local_step == 0
+    m.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ev = m.render(o, d, bg_color=1, perturb=False)
+    assert ev["image"].shape == (1, 1024, 3) and torch.isfinite(ev["image"]).all()
+    # mark_untrained_grid: one camera looking at the origin leaves cells behind it untrained (-1)
+    m.density_grid.zero_()
+    pose = S.lookat_pose(3.2, 35.0)[None]
+    m.mark_untrained_grid(pose, (277.8, 277.8, 100.0, 100.0))
+    frac = (m.density_grid < 0).float().mean().item()
+    assert 0.05 < frac < 0.999
