@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the PaletteNeRF hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's PyTorch-only CPU path (restated)
+
+Metric (BASELINE.json): rays/sec of the palette-mode render. Workload at every N: BASELINE config 3 — one 800x800
+view (640 000 rays) of the lego-shaped synthetic scene per GPU, palette model with 4 palettes and random-init
+weights (seed 0), cuda_ray, fp16 autocast, all six auxiliary maps (gui_mode=False). One "step" = one view per rank;
+ranks render different azimuths (weak scaling, no data-path collective: rays are independent).
+Also reported in the same JSON line: the palette training step (config 4: 4096 rays/GPU, fwd+bwd+Adam, one NCCL
+all-reduce of the gradients when N>1) and the hash-grid microbenchmark (config 2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VIEW = 800
+N_RAYS = VIEW * VIEW
+TRAIN_RAYS = 4096
+GRID_POINTS = 1 << 22
+GRID_BYTES_PER_POINT = {"f16": 588, "f32": 1164}  # 12 B xyz + 16 levels * 8 corners * F*s B + 32*s B out
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's PyTorch-only CPU path (restated in oracle/cpu_render.py)
+# -------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import cpu_render
+    from palettenerf_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_rays = 1024
+    model = S.build_palette_model("cpu", seed=0, pred_clip=False)
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(args.warmup + args.steps):
+        inds = torch.randint(0, N_RAYS, (sample_rays,), generator=g)
+        o, d = S.camera_rays(VIEW, VIEW, inds=inds)
+        t0 = time.perf_counter()
+        cpu_render.render_sampler(params, o, d, num_steps=512, pred_clip=False)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample_rays / (ms / 1e3)
+    sample = (f"{sample_rays} random pixels of the 800x800 view per step, 512 uniform samples per ray "
+              "(NeRFRenderer.run sampler, upsample_steps=0), torch fp32 CPU")
+    line = {"impl": "reference", "metric": "rays/sec palette-mode render", "value": value, "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "palette-mode inference render 800x800 lego-shaped, 4 palettes (BASELINE config 3), "
+                                   "rendered by the reference's PyTorch-only CPU path on a bounded sample"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# main arm
+# -------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
+    ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
+    ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from palettenerf_b200 import _lib as L
+    from palettenerf_b200 import synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    hbm_peak, tf_peak, peak_kind = _peaks()
+    model = S.build_palette_model(dev, seed=0, pred_clip=False)
+    model.eval()
+    fused = None if args.fused < 0 else bool(args.fused)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # one view per rank, different azimuths
+    o_host, d_host = S.camera_rays(VIEW, VIEW, azimuth_deg=35.0 + 45.0 * rank)
+    o_pin, d_pin = o_host.pin_memory(), d_host.pin_memory()
+    o_dev, d_dev = o_host.to(dev), d_host.to(dev)
+    img_host = torch.empty(N_RAYS, 3).pin_memory()
+
+    def render(o, d):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model.render(o[None], d[None], staged=True, bg_color=1, perturb=False, gui_mode=args.gui_mode,
+                                fused=fused, dt_gamma=S.LEGO["dt_gamma"], max_steps=S.LEGO["max_steps"], T_thresh=1e-4)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        if profile:
+            L.profile_start()
+        l0 = L.launch_count
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush between timed iterations (not timed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        prof = L.profile_stop() if profile else None
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        return max_over_ranks(ms), L.launch_count - l0, prof
+
+    # ---- headline: device-resident rays --------------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches, prof = timed(lambda: render(o_dev, d_dev), args.steps, args.warmup, profile=True)
+    clock_info = clocks.stop() if rank == 0 else None
+    value = world * N_RAYS / (ms_step / 1e3)
+
+    # ---- e2e: pinned host rays -> H2D -> render through the public API -> D2H image --------------------------------
+    def e2e_step():
+        o = o_pin.to(dev, non_blocking=True)
+        d = d_pin.to(dev, non_blocking=True)
+        out = render(o, d)
+        img_host.copy_(out["image"].view(-1, 3), non_blocking=True)
+    ms_e2e, _, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e = {"value": world * N_RAYS / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 2 * N_RAYS * 12,
+           "d2h_bytes_per_step": N_RAYS * 12, "ms_per_step": ms_e2e}
+
+    # ---- roofline of the dominant kernel of the step (CUDA events around each C-ABI launch, timed region) ---------
+    total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    shares = {k.replace("pnerf_", ""): round(v[0] / total_kernel_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    roofline = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                "kernel": top[0], "peak_kind": peak_kind, "kernel_time_share_of_own_kernels": shares}
+    samples_per_step = getattr(model, "_last_sample_count", None)
+
+    extras = {}
+    if not args.no_extras:
+        extras.update(bench_hashgrid(torch, dev, L, hbm_peak, flush))
+        extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush))
+    # the dominant kernel of this path is the hash-grid gather (3 grids per sample); its roofline comes from the
+    # isolated microbenchmark run on the same kernel (config 2 shape) with CUDA events
+    if "hashgrid" in extras:
+        hg = extras["hashgrid"]
+        roofline.update(achieved=hg["fwd_f16_eff_gbs"], frac=hg["fwd_f16_eff_gbs"] / hbm_peak,
+                        note="grid_encode_forward fp16, 2^22 points: 588 algorithmic B/point / event time; table is "
+                             "L2-resident so compulsory HBM bytes are 76 B/point (hbm_gbs field)",
+                        hbm_only_gbs=hg["fwd_f16_hbm_gbs"], traffic=_ncu_traffic())
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        cpu_baseline = bench_cpu_baseline(S)
+
+    if rank == 0:
+        line = {"metric": "rays/sec palette-mode render", "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": "palette-mode inference render 800x800 lego-shaped, cuda_ray, 4 palettes "
+                                       "(BASELINE config 3), one view per GPU",
+                           "rays_per_step_per_gpu": N_RAYS, "gui_mode": bool(args.gui_mode),
+                           "schedule": getattr(model, "_last_schedule", "loop"),
+                           "samples_per_step": samples_per_step, "l2": "flushed between timed iterations (256 MB write)"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
+                "cpu_baseline": cpu_baseline}
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if present"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("grid_encode_forward_f16_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def bench_hashgrid(torch, dev, L, hbm_peak, flush):
+    """BASELINE config 2: 2^22 points, 16 levels, F=2, log2T=19, fwd + bwd, fp16 and fp32 tables"""
+    from palettenerf_b200.gridencoder import GridEncoder
+    from palettenerf_b200.gridencoder.backend import _backend as GB
+    import numpy as np
+    res = {}
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, desired_resolution=4096).to(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand(GRID_POINTS, 3, device=dev, generator=g)
+    S_ = float(np.log2(enc.per_level_scale))
+    for name, dt in (("f16", torch.float16), ("f32", torch.float32)):
+        emb = enc.embeddings.detach().to(dt)
+        out = torch.empty(GRID_POINTS, 32, device=dev, dtype=dt)
+        grad = torch.randn(GRID_POINTS, 32, device=dev, generator=g).to(dt)
+        gemb = torch.zeros_like(emb)
+
+        def fwd():
+            GB.grid_encode_forward_blc(x, emb, enc.offsets, out, GRID_POINTS, 3, 2, 16, S_, 16, None, 0, False)
+
+        def bwd():
+            GB.grid_encode_backward_blc(grad, x, emb, enc.offsets, gemb, GRID_POINTS, 3, 2, 16, S_, 16, None, None, 0, False)
+        for fn, tag in ((fwd, "fwd"), (bwd, "bwd")):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(10):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = sum(ts) / len(ts)
+            s = 2 if name == "f16" else 4
+            res[f"{tag}_{name}_ms"] = ms
+            res[f"{tag}_{name}_eff_gbs"] = GRID_BYTES_PER_POINT[name] * GRID_POINTS / (ms / 1e3) / 1e9
+            res[f"{tag}_{name}_hbm_gbs"] = (12 + 32 * s) * GRID_POINTS / (ms / 1e3) / 1e9
+    res["points"] = GRID_POINTS
+    res["note"] = "eff = 588 (fp16) / 1164 (fp32) algorithmic B per point; hbm = compulsory 12 + 32*s B per point; L2 flushed"
+    return {"hashgrid": res}
+
+
+def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush):
+    """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
+    GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1."""
+    model = S.build_palette_model(dev, seed=0, pred_clip=False)
+    model.train()
+    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
+    scaler = torch.amp.GradScaler("cuda")
+    o, d = S.training_rays(TRAIN_RAYS, seed=rank)
+    o, d = o.to(dev), d.to(dev)
+    gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+    state = {}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.render(o[None], d[None], staged=False, bg_color=1, perturb=True, force_all_rays=True,
+                               dt_gamma=0.0, max_steps=1024)
+            loss = ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
+                + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+        scaler.scale(loss).backward()
+        if world > 1:
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch.cat([g_.reshape(-1) for g_ in grads])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            off = 0
+            for g_ in grads:
+                g_.copy_(flat[off:off + g_.numel()].view_as(g_))
+                off += g_.numel()
+        scaler.step(opt)
+        scaler.update()
+        state["m"] = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
+
+    for _ in range(3):
+        step()
+    barrier()
+    ts = []
+    for _ in range(5):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    barrier()
+    ms = max_over_ranks(sum(ts) / len(ts))
+    return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
+                      "samples_per_step_rank0": state.get("m"), "optimizer": "Adam(0.9,0.99,1e-15)+GradScaler",
+                      "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
+
+
+def bench_cpu_baseline(S):
+    """the oracle's restatement of the reference's PyTorch-only CPU path, timed on this box's host cores on a bounded
+    sample of the same 800x800 view (reported baseline, not the optimisation target)"""
+    import torch
+    from oracle import cpu_render
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = S.build_palette_model("cpu", seed=0, pred_clip=False)
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    n = 1024
+    inds = torch.randint(0, N_RAYS, (n,), generator=torch.Generator().manual_seed(0))
+    o, d = S.camera_rays(VIEW, VIEW, inds=inds)
+    cpu_render.render_sampler(params, o[:256], d[:256], num_steps=512)  # warm-up
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        cpu_render.render_sampler(params, o, d, num_steps=512)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n} random pixels of the 800x800 view, 512 uniform samples/ray (NeRFRenderer.run sampler), torch fp32, "
+                      f"{reps} repetitions after one warm-up"}
+
+
+if __name__ == "__main__":
+    main()

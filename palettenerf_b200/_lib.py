@@ -96,8 +96,37 @@ def check(status, what):
         raise RuntimeError(f"pnerf_b200.{what} failed: {msg}")
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim and per-kernel CUDA-event timing)
+LAUNCHES = {"pnerf_march_rays_train": 3}
+launch_count = 0
+_profile = None  # when set: dict name -> [list of (start_event, end_event), units]
+
+
+def profile_start():
+    """record a CUDA-event pair around every C-ABI call (on torch's current stream, where the kernels run)"""
+    global _profile
+    _profile = {}
+
+
+def profile_stop():
+    """-> {name: (total_ms, n_calls)}; synchronises"""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (prof or {}).items()}
+
+
 def call(name, *args):
+    global launch_count
+    launch_count += LAUNCHES.get(name, 1)
+    if _profile is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     check(getattr(lib, name)(*args), name)
+    b.record()
+    _profile.setdefault(name, []).append((a, b))
 
 
 def require_cuda(*tensors):
