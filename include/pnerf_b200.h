@@ -176,6 +176,39 @@ PNERF_API int pnerf_hsv_to_rgb(uint32_t n, const float* input, float* output, vo
 PNERF_API int pnerf_compute_rgb_histogram(const float* colors_rgb, const float* weights, uint64_t n,
                                           int bits_per_channel, double* bin_weights, float* bin_centers_rgb);
 
+/* ------------------------------------------------------------------------------------------------
+ * fused palette field + persistent fused renderer (new entry points; no reference counterpart at the kernel level)
+ * They replace, as ONE launch each, what the reference does with many:
+ *   pnerf_palette_field_forward  <->  PaletteNetwork.forward in eval mode      (ref: palette/network.py:156-280)
+ *   pnerf_palette_render_fused   <->  the inference loop of PaletteRenderer.run_cuda (ref: palette/renderer.py:430-523)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pnerf_palette_field {
+    const void* table_sigma;    /* fp16 [n_entries,2] : encoder.embeddings          */
+    const void* table_palette;  /* fp16               : encoder_palette.embeddings  */
+    const void* table_clip;     /* fp16               : encoder_clip.embeddings (NULL unless pred_clip) */
+    const int32_t* offsets;     /* [L+1]                                             */
+    const void* wpack;          /* fp16 mma.m16n8k16 B fragments, palettenerf_b200/fused.py::pack_weights */
+    const float* head_bias;     /* [16] offsets_radiance_net.bias (13) + zeros      */
+    const float* palette;       /* [4*3] basis_color clamped to [0,1]               */
+    uint32_t L, H, pred_clip, clip_dim;
+    float S, bound, density_scale, offsets_weight, view_dep_weight;
+} pnerf_palette_field;
+
+/* xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (NULL unless pred_clip), omega [M,4], off_rad [M,13],
+ * view_dep [M,3], diffuse [M,3]; fp16 tensor-core math with fp32 accumulation */
+PNERF_API int pnerf_palette_field_forward(const float* xyzs, const float* dirs, uint32_t M,
+                                          const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
+                                          float* off_rad, float* view_dep, float* diffuse, void* stream);
+
+/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[2] zeroed:
+ * on return queue[0] >= N and queue[1] = number of samples shaded */
+PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                                         const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
+                                         uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
+                                         const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
+                                         float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
+                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

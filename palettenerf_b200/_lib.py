@@ -55,7 +55,8 @@ _SIGS = {
     "pnerf_hsv_to_rgb": [U, P, P, P],
     "pnerf_compute_rgb_histogram": [P, P, c_uint64, I, P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["pnerf_status_string", "pnerf_last_cuda_error", "pnerf_abi_version", "pnerf_build_arch"])
+EXPORTS = sorted(list(_SIGS) + ["pnerf_status_string", "pnerf_last_cuda_error", "pnerf_abi_version", "pnerf_build_arch",
+                  "pnerf_palette_field_forward", "pnerf_palette_render_fused"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)

@@ -1,0 +1,633 @@
+// fused.cu — the fused per-sample field of PaletteNeRF (hash grids -> sigma / diffuse / view-dependent / palette-basis /
+// semantic MLPs -> palette heads) and the persistent fused renderer built on it, for B200 (sm_100a).
+//
+// The reference evaluates this field as ~14 cuBLAS GEMMs + ~30 elementwise kernels per call, round-tripping every
+// [M,64] activation through HBM (palette/network.py:156-280), inside a host loop of march / shade / composite /
+// compact launches (palette/renderer.py:430-523). Here:
+//
+//   * one warp owns 32 samples. Lanes gather the 16-level hash-grid features of their own sample (8 corners x 2
+//     levels in flight, fp16x2 entries, fp32 interpolation), park them as fp16 rows in a per-warp shared-memory
+//     tile, and the warp then runs the whole MLP chain on tensor cores: mma.sync.m16n8k16 (f16 x f16 -> f32) with
+//     the A operand chained layer to layer IN REGISTERS (an m16n8 accumulator pair is exactly an m16k16 A fragment)
+//     and the B operand (all ~20 k weights, 40-46 KB) resident in shared memory in fragment order, so a layer is
+//     one conflict-free LDS.64 + one HMMA per (k-step, n-tile). No activation ever touches HBM.
+//     Why mma.sync and not tcgen05: per sample the field needs ~10 KB of L2 gather traffic against 21 k MACs, so the
+//     kernel is bound by the gathers (L2 sector throughput), not by the tensor pipe; the 64-wide layers would fill
+//     at most a 128x64 UMMA tile per warpgroup, and the TMEM round trip (tcgen05.ld -> activation -> st.shared ->
+//     fence -> next MMA) per layer costs more than the register-chained HMMA path saves. DESIGN.md has the numbers.
+//   * the concatenations of the reference ([SH16 | geo15], [grid32 | diffuse3], geo = h[1:16]) cost nothing: the
+//     weight columns are permuted / zero-padded when the fragments are packed on the host (fused.py), so the
+//     register fragments of one layer feed the next as they are.
+//   * the renderer is ONE persistent kernel: each lane owns a ray (origin, direction, march position, compositing
+//     accumulators in registers), marches to its next occupied sample, the warp evaluates the field for its 32
+//     samples, lanes composite, finished rays are replaced from a global queue (one warp-aggregated atomic). There is
+//     no host loop, no alive-list compaction, no xyzs/dirs/deltas/sigmas/rgbs buffer and no host synchronisation.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "grid_common.cuh"
+#include "march_common.cuh"
+#include "sh_common.cuh"
+
+namespace pnerf {
+
+constexpr int kNB = 4;            // palette bases supported by the fused path (reference default, main_palette.py:99)
+constexpr int kClipMax = 16;      // semantic feature width supported by the fused path (main_palette.py:76)
+constexpr int kFusedWarps = 8;
+constexpr int kFeatStride = 40;   // halfs per feature row: 32 + 8 pad -> ldmatrix rows hit distinct bank groups
+constexpr int kOutStride = 41;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
+
+// packed weight blob: per layer [NT][KS][32 lanes] x uint2 (= the m16n8k16 B fragment of that (n-tile, k-step))
+enum Layer { LS0, LS1, LD0, LD1, LD2, LV0, LV1, LV2, LB0, LB1, LH, LC0, LC1, kNumLayers };
+__host__ __device__ constexpr int layer_ks(int l) {
+    return l == LS0 ? 2 : l == LS1 ? 4 : l == LD0 ? 1 : l == LD1 ? 4 : l == LD2 ? 4 : l == LV0 ? 2 : l == LV1 ? 4
+         : l == LV2 ? 4 : l == LB0 ? 3 : l == LB1 ? 4 : l == LH ? 1 : l == LC0 ? 2 : 4;
+}
+__host__ __device__ constexpr int layer_nt(int l) {
+    return l == LS0 ? 8 : l == LS1 ? 2 : l == LD0 ? 8 : l == LD1 ? 8 : l == LD2 ? 1 : l == LV0 ? 8 : l == LV1 ? 8
+         : l == LV2 ? 1 : l == LB0 ? 8 : l == LB1 ? 2 : l == LH ? 3 : l == LC0 ? 8 : 2;
+}
+__host__ __device__ constexpr int layer_off(int l) {  // in uint2 units
+    int o = 0;
+    for (int i = 0; i < l; i++) o += layer_ks(i) * layer_nt(i) * 32;
+    return o;
+}
+constexpr int kWUnitsNoClip = layer_off(LC0);
+constexpr int kWUnitsClip = layer_off(kNumLayers);
+
+// output staging columns
+enum OutCol { O_SIGMA = 0, O_DIFF = 1, O_VIEW = 4, O_OFFRAD = 7, O_OMEGA = 20, O_CLIP = 24 };
+
+struct WarpScratch {
+    __half feat[32][kFeatStride];
+    float out[32][kOutStride];
+};
+
+struct FusedSmem {
+    LevelParams lp[kMaxLevels];
+    float head_bias[16];
+    float palette[kNB * 3];
+    // followed by: uint2 weights[units]; WarpScratch scratch[kFusedWarps]
+};
+
+}  // namespace pnerf
+
+namespace pnerf {
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragment (m16 x k16, fp16) from a row-major shared-memory tile: rows [row0, row0+16), cols [col0, col0+16)
+__device__ __forceinline__ void ldmatrix_a(uint32_t (&a)[4], const __half* tile, int row0, int col0, int lane) {
+    const __half* p = tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kFeatStride + col0 + (lane >> 4) * 8;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                 : "r"(addr));
+}
+
+template <int KS, int NT>
+__device__ __forceinline__ void mma_layer(const uint2* __restrict__ w, const uint32_t (&a)[KS][4], float (&c)[NT][4],
+                                          int lane) {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const uint2 b = w[(nt * KS + ks) * 32 + lane];
+            mma16816(c[nt], a[ks], b.x, b.y);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+enum Act { ACT_NONE, ACT_RELU, ACT_ELU };
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_ELU) return v > 0.f ? v : (__expf(v) - 1.0f);
+    return v;
+}
+
+// accumulators of NT n-tiles -> A fragments of NT/2 k-steps (layout identity of mma.m16n8k16, no shuffles)
+template <int NT, int ACT>
+__device__ __forceinline__ void chain(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+    for (int j = 0; j < NT / 2; j++) {
+        a[j][0] = pack_h2(activate<ACT>(c[2 * j][0]), activate<ACT>(c[2 * j][1]));
+        a[j][1] = pack_h2(activate<ACT>(c[2 * j][2]), activate<ACT>(c[2 * j][3]));
+        a[j][2] = pack_h2(activate<ACT>(c[2 * j + 1][0]), activate<ACT>(c[2 * j + 1][1]));
+        a[j][3] = pack_h2(activate<ACT>(c[2 * j + 1][2]), activate<ACT>(c[2 * j + 1][3]));
+    }
+}
+
+// write an n-tile accumulator (rows r / r+8 of the m16 tile, cols 2q, 2q+1) into the fp32 output staging
+template <int NT>
+__device__ __forceinline__ void store_out(float (*out)[kOutStride], int row0, int col0, int ncols, const float (&c)[NT][4],
+                                          int lane) {
+    const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const int col = nt * 8 + 2 * q;
+        if (col < ncols) { out[row0 + r][col0 + col] = c[nt][0]; out[row0 + r + 8][col0 + col] = c[nt][2]; }
+        if (col + 1 < ncols) { out[row0 + r][col0 + col + 1] = c[nt][1]; out[row0 + r + 8][col0 + col + 1] = c[nt][3]; }
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : log1pf(__expf(v)); }  // torch threshold 20
+
+// ------------------------------------------------------------------------------------------------
+// hash-grid gather of one sample (this lane) into its fp16 feature row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_features(const __half* __restrict__ table, const LevelParams* __restrict__ lp,
+                                                uint32_t L, float u, float v, float w, bool active,
+                                                __half* __restrict__ row) {
+    for (uint32_t l0 = 0; l0 < L; l0 += 2) {
+        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (active) {
+            float2 val[2][8];
+            float wt[2][8];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (l0 + j < L) {
+                    const LevelParams& p = lp[l0 + j];
+                    uint32_t idx[8];
+                    corner_setup(p, u, v, w, idx, wt[j], false);
+                    const __half2* g = reinterpret_cast<const __half2*>(table) + p.offset;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) val[j][c] = __half22float2(__ldg(g + idx[c]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (l0 + j < L) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        acc[j].x += wt[j][c] * val[j][c].x;
+                        acc[j].y += wt[j][c] * val[j][c].y;
+                    }
+                }
+            }
+        }
+        reinterpret_cast<__half2*>(row)[l0] = __floats2half2_rn(acc[0].x, acc[0].y);
+        if (l0 + 1 < L) reinterpret_cast<__half2*>(row)[l0 + 1] = __floats2half2_rn(acc[1].x, acc[1].y);
+    }
+}
+
+// per-sample result of the field, held by the lane that owns the sample
+struct FieldOut {
+    float sigma;          // exp(logit) (NOT yet scaled by density_scale)
+    float diffuse[3], view_dep[3];
+    float off_rad[13];    // offsets (12) + radiance (1), bias added
+    float omega[kNB];     // normalised blending weights
+    float clip[kClipMax];
+};
+
+// ------------------------------------------------------------------------------------------------
+// the fused field: 32 samples per warp (lane = sample), L must be 16 (feature rows are 32 wide)
+// ------------------------------------------------------------------------------------------------
+template <bool CLIP>
+__device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const FusedSmem& sm, const uint2* __restrict__ wts,
+                                           WarpScratch& ws, float x, float y, float z, float dx, float dy, float dz,
+                                           bool active, int lane, FieldOut& o) {
+    const float u = (x + f.bound) / (2 * f.bound), v = (y + f.bound) / (2 * f.bound), w = (z + f.bound) / (2 * f.bound);
+    const bool in_range = active && !((u < 0 || u > 1) || (v < 0 || v > 1) || (w < 0 || w > 1));
+
+    // Per-tile fragments that outlive a phase ([logit | geo15] k-step: 4 words, [diffuse3 | pad] k-step: 2 words) are
+    // parked in this lane's own output row, in the columns the clip head only writes in phase 4 (after they are dead).
+    uint32_t* carry = reinterpret_cast<uint32_t*>(&ws.out[lane][O_CLIP]);   // [t][6]
+
+    // ---------------- phase 1: density grid -> sigma net -> geo; geo -> diffuse net ----------------
+    gather_features((const __half*)f.table_sigma, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        uint32_t a2[2][4];
+        ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
+        ldmatrix_a(a2[1], &ws.feat[0][0], 16 * t, 16, lane);
+        float c8[8][4];
+        mma_layer<2, 8>(wts + layer_off(LS0), a2, c8, lane);
+        uint32_t a4[4][4];
+        chain<8, ACT_RELU>(c8, a4);
+        float c2[2][4];
+        mma_layer<4, 2>(wts + layer_off(LS1), a4, c2, lane);
+        if ((lane & 3) == 0) {
+            ws.out[16 * t + (lane >> 2)][O_SIGMA] = c2[0][0];
+            ws.out[16 * t + (lane >> 2) + 8][O_SIGMA] = c2[0][2];
+        }
+        uint32_t geo[1][4];
+        chain<2, ACT_NONE>(c2, geo);
+#pragma unroll
+        for (int i = 0; i < 4; i++) carry[t * 6 + i] = geo[0][i];
+        // diffuse net 15 -> 64 -> 64 -> 3
+        mma_layer<1, 8>(wts + layer_off(LD0), geo, c8, lane);
+        chain<8, ACT_RELU>(c8, a4);
+        mma_layer<4, 8>(wts + layer_off(LD1), a4, c8, lane);
+        chain<8, ACT_RELU>(c8, a4);
+        float c1[1][4];
+        mma_layer<4, 1>(wts + layer_off(LD2), a4, c1, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) c1[0][i] = sigmoidf_(c1[0][i]);
+        store_out<1>(ws.out, 16 * t, O_DIFF, 3, c1, lane);
+        carry[t * 6 + 4] = pack_h2(c1[0][0], c1[0][1]);
+        carry[t * 6 + 5] = pack_h2(c1[0][2], c1[0][3]);
+    }
+    __syncwarp();
+
+    // ---------------- phase 2: SH(4) of the view direction ++ geo -> view-dependent colour net ----------------
+    {
+        float sh[16];
+        sh_eval<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
+#pragma unroll
+        for (int i = 0; i < 8; i++) reinterpret_cast<__half2*>(ws.feat[lane])[i] = __floats2half2_rn(sh[2 * i], sh[2 * i + 1]);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        uint32_t a2[2][4];
+        ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) a2[1][i] = carry[t * 6 + i];
+        float c8[8][4];
+        mma_layer<2, 8>(wts + layer_off(LV0), a2, c8, lane);
+        uint32_t a4[4][4];
+        chain<8, ACT_RELU>(c8, a4);
+        mma_layer<4, 8>(wts + layer_off(LV1), a4, c8, lane);
+        chain<8, ACT_RELU>(c8, a4);
+        float c1[1][4];
+        mma_layer<4, 1>(wts + layer_off(LV2), a4, c1, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) c1[0][i] = sigmoidf_(c1[0][i]);
+        store_out<1>(ws.out, 16 * t, O_VIEW, 3, c1, lane);
+    }
+    __syncwarp();
+
+    // ---------------- phase 3: palette grid ++ diffuse -> basis net -> offsets/radiance + omega heads ----------------
+    gather_features((const __half*)f.table_palette, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        uint32_t a3[3][4];
+        ldmatrix_a(a3[0], &ws.feat[0][0], 16 * t, 0, lane);
+        ldmatrix_a(a3[1], &ws.feat[0][0], 16 * t, 16, lane);
+        a3[2][0] = carry[t * 6 + 4];
+        a3[2][1] = carry[t * 6 + 5];
+        a3[2][2] = 0u;
+        a3[2][3] = 0u;
+        float c8[8][4];
+        mma_layer<3, 8>(wts + layer_off(LB0), a3, c8, lane);
+        uint32_t a4[4][4];
+        chain<8, ACT_ELU>(c8, a4);
+        float c2[2][4];
+        mma_layer<4, 2>(wts + layer_off(LB1), a4, c2, lane);
+        uint32_t a1[1][4];
+        chain<2, ACT_NONE>(c2, a1);
+        float c3[3][4];
+        mma_layer<1, 3>(wts + layer_off(LH), a1, c3, lane);
+        store_out<3>(ws.out, 16 * t, O_OFFRAD, 13 + kNB, c3, lane);   // cols 7..19 offsets/radiance, 20..23 omega logits
+    }
+    __syncwarp();
+
+    // ---------------- phase 4 (optional): semantic grid -> clip net ----------------
+    if (CLIP) {
+        gather_features((const __half*)f.table_clip, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        __syncwarp();
+#pragma unroll 1
+        for (int t = 0; t < 2; t++) {
+            uint32_t a2[2][4];
+            ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
+            ldmatrix_a(a2[1], &ws.feat[0][0], 16 * t, 16, lane);
+            float c8[8][4];
+            mma_layer<2, 8>(wts + layer_off(LC0), a2, c8, lane);
+            uint32_t a4[4][4];
+            chain<8, ACT_RELU>(c8, a4);
+            float c2[2][4];
+            mma_layer<4, 2>(wts + layer_off(LC1), a4, c2, lane);
+            store_out<2>(ws.out, 16 * t, O_CLIP, (int)f.clip_dim, c2, lane);
+        }
+        __syncwarp();
+    }
+
+    // ---------------- collect this lane's sample ----------------
+    const float* row = ws.out[lane];
+    o.sigma = __expf(row[O_SIGMA]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { o.diffuse[i] = row[O_DIFF + i]; o.view_dep[i] = row[O_VIEW + i]; }
+#pragma unroll
+    for (int i = 0; i < 13; i++) o.off_rad[i] = row[O_OFFRAD + i] + sm.head_bias[i];
+    float osum = 0.f;
+#pragma unroll
+    for (int b = 0; b < kNB; b++) { o.omega[b] = softplusf_(row[O_OMEGA + b]) + 0.05f; osum += o.omega[b]; }
+    const float rinv = 1.0f / osum;
+#pragma unroll
+    for (int b = 0; b < kNB; b++) o.omega[b] *= rinv;
+#pragma unroll
+    for (int i = 0; i < kClipMax; i++) o.clip[i] = (CLIP && i < (int)f.clip_dim) ? row[O_CLIP + i] : 0.f;
+    __syncwarp();
+}
+
+// palette blend of one sample (ref: palette/renderer.py:470-494): basis_rgb[b][c] = omega_b * softplus(radiance) *
+// (palette_bc + offsets_weight * offsets_bc); rgb = sum_b basis_rgb + view_dep_weight * view_dep
+__device__ __forceinline__ void blend(const pnerf_palette_field& f, const FusedSmem& sm, const FieldOut& o, float (&rgb)[3],
+                                      float (&basis_rgb)[kNB * 3], float (&unscaled)[kNB * 3]) {
+    const float sp = softplusf_(o.off_rad[12]);
+    rgb[0] = rgb[1] = rgb[2] = 0.f;
+#pragma unroll
+    for (int b = 0; b < kNB; b++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float off = o.off_rad[b * 3 + c];
+            unscaled[b * 3 + c] = sm.palette[b * 3 + c] + off;
+            basis_rgb[b * 3 + c] = o.omega[b] * (sp * (sm.palette[b * 3 + c] + f.offsets_weight * off));
+            rgb[c] += basis_rgb[b * 3 + c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA prologue shared by both kernels: level table, head bias, palette, weights -> shared memory
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fused_prologue(const pnerf_palette_field& f, FusedSmem* sm, uint2* wts) {
+    if (threadIdx.x < f.L) make_level(sm->lp[threadIdx.x], threadIdx.x, f.offsets, f.S, f.H, 3, 0, false);
+    if (threadIdx.x < 16) sm->head_bias[threadIdx.x] = f.head_bias[threadIdx.x];
+    if (threadIdx.x < kNB * 3) sm->palette[threadIdx.x] = f.palette[threadIdx.x];
+    const int units = f.pred_clip ? kWUnitsClip : kWUnitsNoClip;   // uint2 units; both counts are even
+    const uint4* src = reinterpret_cast<const uint4*>(f.wpack);
+    uint4* dst = reinterpret_cast<uint4*>(wts);
+    for (int i = threadIdx.x; i < units / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+__host__ __device__ constexpr size_t fused_smem_bytes(bool clip) {
+    return sizeof(FusedSmem) + (size_t)(clip ? kWUnitsClip : kWUnitsNoClip) * sizeof(uint2) +
+           sizeof(WarpScratch) * kFusedWarps + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: field evaluation for a batch of samples (drop-in for PaletteNetwork.forward in eval mode)
+// ------------------------------------------------------------------------------------------------
+template <bool CLIP>
+__global__ void __launch_bounds__(kFusedWarps * 32, 2)
+k_field_forward(const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M, pnerf_palette_field f,
+                float* __restrict__ sigma, float* __restrict__ clip, float* __restrict__ omega,
+                float* __restrict__ off_rad, float* __restrict__ view_dep, float* __restrict__ diffuse) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem* sm = reinterpret_cast<FusedSmem*>(smem_raw);
+    uint2* wts = reinterpret_cast<uint2*>(smem_raw + ((sizeof(FusedSmem) + 15) & ~(size_t)15));
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(wts + (f.pred_clip ? kWUnitsClip : kWUnitsNoClip));
+    fused_prologue(f, sm, wts);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[wid];
+    const uint32_t n_tiles = ceil_div(M, 32u);
+    for (uint32_t tile = blockIdx.x * kFusedWarps + wid; tile < n_tiles; tile += gridDim.x * kFusedWarps) {
+        const uint32_t s = tile * 32 + lane;
+        const bool active = s < M;
+        float x = 0, y = 0, z = 0, dx = 0, dy = 0, dz = 1;
+        if (active) {
+            x = xyzs[(size_t)s * 3]; y = xyzs[(size_t)s * 3 + 1]; z = xyzs[(size_t)s * 3 + 2];
+            dx = dirs[(size_t)s * 3]; dy = dirs[(size_t)s * 3 + 1]; dz = dirs[(size_t)s * 3 + 2];
+        }
+        FieldOut o;
+        eval_field<CLIP>(f, *sm, wts, ws, x, y, z, dx, dy, dz, active, lane, o);
+        if (active) {
+            sigma[s] = o.sigma;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { diffuse[(size_t)s * 3 + i] = o.diffuse[i]; view_dep[(size_t)s * 3 + i] = o.view_dep[i]; }
+#pragma unroll
+            for (int i = 0; i < 13; i++) off_rad[(size_t)s * 13 + i] = o.off_rad[i];
+#pragma unroll
+            for (int b = 0; b < kNB; b++) omega[(size_t)s * kNB + b] = o.omega[b];
+            if (clip) {
+                for (uint32_t i = 0; i < f.clip_dim; i++) clip[(size_t)s * f.clip_dim + i] = o.clip[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: persistent fused renderer (march -> field -> blend -> composite), one ray per lane
+// ------------------------------------------------------------------------------------------------
+struct RenderArgs {
+    const float* rays_o; const float* rays_d; const float* nears; const float* fars; const float* noises;  // noises may be NULL
+    const uint8_t* bitfield;
+    uint32_t N, C, Hgrid, max_steps;
+    float dt_gamma, T_thresh;
+    float* weights_sum; float* depth; float* image;          // [N], [N], [N,3]   (written once per ray)
+    float* direct_rgb; float* view_dep_rgb; float* basis_acc; float* basis_rgb; float* unscaled_basis_rgb;  // aux (NULL in gui mode)
+    float* clip_feat;                                         // [N, clip_dim] or NULL
+    unsigned int* queue;                                      // [2]: next ray index, total samples shaded
+};
+
+template <bool CLIP, bool AUX>
+__global__ void __launch_bounds__(kFusedWarps * 32, 2) k_render_fused(RenderArgs a, pnerf_palette_field f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem* sm = reinterpret_cast<FusedSmem*>(smem_raw);
+    uint2* wts = reinterpret_cast<uint2*>(smem_raw + ((sizeof(FusedSmem) + 15) & ~(size_t)15));
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(wts + (f.pred_clip ? kWUnitsClip : kWUnitsNoClip));
+    fused_prologue(f, sm, wts);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[wid];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // per-lane ray state (the Marcher is rebuilt from rays_o/rays_d at each march call to keep registers free)
+    bool has_ray = false, first = false;
+    float ddx = 0.f, ddy = 0.f, ddz = 1.f;
+    uint32_t ray = 0, count = 0;
+    float far = 0.f, tc = 0.f;                 // tc: the compositor's ray parameter (== rays_t of the reference)
+    float wsum = 0.f, dep = 0.f, r = 0.f, g = 0.f, b = 0.f;
+    bool exhausted = false;                    // warp-uniform: the ray queue is empty
+    uint32_t shaded = 0;
+
+    for (;;) {
+        // ---- find the next sample of every lane; lanes whose ray ended pull a new one (a few attempts) ----
+        bool sample = false;
+        float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, rdt = 0.f;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 4; attempt++) {
+            const uint32_t need = __ballot_sync(0xffffffffu, !has_ray);
+            if (need && !exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(a.queue, (unsigned int)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + __popc(need) >= a.N) exhausted = true;
+                if (!has_ray) {
+                    const uint32_t idx = base + __popc(need & lt_mask);
+                    if (idx < a.N) {
+                        ray = idx;
+                        tc = a.nears[ray];
+                        far = a.fars[ray];
+                        has_ray = true; first = true; count = 0;
+                        wsum = dep = r = g = b = 0.f;
+                    }
+                }
+            }
+            if (has_ray && !sample) {
+                // one march call of the reference with n_step = 1 (raymarching.cu:936-1010)
+                Marcher m;
+                m.init(a.rays_o + (size_t)ray * 3, a.rays_d + (size_t)ray * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid,
+                       a.bitfield);
+                ddx = m.dx; ddy = m.dy; ddz = m.dz;
+                float t = tc;
+                if (first && a.noises) t += m.step_size(t) * a.noises[ray];
+                first = false;
+                const float last_t = t;
+                while (t < far) {
+                    if (m.probe(t, x, y, z, dt)) {
+                        t += dt;
+                        rdt = t - last_t;
+                        sample = true;
+                        break;
+                    }
+                }
+                if (!sample || count >= a.max_steps) {   // ray left the volume (or used its sample budget): retire it
+                    sample = false;
+                    a.weights_sum[ray] = wsum; a.depth[ray] = dep;
+                    a.image[(size_t)ray * 3] = r; a.image[(size_t)ray * 3 + 1] = g; a.image[(size_t)ray * 3 + 2] = b;
+                    has_ray = false;
+                }
+            }
+            const uint32_t idle = __ballot_sync(0xffffffffu, !sample);
+            if (idle == 0u || (exhausted && __ballot_sync(0xffffffffu, has_ray && !sample) == 0u)) break;
+        }
+        const uint32_t smask = __ballot_sync(0xffffffffu, sample);
+        if (smask == 0u) {
+            if (exhausted && __ballot_sync(0xffffffffu, has_ray) == 0u) break;
+            continue;
+        }
+
+        // ---- shade the warp's 32 samples ----
+        FieldOut o;
+        eval_field<CLIP>(f, *sm, wts, ws, x, y, z, sample ? ddx : 0.f, sample ? ddy : 0.f, sample ? ddz : 1.f, sample, lane, o);
+
+        // ---- composite (ref: raymarching.cu:1051-1110, one sample) ----
+        if (sample) {
+            shaded++;
+            count++;
+            float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
+            blend(f, *sm, o, rgb, basis_rgb, unscaled);
+            const float alpha = 1.0f - __expf(-(f.density_scale * o.sigma) * dt);
+            const float T = 1 - wsum;
+            const float wgt = alpha * T;
+            wsum += wgt;
+            tc += rdt;
+            dep += wgt * tc;
+            r += wgt * rgb[0]; g += wgt * rgb[1]; b += wgt * rgb[2];
+            if (AUX) {
+                float* p = a.direct_rgb + (size_t)ray * 3;
+                float* q = a.view_dep_rgb + (size_t)ray * 3;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { p[c] += wgt * (o.diffuse[c] + o.view_dep[c]); q[c] += wgt * o.view_dep[c]; }
+                float* pa = a.basis_acc + (size_t)ray * kNB;
+#pragma unroll
+                for (int k = 0; k < kNB; k++) pa[k] += wgt * o.omega[k];
+                float* pb = a.basis_rgb + (size_t)ray * kNB * 3;
+                float* pu = a.unscaled_basis_rgb + (size_t)ray * kNB * 3;
+#pragma unroll
+                for (int k = 0; k < kNB * 3; k++) { pb[k] += wgt * basis_rgb[k]; pu[k] += wgt * unscaled[k]; }
+            }
+            if (CLIP && a.clip_feat) {
+                float* pc = a.clip_feat + (size_t)ray * f.clip_dim;
+                for (uint32_t k = 0; k < f.clip_dim; k++) pc[k] += wgt * o.clip[k];
+            }
+            if (T < a.T_thresh) {   // early termination (the terminating sample is accumulated, like the reference)
+                a.weights_sum[ray] = wsum; a.depth[ray] = dep;
+                a.image[(size_t)ray * 3] = r; a.image[(size_t)ray * 3 + 1] = g; a.image[(size_t)ray * 3 + 2] = b;
+                has_ray = false;
+            }
+        }
+    }
+    // sample statistics (one atomic per warp)
+    shaded = (uint32_t)warp_sum((float)shaded);  // exact below 2^24 per warp
+    if (lane == 0 && shaded) atomicAdd(a.queue + 1, shaded);
+}
+
+}  // namespace pnerf
+
+using namespace pnerf;
+
+extern "C" {
+
+/* fused field: xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (may be NULL), omega [M,4], off_rad [M,13],
+ * view_dep [M,3], diffuse [M,3], all fp32. Replaces PaletteNetwork.forward (palette/network.py:156-185) in eval mode. */
+int pnerf_palette_field_forward(const float* xyzs, const float* dirs, uint32_t M,
+                                          const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
+                                          float* off_rad, float* view_dep, float* diffuse, void* stream) {
+    if (M == 0) return PNERF_OK;
+    PNERF_REQUIRE(xyzs && dirs && field && sigma && omega && off_rad && view_dep && diffuse);
+    PNERF_REQUIRE(field->table_sigma && field->table_palette && field->offsets && field->wpack && field->head_bias &&
+                  field->palette);
+    if (field->L != 16 || field->clip_dim > (uint32_t)kClipMax) return PNERF_ERR_UNSUPPORTED;
+    if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool clip_on = field->pred_clip != 0;
+    const size_t smem = fused_smem_bytes(clip_on);
+    const uint32_t tiles = ceil_div(M, 32u);
+    const uint32_t grid = min(ceil_div(tiles, (uint32_t)kFusedWarps), (uint32_t)(2 * kNumSMs));
+    cudaError_t e;
+    if (clip_on) {
+        e = cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_cuda_error(e, "field_forward attr"); return PNERF_ERR_CUDA; }
+        k_field_forward<true><<<grid, kFusedWarps * 32, smem, s>>>(xyzs, dirs, M, *field, sigma, clip, omega, off_rad, view_dep, diffuse);
+    } else {
+        e = cudaFuncSetAttribute(k_field_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_cuda_error(e, "field_forward attr"); return PNERF_ERR_CUDA; }
+        k_field_forward<false><<<grid, kFusedWarps * 32, smem, s>>>(xyzs, dirs, M, *field, sigma, nullptr, omega, off_rad, view_dep, diffuse);
+    }
+    return check_launch("palette_field_forward");
+}
+
+/* persistent fused renderer: replaces the inference loop of PaletteRenderer.run_cuda (palette/renderer.py:430-523).
+ * All outputs must be zero-initialised; queue[2] must be zero. Aux maps may all be NULL (gui_mode). */
+int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                                         const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
+                                         uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
+                                         const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
+                                         float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
+                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, void* stream) {
+    if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
+    PNERF_REQUIRE(field->table_sigma && field->table_palette && field->offsets && field->wpack && field->head_bias &&
+                  field->palette);
+    PNERF_REQUIRE(C >= 1 && C <= 16 && Hgrid >= 1 && max_steps >= 1);
+    if (field->L != 16 || field->clip_dim > (uint32_t)kClipMax || Hgrid > 1024) return PNERF_ERR_UNSUPPORTED;
+    if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
+    const bool aux = direct_rgb != nullptr;
+    if (aux) PNERF_REQUIRE(view_dep_rgb && basis_acc && basis_rgb && unscaled_basis_rgb);
+    RenderArgs a;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.nears = nears; a.fars = fars; a.noises = noises; a.bitfield = bitfield;
+    a.N = N; a.C = C; a.Hgrid = Hgrid; a.max_steps = max_steps; a.dt_gamma = dt_gamma; a.T_thresh = T_thresh;
+    a.weights_sum = weights_sum; a.depth = depth; a.image = image;
+    a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
+    a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool clip_on = field->pred_clip != 0;
+    const size_t smem = fused_smem_bytes(clip_on);
+    const uint32_t warps_needed = ceil_div(N, 32u);
+    const uint32_t grid = min(ceil_div(warps_needed, (uint32_t)kFusedWarps), (uint32_t)(2 * kNumSMs));  // persistent: 2 CTAs per SM
+#define PNERF_LAUNCH_RENDER(CL, AX)                                                                                   \
+    do {                                                                                                              \
+        cudaError_t e = cudaFuncSetAttribute(k_render_fused<CL, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_last_cuda_error(e, "render_fused attr"); return PNERF_ERR_CUDA; }                 \
+        k_render_fused<CL, AX><<<grid, kFusedWarps * 32, smem, s>>>(a, *field);                                       \
+    } while (0)
+    if (clip_on) { if (aux) PNERF_LAUNCH_RENDER(true, true); else PNERF_LAUNCH_RENDER(true, false); }
+    else { if (aux) PNERF_LAUNCH_RENDER(false, true); else PNERF_LAUNCH_RENDER(false, false); }
+#undef PNERF_LAUNCH_RENDER
+    return check_launch("palette_render_fused");
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// grid_common.cuh — per-level constants and corner indexing of the multiresolution hash grid, shared by the
+// stand-alone encoder kernels (gridenc.cu) and the fused field / render kernels (fused.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pnerf {
+
+constexpr int kMaxLevels = 32;
+
+struct LevelParams {
+    float scale;         // exp2f(level * S) * H - 1
+    uint32_t stride[5];  // dense strides per dimension; 0 for dimensions the reference's loop never reaches
+    uint32_t size;       // hashmap_size = offsets[l+1] - offsets[l]
+    uint32_t offset;     // offsets[l] (in entries)
+    uint32_t use_hash;   // gridtype == hash && (res+1)^D overflowed the table
+    uint32_t mask;       // size - 1 if size is a power of two, else 0
+};
+
+// ref: gridencoder.cu:54-72,97-99 — the index loop stops multiplying once stride > hashmap_size.
+__device__ __forceinline__ void make_level(LevelParams& p, uint32_t level, const int32_t* offsets, float S, uint32_t H,
+                                           uint32_t D, uint32_t gridtype, bool align_corners) {
+    p.offset = (uint32_t)offsets[level];
+    p.size = (uint32_t)offsets[level + 1] - (uint32_t)offsets[level];
+    p.scale = exp2f(level * S) * H - 1.0f;
+    const uint32_t resolution = (uint32_t)ceilf(p.scale) + 1;
+    uint32_t stride = 1;
+    for (uint32_t d = 0; d < 5; d++) {
+        if (d < D && stride <= p.size) {
+            p.stride[d] = stride;
+            stride *= align_corners ? resolution : (resolution + 1);
+        } else {
+            p.stride[d] = 0;
+        }
+    }
+    p.use_hash = (gridtype == 0 && stride > p.size) ? 1u : 0u;
+    p.mask = ((p.size & (p.size - 1)) == 0) ? (p.size - 1) : 0u;
+}
+
+__device__ __forceinline__ uint32_t wrap_index(uint32_t index, const LevelParams& p) {
+    return p.mask ? (index & p.mask) : (index % p.size);
+}
+
+__device__ __forceinline__ void corner_setup(const LevelParams& p, float x, float y, float z, uint32_t (&idx)[8],
+                                             float (&w)[8], bool align_corners) {
+    const float half = align_corners ? 0.0f : 0.5f;
+    float px = x * p.scale + half, py = y * p.scale + half, pz = z * p.scale + half;
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+    px -= (float)gx; py -= (float)gy; pz -= (float)gz;
+    const float wx[2] = {1 - px, px}, wy[2] = {1 - py, py}, wz[2] = {1 - pz, pz};
+    if (p.use_hash) {
+        const uint32_t hx[2] = {gx, gx + 1};  // prime 1
+        const uint32_t hy[2] = {gy * 2654435761u, (gy + 1) * 2654435761u};
+        const uint32_t hz[2] = {gz * 805459861u, (gz + 1) * 805459861u};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            idx[c] = wrap_index(hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1], p);
+            w[c] = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+        }
+    } else {
+        const uint32_t ix[2] = {gx * p.stride[0], (gx + 1) * p.stride[0]};
+        const uint32_t iy[2] = {gy * p.stride[1], (gy + 1) * p.stride[1]};
+        const uint32_t iz[2] = {gz * p.stride[2], (gz + 1) * p.stride[2]};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            idx[c] = wrap_index(ix[c & 1] + iy[(c >> 1) & 1] + iz[(c >> 2) & 1], p);
+            w[c] = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+        }
+    }
+}
+
+
+}  // namespace pnerf

@@ -11,108 +11,9 @@
 //     leave the SM as coalesced runs;
 //   - packbits reads 2x float4 per byte, morton/near-far read and write through coalesced vector accesses.
 #include "common.cuh"
+#include "march_common.cuh"
 
 namespace pnerf {
-
-// ------------------------------------------------------------------------------------------------
-// bit tricks (ref: raymarching.cu:59-84)
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
-    // 10 input bits -> every third bit
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
-__host__ __device__ __forceinline__ uint32_t morton_encode(uint32_t x, uint32_t y, uint32_t z) {
-    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
-}
-__host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
-    x &= 0x49249249u;
-    x = (x | (x >> 2)) & 0xc30c30c3u;
-    x = (x | (x >> 4)) & 0x0f00f00fu;
-    x = (x | (x >> 8)) & 0xff0000ffu;
-    x = (x | (x >> 16)) & 0x0000ffffu;
-    return x;
-}
-
-// exponent e with v = m * 2^e, m in [0.5, 1) — frexpf semantics for the values that matter here
-// (normal floats; zero/denormals give e <= 0 which every caller clamps to 0, as frexpf's would be).
-__device__ __forceinline__ int frexp_exponent(float v) {
-    return (int)((__float_as_uint(v) >> 23) & 0xffu) - 126;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-ray marcher. One instance per thread; `probe(t)` evaluates the lattice point t and either reports an
-// occupied sample or advances t past the empty voxel. Arithmetic follows raymarching.cu:364-403 exactly.
-// ------------------------------------------------------------------------------------------------
-struct Marcher {
-    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
-    float bound, dt_gamma, dt_min, dt_max;
-    float rH, Hf, halfH, Hm1, H3f, Cm1;
-    const uint8_t* __restrict__ grid;
-
-    __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d, float bound_,
-                                         float dt_gamma_, uint32_t max_steps, uint32_t C, uint32_t H,
-                                         const uint8_t* __restrict__ grid_) {
-        ox = o[0]; oy = o[1]; oz = o[2];
-        dx = d[0]; dy = d[1]; dz = d[2];
-        rdx = 1 / dx; rdy = 1 / dy; rdz = 1 / dz;
-        bound = bound_;
-        dt_gamma = dt_gamma_;
-        const float two_sqrt3 = 2 * 1.7320508075688772f;
-        dt_min = two_sqrt3 / max_steps;
-        dt_max = two_sqrt3 * (1u << (C - 1)) / H;
-        Hf = (float)H;
-        rH = 1 / Hf;
-        halfH = 0.5f * Hf;  // exact; (0.5 * v * H) in double rounds once, same as v * halfH in float
-        Hm1 = (float)(H - 1);
-        H3f = (float)(H * H * H);
-        Cm1 = (float)C - 1.0f;
-        grid = grid_;
-    }
-
-    __device__ __forceinline__ float step_size(float t) const { return clampf(t * dt_gamma, dt_min, dt_max); }
-
-    // Evaluate lattice point t. Returns true if (x,y,z) is an occupied sample (t is NOT advanced; caller adds dt).
-    // Otherwise advances t to the first lattice point at/after the voxel exit and returns false.
-    __device__ __forceinline__ bool probe(float& t, float& x, float& y, float& z, float& dt) const {
-        x = clampf(ox + t * dx, -bound, bound);
-        y = clampf(oy + t * dy, -bound, bound);
-        z = clampf(oz + t * dz, -bound, bound);
-        dt = step_size(t);
-
-        // cascade from position and from step size (ref: raymarching.cu:45-57)
-        const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-        const int lp = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(mx)));
-        const int ld = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(dt * Hf * 0.5f)));
-        const int level = max(lp, ld);
-
-        const float mip_bound = fminf(scalbnf(1.0f, level), bound);
-        const float mip_rbound = 1 / mip_bound;
-
-        const int nx = (int)clampf((x * mip_rbound + 1) * halfH, 0.0f, Hm1);
-        const int ny = (int)clampf((y * mip_rbound + 1) * halfH, 0.0f, Hm1);
-        const int nz = (int)clampf((z * mip_rbound + 1) * halfH, 0.0f, Hm1);
-
-        // the reference forms this index in fp32 (level * H3 + morton); keep its rounding behaviour
-        const uint32_t index = (uint32_t)((float)level * H3f + (float)morton_encode(nx, ny, nz));
-        const bool occ = grid[index >> 3] & (1u << (index & 7u));
-        if (occ) return true;
-
-        // distance to the exit face of this voxel along each axis
-        const float sx = copysignf(1.0f, dx), sy = copysignf(1.0f, dy), sz = copysignf(1.0f, dz);
-        const float tx = (((nx + 0.5f + 0.5f * sx) * rH * 2 - 1) * mip_bound - x) * rdx;
-        const float ty = (((ny + 0.5f + 0.5f * sy) * rH * 2 - 1) * mip_bound - y) * rdy;
-        const float tz = (((nz + 0.5f + 0.5f * sz) * rH * 2 - 1) * mip_bound - z) * rdz;
-        const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
-        do {
-            t += step_size(t);
-        } while (t < tt);
-        return false;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // near / far  (ref: raymarching.cu:95-148)

@@ -1,0 +1,182 @@
+"""Host side of the fused field / fused renderer (csrc/fused.cu): weight packing, fp16 table cache, C-ABI calls.
+
+`pack_weights` turns the model's nn.Linear weights into the shared-memory image the kernels expect: per layer
+[n-tile][k-step][lane] -> the two 32-bit registers of the mma.m16n8k16 B fragment. The reference's concatenations are
+folded into the packing:
+    diff_net.0   [64,15]  -> K=16 : column 0 multiplies the sigma logit -> zero, columns 1..15 = geo features
+    color_net.0  [64,31]  -> K=32 : 0..15 SH, 16 -> zero (logit), 17..31 geo
+    basis_net.0  [64,35]  -> K=48 : 0..31 palette grid, 32..34 diffuse, rest zero
+    heads                 -> K=16, N=24 : rows 0..12 offsets_radiance_net.weight, rows 13..16 omega_net.0.weight
+Nothing here computes on the CPU at render time; the cache is rebuilt only when a parameter's version counter moves.
+"""
+import ctypes
+from ctypes import c_float, c_uint32, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import ptr, stream
+
+NB = 4          # bases supported by the fused kernels
+CLIP_MAX = 16
+
+
+class PaletteField(ctypes.Structure):
+    """mirror of `struct pnerf_palette_field` (csrc/fused.cu)"""
+    _fields_ = [("table_sigma", c_void_p), ("table_palette", c_void_p), ("table_clip", c_void_p), ("offsets", c_void_p),
+                ("wpack", c_void_p), ("head_bias", c_void_p), ("palette", c_void_p),
+                ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
+                ("S", c_float), ("bound", c_float), ("density_scale", c_float), ("offsets_weight", c_float),
+                ("view_dep_weight", c_float)]
+
+
+P, U, F = c_void_p, c_uint32, c_float
+L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P])
+
+
+def _frag(W, n_pad, k_pad):
+    """W [N,K] (torch, any float dtype) -> fp16 B-fragment image [n_pad/8][k_pad/16][32][4]"""
+    Wp = torch.zeros(n_pad, k_pad, dtype=torch.float32, device=W.device)
+    Wp[: W.shape[0], : W.shape[1]] = W.float()
+    nt, ks = n_pad // 8, k_pad // 16
+    lane = torch.arange(32, device=W.device)
+    n = lane // 4
+    k = (lane % 4) * 2
+    out = torch.empty(nt, ks, 32, 4, dtype=torch.float32, device=W.device)
+    for a in range(nt):
+        for b in range(ks):
+            rows = a * 8 + n
+            base = b * 16 + k
+            out[a, b, :, 0] = Wp[rows, base]
+            out[a, b, :, 1] = Wp[rows, base + 1]
+            out[a, b, :, 2] = Wp[rows, base + 8]
+            out[a, b, :, 3] = Wp[rows, base + 9]
+    return out.to(torch.float16).reshape(-1)
+
+
+def pack_weights(model):
+    """-> (wpack fp16 [units*4], head_bias fp32 [16]) on the model's device; layer order must match enum Layer"""
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    dev = sd["sigma_net.0.weight"].device
+    z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+
+    d0 = z(64, 16); d0[:, 1:16] = sd["diff_net.0.weight"].float()
+    v0 = z(64, 32); v0[:, 0:16] = sd["color_net.0.weight"][:, 0:16].float(); v0[:, 17:32] = sd["color_net.0.weight"][:, 16:31].float()
+    b0 = z(64, 48); b0[:, 0:35] = sd["basis_net.0.weight"].float()
+    heads = z(24, 16)
+    heads[0:13, 0:15] = sd["offsets_radiance_net.weight"].float()
+    heads[13:17, 0:15] = sd["omega_net.0.weight"].float()
+    layers = [
+        _frag(sd["sigma_net.0.weight"], 64, 32), _frag(sd["sigma_net.1.weight"], 16, 64),
+        _frag(d0, 64, 16), _frag(sd["diff_net.1.weight"], 64, 64), _frag(sd["diff_net.2.weight"], 8, 64),
+        _frag(v0, 64, 32), _frag(sd["color_net.1.weight"], 64, 64), _frag(sd["color_net.2.weight"], 8, 64),
+        _frag(b0, 64, 48), _frag(sd["basis_net.1.weight"], 16, 64), _frag(heads, 24, 16),
+    ]
+    if model.opt.pred_clip:
+        layers += [_frag(sd["clip_net.0.weight"], 64, 32), _frag(sd["clip_net.1.weight"], 16, 64)]
+    bias = z(16)
+    bias[0:13] = sd["offsets_radiance_net.bias"].float()
+    return torch.cat(layers).contiguous(), bias.contiguous()
+
+
+def supported(model):
+    """the fused kernels cover the reference's default architecture; anything else uses the unfused path"""
+    try:
+        enc = model.encoder
+        return (model.num_basis == NB and model.opt.clip_dim <= CLIP_MAX and model.num_layers == 2 and model.hidden_dim == 64
+                and model.geo_feat_dim == 15 and model.num_layers_color == 3 and enc.num_levels == 16 and enc.level_dim == 2
+                and enc.input_dim == 3 and enc.gridtype == "hash" and not enc.align_corners
+                and getattr(model.encoder_dir, "degree", 0) == 4 and model.bg_radius <= 0
+                and model.encoder.embeddings.is_cuda)
+    except AttributeError:
+        return False
+
+
+class FieldCache:
+    """device-resident fp16 tables + packed weights of one model, refreshed when parameters change"""
+
+    def __init__(self, model):
+        self.model = model
+        self.key = None
+        self.keep = None
+        self.field = None
+
+    def _version_key(self):
+        m = self.model
+        ps = list(m.parameters())
+        return tuple(p._version for p in ps) + (m.density_scale, m.offsets_weight, m.view_dep_weight,
+                                                id(m.basis_color), m.encoder.embeddings.device)
+
+    def get(self):
+        key = self._version_key()
+        if key == self.key:
+            return self.field
+        m = self.model
+        with torch.no_grad():
+            t_sigma = m.encoder.embeddings.detach().to(torch.float16).contiguous()
+            t_pal = m.encoder_palette.embeddings.detach().to(torch.float16).contiguous()
+            t_clip = m.encoder_clip.embeddings.detach().to(torch.float16).contiguous() if m.opt.pred_clip else None
+            wpack, bias = pack_weights(m)
+            palette = m.basis_color.detach().float().clamp(0, 1).contiguous()
+            offsets = m.encoder.offsets.contiguous()
+        f = PaletteField()
+        f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
+        f.offsets, f.wpack, f.head_bias, f.palette = ptr(offsets), ptr(wpack), ptr(bias), ptr(palette)
+        f.L, f.H = m.encoder.num_levels, m.encoder.base_resolution
+        f.pred_clip, f.clip_dim = int(bool(m.opt.pred_clip)), m.opt.clip_dim
+        f.S = float(np.float32(np.log2(m.encoder.per_level_scale)))
+        f.bound, f.density_scale = float(m.bound), float(m.density_scale)
+        f.offsets_weight, f.view_dep_weight = float(m.offsets_weight), float(m.view_dep_weight)
+        self.keep = (t_sigma, t_pal, t_clip, wpack, bias, palette, offsets)  # keep the device buffers alive
+        self.field, self.key = f, key
+        return f
+
+
+def _cache(model):
+    c = getattr(model, "_fused_cache", None)
+    if c is None:
+        c = FieldCache(model)
+        object.__setattr__(model, "_fused_cache", c)
+    return c
+
+
+@torch.no_grad()
+def field_forward(model, xyzs, dirs):
+    """fused PaletteNetwork.forward (eval): -> (sigma [M], clip [M,cd], omega [M,4], offsets_radiance [M,13],
+    view_dep [M,3], diffuse [M,3]), fp32"""
+    L.require_cuda(xyzs, dirs)
+    f = _cache(model).get()
+    xyzs, dirs = xyzs.contiguous().float(), dirs.contiguous().float()
+    M, dev = xyzs.shape[0], xyzs.device
+    e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    sigma, omega, off_rad, view_dep, diffuse = e(M), e(M, NB), e(M, 13), e(M, 3), e(M, 3)
+    cd = model.opt.clip_dim
+    clip = e(M, cd) if model.opt.pred_clip else torch.zeros(M, cd, dtype=torch.float32, device=dev)
+    L.call("pnerf_palette_field_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(sigma),
+           ptr(clip) if model.opt.pred_clip else None, ptr(omega), ptr(off_rad), ptr(view_dep), ptr(diffuse), stream())
+    return sigma, clip, omega, off_rad, view_dep, diffuse
+
+
+@torch.no_grad()
+def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
+    """persistent fused renderer -> dict of accumulators like PaletteRenderer._infer_loop"""
+    f = _cache(model).get()
+    N, dev = rays_o.shape[0], rays_o.device
+    nb, cd = model.num_basis, model.opt.clip_dim
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    acc = {"weights_sum": z(N), "depth": z(N), "image": z(N, 3), "clip_feat": z(N, cd)}
+    if not gui_mode:
+        acc.update(direct_rgb=z(N, 3), view_dep_rgb=z(N, 3), basis_acc=z(N, nb), basis_rgb=z(N, 3 * nb),
+                   unscaled_basis_rgb=z(N, 3 * nb))
+    queue = torch.zeros(2, dtype=torch.int32, device=dev)
+    noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
+    aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
+    L.call("pnerf_palette_render_fused", ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises),
+           ptr(model.density_bitfield), N, model.cascade, model.grid_size, max_steps, float(dt_gamma), float(T_thresh),
+           ctypes.addressof(f), ptr(acc["weights_sum"]), ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"),
+           aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"), aux("unscaled_basis_rgb"),
+           ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), stream())
+    acc["_queue"] = queue   # [next ray index, samples shaded]; read lazily (no sync here)
+    return acc

@@ -296,6 +296,8 @@ class PaletteRenderer(nn.Module, OccupancyState):
             acc = self._infer_fused(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode)
         else:
             acc = self._infer_loop(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode)
+        self._last_schedule = "fused" if use_fused else "loop"
+        self._last_queue = acc.get("_queue")
         ws = acc["weights_sum"]
         out = {
             "depth": normalise_depth(acc["depth"], nears, fars).view(*prefix),
@@ -312,12 +314,18 @@ class PaletteRenderer(nn.Module, OccupancyState):
             out["basis_acc"] = acc["basis_acc"].view(*prefix, nb)
         return out
 
-    # fused path hooks (palettenerf_b200/fused.py installs the real implementation)
+    # -- fused schedule (csrc/fused.cu): one persistent kernel instead of the host loop -------------------------
     def _fused_available(self, gui_mode):
-        return False
+        """default policy: use the fused renderer under fp16 autocast (its MLPs run fp16 tensor-core math) whenever
+        the architecture is the one it implements and no GUI edit module is active"""
+        from .. import fused
+        return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None and fused.supported(self))
 
-    def _infer_fused(self, *a, **k):
-        raise RuntimeError("fused render path not available")
+    def _infer_fused(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
+        from .. import fused
+        if self.edit is not None or self.stylizer is not None or not fused.supported(self):
+            raise RuntimeError("fused render path does not cover this model configuration (edit/stylizer/architecture)")
+        return fused.render(self, rays_o.float(), rays_d.float(), nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode)
 
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, test_mode=False, gui_mode=False, **kwargs):
         run = self.run_cuda if self.cuda_ray else self.run
