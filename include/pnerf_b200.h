@@ -200,14 +200,16 @@ PNERF_API int pnerf_palette_field_forward(const float* xyzs, const float* dirs, 
                                           const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
                                           float* off_rad, float* view_dep, float* diffuse, void* stream);
 
-/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[2] zeroed:
- * on return queue[0] >= N and queue[1] = number of samples shaded */
+/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[3] zeroed:
+ * on return queue[1] = number of samples shaded, queue[2] = number of rays with at least one sample.
+ * hit_list (int32), t_first, t_last (fp32) are [N] scratch buffers. */
 PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
                                          uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
                                          const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                                          float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
-                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, void* stream);
+                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue,
+                                         int32_t* hit_list, float* t_first, float* t_last, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,8 @@ namespace pnerf {
 
 constexpr int kNB = 4;            // palette bases supported by the fused path (reference default, main_palette.py:99)
 constexpr int kClipMax = 16;      // semantic feature width supported by the fused path (main_palette.py:76)
-constexpr int kFusedWarps = 8;
+constexpr int kFusedWarps = 12;     // one 384-thread CTA per SM: <= 168 registers/thread, no spills in the MMA chain
+constexpr int kAuxCh = 3 + 3 + kNB + 2 * kNB * 3;   // direct_rgb, view_dep_rgb, basis_acc, basis_rgb, unscaled_basis_rgb
 constexpr int kFeatStride = 40;   // halfs per feature row: 32 + 8 pad -> ldmatrix rows hit distinct bank groups
 constexpr int kOutStride = 41;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
 
@@ -61,6 +62,10 @@ enum OutCol { O_SIGMA = 0, O_DIFF = 1, O_VIEW = 4, O_OFFRAD = 7, O_OMEGA = 20, O
 struct WarpScratch {
     __half feat[32][kFeatStride];
     float out[32][kOutStride];
+};
+// per-warp auxiliary-map accumulators of the renderer, channel-major so that lane-per-ray accesses are conflict-free
+struct WarpAux {
+    float acc[kAuxCh][32];
 };
 
 struct FusedSmem {
@@ -151,7 +156,7 @@ __device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : log
 // ------------------------------------------------------------------------------------------------
 // hash-grid gather of one sample (this lane) into its fp16 feature row
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gather_features(const __half* __restrict__ table, const LevelParams* __restrict__ lp,
+__device__ __noinline__ void gather_features(const __half* __restrict__ table, const LevelParams* __restrict__ lp,
                                                 uint32_t L, float u, float v, float w, bool active,
                                                 __half* __restrict__ row) {
     for (uint32_t l0 = 0; l0 < L; l0 += 2) {
@@ -372,16 +377,16 @@ __device__ __forceinline__ void fused_prologue(const pnerf_palette_field& f, Fus
     __syncthreads();
 }
 
-__host__ __device__ constexpr size_t fused_smem_bytes(bool clip) {
+__host__ __device__ constexpr size_t fused_smem_bytes(bool clip, bool aux) {
     return sizeof(FusedSmem) + (size_t)(clip ? kWUnitsClip : kWUnitsNoClip) * sizeof(uint2) +
-           sizeof(WarpScratch) * kFusedWarps + 16;
+           sizeof(WarpScratch) * kFusedWarps + (aux ? sizeof(WarpAux) * kFusedWarps : 0) + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1: field evaluation for a batch of samples (drop-in for PaletteNetwork.forward in eval mode)
 // ------------------------------------------------------------------------------------------------
 template <bool CLIP>
-__global__ void __launch_bounds__(kFusedWarps * 32, 2)
+__global__ void __launch_bounds__(kFusedWarps * 32, 1)
 k_field_forward(const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M, pnerf_palette_field f,
                 float* __restrict__ sigma, float* __restrict__ clip, float* __restrict__ omega,
                 float* __restrict__ off_rad, float* __restrict__ view_dep, float* __restrict__ diffuse) {
@@ -429,11 +434,70 @@ struct RenderArgs {
     float* weights_sum; float* depth; float* image;          // [N], [N], [N,3]   (written once per ray)
     float* direct_rgb; float* view_dep_rgb; float* basis_acc; float* basis_rgb; float* unscaled_basis_rgb;  // aux (NULL in gui mode)
     float* clip_feat;                                         // [N, clip_dim] or NULL
-    unsigned int* queue;                                      // [2]: next ray index, total samples shaded
+    unsigned int* queue;                                      // [3]: next hit-list slot, samples shaded, rays with samples
+    const int32_t* hit_list;                                  // [N] ids of the rays that own at least one sample
+    const float* t_first; const float* t_last;                // [N] lattice t of each ray's first / last occupied point
 };
 
+// ------------------------------------------------------------------------------------------------
+// pre-pass: one thread per ray walks the occupancy grid once (same lattice walk as the reference's march) and
+// records the first and last occupied lattice point. Rays without samples (79% of an 800x800 lego view) never
+// enter the persistent kernel, and rays inside it never march the empty tail behind their last sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                     const float* __restrict__ nears, const float* __restrict__ fars,
+                                                     const float* __restrict__ noises, const uint8_t* __restrict__ bitfield,
+                                                     uint32_t N, uint32_t C, uint32_t H, uint32_t max_steps, float bound,
+                                                     float dt_gamma, int32_t* __restrict__ hit_list,
+                                                     float* __restrict__ t_first, float* __restrict__ t_last,
+                                                     unsigned int* __restrict__ queue) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool hit = false;
+    float tf = 0.f, tl = 0.f;
+    if (n < N) {
+        Marcher m;
+        m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, bitfield);
+        // The walk below is the reference's inference schedule with n_step = 1: after every sample the march
+        // restarts from the compositor's ray parameter tc = tc + (t_end_of_sample - last_t) (raymarching.cu:1073,
+        // 984-986), which is NOT always bit-identical to the marcher's own t (the subtraction rounds when the sample
+        // lies beyond 2x the restart point). The persistent kernel performs the same walk, so t_first / t_last are
+        // exact lattice points of it.
+        const float far = fars[n];
+        float tc = nears[n];
+        float t = tc;
+        if (noises) t += m.step_size(t) * noises[n];
+        float t_mark = t;
+        uint32_t count = 0;
+        float x, y, z, dt;
+        while (t < far && count < max_steps) {
+            if (m.probe(t, x, y, z, dt)) {
+                if (count == 0) tf = t;
+                tl = t;
+                count++;
+                t += dt;
+                tc += t - t_mark;
+                t = tc;
+                t_mark = tc;
+            }
+        }
+        hit = count > 0;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(queue + 2, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) {
+            hit_list[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)n;
+            t_first[n] = tf;
+            t_last[n] = tl;
+        }
+    }
+}
+
 template <bool CLIP, bool AUX>
-__global__ void __launch_bounds__(kFusedWarps * 32, 2) k_render_fused(RenderArgs a, pnerf_palette_field f) {
+__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs a, pnerf_palette_field f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem* sm = reinterpret_cast<FusedSmem*>(smem_raw);
     uint2* wts = reinterpret_cast<uint2*>(smem_raw + ((sizeof(FusedSmem) + 15) & ~(size_t)15));
@@ -441,67 +505,100 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 2) k_render_fused(RenderArgs
     fused_prologue(f, sm, wts);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpScratch& ws = scratch[wid];
+    WarpAux* auxs = reinterpret_cast<WarpAux*>(scratch + kFusedWarps);
+    float (*aux)[32] = AUX ? auxs[wid].acc : nullptr;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // retire a ray: its accumulators go to global memory once
+    auto retire = [&](uint32_t ray_, float wsum_, float dep_, float r_, float g_, float b_) {
+        a.weights_sum[ray_] = wsum_; a.depth[ray_] = dep_;
+        a.image[(size_t)ray_ * 3] = r_; a.image[(size_t)ray_ * 3 + 1] = g_; a.image[(size_t)ray_ * 3 + 2] = b_;
+        if (AUX) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                a.direct_rgb[(size_t)ray_ * 3 + c] = aux[c][lane];
+                a.view_dep_rgb[(size_t)ray_ * 3 + c] = aux[3 + c][lane];
+            }
+#pragma unroll
+            for (int k = 0; k < kNB; k++) a.basis_acc[(size_t)ray_ * kNB + k] = aux[6 + k][lane];
+#pragma unroll
+            for (int k = 0; k < kNB * 3; k++) {
+                a.basis_rgb[(size_t)ray_ * kNB * 3 + k] = aux[6 + kNB + k][lane];
+                a.unscaled_basis_rgb[(size_t)ray_ * kNB * 3 + k] = aux[6 + kNB + kNB * 3 + k][lane];
+            }
+        }
+    };
 
     // per-lane ray state (the Marcher is rebuilt from rays_o/rays_d at each march call to keep registers free)
-    bool has_ray = false, first = false;
+    bool has_ray = false;
     float ddx = 0.f, ddy = 0.f, ddz = 1.f;
     uint32_t ray = 0, count = 0;
-    float far = 0.f, tc = 0.f;                 // tc: the compositor's ray parameter (== rays_t of the reference)
+    float tc = 0.f;        // the compositor's ray parameter (== rays_t of the reference)
+    float t_cur = 0.f;     // march position: next lattice point to probe
+    float t_mark = 0.f;    // "last_t" of the reference's march call (start of the current real-delta interval)
+    float t_end = 0.f;     // lattice t of the ray's last occupied point (from the pre-pass)
     float wsum = 0.f, dep = 0.f, r = 0.f, g = 0.f, b = 0.f;
-    bool exhausted = false;                    // warp-uniform: the ray queue is empty
+    bool exhausted = false;                    // warp-uniform: the hit list is used up
     uint32_t shaded = 0;
+    const uint32_t n_hit = a.queue[2];
+    constexpr int kProbesPerRound = 6;         // bounds SIMT divergence: a lane crossing a gap resumes next round
 
     for (;;) {
-        // ---- find the next sample of every lane; lanes whose ray ended pull a new one (a few attempts) ----
+        // ---- every lane finds its next sample; lanes without a ray pull one from the hit list ----
         bool sample = false;
         float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, rdt = 0.f;
 #pragma unroll 1
-        for (int attempt = 0; attempt < 4; attempt++) {
+        for (int attempt = 0; attempt < 2; attempt++) {
             const uint32_t need = __ballot_sync(0xffffffffu, !has_ray);
             if (need && !exhausted) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(a.queue, (unsigned int)__popc(need));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + __popc(need) >= a.N) exhausted = true;
+                if (base + __popc(need) >= n_hit) exhausted = true;
                 if (!has_ray) {
-                    const uint32_t idx = base + __popc(need & lt_mask);
-                    if (idx < a.N) {
-                        ray = idx;
+                    const uint32_t slot = base + __popc(need & lt_mask);
+                    if (slot < n_hit) {
+                        ray = (uint32_t)a.hit_list[slot];
                         tc = a.nears[ray];
-                        far = a.fars[ray];
-                        has_ray = true; first = true; count = 0;
+                        // first march call of the reference: t = rays_t (+ noise); last_t = t; the walk to the first
+                        // occupied lattice point was done by the pre-pass
+                        t_mark = tc;
+                        if (a.noises) {
+                            const float dt_min = 2 * 1.7320508075688772f / a.max_steps;
+                            const float dt_max = 2 * 1.7320508075688772f * (1u << (a.C - 1)) / a.Hgrid;
+                            t_mark += clampf(tc * a.dt_gamma, dt_min, dt_max) * a.noises[ray];
+                        }
+                        t_cur = a.t_first[ray];
+                        t_end = a.t_last[ray];
+                        has_ray = true; count = 0;
                         wsum = dep = r = g = b = 0.f;
+                        if (AUX) {
+#pragma unroll
+                            for (int c = 0; c < kAuxCh; c++) aux[c][lane] = 0.f;
+                        }
                     }
                 }
             }
             if (has_ray && !sample) {
-                // one march call of the reference with n_step = 1 (raymarching.cu:936-1010)
                 Marcher m;
                 m.init(a.rays_o + (size_t)ray * 3, a.rays_d + (size_t)ray * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid,
                        a.bitfield);
                 ddx = m.dx; ddy = m.dy; ddz = m.dz;
-                float t = tc;
-                if (first && a.noises) t += m.step_size(t) * a.noises[ray];
-                first = false;
-                const float last_t = t;
-                while (t < far) {
-                    if (m.probe(t, x, y, z, dt)) {
-                        t += dt;
-                        rdt = t - last_t;
+                int probes = 0;
+                while (t_cur <= t_end && probes < kProbesPerRound) {
+                    probes++;
+                    if (m.probe(t_cur, x, y, z, dt)) {
+                        t_cur += dt;
+                        rdt = t_cur - t_mark;
                         sample = true;
                         break;
                     }
                 }
-                if (!sample || count >= a.max_steps) {   // ray left the volume (or used its sample budget): retire it
-                    sample = false;
-                    a.weights_sum[ray] = wsum; a.depth[ray] = dep;
-                    a.image[(size_t)ray * 3] = r; a.image[(size_t)ray * 3 + 1] = g; a.image[(size_t)ray * 3 + 2] = b;
+                if (!sample && !(t_cur <= t_end)) {   // no occupied lattice point left: retire the ray
+                    retire(ray, wsum, dep, r, g, b);
                     has_ray = false;
                 }
             }
-            const uint32_t idle = __ballot_sync(0xffffffffu, !sample);
-            if (idle == 0u || (exhausted && __ballot_sync(0xffffffffu, has_ray && !sample) == 0u)) break;
+            if (__ballot_sync(0xffffffffu, !has_ray) == 0u || exhausted) break;
         }
         const uint32_t smask = __ballot_sync(0xffffffffu, sample);
         if (smask == 0u) {
@@ -526,26 +623,30 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 2) k_render_fused(RenderArgs
             tc += rdt;
             dep += wgt * tc;
             r += wgt * rgb[0]; g += wgt * rgb[1]; b += wgt * rgb[2];
+            // the next march call of the reference restarts from rays_t (= tc) with last_t = rays_t
+            t_cur = tc;
+            t_mark = tc;
             if (AUX) {
-                float* p = a.direct_rgb + (size_t)ray * 3;
-                float* q = a.view_dep_rgb + (size_t)ray * 3;
 #pragma unroll
-                for (int c = 0; c < 3; c++) { p[c] += wgt * (o.diffuse[c] + o.view_dep[c]); q[c] += wgt * o.view_dep[c]; }
-                float* pa = a.basis_acc + (size_t)ray * kNB;
+                for (int c = 0; c < 3; c++) {
+                    aux[c][lane] += wgt * (o.diffuse[c] + o.view_dep[c]);
+                    aux[3 + c][lane] += wgt * o.view_dep[c];
+                }
 #pragma unroll
-                for (int k = 0; k < kNB; k++) pa[k] += wgt * o.omega[k];
-                float* pb = a.basis_rgb + (size_t)ray * kNB * 3;
-                float* pu = a.unscaled_basis_rgb + (size_t)ray * kNB * 3;
+                for (int k = 0; k < kNB; k++) aux[6 + k][lane] += wgt * o.omega[k];
 #pragma unroll
-                for (int k = 0; k < kNB * 3; k++) { pb[k] += wgt * basis_rgb[k]; pu[k] += wgt * unscaled[k]; }
+                for (int k = 0; k < kNB * 3; k++) {
+                    aux[6 + kNB + k][lane] += wgt * basis_rgb[k];
+                    aux[6 + kNB + kNB * 3 + k][lane] += wgt * unscaled[k];
+                }
             }
             if (CLIP && a.clip_feat) {
                 float* pc = a.clip_feat + (size_t)ray * f.clip_dim;
                 for (uint32_t k = 0; k < f.clip_dim; k++) pc[k] += wgt * o.clip[k];
             }
-            if (T < a.T_thresh) {   // early termination (the terminating sample is accumulated, like the reference)
-                a.weights_sum[ray] = wsum; a.depth[ray] = dep;
-                a.image[(size_t)ray * 3] = r; a.image[(size_t)ray * 3 + 1] = g; a.image[(size_t)ray * 3 + 2] = b;
+            // early termination (the terminating sample is accumulated, like the reference) or sample budget used up
+            if (T < a.T_thresh || count >= a.max_steps) {
+                retire(ray, wsum, dep, r, g, b);
                 has_ray = false;
             }
         }
@@ -574,9 +675,9 @@ int pnerf_palette_field_forward(const float* xyzs, const float* dirs, uint32_t M
     if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool clip_on = field->pred_clip != 0;
-    const size_t smem = fused_smem_bytes(clip_on);
+    const size_t smem = fused_smem_bytes(clip_on, false);
     const uint32_t tiles = ceil_div(M, 32u);
-    const uint32_t grid = min(ceil_div(tiles, (uint32_t)kFusedWarps), (uint32_t)(2 * kNumSMs));
+    const uint32_t grid = min(ceil_div(tiles, (uint32_t)kFusedWarps), (uint32_t)kNumSMs);
     cudaError_t e;
     if (clip_on) {
         e = cudaFuncSetAttribute(k_field_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -591,15 +692,18 @@ int pnerf_palette_field_forward(const float* xyzs, const float* dirs, uint32_t M
 }
 
 /* persistent fused renderer: replaces the inference loop of PaletteRenderer.run_cuda (palette/renderer.py:430-523).
- * All outputs must be zero-initialised; queue[2] must be zero. Aux maps may all be NULL (gui_mode). */
+ * All outputs must be zero-initialised; queue[3] must be zero; hit_list/t_first/t_last are [N] scratch.
+ * Aux maps may all be NULL (gui_mode). Launches a thread-per-ray pre-pass and the persistent kernel. */
 int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
                                          uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
                                          const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                                          float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
-                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, void* stream) {
+                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue,
+                                         int32_t* hit_list, float* t_first, float* t_last, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
+    PNERF_REQUIRE(hit_list && t_first && t_last);
     PNERF_REQUIRE(field->table_sigma && field->table_palette && field->offsets && field->wpack && field->head_bias &&
                   field->palette);
     PNERF_REQUIRE(C >= 1 && C <= 16 && Hgrid >= 1 && max_steps >= 1);
@@ -613,11 +717,14 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
     a.weights_sum = weights_sum; a.depth = depth; a.image = image;
     a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
     a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue;
+    a.hit_list = hit_list; a.t_first = t_first; a.t_last = t_last;
     cudaStream_t s = (cudaStream_t)stream;
+    k_ray_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, N, C, Hgrid, max_steps,
+                                                    field->bound, dt_gamma, hit_list, t_first, t_last, queue);
     const bool clip_on = field->pred_clip != 0;
-    const size_t smem = fused_smem_bytes(clip_on);
+    const size_t smem = fused_smem_bytes(clip_on, aux);
     const uint32_t warps_needed = ceil_div(N, 32u);
-    const uint32_t grid = min(ceil_div(warps_needed, (uint32_t)kFusedWarps), (uint32_t)(2 * kNumSMs));  // persistent: 2 CTAs per SM
+    const uint32_t grid = min(ceil_div(warps_needed, (uint32_t)kFusedWarps), (uint32_t)kNumSMs);  // persistent: one CTA per SM
 #define PNERF_LAUNCH_RENDER(CL, AX)                                                                                   \
     do {                                                                                                              \
         cudaError_t e = cudaFuncSetAttribute(k_render_fused<CL, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -33,7 +33,8 @@ class PaletteField(ctypes.Structure):
 
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
-L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.LAUNCHES["pnerf_palette_render_fused"] = 2  # pre-pass + persistent kernel
 
 
 def _frag(W, n_pad, k_pad):
@@ -170,13 +171,16 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     if not gui_mode:
         acc.update(direct_rgb=z(N, 3), view_dep_rgb=z(N, 3), basis_acc=z(N, nb), basis_rgb=z(N, 3 * nb),
                    unscaled_basis_rgb=z(N, 3 * nb))
-    queue = torch.zeros(2, dtype=torch.int32, device=dev)
+    queue = torch.zeros(3, dtype=torch.int32, device=dev)
+    hit_list = torch.empty(N, dtype=torch.int32, device=dev)
+    t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
     aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
     L.call("pnerf_palette_render_fused", ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises),
            ptr(model.density_bitfield), N, model.cascade, model.grid_size, max_steps, float(dt_gamma), float(T_thresh),
            ctypes.addressof(f), ptr(acc["weights_sum"]), ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"),
            aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"), aux("unscaled_basis_rgb"),
-           ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), stream())
-    acc["_queue"] = queue   # [next ray index, samples shaded]; read lazily (no sync here)
+           ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), ptr(hit_list), ptr(t_first), ptr(t_last),
+           stream())
+    acc["_queue"] = queue   # [hit-list cursor, samples shaded, rays with samples]; read lazily (no sync here)
     return acc

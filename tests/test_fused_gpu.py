@@ -86,15 +86,23 @@ def test_fused_render_matches_loop_and_oracle(cuda, model, gui_mode):
     assert set(loop.keys()) == set(fus.keys())
     for k in loop:
         err = (loop[k].float() - fus[k].float()).abs().max().item()
-        assert err < 5e-3, f"{k}: fused vs loop max-abs {err}"
+        scale = max(1.0, loop[k].float().abs().max().item())     # depth_origin is in scene units (up to ~5)
+        assert err < 5e-3 * scale, f"{k}: fused vs loop max-abs {err}"
     params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     ref = cpu_render.render_cuda_ray(params, o, d, model.density_bitfield.cpu(), pred_clip=model.opt.pred_clip, gui_mode=gui_mode)
     q = model._last_queue.cpu().numpy()
-    assert q[0] >= 1600 and q[1] == ref["n_samples"]                   # every ray consumed; same samples shaded
+    # every hit ray consumed; same samples shaded (fp16 sigma noise may move an early termination by a sample)
+    assert q[0] >= q[2] > 0 and abs(int(q[1]) - ref["n_samples"]) <= 0.002 * ref["n_samples"]
+    # with termination disabled the sample sets must be identical: exact count
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        model.render(oc, dc, staged=True, bg_color=1, perturb=False, gui_mode=gui_mode, T_thresh=-1.0)
+    ref_all = cpu_render.render_cuda_ray(params, o, d, model.density_bitfield.cpu(), pred_clip=model.opt.pred_clip, gui_mode=True,
+                                         T_thresh=-1.0)
+    assert int(model._last_queue.cpu().numpy()[1]) == ref_all["n_samples"]
     for k in ["image", "depth", "weights_sum", "clip_feat"] + ([] if gui_mode else ["direct_rgb", "view_dep_rgb", "basis_rgb",
                                                                                     "unscaled_basis_rgb", "basis_acc"]):
         a = fus[k].float().cpu().numpy().reshape(ref[k].shape)
-        assert np.abs(a - ref[k]).max() < 5e-3, f"{k}: fused vs oracle {np.abs(a - ref[k]).max()}"
+        assert np.abs(a - ref[k]).max() < 5e-3 * max(1.0, np.abs(ref[k]).max()), f"{k}: fused vs oracle {np.abs(a - ref[k]).max()}"
     assert fus["weights_sum"].max().item() > 0.2
 
 
