@@ -310,7 +310,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1."""
     model = S.build_palette_model(dev, seed=0, pred_clip=False)
     model.train()
-    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda")
     o, d = S.training_rays(TRAIN_RAYS, seed=rank)
@@ -352,7 +352,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     barrier()
     ms = max_over_ranks(sum(ts) / len(ts))
     return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
-                      "samples_per_step_rank0": state.get("m"), "optimizer": "Adam(0.9,0.99,1e-15)+GradScaler",
+                      "samples_per_step_rank0": state.get("m"), "optimizer": "Adam(0.9,0.99,1e-15,fused)+GradScaler",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
 

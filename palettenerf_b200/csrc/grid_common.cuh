@@ -41,11 +41,12 @@ __device__ __forceinline__ uint32_t wrap_index(uint32_t index, const LevelParams
 }
 
 __device__ __forceinline__ void corner_setup(const LevelParams& p, float x, float y, float z, uint32_t (&idx)[8],
-                                             float (&w)[8], bool align_corners) {
+                                             float (&w)[8], bool align_corners, uint32_t* cell = nullptr) {
     const float half = align_corners ? 0.0f : 0.5f;
     float px = x * p.scale + half, py = y * p.scale + half, pz = z * p.scale + half;
     const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
     const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+    if (cell) { cell[0] = gx; cell[1] = gy; cell[2] = gz; }
     px -= (float)gx; py -= (float)gy; pz -= (float)gz;
     const float wx[2] = {1 - px, px}, wy[2] = {1 - py, py}, wz[2] = {1 - pz, pz};
     if (p.use_hash) {

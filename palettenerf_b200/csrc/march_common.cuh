@@ -65,9 +65,9 @@ struct Marcher {
 
     __device__ __forceinline__ float step_size(float t) const { return clampf(t * dt_gamma, dt_min, dt_max); }
 
-    // Evaluate lattice point t. Returns true if (x,y,z) is an occupied sample (t is NOT advanced; caller adds dt).
-    // Otherwise advances t to the first lattice point at/after the voxel exit and returns false.
-    __device__ __forceinline__ bool probe(float& t, float& x, float& y, float& z, float& dt) const {
+    // Classify lattice point t: returns true if (x,y,z) is an occupied sample; otherwise `tt` receives the ray
+    // parameter at which the ray leaves the empty voxel (ref: raymarching.cu:364-403). Does not advance t.
+    __device__ __forceinline__ bool probe_point(float t, float& x, float& y, float& z, float& dt, float& tt) const {
         x = clampf(ox + t * dx, -bound, bound);
         y = clampf(oy + t * dy, -bound, bound);
         z = clampf(oz + t * dz, -bound, bound);
@@ -96,12 +96,104 @@ struct Marcher {
         const float tx = (((nx + 0.5f + 0.5f * sx) * rH * 2 - 1) * mip_bound - x) * rdx;
         const float ty = (((ny + 0.5f + 0.5f * sy) * rH * 2 - 1) * mip_bound - y) * rdy;
         const float tz = (((nz + 0.5f + 0.5f * sz) * rH * 2 - 1) * mip_bound - z) * rdz;
-        const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+        tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+        return false;
+    }
+
+    // Evaluate lattice point t. Returns true if (x,y,z) is an occupied sample (t is NOT advanced; caller adds dt).
+    // Otherwise advances t to the first lattice point at/after the voxel exit and returns false.
+    __device__ __forceinline__ bool probe(float& t, float& x, float& y, float& z, float& dt) const {
+        float tt;
+        if (probe_point(t, x, y, z, dt, tt)) return true;
         do {
             t += step_size(t);
         } while (t < tt);
         return false;
     }
 };
+
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative walk of ONE ray (all 32 lanes call it with the same ray). The reference walks the lattice
+// t_{k+1} = t_k + clamp(t_k * dt_gamma, dt_min, dt_max) serially, probing a point, then either emitting a sample
+// or skipping to the first lattice point past the empty voxel. Here a window of 32 consecutive lattice points is
+// generated (serial fp32 adds, so the values are the reference's bit for bit), all 32 are classified in parallel,
+// and the serial walk over the window is replayed with ballots/shuffles (~10 instructions per visited point).
+// Visited-and-occupied points are exactly the reference's samples, in order.
+//   WRITE = false: returns the sample count (<= budget)
+//   WRITE = true : additionally writes xyz / dir / (dt, real delta) of sample k to row (k) of the output pointers
+// ------------------------------------------------------------------------------------------------
+template <bool WRITE>
+__device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float far, uint32_t budget, uint32_t lane,
+                                              float* __restrict__ xyzs, float* __restrict__ dirs,
+                                              float* __restrict__ deltas) {
+    uint32_t count = 0;
+    float t_start = t0;
+    float last_t = t0;  // end of the previous sample (start of the real-delta interval)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    while (t_start < far && count < budget) {
+        // lattice window: lane i holds t_i
+        float t = t_start;
+#pragma unroll 1
+        for (uint32_t i = 0; i < 31; i++) {
+            const float tn = t + m.step_size(t);
+            if (i < lane) t = tn;
+        }
+        const float t_after = t + m.step_size(t);                 // lattice point following this lane's
+        const bool inside = t < far;
+        float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, tt = 0.f;
+        bool occ = false;
+        if (inside) occ = m.probe_point(t, x, y, z, dt, tt);
+        const uint32_t in_mask = __ballot_sync(0xffffffffu, inside);
+        const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
+        // replay the serial walk over the window (warp-uniform)
+        uint32_t take = 0, cur = 0;
+        bool finished = false, jumped = false;
+        float t_jump = 0.f;
+        while (cur < 32) {
+            if (!((in_mask >> cur) & 1u)) { finished = true; break; }            // t >= far
+            if ((occ_mask >> cur) & 1u) {
+                if (count + __popc(take) >= budget) { finished = true; break; }   // sample budget (max_steps / num_steps)
+                take |= 1u << cur;
+                cur++;
+            } else {
+                const float tt_cur = __shfl_sync(0xffffffffu, tt, cur);
+                const uint32_t above = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
+                const uint32_t ge = __ballot_sync(0xffffffffu, t >= tt_cur) & above;
+                if (ge) {
+                    cur = __ffs(ge) - 1;
+                } else {   // the empty voxel extends past the window: keep stepping from the last lattice point
+                    float tn = __shfl_sync(0xffffffffu, t, 31);
+                    if (cur == 31) { tn = tn + m.step_size(tn); while (tn < tt_cur) tn += m.step_size(tn); }
+                    else { do { tn += m.step_size(tn); } while (tn < tt_cur); }
+                    t_jump = tn;
+                    jumped = true;
+                    break;
+                }
+            }
+        }
+        if (WRITE && take) {
+            // real delta of a sample = (t_i + dt_i) - end of the previous sample
+            const uint32_t below = take & lt_mask;
+            const int prev = below ? (31 - __clz(below)) : -1;
+            const float prev_end = __shfl_sync(0xffffffffu, t_after, prev < 0 ? 0 : prev);
+            if ((take >> lane) & 1u) {
+                const uint32_t k = count + __popc(below);
+                const float lt = prev < 0 ? last_t : prev_end;
+                xyzs[(size_t)k * 3 + 0] = x; xyzs[(size_t)k * 3 + 1] = y; xyzs[(size_t)k * 3 + 2] = z;
+                dirs[(size_t)k * 3 + 0] = m.dx; dirs[(size_t)k * 3 + 1] = m.dy; dirs[(size_t)k * 3 + 2] = m.dz;
+                reinterpret_cast<float2*>(deltas)[k] = make_float2(dt, t_after - lt);
+            }
+        }
+        if (take) {
+            const int top = 31 - __clz(take);
+            last_t = __shfl_sync(0xffffffffu, t_after, top);
+            count += __popc(take);
+        }
+        if (finished) break;
+        t_start = jumped ? t_jump : __shfl_sync(0xffffffffu, t_after, 31);
+    }
+    return count;
+}
 
 }  // namespace pnerf

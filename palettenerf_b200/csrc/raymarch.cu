@@ -7,8 +7,8 @@
 //   - training march = count kernel -> single-CTA exclusive scan in ray order -> write kernel, instead of two
 //     global atomics per ray; slot order is deterministic (ray order), which is one of the orders the
 //     reference's atomic race may produce;
-//   - the write kernel is warp-cooperative per ray group: samples are staged through shared memory and
-//     leave the SM as coalesced runs;
+//   - both marching passes are warp-per-ray (march_common.cuh::warp_walk): 32 lattice points are classified per
+//     step and the lanes of a warp write consecutive samples as coalesced runs;
 //   - packbits reads 2x float4 per byte, morton/near-far read and write through coalesced vector accesses.
 #include "common.cuh"
 #include "march_common.cuh"
@@ -126,8 +126,10 @@ __global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid
 // training march (ref: raymarching.cu:315-483)
 // ------------------------------------------------------------------------------------------------
 
-// pass 1: count occupied steps per ray; rays[n] = (n, <offset later>, count)
-__global__ void __launch_bounds__(128) k_march_train_count(const float* __restrict__ rays_o,
+// pass 1: count occupied steps per ray; rays[n] = (n, <offset later>, count). One WARP per ray (march_common.cuh:
+// warp_walk): 32 lattice points are classified per step instead of one, which matters because a training batch is
+// only 4096 rays — thread-per-ray leaves the chip latency-bound at 32 resident warps.
+__global__ void __launch_bounds__(256) k_march_train_count(const float* __restrict__ rays_o,
                                                            const float* __restrict__ rays_d,
                                                            const uint8_t* __restrict__ grid, float bound,
                                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
@@ -135,23 +137,17 @@ __global__ void __launch_bounds__(128) k_march_train_count(const float* __restri
                                                            const float* __restrict__ fars,
                                                            const float* __restrict__ noises,
                                                            int32_t* __restrict__ rays) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (n >= N) return;
     Marcher m;
     m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
-    const float far = fars[n];
     float t = nears[n];
     t += m.step_size(t) * noises[n];
-    uint32_t num_steps = 0;
-    float x, y, z, dt;
-    while (t < far && num_steps < max_steps) {
-        if (m.probe(t, x, y, z, dt)) {
-            num_steps++;
-            t += dt;
-        }
+    const uint32_t num_steps = warp_walk<false>(m, t, fars[n], max_steps, lane, nullptr, nullptr, nullptr);
+    if (lane == 0) {
+        rays[n * 3 + 0] = (int32_t)n;
+        rays[n * 3 + 2] = (int32_t)num_steps;
     }
-    rays[n * 3 + 0] = (int32_t)n;
-    rays[n * 3 + 2] = (int32_t)num_steps;
 }
 
 // pass 2: single-CTA exclusive scan of the counts in ray order. 1024 threads, each owns a contiguous run.
@@ -198,11 +194,9 @@ __global__ void __launch_bounds__(1024) k_march_train_scan(int32_t* __restrict__
     }
 }
 
-// pass 3: re-march and write. One thread per ray marches; every time the warp has produced samples they are
-// staged in shared memory and flushed by the whole warp so that global stores are coalesced runs per ray.
-constexpr int kStage = 8;  // samples staged per ray before a cooperative flush
-
-__global__ void __launch_bounds__(128) k_march_train_write(const float* __restrict__ rays_o,
+// pass 3: re-march and write, one warp per ray: the lanes of a warp write consecutive samples, so the three
+// output arrays receive contiguous 384 B / 384 B / 256 B runs per store instruction.
+__global__ void __launch_bounds__(256) k_march_train_write(const float* __restrict__ rays_o,
                                                            const float* __restrict__ rays_d,
                                                            const uint8_t* __restrict__ grid, float bound,
                                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
@@ -211,71 +205,16 @@ __global__ void __launch_bounds__(128) k_march_train_write(const float* __restri
                                                            const float* __restrict__ noises,
                                                            const int32_t* __restrict__ rays, float* __restrict__ xyzs,
                                                            float* __restrict__ dirs, float* __restrict__ deltas) {
-    // per warp: 32 rays x kStage samples x (xyz 3 + delta 2) floats
-    __shared__ float s_xyz[4][32][kStage * 3 + 1];
-    __shared__ float s_dl[4][32][kStage * 2 + 1];
-    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t num_steps = (uint32_t)rays[n * 3 + 2], offset = (uint32_t)rays[n * 3 + 1];
+    if (num_steps == 0 || offset + num_steps > M) return;   // ref: raymarching.cu:418-419
     Marcher m;
-    uint32_t num_steps = 0, offset = 0;
-    float far = 0.f, t = 0.f;
-    bool active = false;
-    if (n < N) {
-        num_steps = (uint32_t)rays[n * 3 + 2];
-        offset = (uint32_t)rays[n * 3 + 1];
-        active = (num_steps != 0) && (offset + num_steps <= M);
-    }
-    if (active) {
-        m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
-        far = fars[n];
-        t = nears[n];
-        t += m.step_size(t) * noises[n];
-    }
-    float last_t = t;
-    uint32_t step = 0;     // samples produced so far
-    uint32_t flushed = 0;  // samples already written to global
-
-    while (__any_sync(0xffffffffu, active)) {
-        // each active lane produces up to kStage samples into its staging row
-        uint32_t staged = 0;
-        if (active) {
-            float x, y, z, dt;
-            while (staged < kStage && t < far && step < num_steps) {
-                if (m.probe(t, x, y, z, dt)) {
-                    t += dt;
-                    s_xyz[wid][lane][staged * 3 + 0] = x;
-                    s_xyz[wid][lane][staged * 3 + 1] = y;
-                    s_xyz[wid][lane][staged * 3 + 2] = z;
-                    s_dl[wid][lane][staged * 2 + 0] = dt;
-                    s_dl[wid][lane][staged * 2 + 1] = t - last_t;
-                    last_t = t;
-                    staged++;
-                    step++;
-                }
-            }
-            if (!(t < far && step < num_steps)) active = false;
-        }
-        __syncwarp();
-        // cooperative flush: for each ray r of the warp, lanes write its staged run contiguously
-#pragma unroll 1
-        for (uint32_t r = 0; r < 32; r++) {
-            const uint32_t cnt = __shfl_sync(0xffffffffu, staged, r);
-            if (cnt == 0) continue;
-            const uint32_t base = __shfl_sync(0xffffffffu, offset + flushed, r);
-            const float ddx = __shfl_sync(0xffffffffu, m.dx, r);
-            const float ddy = __shfl_sync(0xffffffffu, m.dy, r);
-            const float ddz = __shfl_sync(0xffffffffu, m.dz, r);
-            if (lane < cnt * 3) {
-                xyzs[(size_t)base * 3 + lane] = s_xyz[wid][r][lane];
-                const uint32_t c = lane % 3;
-                dirs[(size_t)base * 3 + lane] = (c == 0) ? ddx : ((c == 1) ? ddy : ddz);
-            }
-            if (lane < cnt * 2) deltas[(size_t)base * 2 + lane] = s_dl[wid][r][lane];
-        }
-        flushed += staged;
-        __syncwarp();
-    }
+    m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
+    float t = nears[n];
+    t += m.step_size(t) * noises[n];
+    warp_walk<true>(m, t, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3,
+                    deltas + (size_t)offset * 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,11 +331,11 @@ int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8
     PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
     if (H > 1024) return PNERF_ERR_UNSUPPORTED;  // 10-bit Morton coordinates
     cudaStream_t s = (cudaStream_t)stream;
-    k_march_train_count<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                          nears, fars, noises, rays);
+    k_march_train_count<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                        fars, noises, rays);
     k_march_train_scan<<<1, 1024, 0, s>>>(rays, N, counter);
-    k_march_train_write<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                          nears, fars, noises, rays, xyzs, dirs, deltas);
+    k_march_train_write<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                        nears, fars, noises, rays, xyzs, dirs, deltas);
     return check_launch("march_rays_train");
 }
 
