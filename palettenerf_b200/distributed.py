@@ -1,0 +1,116 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, `torch.distributed` (NCCL over NVLink on
+the box, gloo in the CPU tests). Rays are independent, so
+
+  * inference shards the rays (`ray_shard`) — contiguous bands, or interleaved tiles when empty-space rays make
+    bands unbalanced — with NO data-path collective; `gather_maps` assembles per-ray outputs on every rank when a
+    caller wants the full image;
+  * training is ray-batch data parallel: `GradBucket` packs the gradients of the tensors that actually received one
+    (the sigma grid / sigma net get none in the palette stage, palette/network.py:168, palette/renderer.py:335) plus
+    the GradScaler found-inf flag into ONE flat fp32 buffer and all-reduces it once per step;
+  * the stochastic density-grid refresh (nerf/renderer.py:502-519) would make ranks diverge: `cell_shard` splits the
+    (cascade, cell) space between ranks and `merge_density` combines the partial grids with an all-reduce(max).
+
+The reference is single-GPU; none of this has a counterpart there.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def ray_shard(n_rays, world_size, rank, tile=0):
+    """indices of the rays this rank renders.
+    tile == 0: contiguous band [lo, hi) -> returns a slice; tile > 0: round-robin blocks of `tile` rays -> LongTensor."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    if tile <= 0:
+        per = (n_rays + world_size - 1) // world_size
+        lo = min(rank * per, n_rays)
+        return slice(lo, min(lo + per, n_rays))
+    blocks = torch.arange((n_rays + tile - 1) // tile)
+    mine = blocks[blocks % world_size == rank]
+    idx = (mine[:, None] * tile + torch.arange(tile)[None, :]).reshape(-1)
+    return idx[idx < n_rays]
+
+
+def gather_maps(local, n_rays, shard, group=None):
+    """all-gather a per-ray tensor [n_local, ...] rendered for `shard` (from ray_shard) into [n_rays, ...] on every rank"""
+    ws, rank = world()
+    full = torch.zeros((n_rays,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full[shard] = local
+    if ws > 1:
+        dist.all_reduce(full, group=group)   # shards are disjoint: a sum is a gather, one collective, no padding logic
+    return full
+
+
+class GradBucket:
+    """ONE flat fp32 all-reduce per step for all trainable gradients (+ the found-inf flag of the loss scaler)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        self.flat = None
+
+    def _live(self):
+        return [p for p in self.params if p.grad is not None]
+
+    def all_reduce(self, found_inf=None, average=True, group=None):
+        """sums (or averages) gradients across ranks in place; returns the global found-inf flag (max over ranks)"""
+        ws, _ = world()
+        live = self._live()
+        n = sum(p.grad.numel() for p in live) + 1
+        dev = live[0].grad.device if live else torch.device("cpu")
+        if self.flat is None or self.flat.numel() != n or self.flat.device != dev:
+            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        flat = self.flat
+        off = 0
+        for p in live:
+            k = p.grad.numel()
+            flat[off:off + k].copy_(p.grad.reshape(-1))
+            off += k
+        # the flag rides in the same bucket; it is summed, so any rank's inf makes it non-zero everywhere
+        flat[off] = 0.0 if found_inf is None else float(found_inf)
+        if ws > 1:
+            dist.all_reduce(flat, group=group)
+        flag = flat[off].clone()
+        if average and ws > 1:
+            flat[:off].div_(ws)
+        off = 0
+        for p in live:
+            k = p.grad.numel()
+            p.grad.copy_(flat[off:off + k].view_as(p.grad))
+            off += k
+        return flag
+
+    def signature(self):
+        """names-free description of which tensors are in the bucket (ranks must agree; checked by the tests)"""
+        return [tuple(p.shape) for p in self._live()]
+
+
+def cell_shard(n_cells, world_size, rank):
+    """contiguous range of density-grid cells (per cascade) a rank evaluates during update_extra_state"""
+    per = (n_cells + world_size - 1) // world_size
+    lo = min(rank * per, n_cells)
+    return lo, min(lo + per, n_cells)
+
+
+def merge_density(fresh, group=None):
+    """partial `fresh` grids (-1 where a rank evaluated nothing) -> identical merged grid on every rank"""
+    ws, _ = world()
+    if ws > 1:
+        dist.all_reduce(fresh, op=dist.ReduceOp.MAX, group=group)
+    return fresh
+
+
+def shared_seed(seed_tensor=None, group=None):
+    """broadcast rank 0's RNG seed so the stochastic cell selection of the density refresh matches on all ranks"""
+    ws, rank = world()
+    t = torch.zeros(1, dtype=torch.int64) if seed_tensor is None else seed_tensor
+    if rank == 0 and seed_tensor is None:
+        t[0] = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    if ws > 1:
+        dist.broadcast(t, src=0, group=group)
+    return int(t.item())
