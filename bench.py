@@ -217,7 +217,8 @@ def main():
     shares = {k.replace("pnerf_", ""): round(v[0] / total_kernel_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     roofline = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "kernel": top[0], "peak_kind": peak_kind, "kernel_time_share_of_own_kernels": shares}
-    samples_per_step = getattr(model, "_last_sample_count", None)
+    q = getattr(model, "_last_queue", None)          # [hit-list cursor, samples shaded, rays with samples] of the last view
+    samples_per_step = int(q[1].item()) if q is not None else None
 
     extras = {}
     if not args.no_extras:
@@ -313,6 +314,8 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda")
+    from palettenerf_b200.distributed import GradBucket
+    bucket = GradBucket(params)
     o, d = S.training_rays(TRAIN_RAYS, seed=rank)
     o, d = o.to(dev), d.to(dev)
     gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
@@ -327,17 +330,11 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                 + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
         scaler.scale(loss).backward()
         if world > 1:
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch.cat([g_.reshape(-1) for g_ in grads])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            off = 0
-            for g_ in grads:
-                g_.copy_(flat[off:off + g_.numel()].view_as(g_))
-                off += g_.numel()
+            # ONE all-reduce of the (still loss-scaled) gradients: an inf/nan on any rank reaches every rank through
+            # the sum, so GradScaler's found-inf decision is identical everywhere without a second collective
+            bucket.all_reduce(average=True)
         scaler.step(opt)
         scaler.update()
-        state["m"] = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
 
     for _ in range(3):
         step()
@@ -350,9 +347,11 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     barrier()
+    state["m"] = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
     ms = max_over_ranks(sum(ts) / len(ts))
     return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
-                      "samples_per_step_rank0": state.get("m"), "optimizer": "Adam(0.9,0.99,1e-15,fused)+GradScaler",
+                      "samples_per_step_rank0": state.get("m"), "schedule": getattr(model, "_last_train_schedule", "torch"),
+                      "optimizer": "Adam(0.9,0.99,1e-15,fused)+GradScaler",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
 

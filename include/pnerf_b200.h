@@ -211,6 +211,46 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
                                          float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue,
                                          int32_t* hit_list, float* t_first, float* t_last, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fused palette field for TRAINING (new entry points; they replace the field evaluation of the training branch,
+ * ref: palette/renderer.py:322-359 + palette/network.py:156-280, and its autograd graph)
+ *   forward : xyzs, dirs [M,3] -> sigma [M] (= density_scale * exp(logit), a constant of this stage), rgb [M,3]
+ *             (= sum_b omega_b softplus(radiance)(palette_b + offsets_b) + view_dep), flex [M, 13+clip_dim+4] =
+ *             [omega_sparsity, view_dep_norm, offsets_norm, smooth_norm(=0), view_dep(3), direct_rgb(3), diffuse(3),
+ *              clip_feat(clip_dim), omega(4)]; every layer input is saved in xbuf (fp16 mma fragments)
+ *   backward: grad_rgb [M,3], grad_flex [M,nflex], flex (forward values) -> ybuf (per-layer pre-activation gradients, fp16
+ *             fragments), d_enc [M,32] / d_enc_clip [M,32] fp32 (gradients of the palette / semantic grid features, to be
+ *             scattered by pnerf_grid_encode_backward with layout BLC), d_palette [4*3] (+=, may be NULL)
+ *   wgrad   : xbuf, ybuf -> dwbuf (+=, fp32, zero-initialised by the caller): per layer [N_pad][K_pad] row-major in the
+ *             order D0 64x16, D1 64x64, D2 16x64, V0 64x32, V1 64x64, V2 16x64, B0 64x48, B1 16x64, H 32x16
+ *             [, C0 64x32, C1 16x64]; column/row maps to the nn.Linear weights: palettenerf_b200/fused_train.py
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pnerf_palette_train {
+    const void* table_sigma;    /* fp16 [n_entries,2] : encoder.embeddings                       */
+    const void* table_palette;  /* fp16               : encoder_palette.embeddings               */
+    const void* table_clip;     /* fp16               : encoder_clip.embeddings (NULL unless pred_clip) */
+    const int32_t* offsets;     /* [L+1]                                                         */
+    const void* wfwd;           /* fp16 B fragments of the forward layers; head bias folded into column 15 */
+    const void* wbwd;           /* fp16 B fragments of the transposed layers (dX = dY W)        */
+    const float* palette;       /* [4*3] basis_color clamped to [0,1]                            */
+    uint32_t L, H, pred_clip, clip_dim;
+    float S, bound, density_scale;
+} pnerf_palette_train;
+
+PNERF_API uint64_t pnerf_palette_train_xbuf_bytes(uint32_t M, uint32_t pred_clip);
+PNERF_API uint64_t pnerf_palette_train_ybuf_bytes(uint32_t M, uint32_t pred_clip);
+PNERF_API uint32_t pnerf_palette_train_dw_floats(uint32_t pred_clip);
+PNERF_API uint32_t pnerf_palette_train_wfwd_units(uint32_t pred_clip);   /* uint2 units of the forward blob     */
+PNERF_API uint32_t pnerf_palette_train_wbwd_units(uint32_t pred_clip);   /* uint2 units of the transposed blob  */
+
+PNERF_API int pnerf_palette_train_forward(const float* xyzs, const float* dirs, uint32_t M, const pnerf_palette_train* p,
+                                          void* xbuf, float* sigma, float* rgb, float* flex, void* stream);
+PNERF_API int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train* p, const void* xbuf, void* ybuf,
+                                           const float* grad_rgb, const float* grad_flex, const float* flex, float* d_enc,
+                                           float* d_enc_clip, float* d_palette, void* stream);
+PNERF_API int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf,
+                                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

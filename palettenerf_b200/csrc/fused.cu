@@ -22,183 +22,10 @@
 //     accumulators in registers), marches to its next occupied sample, the warp evaluates the field for its 32
 //     samples, lanes composite, finished rays are replaced from a global queue (one warp-aggregated atomic). There is
 //     no host loop, no alive-list compaction, no xyzs/dirs/deltas/sigmas/rgbs buffer and no host synchronisation.
-#include <cuda_fp16.h>
-
-#include "common.cuh"
-#include "grid_common.cuh"
-#include "march_common.cuh"
-#include "sh_common.cuh"
+#include "fused_common.cuh"
 
 namespace pnerf {
 
-constexpr int kNB = 4;            // palette bases supported by the fused path (reference default, main_palette.py:99)
-constexpr int kClipMax = 16;      // semantic feature width supported by the fused path (main_palette.py:76)
-constexpr int kFusedWarps = 12;     // one 384-thread CTA per SM: <= 168 registers/thread, no spills in the MMA chain
-constexpr int kAuxCh = 3 + 3 + kNB + 2 * kNB * 3;   // direct_rgb, view_dep_rgb, basis_acc, basis_rgb, unscaled_basis_rgb
-constexpr int kFeatStride = 40;   // halfs per feature row: 32 + 8 pad -> ldmatrix rows hit distinct bank groups
-constexpr int kOutStride = 41;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
-
-// packed weight blob: per layer [NT][KS][32 lanes] x uint2 (= the m16n8k16 B fragment of that (n-tile, k-step))
-enum Layer { LS0, LS1, LD0, LD1, LD2, LV0, LV1, LV2, LB0, LB1, LH, LC0, LC1, kNumLayers };
-__host__ __device__ constexpr int layer_ks(int l) {
-    return l == LS0 ? 2 : l == LS1 ? 4 : l == LD0 ? 1 : l == LD1 ? 4 : l == LD2 ? 4 : l == LV0 ? 2 : l == LV1 ? 4
-         : l == LV2 ? 4 : l == LB0 ? 3 : l == LB1 ? 4 : l == LH ? 1 : l == LC0 ? 2 : 4;
-}
-__host__ __device__ constexpr int layer_nt(int l) {
-    return l == LS0 ? 8 : l == LS1 ? 2 : l == LD0 ? 8 : l == LD1 ? 8 : l == LD2 ? 1 : l == LV0 ? 8 : l == LV1 ? 8
-         : l == LV2 ? 1 : l == LB0 ? 8 : l == LB1 ? 2 : l == LH ? 3 : l == LC0 ? 8 : 2;
-}
-__host__ __device__ constexpr int layer_off(int l) {  // in uint2 units
-    int o = 0;
-    for (int i = 0; i < l; i++) o += layer_ks(i) * layer_nt(i) * 32;
-    return o;
-}
-constexpr int kWUnitsNoClip = layer_off(LC0);
-constexpr int kWUnitsClip = layer_off(kNumLayers);
-
-// output staging columns
-enum OutCol { O_SIGMA = 0, O_DIFF = 1, O_VIEW = 4, O_OFFRAD = 7, O_OMEGA = 20, O_CLIP = 24 };
-
-struct WarpScratch {
-    __half feat[32][kFeatStride];
-    float out[32][kOutStride];
-};
-// per-warp auxiliary-map accumulators of the renderer, channel-major so that lane-per-ray accesses are conflict-free
-struct WarpAux {
-    float acc[kAuxCh][32];
-};
-
-struct FusedSmem {
-    LevelParams lp[kMaxLevels];
-    float head_bias[16];
-    float palette[kNB * 3];
-    // followed by: uint2 weights[units]; WarpScratch scratch[kFusedWarps]
-};
-
-}  // namespace pnerf
-
-namespace pnerf {
-
-// ------------------------------------------------------------------------------------------------
-// tensor-core helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// A fragment (m16 x k16, fp16) from a row-major shared-memory tile: rows [row0, row0+16), cols [col0, col0+16)
-__device__ __forceinline__ void ldmatrix_a(uint32_t (&a)[4], const __half* tile, int row0, int col0, int lane) {
-    const __half* p = tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kFeatStride + col0 + (lane >> 4) * 8;
-    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-                 : "r"(addr));
-}
-
-template <int KS, int NT>
-__device__ __forceinline__ void mma_layer(const uint2* __restrict__ w, const uint32_t (&a)[KS][4], float (&c)[NT][4],
-                                          int lane) {
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-        c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            const uint2 b = w[(nt * KS + ks) * 32 + lane];
-            mma16816(c[nt], a[ks], b.x, b.y);
-        }
-    }
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-enum Act { ACT_NONE, ACT_RELU, ACT_ELU };
-template <int ACT>
-__device__ __forceinline__ float activate(float v) {
-    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
-    if (ACT == ACT_ELU) return v > 0.f ? v : (__expf(v) - 1.0f);
-    return v;
-}
-
-// accumulators of NT n-tiles -> A fragments of NT/2 k-steps (layout identity of mma.m16n8k16, no shuffles)
-template <int NT, int ACT>
-__device__ __forceinline__ void chain(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
-#pragma unroll
-    for (int j = 0; j < NT / 2; j++) {
-        a[j][0] = pack_h2(activate<ACT>(c[2 * j][0]), activate<ACT>(c[2 * j][1]));
-        a[j][1] = pack_h2(activate<ACT>(c[2 * j][2]), activate<ACT>(c[2 * j][3]));
-        a[j][2] = pack_h2(activate<ACT>(c[2 * j + 1][0]), activate<ACT>(c[2 * j + 1][1]));
-        a[j][3] = pack_h2(activate<ACT>(c[2 * j + 1][2]), activate<ACT>(c[2 * j + 1][3]));
-    }
-}
-
-// write an n-tile accumulator (rows r / r+8 of the m16 tile, cols 2q, 2q+1) into the fp32 output staging
-template <int NT>
-__device__ __forceinline__ void store_out(float (*out)[kOutStride], int row0, int col0, int ncols, const float (&c)[NT][4],
-                                          int lane) {
-    const int r = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-        const int col = nt * 8 + 2 * q;
-        if (col < ncols) { out[row0 + r][col0 + col] = c[nt][0]; out[row0 + r + 8][col0 + col] = c[nt][2]; }
-        if (col + 1 < ncols) { out[row0 + r][col0 + col + 1] = c[nt][1]; out[row0 + r + 8][col0 + col + 1] = c[nt][3]; }
-    }
-}
-
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
-__device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : log1pf(__expf(v)); }  // torch threshold 20
-
-// ------------------------------------------------------------------------------------------------
-// hash-grid gather of one sample (this lane) into its fp16 feature row
-// ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void gather_features(const __half* __restrict__ table, const LevelParams* __restrict__ lp,
-                                                uint32_t L, float u, float v, float w, bool active,
-                                                __half* __restrict__ row) {
-    for (uint32_t l0 = 0; l0 < L; l0 += 2) {
-        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        if (active) {
-            float2 val[2][8];
-            float wt[2][8];
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                if (l0 + j < L) {
-                    const LevelParams& p = lp[l0 + j];
-                    uint32_t idx[8];
-                    corner_setup(p, u, v, w, idx, wt[j], false);
-                    const __half2* g = reinterpret_cast<const __half2*>(table) + p.offset;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) val[j][c] = __half22float2(__ldg(g + idx[c]));
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                if (l0 + j < L) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        acc[j].x += wt[j][c] * val[j][c].x;
-                        acc[j].y += wt[j][c] * val[j][c].y;
-                    }
-                }
-            }
-        }
-        reinterpret_cast<__half2*>(row)[l0] = __floats2half2_rn(acc[0].x, acc[0].y);
-        if (l0 + 1 < L) reinterpret_cast<__half2*>(row)[l0 + 1] = __floats2half2_rn(acc[1].x, acc[1].y);
-    }
-}
-
-// per-sample result of the field, held by the lane that owns the sample
-struct FieldOut {
-    float sigma;          // exp(logit) (NOT yet scaled by density_scale)
-    float diffuse[3], view_dep[3];
-    float off_rad[13];    // offsets (12) + radiance (1), bias added
-    float omega[kNB];     // normalised blending weights
-    float clip[kClipMax];
-};
 
 // ------------------------------------------------------------------------------------------------
 // the fused field: 32 samples per warp (lane = sample), L must be 16 (feature rows are 32 wide)

@@ -1,0 +1,255 @@
+"""Host side of the fused TRAINING field (csrc/fused_train.cu): weight packing by one gather, the autograd Function that
+routes gradients to the reference's parameters, and the mapping from the packed weight-gradient buffer to nn.Linear shapes.
+
+Replaces the field evaluation of the training branch (palette/renderer.py:322-359 calling palette/network.py:156-280) and
+its autograd graph. The reference's detach() placements are part of the contract (see fused_train.cu header).
+
+Packing: the fp16 mma B-fragment images of all forward layers and all transposed (backward) layers are ONE
+`flat[index]` gather from the concatenated fp32 parameters; `index` is built once per model (padding -> a trailing 0.0,
+column permutations of the concatenated inputs, head bias -> column 15 of the head layer).
+"""
+import ctypes
+from ctypes import c_float, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from ._lib import ptr, stream
+from . import fused as _fused
+
+NB = 4
+
+
+class PaletteTrain(ctypes.Structure):
+    """mirror of `struct pnerf_palette_train` (include/pnerf_b200.h)"""
+    _fields_ = [("table_sigma", c_void_p), ("table_palette", c_void_p), ("table_clip", c_void_p), ("offsets", c_void_p),
+                ("wfwd", c_void_p), ("wbwd", c_void_p), ("palette", c_void_p),
+                ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
+                ("S", c_float), ("bound", c_float), ("density_scale", c_float)]
+
+
+P, U = c_void_p, c_uint32
+L.register("pnerf_palette_train_forward", [P, P, U, P, P, P, P, P, P])
+L.register("pnerf_palette_train_backward", [U, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_train_wgrad", [U, U, P, P, P, P])
+for _n in ("pnerf_palette_train_xbuf_bytes", "pnerf_palette_train_ybuf_bytes"):
+    getattr(L.lib, _n).argtypes = [U, U]
+    getattr(L.lib, _n).restype = c_uint64
+for _n in ("pnerf_palette_train_dw_floats", "pnerf_palette_train_wfwd_units", "pnerf_palette_train_wbwd_units"):
+    getattr(L.lib, _n).argtypes = [U]
+    getattr(L.lib, _n).restype = c_uint32
+
+# parameter order of the flat vector (and of the Function's weight arguments)
+WEIGHT_NAMES = ["sigma_net.0.weight", "sigma_net.1.weight", "diff_net.0.weight", "diff_net.1.weight", "diff_net.2.weight",
+                "color_net.0.weight", "color_net.1.weight", "color_net.2.weight", "basis_net.0.weight", "basis_net.1.weight",
+                "offsets_radiance_net.weight", "offsets_radiance_net.bias", "omega_net.0.weight"]
+CLIP_NAMES = ["clip_net.0.weight", "clip_net.1.weight"]
+
+# packed weight-gradient buffer: (name, N_pad, K_pad) in kernel order (fused_train.cu::DwLayer)
+DW_LAYERS = [("D0", 64, 16), ("D1", 64, 64), ("D2", 16, 64), ("V0", 64, 32), ("V1", 64, 64), ("V2", 16, 64), ("B0", 64, 48),
+             ("B1", 16, 64), ("H", 32, 16), ("C0", 64, 32), ("C1", 16, 64)]
+
+
+def _frag_idx(Wi):
+    """index matrix [n_pad, k_pad] (int64) -> B-fragment order [n_pad/8][k_pad/16][32 lanes][4]; same map as fused._frag"""
+    n_pad, k_pad = Wi.shape
+    nt, ks = n_pad // 8, k_pad // 16
+    lane = torch.arange(32)
+    n, k = lane // 4, (lane % 4) * 2
+    out = torch.empty(nt, ks, 32, 4, dtype=torch.int64)
+    for a in range(nt):
+        for b in range(ks):
+            rows, base = a * 8 + n, b * 16 + k
+            out[a, b, :, 0] = Wi[rows, base]
+            out[a, b, :, 1] = Wi[rows, base + 1]
+            out[a, b, :, 2] = Wi[rows, base + 8]
+            out[a, b, :, 3] = Wi[rows, base + 9]
+    return out.reshape(-1)
+
+
+def build_pack_index(shapes, pred_clip, clip_dim):
+    """shapes: {name: torch.Size}. -> (index int64 [fwd halfs + bwd halfs], n_fwd_halfs, zero_slot)"""
+    names = WEIGHT_NAMES + (CLIP_NAMES if pred_clip else [])
+    base, off = {}, 0
+    for nme in names:
+        base[nme] = off
+        off += int(np.prod(shapes[nme]))
+    zero = off                                  # index of the trailing 0.0
+
+    def idx(nme):
+        return (base[nme] + torch.arange(int(np.prod(shapes[nme])))).reshape(tuple(shapes[nme]))
+
+    def pad(n_pad, k_pad):
+        return torch.full((n_pad, k_pad), zero, dtype=torch.int64)
+
+    s0, s1 = idx("sigma_net.0.weight"), pad(16, 64)
+    s1[:16] = idx("sigma_net.1.weight")
+    d0 = pad(64, 16); d0[:, 1:16] = idx("diff_net.0.weight")
+    d1 = idx("diff_net.1.weight")
+    d2 = pad(16, 64); d2[0:3] = idx("diff_net.2.weight")
+    c0 = idx("color_net.0.weight")
+    v0 = pad(64, 32); v0[:, 0:16] = c0[:, 0:16]; v0[:, 17:32] = c0[:, 16:31]
+    v1 = idx("color_net.1.weight")
+    v2 = pad(16, 64); v2[0:3] = idx("color_net.2.weight")
+    b0 = pad(64, 48); b0[:, 0:35] = idx("basis_net.0.weight")
+    b1 = pad(16, 64); b1[0:15] = idx("basis_net.1.weight")
+    h = pad(32, 16)
+    h[0:13, 0:15] = idx("offsets_radiance_net.weight")
+    h[0:13, 15] = idx("offsets_radiance_net.bias")       # the head input carries a constant 1 in column 15
+    h[13:17, 0:15] = idx("omega_net.0.weight")
+    h_nobias = h.clone(); h_nobias[:, 15] = zero
+    fwd = [_frag_idx(s0), _frag_idx(s1), _frag_idx(d0), _frag_idx(d1), _frag_idx(d2[:8]), _frag_idx(v0), _frag_idx(v1),
+           _frag_idx(v2[:8]), _frag_idx(b0), _frag_idx(b1), _frag_idx(h[:24])]
+    bwd = [_frag_idx(h_nobias.t().contiguous()), _frag_idx(b1.t().contiguous()), _frag_idx(b0[:, 0:32].t().contiguous()),
+           _frag_idx(d2.t().contiguous()), _frag_idx(d1.t().contiguous()), _frag_idx(v2.t().contiguous()),
+           _frag_idx(v1.t().contiguous())]
+    if pred_clip:
+        q0 = idx("clip_net.0.weight")
+        q1 = pad(16, 64); q1[0:clip_dim] = idx("clip_net.1.weight")
+        fwd += [_frag_idx(q0), _frag_idx(q1)]
+        bwd += [_frag_idx(q1.t().contiguous()), _frag_idx(q0.t().contiguous())]
+    fwd, bwd = torch.cat(fwd), torch.cat(bwd)
+    return torch.cat([fwd, bwd]), fwd.numel(), zero
+
+
+def dw_views(dwbuf, pred_clip, clip_dim):
+    """packed fp32 weight-gradient buffer -> {parameter name: gradient in the parameter's own shape}"""
+    v, off = {}, 0
+    for nme, n, k in DW_LAYERS:
+        if nme.startswith("C") and not pred_clip:
+            break
+        v[nme] = dwbuf[off:off + n * k].view(n, k)
+        off += n * k
+    g = {
+        "diff_net.0.weight": v["D0"][:, 1:16], "diff_net.1.weight": v["D1"], "diff_net.2.weight": v["D2"][0:3],
+        "color_net.0.weight": torch.cat([v["V0"][:, 0:16], v["V0"][:, 17:32]], dim=1), "color_net.1.weight": v["V1"],
+        "color_net.2.weight": v["V2"][0:3], "basis_net.0.weight": v["B0"][:, 0:35], "basis_net.1.weight": v["B1"][0:15],
+        "offsets_radiance_net.weight": v["H"][0:13, 0:15], "offsets_radiance_net.bias": v["H"][0:13, 15],
+        "omega_net.0.weight": v["H"][13:17, 0:15],
+    }
+    if pred_clip:
+        g["clip_net.0.weight"] = v["C0"]
+        g["clip_net.1.weight"] = v["C1"][0:clip_dim]
+    return g
+
+
+class _Tables:
+    """fp16 copies of the hash tables, each refreshed only when ITS parameter changed (the sigma grid is frozen in the
+    palette stage, so it is converted once; the reference casts every table on every forward, gridencoder/grid.py:38-39)"""
+
+    def __init__(self):
+        self.c = {}
+
+    def get(self, name, p):
+        key = (p._version, p.data_ptr())
+        hit = self.c.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, p.detach().to(torch.float16).contiguous())
+            self.c[name] = hit
+        return hit[1]
+
+
+def _state(model):
+    st = getattr(model, "_fused_train_state", None)
+    dev = model.encoder.embeddings.device
+    if st is None or st["device"] != dev:
+        sd = dict(model.named_parameters())
+        pred_clip, cd = bool(model.opt.pred_clip), int(model.opt.clip_dim)
+        names = WEIGHT_NAMES + (CLIP_NAMES if pred_clip else [])
+        index, n_fwd, _ = build_pack_index({n: sd[n].shape for n in names}, pred_clip, cd)
+        st = dict(device=dev, index=index.to(dev), n_fwd=n_fwd, names=names, tables=_Tables(), pred_clip=pred_clip, cd=cd,
+                  zero=torch.zeros(1, dtype=torch.float32, device=dev))
+        assert n_fwd == 4 * L.lib.pnerf_palette_train_wfwd_units(int(pred_clip))
+        assert index.numel() - n_fwd == 4 * L.lib.pnerf_palette_train_wbwd_units(int(pred_clip))
+        object.__setattr__(model, "_fused_train_state", st)
+    return st
+
+
+def supported(model):
+    return _fused.supported(model)
+
+
+class _TrainField(Function):
+    """(model, xyzs, dirs, palette, embeddings_palette, embeddings_clip | None, *weights) -> sigma, rgb, flex"""
+
+    @staticmethod
+    def forward(ctx, model, xyzs, dirs, palette, emb_palette, emb_clip, *weights):
+        st = _state(model)
+        L.require_cuda(xyzs, dirs, emb_palette)
+        dev = xyzs.device
+        xyzs, dirs = xyzs.detach().contiguous().float(), dirs.detach().contiguous().float()
+        M, pc, cd = xyzs.shape[0], st["pred_clip"], st["cd"]
+        nflex = 13 + cd + NB
+        flat = torch.cat([w.detach().reshape(-1).float() for w in weights] + [st["zero"]])
+        blob = flat[st["index"]].to(torch.float16)
+        tabs = st["tables"]
+        t_sigma = tabs.get("sigma", model.encoder.embeddings)
+        t_pal = tabs.get("palette", emb_palette)
+        t_clip = tabs.get("clip", emb_clip) if pc else None
+        pal = palette.detach().float().contiguous()
+        offsets = model.encoder.offsets
+        f = PaletteTrain()
+        f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
+        f.offsets, f.palette = ptr(offsets), ptr(pal)
+        f.wfwd, f.wbwd = blob.data_ptr(), blob.data_ptr() + 2 * st["n_fwd"]
+        f.L, f.H, f.pred_clip, f.clip_dim = model.encoder.num_levels, model.encoder.base_resolution, int(pc), cd
+        f.S = float(np.float32(np.log2(model.encoder.per_level_scale)))
+        f.bound, f.density_scale = float(model.bound), float(model.density_scale)
+        xbuf = torch.empty(int(L.lib.pnerf_palette_train_xbuf_bytes(M, int(pc))), dtype=torch.uint8, device=dev)
+        sigma = torch.empty(M, dtype=torch.float32, device=dev)
+        rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        flex = torch.empty(M, nflex, dtype=torch.float32, device=dev)
+        L.call("pnerf_palette_train_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(xbuf), ptr(sigma), ptr(rgb),
+               ptr(flex), stream())
+        ctx.keep = (f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs)
+        ctx.model, ctx.M, ctx.n_weights = model, M, len(weights)
+        ctx.need_palette = palette.requires_grad
+        ctx.mark_non_differentiable(sigma)
+        return sigma, rgb, flex
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb, g_flex):
+        model, M = ctx.model, ctx.M
+        st = _state(model)
+        pc, cd = st["pred_clip"], st["cd"]
+        f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs = ctx.keep
+        dev = xyzs.device
+        nflex = 13 + cd + NB
+        g_rgb = torch.zeros(M, 3, device=dev) if g_rgb is None else g_rgb.contiguous().float()
+        g_flex = torch.zeros(M, nflex, device=dev) if g_flex is None else g_flex.contiguous().float()
+        ybuf = torch.empty(int(L.lib.pnerf_palette_train_ybuf_bytes(M, int(pc))), dtype=torch.uint8, device=dev)
+        d_enc = torch.empty(M, 32, dtype=torch.float32, device=dev)
+        d_enc_clip = torch.empty(M, 32, dtype=torch.float32, device=dev) if pc else None
+        d_pal = torch.zeros(NB, 3, dtype=torch.float32, device=dev) if ctx.need_palette else None
+        dw = torch.zeros(int(L.lib.pnerf_palette_train_dw_floats(int(pc))), dtype=torch.float32, device=dev)
+        L.call("pnerf_palette_train_backward", M, ctypes.addressof(f), ptr(xbuf), ptr(ybuf), ptr(g_rgb), ptr(g_flex), ptr(flex),
+               ptr(d_enc), ptr(d_enc_clip), ptr(d_pal), stream())
+        L.call("pnerf_palette_train_wgrad", M, int(pc), ptr(xbuf), ptr(ybuf), ptr(dw), stream())
+        # hash-grid scatter of the feature gradients (run-length kernel, fp32 accumulation, [B, L*C] layout)
+        from .gridencoder.backend import _backend as GB
+        enc = model.encoder_palette
+        x01 = ((xyzs + model.bound) / (2 * model.bound)).contiguous()
+        S_ = float(np.float32(np.log2(enc.per_level_scale)))
+
+        def scatter(emb, d):
+            g = torch.zeros_like(emb, dtype=torch.float32)
+            GB.grid_encode_backward_blc(d, x01, g, offsets, g, M, 3, 2, enc.num_levels, S_, enc.base_resolution, None, None,
+                                        0, False)
+            return g
+        emb_pal, emb_clip = model.encoder_palette.embeddings, model.encoder_clip.embeddings
+        g_pal_tab = scatter(emb_pal, d_enc) if M > 0 else torch.zeros_like(emb_pal)
+        g_clip_tab = (scatter(emb_clip, d_enc_clip) if M > 0 else torch.zeros_like(emb_clip)) if pc else None
+        gw = dw_views(dw, pc, cd)
+        grads = [gw.get(n) for n in st["names"]]           # sigma_net.* -> None (constants of this stage)
+        return (None, None, None, d_pal, g_pal_tab, g_clip_tab, *grads)
+
+
+def field(model, xyzs, dirs, palette):
+    """fused training field: -> (sigmas [M] (density_scale applied, no grad), rgbs [M,3], channels [M, 13+clip+Nb])"""
+    st = _state(model)
+    sd = dict(model.named_parameters())
+    weights = [sd[n] for n in st["names"]]
+    emb_clip = model.encoder_clip.embeddings if st["pred_clip"] else None
+    return _TrainField.apply(model, xyzs, dirs, palette, model.encoder_palette.embeddings, emb_clip, *weights)

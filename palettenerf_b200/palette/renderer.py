@@ -152,13 +152,9 @@ class PaletteRenderer(nn.Module, OccupancyState):
             return self.background(raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius), rays_d)
         return 1 if bg_color is None else bg_color
 
-    # ------------------------------------------------------------------------------------------------
-    def _train_branch(self, rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays, max_steps,
-                      T_thresh):
+    def _train_field_torch(self, xyzs, dirs, deltas, rays, palette, T_thresh):
+        """the reference's per-op schedule of the training field (palette/renderer.py:333-385) on the new kernels"""
         nb, cd = self.num_basis, self.opt.clip_dim
-        xyzs, dirs, deltas, rays = raymarching.march_rays_train(
-            rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars,
-            self._next_counter(), self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
         M = xyzs.shape[0]
         sigmas, clip_feat, omega, offsets_radiance, view_dep, diffuse = self(xyzs, dirs)
         sigmas = (self.density_scale * sigmas).detach()      # geometry is frozen in the palette stage (ref :334-335)
@@ -167,9 +163,6 @@ class PaletteRenderer(nn.Module, OccupancyState):
         omega = omega.reshape(M, nb, 1)
         view_dep, diffuse, clip_feat = view_dep.reshape(M, 3), diffuse.reshape(M, 3), clip_feat.reshape(M, cd)
 
-        palette = self.basis_color[None].clamp(0, 1)
-        if self.freeze_basis_color:
-            palette = palette.detach()
         rgbs = (omega * (F.softplus(radiance) * (palette + offsets))).sum(dim=-2) + view_dep.detach()
         direct_rgb = diffuse + view_dep
         weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
@@ -194,9 +187,34 @@ class PaletteRenderer(nn.Module, OccupancyState):
         else:
             smooth_norm = torch.zeros_like(omega_sparsity)
 
-        # all auxiliary channels ride through ONE n-channel composite: [M, 13 + clip_dim + Nb]
         channels = torch.cat([omega_sparsity, view_dep_norm, offsets_norm, smooth_norm, view_dep, direct_rgb, diffuse,
                               clip_feat, w], dim=-1)
+        return sigmas, rgbs, channels, weights_sum, depth, image
+
+    # ------------------------------------------------------------------------------------------------
+    def _train_branch(self, rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays, max_steps,
+                      T_thresh, fused=None):
+        nb, cd = self.num_basis, self.opt.clip_dim
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+            rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars,
+            self._next_counter(), self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
+        M = xyzs.shape[0]
+        palette = self.basis_color[None].clamp(0, 1)
+        if self.freeze_basis_color:
+            palette = palette.detach()
+        use_fused = self._fused_train_available() if fused is None else bool(fused)
+        self._last_train_schedule = "fused" if use_fused else "torch"
+        if use_fused:
+            # ONE forward kernel (hash grids + MLPs + blend + regulariser channels) with a hand-written backward
+            from .. import fused_train
+            if self.require_smooth_loss:
+                raise RuntimeError("the fused training field does not cover the smooth-loss branch")
+            sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0])
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+        else:
+            sigmas, rgbs, channels, weights_sum, depth, image = self._train_field_torch(xyzs, dirs, deltas, rays, palette,
+                                                                                        T_thresh)
+        # all auxiliary channels ride through ONE n-channel composite: [M, 13 + clip_dim + Nb]
         maps = raymarching.composite_rays_flex_train(sigmas, channels, deltas, rays, T_thresh)
 
         out = {
@@ -288,7 +306,7 @@ class PaletteRenderer(nn.Module, OccupancyState):
         bg_color = self._background(rays_o, rays_d, bg_color)
         if self.training:
             return self._train_branch(rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays,
-                                      max_steps, T_thresh)
+                                      max_steps, T_thresh, fused=fused)
 
         nb, cd = self.num_basis, self.opt.clip_dim
         use_fused = self._fused_available(gui_mode) if fused is None else fused
@@ -320,6 +338,12 @@ class PaletteRenderer(nn.Module, OccupancyState):
         the architecture is the one it implements and no GUI edit module is active"""
         from .. import fused
         return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None and fused.supported(self))
+
+    def _fused_train_available(self):
+        """fused training field: same policy as inference, and only without the smooth-loss branch"""
+        from .. import fused
+        return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None
+                and not self.require_smooth_loss and fused.supported(self))
 
     def _infer_fused(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
         from .. import fused
