@@ -219,6 +219,7 @@ def main():
                 "kernel": top[0], "peak_kind": peak_kind, "kernel_time_share_of_own_kernels": shares}
     q = getattr(model, "_last_queue", None)          # [hit-list cursor, samples shaded, rays with samples] of the last view
     samples_per_step = int(q[1].item()) if q is not None else None
+    tile_fill = (float(q[1].item()) / (32.0 * max(1, int(q[3].item())))) if q is not None else None
 
     extras = {}
     if not args.no_extras:
@@ -245,7 +246,7 @@ def main():
                                        "(BASELINE config 3), one view per GPU",
                            "rays_per_step_per_gpu": N_RAYS, "gui_mode": bool(args.gui_mode),
                            "schedule": getattr(model, "_last_schedule", "loop"),
-                           "samples_per_step": samples_per_step, "l2": "flushed between timed iterations (256 MB write)"},
+                           "samples_per_step": samples_per_step, "tile_fill": tile_fill, "l2": "flushed between timed iterations (256 MB write)"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         line.update(extras)
@@ -306,52 +307,56 @@ def bench_hashgrid(torch, dev, L, hbm_peak, flush):
     return {"hashgrid": res}
 
 
-def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush):
+def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True):
     """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
-    GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1."""
+    GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1.
+    The step (static-capacity march, fused field fwd/bwd/wgrad, one-pass compositor, loss, all-reduce, GradScaler, fused
+    Adam) has data-independent shapes and no host synchronisation, so it is captured ONCE in a CUDA graph and replayed."""
+    from palettenerf_b200.distributed import GradBucket
+    from palettenerf_b200.graphs import GraphedStep, make_palette_train_step
     model = S.build_palette_model(dev, seed=0, pred_clip=False)
     model.train()
-    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
+    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda")
-    from palettenerf_b200.distributed import GradBucket
-    bucket = GradBucket(params)
+    bucket = GradBucket(params) if world > 1 else None
     o, d = S.training_rays(TRAIN_RAYS, seed=rank)
-    o, d = o.to(dev), d.to(dev)
+    o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
     gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
-    state = {}
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.float16):
-            out = model.render(o[None], d[None], staged=False, bg_color=1, perturb=True, force_all_rays=True,
-                               dt_gamma=0.0, max_steps=1024)
-            loss = ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
-                + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
-        scaler.scale(loss).backward()
-        if world > 1:
-            # ONE all-reduce of the (still loss-scaled) gradients: an inf/nan on any rank reaches every rank through
-            # the sum, so GradScaler's found-inf decision is identical everywhere without a second collective
-            bucket.all_reduce(average=True)
-        scaler.step(opt)
-        scaler.update()
+    def loss_fn(out):
+        return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
+            + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
 
+    step_fn = make_palette_train_step(model, opt, scaler, o, d, loss_fn, bucket=bucket)
+    mode = "eager"
+    step = step_fn
+    l0 = L.launch_count
+    step_fn()
+    own_launches = L.launch_count - l0          # C-ABI kernels per step (torch's own kernels are not counted)
+    if use_graph:
+        try:
+            g = GraphedStep(step_fn, warmup=3)
+            step, mode = g.replay, "cuda_graph"
+        except Exception as e:  # noqa: BLE001  (report and fall back; the eager schedule is the same kernels)
+            mode = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
     for _ in range(3):
         step()
     barrier()
     ts = []
-    for _ in range(5):
+    for _ in range(10):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); step(); b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     barrier()
-    state["m"] = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
+    m = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
     ms = max_over_ranks(sum(ts) / len(ts))
     return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
-                      "samples_per_step_rank0": state.get("m"), "schedule": getattr(model, "_last_train_schedule", "torch"),
-                      "optimizer": "Adam(0.9,0.99,1e-15,fused)+GradScaler",
+                      "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
+                      "launch": mode, "own_kernel_launches_per_step": own_launches,
+                      "optimizer": "Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
 

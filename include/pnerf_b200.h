@@ -200,8 +200,9 @@ PNERF_API int pnerf_palette_field_forward(const float* xyzs, const float* dirs, 
                                           const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
                                           float* off_rad, float* view_dep, float* diffuse, void* stream);
 
-/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[3] zeroed:
- * on return queue[1] = number of samples shaded, queue[2] = number of rays with at least one sample.
+/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[4] zeroed:
+ * on return queue[1] = number of samples shaded, queue[2] = number of rays with at least one sample,
+ * queue[3] = number of 32-sample tiles evaluated (queue[1] / (32 queue[3]) = tile fill).
  * hit_list (int32), t_first, t_last (fp32) are [N] scratch buffers. */
 PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
@@ -233,6 +234,8 @@ typedef struct pnerf_palette_train {
     const void* wfwd;           /* fp16 B fragments of the forward layers; head bias folded into column 15 */
     const void* wbwd;           /* fp16 B fragments of the transposed layers (dX = dY W)        */
     const float* palette;       /* [4*3] basis_color clamped to [0,1]                            */
+    const int32_t* m_dev;       /* optional: device-side sample count (march counter[0]); the kernels then process
+                                   min(M, *m_dev) samples and M is only the capacity of the buffers */
     uint32_t L, H, pred_clip, clip_dim;
     float S, bound, density_scale;
 } pnerf_palette_train;
@@ -249,7 +252,29 @@ PNERF_API int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train
                                            const float* grad_rgb, const float* grad_flex, const float* flex, float* d_enc,
                                            float* d_enc_clip, float* d_palette, void* stream);
 PNERF_API int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf,
-                                        void* stream);
+                                        const int32_t* m_dev, void* stream);
+
+/* ONE-pass compositor of the palette training step: composite_rays_train on (sigma, rgb) and composite_rays_flex_train
+ * on the nflex auxiliary channels together (ref: raymarching.cu:504-645, palette/renderer.py:354, 387-397).
+ * backward: gradients w.r.t. rgb and flex only (sigma is a constant of the palette stage); EVERY sample row of every ray
+ * is written (zeros after termination), so grad_rgbs / grad_flex need not be zero-initialised. nflex must be 33. */
+PNERF_API int pnerf_palette_composite_train_forward(const float* sigmas, const float* rgbs, const float* flex,
+                                                    const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                                    uint32_t nflex, float T_thresh, float* weights_sum, float* depth,
+                                                    float* image, float* maps, void* stream);
+PNERF_API int pnerf_palette_composite_train_backward(const float* grad_image, const float* grad_maps, const float* sigmas,
+                                                     const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                                     uint32_t nflex, float T_thresh, float* grad_rgbs, float* grad_flex,
+                                                     void* stream);
+
+/* pnerf_grid_encode_backward for D = 3, C = 2 with the number of points taken from device memory: processes
+ * min(B, *count_dev) rows (static-capacity training step, no host synchronisation). bound > 0: `inputs` are world
+ * coordinates in [-bound, bound] and are mapped to [0,1] inside the kernel like GridEncoder.forward does; bound = 0:
+ * inputs are already in [0,1]. */
+PNERF_API int pnerf_grid_encode_backward_counted(const void* grad, const float* inputs, const int32_t* offsets,
+                                                 void* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H,
+                                                 uint32_t gridtype, int align_corners, int dtype, int grad_layout,
+                                                 const int32_t* count_dev, float bound, void* stream);
 
 #ifdef __cplusplus
 }

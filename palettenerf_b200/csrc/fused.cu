@@ -261,7 +261,7 @@ struct RenderArgs {
     float* weights_sum; float* depth; float* image;          // [N], [N], [N,3]   (written once per ray)
     float* direct_rgb; float* view_dep_rgb; float* basis_acc; float* basis_rgb; float* unscaled_basis_rgb;  // aux (NULL in gui mode)
     float* clip_feat;                                         // [N, clip_dim] or NULL
-    unsigned int* queue;                                      // [3]: next hit-list slot, samples shaded, rays with samples
+    unsigned int* queue;                                      // [4]: next hit-list slot, samples shaded, rays with samples, 32-sample tiles evaluated
     const int32_t* hit_list;                                  // [N] ids of the rays that own at least one sample
     const float* t_first; const float* t_last;                // [N] lattice t of each ray's first / last occupied point
 };
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
     float t_end = 0.f;     // lattice t of the ray's last occupied point (from the pre-pass)
     float wsum = 0.f, dep = 0.f, r = 0.f, g = 0.f, b = 0.f;
     bool exhausted = false;                    // warp-uniform: the hit list is used up
-    uint32_t shaded = 0;
+    uint32_t shaded = 0, rounds = 0;
     const uint32_t n_hit = a.queue[2];
     constexpr int kProbesPerRound = 6;         // bounds SIMT divergence: a lane crossing a gap resumes next round
 
@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
         }
 
         // ---- shade the warp's 32 samples ----
+        rounds++;
         FieldOut o;
         eval_field<CLIP>(f, *sm, wts, ws, x, y, z, sample ? ddx : 0.f, sample ? ddy : 0.f, sample ? ddz : 1.f, sample, lane, o);
 
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
     }
     // sample statistics (one atomic per warp)
     shaded = (uint32_t)warp_sum((float)shaded);  // exact below 2^24 per warp
-    if (lane == 0 && shaded) atomicAdd(a.queue + 1, shaded);
+    if (lane == 0 && shaded) { atomicAdd(a.queue + 1, shaded); atomicAdd(a.queue + 3, rounds); }
 }
 
 }  // namespace pnerf

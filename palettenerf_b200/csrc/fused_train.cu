@@ -15,9 +15,12 @@
 //                       of every layer in fragment order (ybuf) and d(loss)/d(grid features) [M,32] fp32 for the
 //                       palette (and semantic) hash grid, which go to the run-length hash-grid backward (gridenc.cu).
 //   k_field_wgrad       all weight gradients dW = dY^T X as a tensor-core split-K over the samples: a warp owns one
-//                       (layer, 16-row block) job and a chunk of half-tiles, transposes the saved fragments with
-//                       movmatrix (both operands are exactly the transposes of what was stored) and adds its partial
-//                       sum once with fp32 red.global.add.
+//                       layer and a chunk of half-tiles, transposes the saved fragments with movmatrix (both operands
+//                       are exactly the transposes of what was stored), prefetches the next half-tile while the MMAs of
+//                       the current one run, and adds its partial sum once with fp32 red.global.add. Every saved
+//                       fragment is read exactly once.
+// Static-capacity mode: when `m_dev` is set the kernels take the sample count from device memory (the march kernel's
+// counter), so a training step needs no host synchronisation and can be captured in a CUDA graph.
 //
 // The reference's detach() placements are honoured: sigma and geo features are constants in this stage (no sigma-net or
 // sigma-grid gradient; palette/network.py:168, palette/renderer.py:334-335), diffuse enters the basis net detached
@@ -151,6 +154,7 @@ k_field_train_fwd(const float* __restrict__ xyzs, const float* __restrict__ dirs
     WarpScratch& ws = scratch[wid];
     constexpr int UX = CLIP ? kUXClip : kUXNoClip;
     const uint32_t cd = f.clip_dim, nflex = 13 + cd + kNB;
+    if (f.m_dev) M = min(M, (uint32_t)__ldg(f.m_dev));      // static-capacity mode: the sample count lives on the device
     const uint32_t n_tiles = ceil_div(M, 32u);
 
     for (uint32_t tile = blockIdx.x * kFusedWarps + wid; tile < n_tiles; tile += gridDim.x * kFusedWarps) {
@@ -391,6 +395,7 @@ k_field_train_bwd(uint32_t M, pnerf_palette_train f, const uint32_t* __restrict_
     BwdScratch& bs = scratch[wid];
     constexpr int UX = CLIP ? kUXClip : kUXNoClip, UY = CLIP ? kUYClip : kUYNoClip;
     const uint32_t cd = f.clip_dim, nflex = 13 + cd + kNB;
+    if (f.m_dev) M = min(M, (uint32_t)__ldg(f.m_dev));
     const uint32_t n_tiles = ceil_div(M, 32u);
 
     for (uint32_t tile = blockIdx.x * kTrainWarps + wid; tile < n_tiles; tile += gridDim.x * kTrainWarps) {
@@ -545,59 +550,98 @@ k_field_train_bwd(uint32_t M, pnerf_palette_train f, const uint32_t* __restrict_
 // =====================================================================================================================
 // weight gradients: dW[n_out][k_in] = sum_s dY[s][n_out] X[s][k_in]
 // =====================================================================================================================
-struct WJob { uint16_t yslot, xslot, ux, kpad; uint32_t dwoff; };
-struct WJobs { WJob j[32]; uint32_t n; };
+// One warp owns ALL 16-row blocks of one layer for a chunk of half-tiles, so every saved fragment is read exactly once
+// (203 MB at 122 k samples instead of 371 MB when a warp owned a single 16-row block), and the loads of the next
+// half-tile are issued before the MMAs of the current one.
+struct WJob { uint16_t yslot, xslot, ny, ux, kpad, pad; uint32_t dwoff; };
+struct WJobs { WJob j[16]; uint32_t n; };
 
-__host__ inline void add_jobs(WJobs& J, int yslot, int ny, int xslot, int ux, int dwl) {
-    for (int m = 0; m < ny; m++) {
-        WJob& w = J.j[J.n++];
-        w.yslot = (uint16_t)(yslot + m); w.xslot = (uint16_t)xslot; w.ux = (uint16_t)ux; w.kpad = (uint16_t)dw_k(dwl);
-        w.dwoff = (uint32_t)(dw_off(dwl) + m * 16 * dw_k(dwl));
-    }
+__host__ inline void add_job(WJobs& J, int yslot, int ny, int xslot, int ux, int dwl) {
+    WJob& w = J.j[J.n++];
+    w.yslot = (uint16_t)yslot; w.xslot = (uint16_t)xslot; w.ny = (uint16_t)ny; w.ux = (uint16_t)ux;
+    w.kpad = (uint16_t)dw_k(dwl); w.pad = 0; w.dwoff = (uint32_t)dw_off(dwl);
 }
 
 constexpr int kWgradWarps = 4;
 
+template <int NY, int UX>
+__device__ __forceinline__ void wgrad_job(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t h0,
+                                          uint32_t h1, uint32_t UXT, uint32_t UYT, const WJob& job, float* __restrict__ dwbuf,
+                                          int lane) {
+    float c[NY][2 * UX][4];
+#pragma unroll
+    for (int m = 0; m < NY; m++)
+#pragma unroll
+        for (int i = 0; i < 2 * UX; i++) c[m][i][0] = c[m][i][1] = c[m][i][2] = c[m][i][3] = 0.f;
+    uint32_t p[NY][4], q[UX][4];
+    auto load = [&](uint32_t h) {
+        const uint32_t* yb = ybuf + (size_t)h * UYT * 128;
+        const uint32_t* xb = xbuf + (size_t)h * UXT * 128;
+#pragma unroll
+        for (int m = 0; m < NY; m++) ld_unit(yb, job.yslot + m, p[m], lane);
+#pragma unroll
+        for (int j = 0; j < UX; j++) ld_unit(xb, job.xslot + j, q[j], lane);
+    };
+    load(h0);
+#pragma unroll 1
+    for (uint32_t h = h0; h < h1; h++) {
+        // transposes of the current half-tile's fragments (registers), then prefetch the next half-tile
+        uint32_t a[NY][4], b[UX][4];
+#pragma unroll
+        for (int m = 0; m < NY; m++) {   // A = (dY block)^T: 8x8 transposes + swap of the off-diagonal blocks
+            a[m][0] = movmatrix_t(p[m][0]); a[m][1] = movmatrix_t(p[m][2]); a[m][2] = movmatrix_t(p[m][1]); a[m][3] = movmatrix_t(p[m][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < UX; j++) {   // B (k = sample, n = k_in), .col fragment order = transposes of the stored blocks
+#pragma unroll
+            for (int i = 0; i < 4; i++) b[j][i] = movmatrix_t(q[j][i]);
+        }
+        if (h + 1 < h1) load(h + 1);
+#pragma unroll
+        for (int m = 0; m < NY; m++)
+#pragma unroll
+            for (int j = 0; j < UX; j++) {
+                mma16816(c[m][2 * j], a[m], b[j][0], b[j][1]);
+                mma16816(c[m][2 * j + 1], a[m], b[j][2], b[j][3]);
+            }
+    }
+    const int g = lane >> 2, q2 = (lane & 3) * 2;
+#pragma unroll
+    for (int m = 0; m < NY; m++) {
+        float* dw = dwbuf + job.dwoff + m * 16 * job.kpad;
+#pragma unroll
+        for (int nt = 0; nt < 2 * UX; nt++) {
+            const int col = nt * 8 + q2;
+            atomicAdd(dw + g * job.kpad + col, c[m][nt][0]);
+            atomicAdd(dw + g * job.kpad + col + 1, c[m][nt][1]);
+            atomicAdd(dw + (g + 8) * job.kpad + col, c[m][nt][2]);
+            atomicAdd(dw + (g + 8) * job.kpad + col + 1, c[m][nt][3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kWgradWarps * 32)
-k_field_wgrad(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t n_half, uint32_t per_chunk,
+k_field_wgrad(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t M, const int32_t* __restrict__ m_dev,
               uint32_t UX, uint32_t UY, const __grid_constant__ WJobs jobs, float* __restrict__ dwbuf) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const WJob job = jobs.j[blockIdx.y];
-    const uint32_t chunk = blockIdx.x * kWgradWarps + wid;
-    const uint32_t h0 = chunk * per_chunk, h1 = min(n_half, h0 + per_chunk);
-    if (h0 >= n_half) return;
-    float c[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
-#pragma unroll 1
-    for (uint32_t h = h0; h < h1; h++) {
-        uint32_t p[4], a[4];
-        ld_unit(ybuf + (size_t)h * UY * 128, job.yslot, p, lane);
-        // A = (dY block)^T : block transposes + swap of the off-diagonal 8x8 blocks
-        a[0] = movmatrix_t(p[0]); a[1] = movmatrix_t(p[2]); a[2] = movmatrix_t(p[1]); a[3] = movmatrix_t(p[3]);
-        const uint32_t* xb = xbuf + (size_t)h * UX * 128;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j < (int)job.ux) {
-                uint32_t q[4];
-                ld_unit(xb, job.xslot + j, q, lane);
-                // B (k = sample, n = k_in) in .col fragment order = transposes of the stored 8x8 blocks
-                const uint32_t b00 = movmatrix_t(q[0]), b01 = movmatrix_t(q[1]), b10 = movmatrix_t(q[2]), b11 = movmatrix_t(q[3]);
-                mma16816(c[2 * j], a, b00, b01);
-                mma16816(c[2 * j + 1], a, b10, b11);
-            }
-        }
-    }
-    float* dw = dwbuf + job.dwoff;
-    const int g = lane >> 2, q2 = (lane & 3) * 2;
-#pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-        if (nt < 2 * (int)job.ux) {
-            const int col = nt * 8 + q2;
-            atomicAdd(dw + g * job.kpad + col, c[nt][0]);
-            atomicAdd(dw + g * job.kpad + col + 1, c[nt][1]);
-            atomicAdd(dw + (g + 8) * job.kpad + col, c[nt][2]);
-            atomicAdd(dw + (g + 8) * job.kpad + col + 1, c[nt][3]);
+    if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
+    const uint32_t n_half = ceil_div(M, 32u) * 2;
+    // every warp of this job gets one chunk of half-tiles when there is enough work, but never fewer than 32 half-tiles
+    // (512 samples) so that the closing atomics (one per weight per chunk) stay negligible; long inputs loop.
+    const uint32_t n_warps = gridDim.x * kWgradWarps;
+    const uint32_t per_chunk = min(128u, max(32u, ceil_div(n_half, n_warps)));
+    const int shape = job.ny * 8 + job.ux;   // uniform per blockIdx.y
+    for (uint32_t chunk = blockIdx.x * kWgradWarps + wid; chunk * per_chunk < n_half; chunk += n_warps) {
+        const uint32_t h0 = chunk * per_chunk, h1 = min(n_half, h0 + per_chunk);
+        switch (shape) {
+            case 4 * 8 + 1: wgrad_job<4, 1>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            case 4 * 8 + 2: wgrad_job<4, 2>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            case 4 * 8 + 3: wgrad_job<4, 3>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            case 4 * 8 + 4: wgrad_job<4, 4>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            case 1 * 8 + 4: wgrad_job<1, 4>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            case 2 * 8 + 1: wgrad_job<2, 1>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
+            default: break;
         }
     }
 }
@@ -635,14 +679,16 @@ int pnerf_palette_train_forward(const float* xyzs, const float* dirs, uint32_t M
     const size_t smem = ((sizeof(TrainSmem) + 15) & ~(size_t)15) + (size_t)(clip ? kWUnitsClip : kWUnitsNoClip) * sizeof(uint2) +
                         sizeof(WarpScratch) * kFusedWarps;
     const uint32_t grid = min(ceil_div(ceil_div(M, 32u), (uint32_t)kFusedWarps), (uint32_t)kNumSMs);
-    cudaError_t e;
-    if (clip) {
-        e = cudaFuncSetAttribute(k_field_train_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_done[2] = {false, false};   // set once per process (keeps cudaFuncSetAttribute out of graph capture)
+    if (!attr_done[clip]) {
+        cudaError_t e = clip ? cudaFuncSetAttribute(k_field_train_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_field_train_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_cuda_error(e, "palette_train_forward attr"); return PNERF_ERR_CUDA; }
+        attr_done[clip] = true;
+    }
+    if (clip) {
         k_field_train_fwd<true><<<grid, kFusedWarps * 32, smem, s>>>(xyzs, dirs, M, *p, (uint32_t*)xbuf, sigma, rgb, flex);
     } else {
-        e = cudaFuncSetAttribute(k_field_train_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_last_cuda_error(e, "palette_train_forward attr"); return PNERF_ERR_CUDA; }
         k_field_train_fwd<false><<<grid, kFusedWarps * 32, smem, s>>>(xyzs, dirs, M, *p, (uint32_t*)xbuf, sigma, rgb, flex);
     }
     return check_launch("palette_train_forward");
@@ -659,47 +705,47 @@ int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train* p, const
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = 64 + (size_t)(3 * 32 + (clip ? kTUnitsClip : kTUnitsNoClip)) * sizeof(uint2) + sizeof(BwdScratch) * kTrainWarps;
     const uint32_t grid = min(ceil_div(ceil_div(M, 32u), (uint32_t)kTrainWarps), 2u * (uint32_t)kNumSMs);
-    cudaError_t e;
-    if (clip) {
-        e = cudaFuncSetAttribute(k_field_train_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[clip]) {
+        cudaError_t e = clip ? cudaFuncSetAttribute(k_field_train_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_field_train_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_cuda_error(e, "palette_train_backward attr"); return PNERF_ERR_CUDA; }
+        attr_done[clip] = true;
+    }
+    if (clip) {
         k_field_train_bwd<true><<<grid, kTrainWarps * 32, smem, s>>>(M, *p, (const uint32_t*)xbuf, (uint32_t*)ybuf, grad_rgb,
                                                                    grad_flex, flex, d_enc, d_enc_clip, d_palette);
     } else {
-        e = cudaFuncSetAttribute(k_field_train_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_last_cuda_error(e, "palette_train_backward attr"); return PNERF_ERR_CUDA; }
         k_field_train_bwd<false><<<grid, kTrainWarps * 32, smem, s>>>(M, *p, (const uint32_t*)xbuf, (uint32_t*)ybuf, grad_rgb,
                                                                     grad_flex, flex, d_enc, d_enc_clip, d_palette);
     }
     return check_launch("palette_train_backward");
 }
 
-int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf, void* stream) {
+int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf,
+                              const int32_t* m_dev, void* stream) {
     if (M == 0) return PNERF_OK;
     PNERF_REQUIRE(xbuf && ybuf && dwbuf);
     WJobs J;
     J.n = 0;
-    add_jobs(J, YD0, 4, XD0, 1, DW_D0);
-    add_jobs(J, YD1, 4, XD1, 4, DW_D1);
-    add_jobs(J, YD2, 1, XD2, 4, DW_D2);
-    add_jobs(J, YV0, 4, XV0, 2, DW_V0);
-    add_jobs(J, YV1, 4, XV1, 4, DW_V1);
-    add_jobs(J, YV2, 1, XV2, 4, DW_V2);
-    add_jobs(J, YB0, 4, XB0, 3, DW_B0);
-    add_jobs(J, YB1, 1, XB1, 4, DW_B1);
-    add_jobs(J, YH, 2, XH, 1, DW_H);
+    add_job(J, YD0, 4, XD0, 1, DW_D0);
+    add_job(J, YD1, 4, XD1, 4, DW_D1);
+    add_job(J, YD2, 1, XD2, 4, DW_D2);
+    add_job(J, YV0, 4, XV0, 2, DW_V0);
+    add_job(J, YV1, 4, XV1, 4, DW_V1);
+    add_job(J, YV2, 1, XV2, 4, DW_V2);
+    add_job(J, YB0, 4, XB0, 3, DW_B0);
+    add_job(J, YB1, 1, XB1, 4, DW_B1);
+    add_job(J, YH, 2, XH, 1, DW_H);
     if (pred_clip) {
-        add_jobs(J, YC0, 4, XC0, 2, DW_C0);
-        add_jobs(J, YC1, 1, XC1, 4, DW_C1);
+        add_job(J, YC0, 4, XC0, 2, DW_C0);
+        add_job(J, YC1, 1, XC1, 4, DW_C1);
     }
-    const uint32_t n_half = ceil_div(M, 32u) * 2;
-    // chunk length: enough warps to fill the machine, few enough that the final atomics stay negligible
-    uint32_t per_chunk = 64;
-    while (per_chunk > 8 && ceil_div(n_half, per_chunk) * J.n < 4u * kNumSMs * kWgradWarps) per_chunk >>= 1;
-    const uint32_t chunks = ceil_div(n_half, per_chunk);
-    const dim3 grid(ceil_div(chunks, (uint32_t)kWgradWarps), J.n, 1);
-    k_field_wgrad<<<grid, kWgradWarps * 32, 0, (cudaStream_t)stream>>>((const uint32_t*)xbuf, (const uint32_t*)ybuf, n_half,
-                                                                       per_chunk, pred_clip ? kUXClip : kUXNoClip,
+    const uint32_t n_half_cap = ceil_div(M, 32u) * 2;
+    const uint32_t grid_x = min(ceil_div(ceil_div(n_half_cap, 32u), (uint32_t)kWgradWarps), 2u * (uint32_t)kNumSMs);
+    const dim3 grid(max(grid_x, 1u), J.n, 1);
+    k_field_wgrad<<<grid, kWgradWarps * 32, 0, (cudaStream_t)stream>>>((const uint32_t*)xbuf, (const uint32_t*)ybuf, M, m_dev,
+                                                                       pred_clip ? kUXClip : kUXNoClip,
                                                                        pred_clip ? kUYClip : kUYNoClip, J, dwbuf);
     return check_launch("palette_train_wgrad");
 }

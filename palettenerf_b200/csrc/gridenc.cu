@@ -312,10 +312,12 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ grad, const float* __restrict__ inputs,
                                                        const int32_t* __restrict__ offsets, T* __restrict__ grad_grid,
                                                        uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                                                       bool align_corners, bool layout_blc) {
+                                                       bool align_corners, bool layout_blc,
+                                                       const int32_t* __restrict__ count_dev = nullptr, float bound = 0.f) {
     __shared__ LevelParams lp[kMaxLevels];
     if (threadIdx.x < L) make_level(lp[threadIdx.x], threadIdx.x, offsets, S, H, 3, gridtype, align_corners);
     __syncthreads();
+    if (count_dev) B = min(B, (uint32_t)__ldg(count_dev));
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t level = (uint32_t)(tid % L);
     const uint64_t seg = tid / L;
@@ -331,7 +333,10 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
     for (int k = 0; k < K; k++) {
         const uint64_t b = b0 + k;
         if (b >= B) break;
-        const float x = inputs[b * 3 + 0], y = inputs[b * 3 + 1], z = inputs[b * 3 + 2];
+        float x = inputs[b * 3 + 0], y = inputs[b * 3 + 1], z = inputs[b * 3 + 2];
+        if (bound > 0.f) {   // world coordinates: the [0,1] map of GridEncoder.forward (gridencoder/grid.py:142), same fp32 ops
+            x = (x + bound) / (2 * bound); y = (y + bound) / (2 * bound); z = (z + bound) / (2 * bound);
+        }
         if ((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1)) continue;
         const T* gp = layout_blc ? grad + (b * L + level) * 2 : grad + ((size_t)level * B + b) * 2;
         const float2 g = Pair<T>::load(gp);
@@ -500,6 +505,29 @@ int pnerf_grid_encode_forward(const float* inputs, const void* embeddings, const
         case PNERF_F64: return grid_forward_t<double>(inputs, (const double*)embeddings, offsets, (double*)outputs, B, D, C, L, S, H, (double*)dy_dx, gridtype, al, blc, s);
         default: return PNERF_ERR_INVALID_ARG;
     }
+}
+
+int pnerf_grid_encode_backward_counted(const void* grad, const float* inputs, const int32_t* offsets, void* grad_embeddings,
+                                       uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                       int dtype, int grad_layout, const int32_t* count_dev, float bound, void* stream) {
+    if (B == 0) return PNERF_OK;
+    PNERF_REQUIRE(grad && inputs && offsets && grad_embeddings && count_dev);
+    PNERF_REQUIRE(gridtype <= 1 && (grad_layout == PNERF_LAYOUT_LBC || grad_layout == PNERF_LAYOUT_BLC));
+    if (L < 1 || L > (uint32_t)kMaxLevels) return PNERF_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool blc = grad_layout == PNERF_LAYOUT_BLC, al = align_corners != 0;
+    constexpr int K = 8;
+    const uint64_t threads = ceil_div<uint64_t>(B, K) * L;
+    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(threads, 256);
+    if (dtype == PNERF_F32)
+        k_grid_bwd_runs<float, K><<<grid, 256, 0, s>>>((const float*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
+                                                      gridtype, al, blc, count_dev, bound);
+    else if (dtype == PNERF_F16)
+        k_grid_bwd_runs<__half, K><<<grid, 256, 0, s>>>((const __half*)grad, inputs, offsets, (__half*)grad_embeddings, B, L, S,
+                                                       H, gridtype, al, blc, count_dev, bound);
+    else
+        return PNERF_ERR_UNSUPPORTED;
+    return check_launch("grid_encode_backward_counted");
 }
 
 int pnerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,

@@ -171,7 +171,7 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     if not gui_mode:
         acc.update(direct_rgb=z(N, 3), view_dep_rgb=z(N, 3), basis_acc=z(N, nb), basis_rgb=z(N, 3 * nb),
                    unscaled_basis_rgb=z(N, 3 * nb))
-    queue = torch.zeros(3, dtype=torch.int32, device=dev)
+    queue = torch.zeros(4, dtype=torch.int32, device=dev)
     hit_list = torch.empty(N, dtype=torch.int32, device=dev)
     t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
@@ -182,5 +182,5 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
            aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"), aux("unscaled_basis_rgb"),
            ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), ptr(hit_list), ptr(t_first), ptr(t_last),
            stream())
-    acc["_queue"] = queue   # [hit-list cursor, samples shaded, rays with samples]; read lazily (no sync here)
+    acc["_queue"] = queue   # [hit-list cursor, samples shaded, rays with samples, tiles evaluated]; read lazily (no sync here)
     return acc

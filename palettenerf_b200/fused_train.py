@@ -25,7 +25,7 @@ NB = 4
 class PaletteTrain(ctypes.Structure):
     """mirror of `struct pnerf_palette_train` (include/pnerf_b200.h)"""
     _fields_ = [("table_sigma", c_void_p), ("table_palette", c_void_p), ("table_clip", c_void_p), ("offsets", c_void_p),
-                ("wfwd", c_void_p), ("wbwd", c_void_p), ("palette", c_void_p),
+                ("wfwd", c_void_p), ("wbwd", c_void_p), ("palette", c_void_p), ("m_dev", c_void_p),
                 ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
                 ("S", c_float), ("bound", c_float), ("density_scale", c_float)]
 
@@ -33,7 +33,11 @@ class PaletteTrain(ctypes.Structure):
 P, U = c_void_p, c_uint32
 L.register("pnerf_palette_train_forward", [P, P, U, P, P, P, P, P, P])
 L.register("pnerf_palette_train_backward", [U, P, P, P, P, P, P, P, P, P, P])
-L.register("pnerf_palette_train_wgrad", [U, U, P, P, P, P])
+L.register("pnerf_palette_train_wgrad", [U, U, P, P, P, P, P])
+F_ = c_float
+L.register("pnerf_palette_composite_train_forward", [P, P, P, P, P, U, U, U, F_, P, P, P, P, P])
+L.register("pnerf_palette_composite_train_backward", [P, P, P, P, P, U, U, U, F_, P, P, P])
+L.register("pnerf_grid_encode_backward_counted", [P, P, P, P, U, U, F_, U, U, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, F_, P])
 for _n in ("pnerf_palette_train_xbuf_bytes", "pnerf_palette_train_ybuf_bytes"):
     getattr(L.lib, _n).argtypes = [U, U]
     getattr(L.lib, _n).restype = c_uint64
@@ -142,10 +146,12 @@ class _Tables:
     def __init__(self):
         self.c = {}
 
-    def get(self, name, p):
+    def get(self, name, p, always=False):
+        """always=True: convert unconditionally (tables that are trained change every step; a CUDA-graph capture must
+        contain the conversion no matter what the cache looked like at capture time)"""
         key = (p._version, p.data_ptr())
         hit = self.c.get(name)
-        if hit is None or hit[0] != key:
+        if always or hit is None or hit[0] != key:
             hit = (key, p.detach().to(torch.float16).contiguous())
             self.c[name] = hit
         return hit[1]
@@ -172,10 +178,11 @@ def supported(model):
 
 
 class _TrainField(Function):
-    """(model, xyzs, dirs, palette, embeddings_palette, embeddings_clip | None, *weights) -> sigma, rgb, flex"""
+    """(model, count | None, xyzs, dirs, palette, embeddings_palette, embeddings_clip | None, *weights) -> sigma, rgb, flex
+    count: optional int32 device tensor holding the number of valid rows of xyzs/dirs (static-capacity mode)"""
 
     @staticmethod
-    def forward(ctx, model, xyzs, dirs, palette, emb_palette, emb_clip, *weights):
+    def forward(ctx, model, count, xyzs, dirs, palette, emb_palette, emb_clip, *weights):
         st = _state(model)
         L.require_cuda(xyzs, dirs, emb_palette)
         dev = xyzs.device
@@ -186,14 +193,15 @@ class _TrainField(Function):
         blob = flat[st["index"]].to(torch.float16)
         tabs = st["tables"]
         t_sigma = tabs.get("sigma", model.encoder.embeddings)
-        t_pal = tabs.get("palette", emb_palette)
-        t_clip = tabs.get("clip", emb_clip) if pc else None
+        t_pal = tabs.get("palette", emb_palette, always=emb_palette.requires_grad)
+        t_clip = tabs.get("clip", emb_clip, always=emb_clip.requires_grad) if pc else None
         pal = palette.detach().float().contiguous()
         offsets = model.encoder.offsets
         f = PaletteTrain()
         f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
         f.offsets, f.palette = ptr(offsets), ptr(pal)
         f.wfwd, f.wbwd = blob.data_ptr(), blob.data_ptr() + 2 * st["n_fwd"]
+        f.m_dev = ptr(count)
         f.L, f.H, f.pred_clip, f.clip_dim = model.encoder.num_levels, model.encoder.base_resolution, int(pc), cd
         f.S = float(np.float32(np.log2(model.encoder.per_level_scale)))
         f.bound, f.density_scale = float(model.bound), float(model.density_scale)
@@ -203,7 +211,7 @@ class _TrainField(Function):
         flex = torch.empty(M, nflex, dtype=torch.float32, device=dev)
         L.call("pnerf_palette_train_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(xbuf), ptr(sigma), ptr(rgb),
                ptr(flex), stream())
-        ctx.keep = (f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs)
+        ctx.keep = (f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count)
         ctx.model, ctx.M, ctx.n_weights = model, M, len(weights)
         ctx.need_palette = palette.requires_grad
         ctx.mark_non_differentiable(sigma)
@@ -214,7 +222,7 @@ class _TrainField(Function):
         model, M = ctx.model, ctx.M
         st = _state(model)
         pc, cd = st["pred_clip"], st["cd"]
-        f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs = ctx.keep
+        f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count = ctx.keep
         dev = xyzs.device
         nflex = 13 + cd + NB
         g_rgb = torch.zeros(M, 3, device=dev) if g_rgb is None else g_rgb.contiguous().float()
@@ -226,30 +234,72 @@ class _TrainField(Function):
         dw = torch.zeros(int(L.lib.pnerf_palette_train_dw_floats(int(pc))), dtype=torch.float32, device=dev)
         L.call("pnerf_palette_train_backward", M, ctypes.addressof(f), ptr(xbuf), ptr(ybuf), ptr(g_rgb), ptr(g_flex), ptr(flex),
                ptr(d_enc), ptr(d_enc_clip), ptr(d_pal), stream())
-        L.call("pnerf_palette_train_wgrad", M, int(pc), ptr(xbuf), ptr(ybuf), ptr(dw), stream())
+        L.call("pnerf_palette_train_wgrad", M, int(pc), ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
         # hash-grid scatter of the feature gradients (run-length kernel, fp32 accumulation, [B, L*C] layout)
         from .gridencoder.backend import _backend as GB
         enc = model.encoder_palette
-        x01 = ((xyzs + model.bound) / (2 * model.bound)).contiguous()
+        x01 = ((xyzs + model.bound) / (2 * model.bound)).contiguous() if count is None else None
         S_ = float(np.float32(np.log2(enc.per_level_scale)))
 
         def scatter(emb, d):
             g = torch.zeros_like(emb, dtype=torch.float32)
-            GB.grid_encode_backward_blc(d, x01, g, offsets, g, M, 3, 2, enc.num_levels, S_, enc.base_resolution, None, None,
-                                        0, False)
+            if count is None:
+                GB.grid_encode_backward_blc(d, x01, g, offsets, g, M, 3, 2, enc.num_levels, S_, enc.base_resolution, None,
+                                            None, 0, False)
+            else:   # number of rows taken from device memory
+                L.call("pnerf_grid_encode_backward_counted", ptr(d), ptr(xyzs), ptr(offsets), ptr(g), M, enc.num_levels, S_,
+                       enc.base_resolution, 0, 0, L.F32, L.LAYOUT_BLC, ptr(count), float(model.bound), stream())
             return g
         emb_pal, emb_clip = model.encoder_palette.embeddings, model.encoder_clip.embeddings
         g_pal_tab = scatter(emb_pal, d_enc) if M > 0 else torch.zeros_like(emb_pal)
         g_clip_tab = (scatter(emb_clip, d_enc_clip) if M > 0 else torch.zeros_like(emb_clip)) if pc else None
         gw = dw_views(dw, pc, cd)
         grads = [gw.get(n) for n in st["names"]]           # sigma_net.* -> None (constants of this stage)
-        return (None, None, None, d_pal, g_pal_tab, g_clip_tab, *grads)
+        return (None, None, None, None, d_pal, g_pal_tab, g_clip_tab, *grads)
 
 
-def field(model, xyzs, dirs, palette):
-    """fused training field: -> (sigmas [M] (density_scale applied, no grad), rgbs [M,3], channels [M, 13+clip+Nb])"""
+def field(model, xyzs, dirs, palette, count=None):
+    """fused training field: -> (sigmas [M] (density_scale applied, no grad), rgbs [M,3], channels [M, 13+clip+Nb]).
+    count: optional int32 device tensor (1 element) = number of valid rows; rows beyond it are neither read nor written."""
     st = _state(model)
-    sd = dict(model.named_parameters())
-    weights = [sd[n] for n in st["names"]]
+    if "weights" not in st:
+        sd = dict(model.named_parameters())
+        st["weights"] = [sd[n] for n in st["names"]]
     emb_clip = model.encoder_clip.embeddings if st["pred_clip"] else None
-    return _TrainField.apply(model, xyzs, dirs, palette, model.encoder_palette.embeddings, emb_clip, *weights)
+    return _TrainField.apply(model, count, xyzs, dirs, palette, model.encoder_palette.embeddings, emb_clip, *st["weights"])
+
+
+class _CompositeTrain(Function):
+    """one-pass compositor of the palette training step (csrc/composite_palette.cu): (sigmas, rgbs, channels, deltas, rays)
+    -> weights_sum [N], depth [N], image [N,3], maps [N, nflex]. Gradients flow to rgbs and channels only (sigma is a
+    constant of this stage); the backward kernel writes every sample row, so no gradient buffer is memset."""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, channels, deltas, rays, T_thresh):
+        sigmas, rgbs, channels, deltas = (t.contiguous().float() for t in (sigmas, rgbs, channels, deltas))
+        M, N, nf = sigmas.shape[0], rays.shape[0], channels.shape[1]
+        dev = sigmas.device
+        ws, depth = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        image, maps = torch.empty(N, 3, device=dev), torch.empty(N, nf, device=dev)
+        L.call("pnerf_palette_composite_train_forward", ptr(sigmas), ptr(rgbs), ptr(channels), ptr(deltas), ptr(rays), M, N, nf,
+               float(T_thresh), ptr(ws), ptr(depth), ptr(image), ptr(maps), stream())
+        ctx.save_for_backward(sigmas, deltas, rays)
+        ctx.dims = (M, N, nf, float(T_thresh))
+        ctx.mark_non_differentiable(depth)
+        return ws, depth, image, maps
+
+    @staticmethod
+    def backward(ctx, g_ws, g_depth, g_image, g_maps):
+        sigmas, deltas, rays = ctx.saved_tensors
+        M, N, nf, T_thresh = ctx.dims
+        dev = sigmas.device
+        g_image = torch.zeros(N, 3, device=dev) if g_image is None else g_image.contiguous().float()
+        g_maps = torch.zeros(N, nf, device=dev) if g_maps is None else g_maps.contiguous().float()
+        g_rgbs, g_ch = torch.empty(M, 3, device=dev), torch.empty(M, nf, device=dev)
+        L.call("pnerf_palette_composite_train_backward", ptr(g_image), ptr(g_maps), ptr(sigmas), ptr(deltas), ptr(rays), M, N, nf,
+               T_thresh, ptr(g_rgbs), ptr(g_ch), stream())
+        return None, g_rgbs, g_ch, None, None, None
+
+
+def composite(sigmas, rgbs, channels, deltas, rays, T_thresh=1e-4):
+    return _CompositeTrain.apply(sigmas, rgbs, channels, deltas, rays, T_thresh)

@@ -195,27 +195,36 @@ class PaletteRenderer(nn.Module, OccupancyState):
     def _train_branch(self, rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays, max_steps,
                       T_thresh, fused=None):
         nb, cd = self.num_basis, self.opt.clip_dim
-        xyzs, dirs, deltas, rays = raymarching.march_rays_train(
-            rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars,
-            self._next_counter(), self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
-        M = xyzs.shape[0]
+        use_fused = self._fused_train_available() if fused is None else bool(fused)
+        self._last_train_schedule = "fused" if use_fused else "torch"
         palette = self.basis_color[None].clamp(0, 1)
         if self.freeze_basis_color:
             palette = palette.detach()
-        use_fused = self._fused_train_available() if fused is None else bool(fused)
-        self._last_train_schedule = "fused" if use_fused else "torch"
+        counter = self._next_counter()
         if use_fused:
-            # ONE forward kernel (hash grids + MLPs + blend + regulariser channels) with a hand-written backward
+            # Static-capacity schedule: the march leaves the sample count on the device (no D2H sync, shapes independent
+            # of the data -> the whole step can be captured in a CUDA graph); ONE forward kernel (hash grids + MLPs +
+            # blend + regulariser channels) with a hand-written backward; ONE compositing pass for rgb + all channels.
             from .. import fused_train
             if self.require_smooth_loss:
                 raise RuntimeError("the fused training field does not cover the smooth-loss branch")
-            sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0])
-            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, True)
+            sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0], count=counter[0:1])
+            if channels.shape[1] == 33:
+                weights_sum, depth, image, maps = fused_train.composite(sigmas, rgbs, channels, deltas, rays, T_thresh)
+            else:
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+                maps = raymarching.composite_rays_flex_train(sigmas, channels, deltas, rays, T_thresh)
         else:
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
             sigmas, rgbs, channels, weights_sum, depth, image = self._train_field_torch(xyzs, dirs, deltas, rays, palette,
                                                                                         T_thresh)
-        # all auxiliary channels ride through ONE n-channel composite: [M, 13 + clip_dim + Nb]
-        maps = raymarching.composite_rays_flex_train(sigmas, channels, deltas, rays, T_thresh)
+            # all auxiliary channels ride through ONE n-channel composite: [M, 13 + clip_dim + Nb]
+            maps = raymarching.composite_rays_flex_train(sigmas, channels, deltas, rays, T_thresh)
 
         out = {
             "depth": normalise_depth(depth, nears, fars).view(*prefix),

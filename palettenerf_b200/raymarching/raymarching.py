@@ -101,7 +101,10 @@ class _march_rays_train(Function):
     @staticmethod
     @_fwd32
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
-                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, static=False):
+        """`static=True` (not in the reference): return the full-capacity buffers without reading the sample count back
+        (no D2H sync, shapes independent of the data -> CUDA-graph capturable); the count stays in step_counter[0] and
+        rows beyond it are uninitialised. Slot order is the deterministic ray order, so rows [0, count) are all valid."""
         rays_o = _cuda(rays_o).contiguous().view(-1, 3)
         rays_d = _cuda(rays_d).contiguous().view(-1, 3)
         density_bitfield = _cuda(density_bitfield).contiguous()
@@ -112,15 +115,18 @@ class _march_rays_train(Function):
                 mean_count += align - mean_count % align
             M = mean_count
         dev, dt = rays_o.device, rays_o.dtype
-        xyzs = torch.zeros(M, 3, dtype=dt, device=dev)
-        dirs = torch.zeros(M, 3, dtype=dt, device=dev)
-        deltas = torch.zeros(M, 2, dtype=dt, device=dev)
+        alloc = torch.empty if static else torch.zeros
+        xyzs = alloc(M, 3, dtype=dt, device=dev)
+        dirs = alloc(M, 3, dtype=dt, device=dev)
+        deltas = alloc(M, 2, dtype=dt, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         noises = torch.rand(N, dtype=dt, device=dev) if perturb else torch.zeros(N, dtype=dt, device=dev)
         _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
                                   xyzs, dirs, deltas, rays, step_counter, noises)
+        if static:
+            return xyzs, dirs, deltas, rays
         if force_all_rays or mean_count <= 0:
             m = step_counter[0].item()  # D2H sync, as in the reference (raymarching.py:224)
             if align > 0:

@@ -180,3 +180,36 @@ def test_training_render_fused_vs_torch_schedule_and_step(cuda):
         scaler.update()
         losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], losses
+
+
+def test_cuda_graph_captured_step_matches_eager_steps(cuda):
+    """the whole step (static-capacity march, fused field fwd/bwd/wgrad, one-pass compositor, loss, GradScaler, Adam) is
+    captured in ONE CUDA graph; replaying it must train exactly like the eager schedule"""
+    from palettenerf_b200.graphs import GraphedStep, make_palette_train_step
+    o, d = S.training_rays(512, seed=4)
+    o, d = o.to(cuda)[None].contiguous(), d.to(cuda)[None].contiguous()
+    gt = torch.rand(1, 512, 3, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+
+    def loss_fn(out):
+        return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() + 2e-4 * out["omega_sparsity"].mean() \
+            + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+
+    def make():
+        m = S.build_palette_model(cuda, seed=7, pred_clip=False, table_scale=0.3)
+        m.train()
+        opt = torch.optim.Adam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+        sc = torch.amp.GradScaler("cuda", init_scale=1024.0)
+        return m, make_palette_train_step(m, opt, sc, o, d, loss_fn, render_kwargs=dict(perturb=False))
+
+    m_eager, step_eager = make()
+    m_graph, step_graph = make()
+    n_warm, n_replay = 2, 4
+    g = GraphedStep(step_graph, warmup=n_warm)          # n_warm eager steps + 1 captured (not executed) step
+    losses_g = [float(g.replay()) for _ in range(n_replay)]
+    losses_e = [float(step_eager()) for _ in range(n_warm + n_replay)][n_warm:]
+    assert m_graph._last_train_schedule == "fused"
+    np.testing.assert_allclose(losses_g, losses_e, rtol=2e-3, atol=1e-5)    # fp32 atomics reorder sums between runs
+    assert losses_g[-1] < losses_g[0]
+    for (n1, p1), (_, p2) in zip(m_graph.named_parameters(), m_eager.named_parameters()):
+        if p1.requires_grad and p1.numel() < 100000:
+            assert torch.allclose(p1, p2, rtol=5e-2, atol=5e-3), n1

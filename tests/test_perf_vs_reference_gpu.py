@@ -1,0 +1,238 @@
+"""Timing of the reference's own CUDA extensions (compiled unmodified for sm_100a into oracle/_ref by oracle/build_ref.py)
+next to this repository's kernels, on the same B200 and the same inputs, at BASELINE sizes. Test infrastructure: it is the
+only place where the reference kernels are timed (bench.py may not touch oracle/). Results go to
+gpurun_out/perf_vs_reference.json (copied to profiles/ when committed); the test asserts only that every new path is at
+least as fast as the reference path it replaces (with 10 % slack for timer noise on the tiny kernels).
+
+End-to-end arms: the reference's host schedule (palette/renderer.py:430-523 inference loop, :322-429 training branch),
+restated in palettenerf_b200/palette/renderer.py, is run once on the REFERENCE kernels (the `_backend` objects of the
+wrappers are swapped for the reference extension modules; the MLPs are torch.nn.Linear under fp16 autocast = cuBLAS, as
+in the reference) and once on this repository's fused kernels.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_ref, ROOT
+from palettenerf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+RESULTS = {}
+
+
+def _time(fn, iters=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+@pytest.fixture(scope="module")
+def flush(cuda):
+    return torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump():
+    yield
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "perf_vs_reference.json"), "w") as f:
+        json.dump({"gpu": torch.cuda.get_device_name(0), "unit": "ms (median of 10, L2 flushed between iterations)",
+                   "results": RESULTS}, f, indent=1)
+
+
+def _record(name, ref_ms, new_ms, slack=1.10):
+    RESULTS[name] = {"reference_ms": ref_ms, "new_ms": new_ms, "speedup": ref_ms / new_ms}
+    assert new_ms <= ref_ms * slack, f"{name}: new {new_ms:.3f} ms slower than the reference kernel {ref_ms:.3f} ms"
+
+
+def test_hashgrid_vs_reference_kernels(cuda, flush):
+    ref = load_ref("gridencoder")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from palettenerf_b200.gridencoder import GridEncoder
+    from palettenerf_b200.gridencoder.backend import _backend as GB
+    B = 1 << 22
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, desired_resolution=4096).to(cuda)
+    g = torch.Generator(device=cuda).manual_seed(0)
+    x = torch.rand(B, 3, device=cuda, generator=g)
+    S_ = float(np.log2(enc.per_level_scale))
+    for name, dt in (("f16", torch.float16), ("f32", torch.float32)):
+        emb = (enc.embeddings.detach() * 1e4).to(dt)
+        out_new = torch.empty(B, 32, device=cuda, dtype=dt)
+        out_ref = torch.empty(16, B, 2, device=cuda, dtype=dt)
+        grad = torch.randn(B, 32, device=cuda, generator=g).to(dt)
+        gnew, gref = torch.zeros_like(emb), torch.zeros_like(emb)
+
+        def f_new():
+            GB.grid_encode_forward_blc(x, emb, enc.offsets, out_new, B, 3, 2, 16, S_, 16, None, 0, False)
+
+        def f_ref():   # kernel + the permute copy of the reference wrapper (gridencoder/grid.py:41-52)
+            ref.grid_encode_forward(x, emb, enc.offsets, out_ref, B, 3, 2, 16, S_, 16, None, 0, False)
+            return out_ref.permute(1, 0, 2).reshape(B, 32)
+
+        def b_new():
+            GB.grid_encode_backward_blc(grad, x, emb, enc.offsets, gnew, B, 3, 2, 16, S_, 16, None, None, 0, False)
+
+        def b_ref():   # permute().contiguous() of the incoming gradient (grid.py:70) + kernel
+            gl = grad.view(B, 16, 2).permute(1, 0, 2).contiguous()
+            ref.grid_encode_backward(gl, x, emb, enc.offsets, gref, B, 3, 2, 16, S_, 16, None, None, 0, False)
+
+        _record(f"grid_fwd_{name}_2^22", _time(f_ref, flush=flush), _time(f_new, flush=flush))
+        _record(f"grid_bwd_{name}_2^22", _time(b_ref, flush=flush), _time(b_new, flush=flush))
+        a = f_ref().float()
+        f_new()
+        assert (a - out_new.float()).abs().max().item() < (2e-2 if name == "f16" else 1e-4)
+
+
+def test_raymarch_composite_vs_reference_kernels(cuda, flush, scene):
+    ref = load_ref("raymarching")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from palettenerf_b200.raymarching.backend import _backend as B
+    bitfield, aabb = scene["bitfield"].to(cuda), scene["aabb"].to(cuda)
+    # near/far at 800x800, packbits on the full grid
+    o, d = S.camera_rays(800, 800)
+    o, d = o.to(cuda), d.to(cuda)
+    N = o.shape[0]
+    nears, fars = torch.empty(N, device=cuda), torch.empty(N, device=cuda)
+    _record("near_far_640k", _time(lambda: ref.near_far_from_aabb(o, d, aabb, N, 0.2, nears, fars), flush=flush),
+            _time(lambda: B.near_far_from_aabb(o, d, aabb, N, 0.2, nears, fars), flush=flush), slack=1.3)
+    grid = scene["grid"].to(cuda)
+    bf = torch.empty(grid.numel() // 8, dtype=torch.uint8, device=cuda)
+    _record("packbits_2x128^3", _time(lambda: ref.packbits(grid, bf.numel(), 0.5, bf), flush=flush),
+            _time(lambda: B.packbits(grid, bf.numel(), 0.5, bf), flush=flush), slack=1.3)
+
+    # training march: 4096 rays, M = 4096 * 1024 capacity
+    to, td = S.training_rays(4096, seed=0)
+    to, td = to.to(cuda), td.to(cuda)
+    n = 4096
+    tn, tf = torch.empty(n, device=cuda), torch.empty(n, device=cuda)
+    B.near_far_from_aabb(to, td, aabb, n, 0.2, tn, tf)
+    M = n * 256
+    xyzs, dirs, deltas = torch.zeros(M, 3, device=cuda), torch.zeros(M, 3, device=cuda), torch.zeros(M, 2, device=cuda)
+    rays = torch.empty(n, 3, dtype=torch.int32, device=cuda)
+    counter = torch.zeros(2, dtype=torch.int32, device=cuda)
+    noises = torch.rand(n, device=cuda)
+
+    def march(be):
+        counter.zero_()
+        be.march_rays_train(to, td, bitfield, 2.0, 0.0, 1024, n, 2, 128, M, tn, tf, xyzs, dirs, deltas, rays, counter, noises)
+    _record("march_rays_train_4096", _time(lambda: march(ref), flush=flush), _time(lambda: march(B), flush=flush))
+    march(B)
+    m = int(counter[0].item())
+    RESULTS["march_rays_train_4096"]["samples"] = m
+
+    g = torch.Generator(device=cuda).manual_seed(1)
+    sig = torch.rand(M, device=cuda, generator=g) * 5
+    rgb = torch.rand(M, 3, device=cuda, generator=g)
+    flexin = torch.rand(M, 33, device=cuda, generator=g)
+    ws, dep, img = torch.empty(n, device=cuda), torch.empty(n, device=cuda), torch.empty(n, 3, device=cuda)
+    fo = torch.empty(n, 33, device=cuda)
+    gws, gimg, gfo = torch.randn(n, device=cuda), torch.randn(n, 3, device=cuda), torch.randn(n, 33, device=cuda)
+    gs, gr, gfi = torch.zeros(M, device=cuda), torch.zeros(M, 3, device=cuda), torch.zeros(M, 33, device=cuda)
+    for tag, fr, fn_ in (
+        ("composite_train_fwd", lambda be: be.composite_rays_train_forward(sig, rgb, deltas, rays, M, n, 1e-4, ws, dep, img), None),
+        ("composite_train_bwd", lambda be: be.composite_rays_train_backward(gws, gimg, sig, rgb, deltas, rays, ws, img, M, n, 1e-4, gs, gr), None),
+        ("composite_flex33_train_fwd", lambda be: be.composite_rays_flex_train_forward(sig, flexin, deltas, rays, M, n, 33, 1e-4, fo), None),
+        ("composite_flex33_train_bwd", lambda be: be.composite_rays_flex_train_backward(gfo, sig, flexin, deltas, rays, fo, M, n, 33, 1e-4, gfi), None),
+    ):
+        _record(tag + f"_4096rays_{m}samples", _time(lambda: fr(ref), flush=flush), _time(lambda: fr(B), flush=flush), slack=1.25)
+
+
+def _swap_backends(ref_mods):
+    """route the wrappers of this repository to the reference extension modules; returns an undo function"""
+    import palettenerf_b200.raymarching.raymarching as rm
+    import palettenerf_b200.gridencoder.grid as gg
+    import palettenerf_b200.shencoder.sphere_harmonics as sh
+
+    class GridShim:   # the reference wrapper's [L,B,C] kernel + permute copies (gridencoder/grid.py:41-52, 70)
+        def __init__(self, mod):
+            self.m = mod
+
+        def grid_encode_forward_blc(self, inputs, emb, offsets, outputs, B, D, C, L, S_, H, dy_dx, gridtype, align):
+            tmp = torch.empty(L, B, C, device=inputs.device, dtype=emb.dtype)
+            self.m.grid_encode_forward(inputs, emb, offsets, tmp, B, D, C, L, float(S_), H, dy_dx, gridtype, align)
+            outputs.copy_(tmp.permute(1, 0, 2).reshape(B, L * C))
+
+        def grid_encode_backward_blc(self, grad, inputs, emb, offsets, gemb, B, D, C, L, S_, H, dy_dx, gin, gridtype, align):
+            gl = grad.view(B, L, C).permute(1, 0, 2).contiguous()
+            self.m.grid_encode_backward(gl, inputs, emb, offsets, gemb, B, D, C, L, float(S_), H, dy_dx, gin, gridtype, align)
+
+    old = (rm._backend, gg._backend, sh._backend)
+    rm._backend, gg._backend, sh._backend = ref_mods["raymarching"], GridShim(ref_mods["gridencoder"]), ref_mods["shencoder"]
+
+    def undo():
+        rm._backend, gg._backend, sh._backend = old
+    return undo
+
+
+def test_end_to_end_reference_schedule_on_reference_kernels_vs_fused(cuda, flush):
+    mods = {n: load_ref(n) for n in ("raymarching", "gridencoder", "shencoder")}
+    if any(v is None for v in mods.values()):
+        pytest.skip("oracle/_ref not built")
+    # ---- inference: 800x800 palette render (config 3) ----
+    model = S.build_palette_model(cuda, seed=0, pred_clip=False)
+    model.eval()
+    o, d = S.camera_rays(800, 800)
+    o, d = o.to(cuda), d.to(cuda)
+
+    def render(fused):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model.render(o[None], d[None], staged=True, bg_color=1, perturb=False, gui_mode=False, fused=fused,
+                                dt_gamma=0.0, max_steps=1024, T_thresh=1e-4)
+    new_ms = _time(lambda: render(True), iters=5, flush=flush)
+    img_new = render(True)["image"].float()
+    undo = _swap_backends(mods)
+    try:
+        ref_ms = _time(lambda: render(False), iters=3, warm=1, flush=flush)
+        img_ref = render(False)["image"].float()
+    finally:
+        undo()
+    _record("render_800x800_palette", ref_ms, new_ms)
+    RESULTS["render_800x800_palette"].update(rays=640000, reference_rays_per_s=640000 / ref_ms * 1e3, new_rays_per_s=640000 / new_ms * 1e3)
+    assert (img_new - img_ref).abs().max().item() < 2e-2     # fp16 autocast MLPs on both sides, different rounding points
+
+    # ---- training: 4096-ray palette step (config 4), forward + backward + Adam ----
+    def make():
+        m = S.build_palette_model(cuda, seed=0, pred_clip=False)
+        m.train()
+        opt = torch.optim.Adam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
+        return m, opt, torch.amp.GradScaler("cuda")
+    to, td = S.training_rays(4096, seed=0)
+    to, td = to.to(cuda), td.to(cuda)
+    gt = torch.rand(1, 4096, 3, device=cuda, generator=torch.Generator(device=cuda).manual_seed(0))
+
+    def step(m, opt, scaler, fused):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = m.render(to[None], td[None], staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0,
+                           max_steps=1024, fused=fused)
+            loss = ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() + 2e-4 * out["omega_sparsity"].mean() \
+                + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+    m1, o1, s1 = make()
+    new_ms = _time(lambda: step(m1, o1, s1, None), iters=10, warm=5, flush=flush)
+    assert m1._last_train_schedule == "fused"
+    m2, o2, s2 = make()
+    undo = _swap_backends(mods)
+    try:
+        ref_ms = _time(lambda: step(m2, o2, s2, False), iters=10, warm=5, flush=flush)
+    finally:
+        undo()
+    _record("train_step_4096rays_palette", ref_ms, new_ms)
+    RESULTS["train_step_4096rays_palette"].update(reference_rays_per_s=4096 / ref_ms * 1e3, new_rays_per_s=4096 / new_ms * 1e3)
