@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
+    ap.add_argument("--sections", default="hashgrid,train,cpu", help="extra sections to run (comma list of hashgrid,train,cpu)")
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
     ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
     args = ap.parse_args()
@@ -222,9 +224,15 @@ def main():
     tile_fill = (float(q[1].item()) / (32.0 * max(1, int(q[3].item())))) if q is not None else None
 
     extras = {}
-    if not args.no_extras:
+    sections = set() if args.no_extras else set(args.sections.split(","))
+    if "hashgrid" in sections:
         extras.update(bench_hashgrid(torch, dev, L, hbm_peak, flush))
-        extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush))
+    if "train" in sections:
+        try:
+            extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush,
+                                      use_graph=not args.no_graph))
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     # the dominant kernel of this path is the hash-grid gather (3 grids per sample); its roofline comes from the
     # isolated microbenchmark run on the same kernel (config 2 shape) with CUDA events
     if "hashgrid" in extras:
@@ -235,7 +243,7 @@ def main():
                         hbm_only_gbs=hg["fwd_f16_hbm_gbs"], traffic=_ncu_traffic())
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and world == 1 and "cpu" in sections:
         cpu_baseline = bench_cpu_baseline(S)
 
     if rank == 0:
@@ -332,14 +340,13 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     mode = "eager"
     step = step_fn
     l0 = L.launch_count
-    step_fn()
-    own_launches = L.launch_count - l0          # C-ABI kernels per step (torch's own kernels are not counted)
     if use_graph:
-        try:
-            g = GraphedStep(step_fn, warmup=3)
-            step, mode = g.replay, "cuda_graph"
-        except Exception as e:  # noqa: BLE001  (report and fall back; the eager schedule is the same kernels)
-            mode = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        g = GraphedStep(step_fn, warmup=3)      # 3 eager steps on the capture stream, then one captured step
+        step, mode = g.replay, "cuda_graph"
+        own_launches = (L.launch_count - l0) // 4
+    else:
+        step_fn()
+        own_launches = L.launch_count - l0      # C-ABI kernels per step (torch's own kernels are not counted)
     for _ in range(3):
         step()
     barrier()

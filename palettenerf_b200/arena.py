@@ -1,0 +1,46 @@
+"""Reusable device scratch for the static-capacity training step.
+
+The fused training path allocates the same large, data-independent buffers every step (saved activations 3.6 GB at the
+reference's 4096 x 1024 sample capacity, per-layer gradients, per-sample channels ...). Going through torch's caching
+allocator for them fragments its pools when the host runs ahead of the device (large blocks get split for smaller
+requests, the next step needs fresh cudaMallocs: measured 7-30 ms spikes per step and 50 GB reserved). The arena keeps one
+tensor per (name, shape, dtype, device) and hands it out again as soon as nobody else references it — neither Python
+(the caller's variables, ctx attributes) nor C++ (autograd saved tensors, views sharing the storage).
+All users run on one stream at a time (eager: the current stream; CUDA graph: the capture stream), so reuse is
+stream-ordered like torch's own allocator.
+"""
+import sys
+
+import torch
+
+
+def _free(t):
+    # Python side: the pool's list, the loop variable of get(), this function's parameter, getrefcount's argument
+    if sys.getrefcount(t) > 4:
+        return False
+    # C++ side: the TensorImpl is only owned by its Python object, the storage only by that impl (+ the temporary handle)
+    return t._use_count() == 1 and torch._C._storage_Use_Count(t.untyped_storage()._cdata) <= 2
+
+
+class Arena:
+    def __init__(self):
+        self.pool = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(int(s) for s in shape), dtype, str(device))
+        lst = self.pool.setdefault(key, [])
+        for t in lst:
+            if _free(t):
+                return t
+        t = torch.empty(key[1], dtype=dtype, device=device)
+        lst.append(t)
+        return t
+
+    def clear(self):
+        self.pool.clear()
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for lst in self.pool.values() for t in lst)
+
+
+ARENA = Arena()

@@ -89,9 +89,14 @@ __global__ void __launch_bounds__(256) k_pal_comp_bwd(const float* __restrict__ 
     const bool ok_rgb = offset + num_steps <= M, ok_flex = offset + num_steps < M;
     const uint32_t n_write = min(num_steps, M - offset);     // rows of this ray that exist in the buffers
     const float g0 = grad_image[index * 3 + 0], g1 = grad_image[index * 3 + 1], g2 = grad_image[index * 3 + 2];
-    float gm[NF];
+    // lanes = channels for the flex rows: every sample row (NF floats) is written with NF/32 coalesced stores
+    constexpr int KC = (NF + 31) / 32;
+    float gm[KC];
 #pragma unroll
-    for (int c = 0; c < NF; c++) gm[c] = __ldg(grad_maps + (size_t)index * NF + c);
+    for (int i = 0; i < KC; i++) {
+        const uint32_t c = lane + 32u * i;
+        gm[i] = (c < (uint32_t)NF) ? __ldg(grad_maps + (size_t)index * NF + c) : 0.f;
+    }
     float T = 1.0f;
     bool done = !ok_rgb;                                      // warp-uniform: the ray has terminated (or was dropped)
     for (uint32_t base = 0; base < n_write; base += 32) {
@@ -107,13 +112,19 @@ __global__ void __launch_bounds__(256) k_pal_comp_bwd(const float* __restrict__ 
             w = alpha * ct.T_before;
             last = ct.last;
         }
-        if (valid) {
-            const float wr = (!done && lane <= last) ? w : 0.f;              // terminating sample included
-            const float wf = (!done && ok_flex && lane < last) ? w : 0.f;    // terminating sample excluded (ref :806-811)
-            grad_rgbs[s * 3 + 0] = g0 * wr; grad_rgbs[s * 3 + 1] = g1 * wr; grad_rgbs[s * 3 + 2] = g2 * wr;
-            float* row = grad_flex + s * NF;
+        const float wr = (!done && lane <= last) ? w : 0.f;              // terminating sample included
+        const float wf = (!done && ok_flex && lane < last) ? w : 0.f;    // terminating sample excluded (ref :806-811)
+        if (valid) { grad_rgbs[s * 3 + 0] = g0 * wr; grad_rgbs[s * 3 + 1] = g1 * wr; grad_rgbs[s * 3 + 2] = g2 * wr; }
+        const uint32_t cnt = min(32u, n_write - base);
+        float* rows = grad_flex + ((size_t)offset + base) * NF;
+#pragma unroll 4
+        for (uint32_t j = 0; j < cnt; j++) {
+            const float wj = __shfl_sync(0xffffffffu, wf, j);
 #pragma unroll
-            for (int c = 0; c < NF; c++) row[c] = gm[c] * wf;
+            for (int i = 0; i < KC; i++) {
+                const uint32_t c = lane + 32u * i;
+                if (c < (uint32_t)NF) rows[(size_t)j * NF + c] = gm[i] * wj;
+            }
         }
         if (last < 32u) done = true;
     }

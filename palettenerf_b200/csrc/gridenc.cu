@@ -318,49 +318,51 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
     if (threadIdx.x < L) make_level(lp[threadIdx.x], threadIdx.x, offsets, S, H, 3, gridtype, align_corners);
     __syncthreads();
     if (count_dev) B = min(B, (uint32_t)__ldg(count_dev));
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t level = (uint32_t)(tid % L);
-    const uint64_t seg = tid / L;
-    const uint64_t b0 = seg * K;
-    if (b0 >= B) return;
-    const LevelParams& p = lp[level];
-    T* gg = grad_grid + (size_t)p.offset * 2;
-
-    bool have = false;
-    uint32_t cur_cell[3] = {0, 0, 0}, cur_idx[8];
-    float2 acc[8];
+    // grid-stride over (segment, level) work items: with a device-side count the launch is sized for the capacity
+    const uint64_t n_items = ceil_div<uint64_t>(B, K) * L, stride = (uint64_t)gridDim.x * blockDim.x;
 #pragma unroll 1
-    for (int k = 0; k < K; k++) {
-        const uint64_t b = b0 + k;
-        if (b >= B) break;
-        float x = inputs[b * 3 + 0], y = inputs[b * 3 + 1], z = inputs[b * 3 + 2];
-        if (bound > 0.f) {   // world coordinates: the [0,1] map of GridEncoder.forward (gridencoder/grid.py:142), same fp32 ops
-            x = (x + bound) / (2 * bound); y = (y + bound) / (2 * bound); z = (z + bound) / (2 * bound);
-        }
-        if ((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1)) continue;
-        const T* gp = layout_blc ? grad + (b * L + level) * 2 : grad + ((size_t)level * B + b) * 2;
-        const float2 g = Pair<T>::load(gp);
-        uint32_t idx[8], cell[3];
-        float w[8];
-        corner_setup(p, x, y, z, idx, w, align_corners, cell);
-        const bool same = have && cell[0] == cur_cell[0] && cell[1] == cur_cell[1] && cell[2] == cur_cell[2];
-        if (!same) {
-            if (have) {
-#pragma unroll
-                for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+    for (uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < n_items; tid += stride) {
+        const uint32_t level = (uint32_t)(tid % L);
+        const uint64_t b0 = (tid / L) * K;
+        const LevelParams& p = lp[level];
+        T* gg = grad_grid + (size_t)p.offset * 2;
+
+        bool have = false;
+        uint32_t cur_cell[3] = {0, 0, 0}, cur_idx[8];
+        float2 acc[8];
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const uint64_t b = b0 + k;
+            if (b >= B) break;
+            float x = inputs[b * 3 + 0], y = inputs[b * 3 + 1], z = inputs[b * 3 + 2];
+            if (bound > 0.f) {   // world coordinates: the [0,1] map of GridEncoder.forward (gridencoder/grid.py:142), same fp32 ops
+                x = (x + bound) / (2 * bound); y = (y + bound) / (2 * bound); z = (z + bound) / (2 * bound);
             }
+            if ((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1)) continue;
+            const T* gp = layout_blc ? grad + (b * L + level) * 2 : grad + ((size_t)level * B + b) * 2;
+            const float2 g = Pair<T>::load(gp);
+            uint32_t idx[8], cell[3];
+            float w[8];
+            corner_setup(p, x, y, z, idx, w, align_corners, cell);
+            const bool same = have && cell[0] == cur_cell[0] && cell[1] == cur_cell[1] && cell[2] == cur_cell[2];
+            if (!same) {
+                if (have) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) { cur_idx[c] = idx[c]; acc[c] = make_float2(w[c] * g.x, w[c] * g.y); }
-            cur_cell[0] = cell[0]; cur_cell[1] = cell[1]; cur_cell[2] = cell[2];
-            have = true;
-        } else {
+                    for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+                }
 #pragma unroll
-            for (int c = 0; c < 8; c++) { acc[c].x += w[c] * g.x; acc[c].y += w[c] * g.y; }
+                for (int c = 0; c < 8; c++) { cur_idx[c] = idx[c]; acc[c] = make_float2(w[c] * g.x, w[c] * g.y); }
+                cur_cell[0] = cell[0]; cur_cell[1] = cell[1]; cur_cell[2] = cell[2];
+                have = true;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c++) { acc[c].x += w[c] * g.x; acc[c].y += w[c] * g.y; }
+            }
         }
-    }
-    if (have) {
+        if (have) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+            for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+        }
     }
 }
 
@@ -518,7 +520,8 @@ int pnerf_grid_encode_backward_counted(const void* grad, const float* inputs, co
     const bool blc = grad_layout == PNERF_LAYOUT_BLC, al = align_corners != 0;
     constexpr int K = 8;
     const uint64_t threads = ceil_div<uint64_t>(B, K) * L;
-    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(threads, 256);
+    const uint64_t blocks = ceil_div<uint64_t>(threads, 256);
+    const uint32_t grid = (uint32_t)(blocks < 8ull * kNumSMs ? blocks : 8ull * kNumSMs);   // grid-stride kernel
     if (dtype == PNERF_F32)
         k_grid_bwd_runs<float, K><<<grid, 256, 0, s>>>((const float*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
                                                       gridtype, al, blc, count_dev, bound);

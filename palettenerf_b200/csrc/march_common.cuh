@@ -131,16 +131,47 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
     float t_start = t0;
     float last_t = t0;  // end of the previous sample (start of the real-delta interval)
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t dbits = __float_as_uint(m.dt_min);
     while (t_start < far && count < budget) {
-        // lattice window: lane i holds t_i
+        // ---- lattice window: lane i holds t_i = t_start advanced i times by the (serial, fp32) step ----
+        // Constant step (dt_gamma == 0, every Blender config): inside one binade fl(t + dt) = t + dq ulps with a constant
+        // integer dq (dt rounded to the binade's ulp; round-half-even ties and binade crossings excluded), so the lattice
+        // points are consecutive-integer-spaced BIT PATTERNS and lane i gets its point in O(1). The window is accepted
+        // only if every lane verifies t_i == fl(t_{i-1} + dt) with a real fp32 add, i.e. it is the reference's serial
+        // sequence by construction; otherwise (tie, crossing at lane 1, dt_gamma > 0) the serial prefix is used.
         float t = t_start;
-#pragma unroll 1
-        for (uint32_t i = 0; i < 31; i++) {
-            const float tn = t + m.step_size(t);
-            if (i < lane) t = tn;
+        uint32_t nvalid = 32;
+        bool fast = false;
+        if (m.dt_gamma == 0.f) {
+            const uint32_t tb = __float_as_uint(t_start);
+            const int shift = (int)((tb >> 23) & 0xffu) - (int)((dbits >> 23) & 0xffu);
+            if (shift >= 1 && shift <= 23 && (tb >> 23) != 0u && (tb >> 23) < 0xffu) {
+                const uint32_t md = (dbits & 0x7fffffu) | 0x800000u;
+                const uint32_t rem = md & ((1u << shift) - 1u), half = 1u << (shift - 1);
+                const uint32_t dq = (md >> shift) + (rem > half ? 1u : 0u);
+                const uint32_t bi = tb + lane * dq;
+                const bool wv = bi < ((tb | 0x7fffffu) + 1u);            // still inside t_start's binade
+                const float ti = __uint_as_float(bi);
+                const float pa = __shfl_up_sync(0xffffffffu, ti + m.dt_min, 1);
+                const bool ok = (lane == 0) || !wv || (pa == ti);
+                const uint32_t wmask = __ballot_sync(0xffffffffu, wv);
+                if (rem != half && dq != 0u && __all_sync(0xffffffffu, ok)) {
+                    fast = true;
+                    nvalid = __popc(wmask);                               // >= 1 (lane 0 is always inside)
+                    t = wv ? ti : t_start;
+                }
+            }
         }
+        if (!fast) {
+#pragma unroll 1
+            for (uint32_t i = 0; i < 31; i++) {
+                const float tn = t + m.step_size(t);
+                if (i < lane) t = tn;
+            }
+        }
+        const bool wv = lane < nvalid;
         const float t_after = t + m.step_size(t);                 // lattice point following this lane's
-        const bool inside = t < far;
+        const bool inside = wv && t < far;
         float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, tt = 0.f;
         bool occ = false;
         if (inside) occ = m.probe_point(t, x, y, z, dt, tt);
@@ -150,7 +181,7 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
         uint32_t take = 0, cur = 0;
         bool finished = false, jumped = false;
         float t_jump = 0.f;
-        while (cur < 32) {
+        while (cur < nvalid) {
             if (!((in_mask >> cur) & 1u)) { finished = true; break; }            // t >= far
             if ((occ_mask >> cur) & 1u) {
                 if (count + __popc(take) >= budget) { finished = true; break; }   // sample budget (max_steps / num_steps)
@@ -159,13 +190,12 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
             } else {
                 const float tt_cur = __shfl_sync(0xffffffffu, tt, cur);
                 const uint32_t above = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
-                const uint32_t ge = __ballot_sync(0xffffffffu, t >= tt_cur) & above;
+                const uint32_t ge = __ballot_sync(0xffffffffu, wv && t >= tt_cur) & above;
                 if (ge) {
                     cur = __ffs(ge) - 1;
                 } else {   // the empty voxel extends past the window: keep stepping from the last lattice point
-                    float tn = __shfl_sync(0xffffffffu, t, 31);
-                    if (cur == 31) { tn = tn + m.step_size(tn); while (tn < tt_cur) tn += m.step_size(tn); }
-                    else { do { tn += m.step_size(tn); } while (tn < tt_cur); }
+                    float tn = __shfl_sync(0xffffffffu, t, nvalid - 1);
+                    do { tn += m.step_size(tn); } while (tn < tt_cur);
                     t_jump = tn;
                     jumped = true;
                     break;
@@ -191,7 +221,7 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
             count += __popc(take);
         }
         if (finished) break;
-        t_start = jumped ? t_jump : __shfl_sync(0xffffffffu, t_after, 31);
+        t_start = jumped ? t_jump : __shfl_sync(0xffffffffu, t_after, nvalid - 1);
     }
     return count;
 }

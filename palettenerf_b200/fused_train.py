@@ -18,6 +18,7 @@ from torch.autograd import Function
 from . import _lib as L
 from ._lib import ptr, stream
 from . import fused as _fused
+from .arena import ARENA
 
 NB = 4
 
@@ -205,10 +206,13 @@ class _TrainField(Function):
         f.L, f.H, f.pred_clip, f.clip_dim = model.encoder.num_levels, model.encoder.base_resolution, int(pc), cd
         f.S = float(np.float32(np.log2(model.encoder.per_level_scale)))
         f.bound, f.density_scale = float(model.bound), float(model.density_scale)
-        xbuf = torch.empty(int(L.lib.pnerf_palette_train_xbuf_bytes(M, int(pc))), dtype=torch.uint8, device=dev)
-        sigma = torch.empty(M, dtype=torch.float32, device=dev)
-        rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
-        flex = torch.empty(M, nflex, dtype=torch.float32, device=dev)
+        # static-capacity mode: the (large, data-independent) scratch comes from the arena; .detach() = a fresh alias
+        # without autograd history, which also marks the buffer as in use for as long as the alias lives
+        static = count is not None
+        new = (lambda name, *shape, dtype=torch.float32: ARENA.get(name, shape, dtype, dev).detach()) if static else \
+              (lambda name, *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev))
+        xbuf = new("xbuf", int(L.lib.pnerf_palette_train_xbuf_bytes(M, int(pc))), dtype=torch.uint8)
+        sigma, rgb, flex = new("sigma", M), new("rgb", M, 3), new("flex", M, nflex)
         L.call("pnerf_palette_train_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(xbuf), ptr(sigma), ptr(rgb),
                ptr(flex), stream())
         ctx.keep = (f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count)
@@ -227,9 +231,12 @@ class _TrainField(Function):
         nflex = 13 + cd + NB
         g_rgb = torch.zeros(M, 3, device=dev) if g_rgb is None else g_rgb.contiguous().float()
         g_flex = torch.zeros(M, nflex, device=dev) if g_flex is None else g_flex.contiguous().float()
-        ybuf = torch.empty(int(L.lib.pnerf_palette_train_ybuf_bytes(M, int(pc))), dtype=torch.uint8, device=dev)
-        d_enc = torch.empty(M, 32, dtype=torch.float32, device=dev)
-        d_enc_clip = torch.empty(M, 32, dtype=torch.float32, device=dev) if pc else None
+        static = count is not None
+        new = (lambda name, *shape, dtype=torch.float32: ARENA.get(name, shape, dtype, dev).detach()) if static else \
+              (lambda name, *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev))
+        ybuf = new("ybuf", int(L.lib.pnerf_palette_train_ybuf_bytes(M, int(pc))), dtype=torch.uint8)
+        d_enc = new("d_enc", M, 32)
+        d_enc_clip = new("d_enc_clip", M, 32) if pc else None
         d_pal = torch.zeros(NB, 3, dtype=torch.float32, device=dev) if ctx.need_palette else None
         dw = torch.zeros(int(L.lib.pnerf_palette_train_dw_floats(int(pc))), dtype=torch.float32, device=dev)
         L.call("pnerf_palette_train_backward", M, ctypes.addressof(f), ptr(xbuf), ptr(ybuf), ptr(g_rgb), ptr(g_flex), ptr(flex),
@@ -295,7 +302,8 @@ class _CompositeTrain(Function):
         dev = sigmas.device
         g_image = torch.zeros(N, 3, device=dev) if g_image is None else g_image.contiguous().float()
         g_maps = torch.zeros(N, nf, device=dev) if g_maps is None else g_maps.contiguous().float()
-        g_rgbs, g_ch = torch.empty(M, 3, device=dev), torch.empty(M, nf, device=dev)
+        g_rgbs = ARENA.get("g_rgbs", (M, 3), torch.float32, dev).detach()
+        g_ch = ARENA.get("g_ch", (M, nf), torch.float32, dev).detach()
         L.call("pnerf_palette_composite_train_backward", ptr(g_image), ptr(g_maps), ptr(sigmas), ptr(deltas), ptr(rays), M, N, nf,
                T_thresh, ptr(g_rgbs), ptr(g_ch), stream())
         return None, g_rgbs, g_ch, None, None, None

@@ -19,14 +19,18 @@ class GraphedStep:
         self.step_fn = step_fn
         self.graph = torch.cuda.CUDAGraph()
         self.out = None
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        # Warm-up and capture run on ONE side stream: autograd's AccumulateGrad nodes remember the stream they were
+        # created on, and a node that lives on the legacy default stream would make the capture depend on it
+        # (cudaErrorStreamCaptureImplicit). For the same reason the model must not have been stepped on the default
+        # stream before it is handed to GraphedStep.
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 step_fn()
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
-        with torch.cuda.graph(self.graph, pool=pool):
+        with torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
             self.out = step_fn()
 
     def replay(self):

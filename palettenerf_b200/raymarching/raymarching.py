@@ -115,10 +115,15 @@ class _march_rays_train(Function):
                 mean_count += align - mean_count % align
             M = mean_count
         dev, dt = rays_o.device, rays_o.dtype
-        alloc = torch.empty if static else torch.zeros
-        xyzs = alloc(M, 3, dtype=dt, device=dev)
-        dirs = alloc(M, 3, dtype=dt, device=dev)
-        deltas = alloc(M, 2, dtype=dt, device=dev)
+        if static:   # data-independent capacity: reusable scratch (see arena.py), rows beyond the count stay uninitialised
+            from ..arena import ARENA
+            xyzs = ARENA.get("march_xyzs", (M, 3), dt, dev).detach()
+            dirs = ARENA.get("march_dirs", (M, 3), dt, dev).detach()
+            deltas = ARENA.get("march_deltas", (M, 2), dt, dev).detach()
+        else:
+            xyzs = torch.zeros(M, 3, dtype=dt, device=dev)
+            dirs = torch.zeros(M, 3, dtype=dt, device=dev)
+            deltas = torch.zeros(M, 2, dtype=dt, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)

@@ -225,14 +225,27 @@ def test_end_to_end_reference_schedule_on_reference_kernels_vs_fused(cuda, flush
         scaler.scale(loss).backward()
         scaler.step(opt)
         scaler.update()
-    m1, o1, s1 = make()
-    new_ms = _time(lambda: step(m1, o1, s1, None), iters=10, warm=5, flush=flush)
-    assert m1._last_train_schedule == "fused"
     m2, o2, s2 = make()
     undo = _swap_backends(mods)
     try:
         ref_ms = _time(lambda: step(m2, o2, s2, False), iters=10, warm=5, flush=flush)
     finally:
         undo()
-    _record("train_step_4096rays_palette", ref_ms, new_ms)
-    RESULTS["train_step_4096rays_palette"].update(reference_rays_per_s=4096 / ref_ms * 1e3, new_rays_per_s=4096 / new_ms * 1e3)
+    del m2, o2, s2
+    # new path, eager launches (what the reference's Trainer would drive unchanged)
+    m1, o1, s1 = make()
+    eager_ms = _time(lambda: step(m1, o1, s1, None), iters=10, warm=5, flush=flush)
+    assert m1._last_train_schedule == "fused"
+    del m1, o1, s1
+    # new path, the whole step replayed from ONE CUDA graph (static shapes, no host sync: palettenerf_b200/graphs.py)
+    from palettenerf_b200.graphs import GraphedStep
+    m3 = S.build_palette_model(cuda, seed=0, pred_clip=False)
+    m3.train()
+    o3 = torch.optim.Adam(m3.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    s3 = torch.amp.GradScaler("cuda")
+    g = GraphedStep(lambda: step(m3, o3, s3, None), warmup=3)
+    graph_ms = _time(g.replay, iters=10, warm=3, flush=flush)
+    _record("train_step_4096rays_palette_eager", ref_ms, eager_ms)
+    _record("train_step_4096rays_palette", ref_ms, graph_ms)
+    RESULTS["train_step_4096rays_palette"].update(reference_rays_per_s=4096 / ref_ms * 1e3, new_rays_per_s=4096 / graph_ms * 1e3,
+                                                  new_eager_rays_per_s=4096 / eager_ms * 1e3)

@@ -49,22 +49,23 @@ def step(timed=False):
         t = tick("optimizer", t)
 
 
-for _ in range(5):
-    step()
-torch.cuda.synchronize()
-for _ in range(5):
-    step(timed=True)
-print("schedule:", getattr(model, "_last_train_schedule", "?"), " section wall ms/step (synchronised):",
-      {k: round(v / 5 * 1e3, 3) for k, v in sec.items()})
-ts = []
-for _ in range(10):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    a.record(); step(); b.record()
-    cpu = time.perf_counter() - t0
+if "--graph" not in sys.argv:
+    for _ in range(5):
+        step()
     torch.cuda.synchronize()
-    ts.append((a.elapsed_time(b), cpu * 1e3))
-print("event ms/step:", [round(x, 3) for x, _ in ts], " cpu issue ms/step:", [round(c, 3) for _, c in ts])
+    for _ in range(5):
+        step(timed=True)
+    print("schedule:", getattr(model, "_last_train_schedule", "?"), " section wall ms/step (synchronised):",
+          {k: round(v / 5 * 1e3, 3) for k, v in sec.items()})
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record(); step(); b.record()
+        cpu = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        ts.append((a.elapsed_time(b), cpu * 1e3))
+    print("event ms/step:", [round(x, 3) for x, _ in ts], " cpu issue ms/step:", [round(c, 3) for _, c in ts])
 run = step
 if "--graph" in sys.argv:
     from palettenerf_b200.graphs import GraphedStep
