@@ -200,10 +200,11 @@ PNERF_API int pnerf_palette_field_forward(const float* xyzs, const float* dirs, 
                                           const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
                                           float* off_rad, float* view_dep, float* diffuse, void* stream);
 
-/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[4] zeroed:
+/* all outputs zero-initialised by the caller; the five aux maps may all be NULL (gui_mode); queue[68] zeroed
+ * (4 counters + a 32-bucket histogram + 32 cursors used to order the rays longest-first):
  * on return queue[1] = number of samples shaded, queue[2] = number of rays with at least one sample,
  * queue[3] = number of 32-sample tiles evaluated (queue[1] / (32 queue[3]) = tile fill).
- * hit_list (int32), t_first, t_last (fp32) are [N] scratch buffers. */
+ * hit_list (int32) is a [2N] scratch buffer (ordered hit list + samples per ray), t_first, t_last (fp32) are [N]. */
 PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
                                          uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_uint32, c_uint64, c_voi
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libpnerf_b200.so")
+_LIB_PATH = os.environ.get("PNERF_LIB", os.path.join(_PKG, "libpnerf_b200.so"))   # PNERF_LIB: variant build (experiments)
 
 F16, F32, F64 = 0, 1, 2
 LAYOUT_LBC, LAYOUT_BLC = 0, 1

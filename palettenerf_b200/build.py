@@ -11,8 +11,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libpnerf_b200.so")
+OBJ = os.environ.get("PNERF_OBJ_DIR", os.path.join(PKG, "build"))
+LIB = os.environ.get("PNERF_LIB_OUT", os.path.join(PKG, "libpnerf_b200.so"))   # variant builds for A/B experiments
+EXTRA = os.environ.get("PNERF_EXTRA_NVCC_FLAGS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -36,7 +37,7 @@ def _compile(src):
     obj = os.path.join(OBJ, os.path.basename(src) + ".o")
     if not _stale(obj, [src] + _headers()):
         return obj, ""
-    cmd = [NVCC, "-c", src, "-o", obj] + ARCH + FLAGS
+    cmd = [NVCC, "-c", src, "-o", obj] + ARCH + FLAGS + EXTRA
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")

@@ -271,17 +271,22 @@ struct RenderArgs {
 // records the first and last occupied lattice point. Rays without samples (79% of an 800x800 lego view) never
 // enter the persistent kernel, and rays inside it never march the empty tail behind their last sample.
 // ------------------------------------------------------------------------------------------------
+constexpr int kLptBuckets = 32;          // buckets of 16 samples; rays with > 496 samples share the last one
+constexpr int kQueueHist = 4, kQueueCursor = 4 + kLptBuckets;
+__device__ __forceinline__ uint32_t lpt_bucket(uint32_t count) { return min((uint32_t)kLptBuckets - 1u, (count - 1u) >> 4); }
+
 __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                      const float* __restrict__ nears, const float* __restrict__ fars,
                                                      const float* __restrict__ noises, const uint8_t* __restrict__ bitfield,
                                                      uint32_t N, uint32_t C, uint32_t H, uint32_t max_steps, float bound,
                                                      float dt_gamma, int32_t* __restrict__ hit_list,
-                                                     float* __restrict__ t_first, float* __restrict__ t_last,
-                                                     unsigned int* __restrict__ queue) {
+                                                     int32_t* __restrict__ ray_count, float* __restrict__ t_first,
+                                                     float* __restrict__ t_last, unsigned int* __restrict__ queue) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     bool hit = false;
     float tf = 0.f, tl = 0.f;
+    uint32_t count = 0;
     if (n < N) {
         Marcher m;
         m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, bitfield);
@@ -295,7 +300,6 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
         float t = tc;
         if (noises) t += m.step_size(t) * noises[n];
         float t_mark = t;
-        uint32_t count = 0;
         float x, y, z, dt;
         while (t < far && count < max_steps) {
             if (m.probe(t, x, y, z, dt)) {
@@ -310,17 +314,51 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
         }
         hit = count > 0;
     }
-    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-    if (mask) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(queue + 2, (unsigned int)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
+    // longest-processing-time-first order: rays are bucketed by their sample count (16 samples per bucket) and the hit
+    // list is written bucket by bucket, longest first. A lane of the persistent kernel keeps a ray until it ends, so with
+    // pixel order the last rays pulled from the queue decide when a warp finishes (tile fill 0.80 at 800x800); with the
+    // longest rays first the tail consists of the shortest ones.
+    __shared__ unsigned int hist_s[kLptBuckets];
+    if (threadIdx.x < kLptBuckets) hist_s[threadIdx.x] = 0u;
+    __syncthreads();
+    if (n < N) {
+        ray_count[n] = (int32_t)count;
         if (hit) {
-            hit_list[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)n;
             t_first[n] = tf;
             t_last[n] = tl;
+            atomicAdd(&hist_s[lpt_bucket(count)], 1u);
         }
     }
+    __syncthreads();
+    if (threadIdx.x < kLptBuckets && hist_s[threadIdx.x]) atomicAdd(queue + kQueueHist + threadIdx.x, hist_s[threadIdx.x]);
+    (void)lane; (void)hit_list;
+}
+
+// one warp: descending exclusive scan of the bucket histogram -> per-bucket write cursors; total -> queue[2]
+__global__ void k_lpt_offsets(unsigned int* __restrict__ queue) {
+    const uint32_t lane = threadIdx.x;
+    const unsigned int h = queue[kQueueHist + lane];
+    unsigned int suffix = h;   // inclusive suffix sum over buckets >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += v;
+    }
+    queue[kQueueCursor + lane] = suffix - h;      // rays in longer buckets come first
+    if (lane == 0) queue[2] = suffix;             // number of rays with at least one sample
+}
+
+__global__ void __launch_bounds__(256) k_lpt_scatter(const int32_t* __restrict__ ray_count, uint32_t N,
+                                                     int32_t* __restrict__ hit_list, unsigned int* __restrict__ queue) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const uint32_t c = n < N ? (uint32_t)ray_count[n] : 0u;
+    const uint32_t key = c ? lpt_bucket(c) : (kLptBuckets + lane);     // misses: a key nobody shares
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (c && lane == leader) base = atomicAdd(queue + kQueueCursor + key, (unsigned int)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (c) hit_list[base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)n;
 }
 
 template <bool CLIP, bool AUX>
@@ -520,8 +558,8 @@ int pnerf_palette_field_forward(const float* xyzs, const float* dirs, uint32_t M
 }
 
 /* persistent fused renderer: replaces the inference loop of PaletteRenderer.run_cuda (palette/renderer.py:430-523).
- * All outputs must be zero-initialised; queue[3] must be zero; hit_list/t_first/t_last are [N] scratch.
- * Aux maps may all be NULL (gui_mode). Launches a thread-per-ray pre-pass and the persistent kernel. */
+ * All outputs must be zero-initialised; queue[68] must be zero; hit_list is [2N], t_first/t_last are [N] scratch.
+ * Aux maps may all be NULL (gui_mode). Launches a thread-per-ray pre-pass, the two small ordering kernels and the persistent kernel. */
 int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
                                          uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
@@ -547,8 +585,11 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
     a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue;
     a.hit_list = hit_list; a.t_first = t_first; a.t_last = t_last;
     cudaStream_t s = (cudaStream_t)stream;
+    int32_t* ray_count = hit_list + N;       // second half of the scratch: samples per ray
     k_ray_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, N, C, Hgrid, max_steps,
-                                                    field->bound, dt_gamma, hit_list, t_first, t_last, queue);
+                                                    field->bound, dt_gamma, hit_list, ray_count, t_first, t_last, queue);
+    k_lpt_offsets<<<1, 32, 0, s>>>(queue);
+    k_lpt_scatter<<<ceil_div(N, 256u), 256, 0, s>>>(ray_count, N, hit_list, queue);
     const bool clip_on = field->pred_clip != 0;
     const size_t smem = fused_smem_bytes(clip_on, aux);
     const uint32_t warps_needed = ceil_div(N, 32u);

@@ -13,7 +13,10 @@ namespace pnerf {
 
 constexpr int kNB = 4;            // palette bases supported by the fused path (reference default, main_palette.py:99)
 constexpr int kClipMax = 16;      // semantic feature width supported by the fused path (main_palette.py:76)
-constexpr int kFusedWarps = 12;     // one 384-thread CTA per SM: <= 168 registers/thread, no spills in the MMA chain
+#ifndef PNERF_FUSED_WARPS
+#define PNERF_FUSED_WARPS 12
+#endif
+constexpr int kFusedWarps = PNERF_FUSED_WARPS;   // one CTA per SM: 12 warps <= 168 registers/thread, 10 warps <= 204
 constexpr int kAuxCh = 3 + 3 + kNB + 2 * kNB * 3;   // direct_rgb, view_dep_rgb, basis_acc, basis_rgb, unscaled_basis_rgb
 constexpr int kFeatStride = 40;   // halfs per feature row: 32 + 8 pad -> ldmatrix rows hit distinct bank groups
 constexpr int kOutStride = 41;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
@@ -170,6 +173,11 @@ static __device__ __noinline__ void gather_features(const __half* __restrict__ t
         if (l0 + 1 < L) reinterpret_cast<__half2*>(row)[l0 + 1] = __floats2half2_rn(acc[1].x, acc[1].y);
     }
 }
+
+// (Measured and rejected, profiles/README.md "gather variants": computing the corner indices once for the density and
+// palette grids — same geometry — and reading both tables with them cuts ~30 % of the gather's instructions but does not
+// speed the renderer up: the gather is bound by L1/L2 load latency, the index arithmetic hides under it, and the second
+// feature row costs shared memory, i.e. L1 capacity.)
 
 // per-sample result of the field, held by the lane that owns the sample
 struct FieldOut {

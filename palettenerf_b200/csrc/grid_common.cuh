@@ -13,7 +13,7 @@ struct LevelParams {
     uint32_t size;       // hashmap_size = offsets[l+1] - offsets[l]
     uint32_t offset;     // offsets[l] (in entries)
     uint32_t use_hash;   // gridtype == hash && (res+1)^D overflowed the table
-    uint32_t mask;       // size - 1 if size is a power of two, else 0
+    uint32_t mask;       // size - 1 if size is a power of two; all ones if indices cannot reach size (dense level); else 0
 };
 
 // ref: gridencoder.cu:54-72,97-99 — the index loop stops multiplying once stride > hashmap_size.
@@ -34,6 +34,9 @@ __device__ __forceinline__ void make_level(LevelParams& p, uint32_t level, const
     }
     p.use_hash = (gridtype == 0 && stride > p.size) ? 1u : 0u;
     p.mask = ((p.size & (p.size - 1)) == 0) ? (p.size - 1) : 0u;
+    // dense level whose full (res+1)^D lattice fits the table: every index is < stride <= size, so the reference's
+    // `index % hashmap_size` (gridencoder.cu:71) is the identity and the integer division can be dropped
+    if (!p.use_hash && stride <= p.size && D <= 5 && p.stride[D - 1] != 0) p.mask = 0xffffffffu;
 }
 
 __device__ __forceinline__ uint32_t wrap_index(uint32_t index, const LevelParams& p) {

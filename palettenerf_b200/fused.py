@@ -34,7 +34,7 @@ class PaletteField(ctypes.Structure):
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
 L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
-L.LAUNCHES["pnerf_palette_render_fused"] = 2  # pre-pass + persistent kernel
+L.LAUNCHES["pnerf_palette_render_fused"] = 4  # pre-pass + 2 ordering kernels + persistent kernel
 
 
 def _frag(W, n_pad, k_pad):
@@ -171,8 +171,8 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     if not gui_mode:
         acc.update(direct_rgb=z(N, 3), view_dep_rgb=z(N, 3), basis_acc=z(N, nb), basis_rgb=z(N, 3 * nb),
                    unscaled_basis_rgb=z(N, 3 * nb))
-    queue = torch.zeros(4, dtype=torch.int32, device=dev)
-    hit_list = torch.empty(N, dtype=torch.int32, device=dev)
+    queue = torch.zeros(68, dtype=torch.int32, device=dev)   # 4 counters + 32-bucket histogram + 32 cursors
+    hit_list = torch.empty(2 * N, dtype=torch.int32, device=dev)   # ordered hit list + samples per ray
     t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
     aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
