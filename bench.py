@@ -144,6 +144,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # the gradient all-reduce is captured in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -214,14 +215,31 @@ def main():
            "d2h_bytes_per_step": N_RAYS * 12, "ms_per_step": ms_e2e}
 
     # ---- roofline of the dominant kernel of the step (CUDA events around each C-ABI launch, timed region) ---------
+    # pnerf_palette_render_fused = pre-pass + 2 ordering kernels + the persistent k_render_fused (>= 97 % of the call,
+    # profiles/r01_launches_bench_render_*.csv). It is the fused march -> hash-grid gather -> MLP -> blend -> composite
+    # kernel; SURVEY §8(d) puts the MLP on the tensor roofline (36 094 FLOP per sample without the semantic branch).
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     top = max(prof.items(), key=lambda kv: kv[1][0])
     shares = {k.replace("pnerf_", ""): round(v[0] / total_kernel_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-    roofline = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": top[0], "peak_kind": peak_kind, "kernel_time_share_of_own_kernels": shares}
-    q = getattr(model, "_last_queue", None)          # [hit-list cursor, samples shaded, rays with samples] of the last view
+    q = getattr(model, "_last_queue", None)          # [hit-list cursor, samples shaded, rays with samples, tiles] of the last view
     samples_per_step = int(q[1].item()) if q is not None else None
     tile_fill = (float(q[1].item()) / (32.0 * max(1, int(q[3].item())))) if q is not None else None
+    kernel_ms = top[1][0] / max(1, top[1][1])
+    FLOP_PER_SAMPLE = 36094                          # palette field without clip, forward
+    GATHER_B_PER_SAMPLE = 2 * 16 * 8 * 4             # two fp16 F=2 tables, 16 levels, 8 corners
+    roofline = {"bound": "tensor", "achieved": None, "peak": tf_peak, "unit": "TFLOP/s", "frac": None,
+                "traffic": _ncu_traffic("k_render_fused"), "kernel": top[0] + " (k_render_fused)", "kernel_ms": kernel_ms,
+                "peak_kind": peak_kind + " (bf16 dense, burst; fp16 assumed equal)",
+                "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {samples_per_step} samples per launch",
+                "kernel_time_share_of_own_kernels": shares}
+    if samples_per_step and top[0] == "pnerf_palette_render_fused":
+        ach = FLOP_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e12
+        roofline.update(achieved=ach, frac=ach / tf_peak,
+                        note="the kernel is bound by the latency of its L2-resident hash-table gathers, not by the tensor pipe "
+                             "(ncu: tensor pipe 12 % active, DRAM 0.03 %); see l2_gather and profiles/",
+                        l2_gather={"achieved_gbs": GATHER_B_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e9,
+                                   "algorithmic": f"{GATHER_B_PER_SAMPLE} B gathered per sample (2 tables x 16 levels x 8 corners x 4 B)",
+                                   "hbm_peak_gbs_for_scale": hbm_peak})
 
     extras = {}
     sections = set() if args.no_extras else set(args.sections.split(","))
@@ -233,14 +251,15 @@ def main():
                                       use_graph=not args.no_graph))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-    # the dominant kernel of this path is the hash-grid gather (3 grids per sample); its roofline comes from the
-    # isolated microbenchmark run on the same kernel (config 2 shape) with CUDA events
+    # secondary roofline: the stand-alone hash-grid kernel of BASELINE config 2 (HBM-bound I/O, L2-resident table)
     if "hashgrid" in extras:
         hg = extras["hashgrid"]
-        roofline.update(achieved=hg["fwd_f16_eff_gbs"], frac=hg["fwd_f16_eff_gbs"] / hbm_peak,
-                        note="grid_encode_forward fp16, 2^22 points: 588 algorithmic B/point / event time; table is "
-                             "L2-resident so compulsory HBM bytes are 76 B/point (hbm_gbs field)",
-                        hbm_only_gbs=hg["fwd_f16_hbm_gbs"], traffic=_ncu_traffic())
+        roofline["hashgrid_microbench"] = {
+            "bound": "hbm", "kernel": "k_grid_fwd_d3c2<half>", "achieved": hg["fwd_f16_eff_gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": hg["fwd_f16_eff_gbs"] / hbm_peak, "hbm_only_gbs": hg["fwd_f16_hbm_gbs"],
+            "traffic": _ncu_traffic("k_grid_fwd_d3c2_f16"),
+            "algorithmic": "588 B/point (12 xyz + 16 levels x 8 corners x 4 B gathered + 64 out) x 2^22 points; the table is "
+                           "L2-resident, compulsory HBM bytes are 76 B/point (hbm_only_gbs)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and "cpu" in sections:
@@ -263,12 +282,13 @@ def main():
         dist.destroy_process_group()
 
 
-def _ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if present"""
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json, written from the .ncu-rep by tools/ncu_summary.py), or None"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("grid_encode_forward_f16_dram_bytes_per_launch")
+            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
