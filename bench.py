@@ -121,7 +121,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
-    ap.add_argument("--sections", default="hashgrid,train,cpu", help="extra sections to run (comma list of hashgrid,train,cpu)")
+    ap.add_argument("--sections", default="hashgrid,train,mip360,cpu",
+                    help="extra sections to run (comma list of hashgrid,train,mip360,cpu)")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
     ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
@@ -251,6 +252,11 @@ def main():
                                       use_graph=not args.no_graph))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    if "mip360" in sections:
+        try:
+            extras.update(bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world))
+        except Exception as e:  # noqa: BLE001
+            extras["mip360"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     # secondary roofline: the stand-alone hash-grid kernel of BASELINE config 2 (HBM-bound I/O, L2-resident table)
     if "hashgrid" in extras:
         hg = extras["hashgrid"]
@@ -385,6 +391,74 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
                       "optimizer": "Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
+
+
+def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
+    """BASELINE config 5: Mip-NeRF-360-shaped unbounded scene, 1297x840 view (1 089 480 rays), dt_gamma = 1/128,
+    min_near = 0.05, semantic-feature branch on (--pred_clip, clip_dim 16: third hash grid + clip net): one render
+    and one training step (4096 rays, rgb + feature loss) per GPU."""
+    from palettenerf_b200.graphs import GraphedStep, make_palette_train_step
+    Hm, Wm, DTG = 840, 1297, 1.0 / 128
+    res = {"workload": "mip-360-shaped scene (solid x1.5 + ground slab reaching cascade 1), 1297x840, dt_gamma 1/128, "
+                       "min_near 0.05, pred_clip clip_dim 16 (BASELINE config 5)", "rays": Hm * Wm}
+    model = S.build_palette_model(dev, seed=0, pred_clip=True, ground=True, scene_scale=1.5)
+    model.min_near = 0.05
+    model.eval()
+    o, d = S.camera_rays(Hm, Wm, azimuth_deg=35.0 + 45.0 * rank)
+    o, d = o.to(dev), d.to(dev)
+
+    def render():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model.render(o[None], d[None], staged=True, bg_color=1, perturb=False, gui_mode=False, dt_gamma=DTG,
+                                max_steps=1024, T_thresh=1e-4)
+    for _ in range(3):
+        render()
+    barrier()
+    ts = []
+    for _ in range(5):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); render(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = max_over_ranks(sum(ts) / len(ts))
+    q = getattr(model, "_last_queue", None)
+    res.update(render_ms=ms, render_rays_per_s=world * Hm * Wm / (ms / 1e3), schedule=getattr(model, "_last_schedule", "loop"),
+               samples_per_view=int(q[1].item()) if q is not None else None)
+
+    # training step with the semantic-feature loss (palette/utils.py:486-567: rgb + direct rgb + regularisers + feature MSE)
+    tm = S.build_palette_model(dev, seed=0, pred_clip=True, ground=True, scene_scale=1.5)
+    tm.min_near = 0.05
+    tm.train()
+    opt = torch.optim.Adam(tm.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    scaler = torch.amp.GradScaler("cuda")
+    to, td = S.training_rays(TRAIN_RAYS, H=Hm, W=Wm, seed=rank)
+    to, td = to.to(dev)[None].contiguous(), td.to(dev)[None].contiguous()
+    g = torch.Generator(device=dev).manual_seed(rank)
+    gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=g)
+    feat = torch.randn(1, TRAIN_RAYS, 16, device=dev, generator=g)
+
+    def loss_fn(out):
+        return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
+            + ((out["clip_feat"] - feat) ** 2).mean() \
+            + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+    step_fn = make_palette_train_step(tm, opt, scaler, to, td, loss_fn, render_kwargs=dict(dt_gamma=DTG))
+    gs = GraphedStep(step_fn, warmup=3)
+    for _ in range(3):
+        gs.replay()
+    barrier()
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); gs.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = max_over_ranks(sum(ts) / len(ts))
+    res.update(train_ms=ms, train_rays_per_s=world * TRAIN_RAYS / (ms / 1e3),
+               train_samples_rank0=int(tm.step_counter[(tm.local_step - 1) % 16, 0].item()),
+               train_schedule=getattr(tm, "_last_train_schedule", "torch"), train_launch="cuda_graph (per-rank, no all-reduce)")
+    return {"mip360": res}
 
 
 def bench_cpu_baseline(S):

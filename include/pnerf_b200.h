@@ -192,6 +192,10 @@ typedef struct pnerf_palette_field {
     const float* palette;       /* [4*3] basis_color clamped to [0,1]               */
     uint32_t L, H, pred_clip, clip_dim;
     float S, bound, density_scale, offsets_weight, view_dep_weight;
+    /* optional (may be NULL): the density and palette tables interleaved entry by entry, fp16 [n_entries][2 tables][2],
+     * so that one 8-byte load fetches the features of both grids at a lattice corner (the two grids share their
+     * geometry). The inference kernels prefer it; table_sigma / table_palette must still be valid. */
+    const void* table_sigma_palette;
 } pnerf_palette_field;
 
 /* xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (NULL unless pred_clip), omega [M,4], off_rad [M,13],

@@ -24,8 +24,11 @@
 //     no host loop, no alive-list compaction, no xyzs/dirs/deltas/sigmas/rgbs buffer and no host synchronisation.
 #include "fused_common.cuh"
 
-namespace pnerf {
+#ifndef PNERF_GATHER_LV
+#define PNERF_GATHER_LV 1     // levels per gather iteration (x 2 tables x 8 corners loads in flight per lane)
+#endif
 
+namespace pnerf {
 
 // ------------------------------------------------------------------------------------------------
 // the fused field: 32 samples per warp (lane = sample), L must be 16 (feature rows are 32 wide)
@@ -42,7 +45,16 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
     uint32_t* carry = reinterpret_cast<uint32_t*>(&ws.out[lane][O_CLIP]);   // [t][6]
 
     // ---------------- phase 1: density grid -> sigma net -> geo; geo -> diffuse net ----------------
-    gather_features((const __half*)f.table_sigma, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    // The palette grid shares the density grid's geometry: both tables are read here with ONE set of corner indices;
+    // the palette features wait (as fp16 pairs) in this lane's output row, columns O_OFFRAD.. that phase 3 writes last.
+    uint32_t* park = reinterpret_cast<uint32_t*>(&ws.out[lane][O_OFFRAD]);   // 16 words
+    const bool paired = sm.fast_wrap && f.table_sigma_palette != nullptr;      // warp-uniform
+    if (paired) {
+        uint32_t* const rows[2] = {reinterpret_cast<uint32_t*>(ws.feat[lane]), park};
+        gather_fast<2, PNERF_GATHER_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, rows);
+    } else {
+        gather_features((const __half*)f.table_sigma, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    }
     __syncwarp();
 #pragma unroll 1
     for (int t = 0; t < 2; t++) {
@@ -107,7 +119,12 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
     __syncwarp();
 
     // ---------------- phase 3: palette grid ++ diffuse -> basis net -> offsets/radiance + omega heads ----------------
-    gather_features((const __half*)f.table_palette, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    if (paired) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) reinterpret_cast<uint32_t*>(ws.feat[lane])[i] = park[i];
+    } else {
+        gather_features((const __half*)f.table_palette, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+    }
     __syncwarp();
 #pragma unroll 1
     for (int t = 0; t < 2; t++) {
@@ -134,7 +151,12 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
 
     // ---------------- phase 4 (optional): semantic grid -> clip net ----------------
     if (CLIP) {
-        gather_features((const __half*)f.table_clip, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        if (sm.fast_wrap) {
+            uint32_t* const rows[1] = {reinterpret_cast<uint32_t*>(ws.feat[lane])};
+            gather_fast<1, PNERF_GATHER_LV>(f.table_clip, sm.lp, u, v, w, in_range, rows);
+        } else {
+            gather_features((const __half*)f.table_clip, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        }
         __syncwarp();
 #pragma unroll 1
         for (int t = 0; t < 2; t++) {
@@ -195,6 +217,8 @@ __device__ __forceinline__ void blend(const pnerf_palette_field& f, const FusedS
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fused_prologue(const pnerf_palette_field& f, FusedSmem* sm, uint2* wts) {
     if (threadIdx.x < f.L) make_level(sm->lp[threadIdx.x], threadIdx.x, f.offsets, f.S, f.H, 3, 0, false);
+    const int slow = __syncthreads_or(threadIdx.x < f.L && sm->lp[threadIdx.x].mask == 0u);
+    if (threadIdx.x == 0) sm->fast_wrap = slow ? 0u : 1u;
     if (threadIdx.x < 16) sm->head_bias[threadIdx.x] = f.head_bias[threadIdx.x];
     if (threadIdx.x < kNB * 3) sm->palette[threadIdx.x] = f.palette[threadIdx.x];
     const int units = f.pred_clip ? kWUnitsClip : kWUnitsNoClip;   // uint2 units; both counts are even

@@ -19,7 +19,10 @@ constexpr int kClipMax = 16;      // semantic feature width supported by the fus
 constexpr int kFusedWarps = PNERF_FUSED_WARPS;   // one CTA per SM: 12 warps <= 168 registers/thread, 10 warps <= 204
 constexpr int kAuxCh = 3 + 3 + kNB + 2 * kNB * 3;   // direct_rgb, view_dep_rgb, basis_acc, basis_rgb, unscaled_basis_rgb
 constexpr int kFeatStride = 40;   // halfs per feature row: 32 + 8 pad -> ldmatrix rows hit distinct bank groups
-constexpr int kOutStride = 41;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
+#ifndef PNERF_OUT_STRIDE
+#define PNERF_OUT_STRIDE 41
+#endif
+constexpr int kOutStride = PNERF_OUT_STRIDE;    // floats per output row (40 used); odd stride -> conflict-free row-per-lane reads
 
 // packed weight blob: per layer [NT][KS][32 lanes] x uint2 (= the m16n8k16 B fragment of that (n-tile, k-step))
 enum Layer { LS0, LS1, LD0, LD1, LD2, LV0, LV1, LV2, LB0, LB1, LH, LC0, LC1, kNumLayers };
@@ -55,6 +58,7 @@ struct FusedSmem {
     LevelParams lp[kMaxLevels];
     float head_bias[16];
     float palette[kNB * 3];
+    uint32_t fast_wrap;   // every level wraps with a mask (power-of-two hashed level or dense level that fits its table)
     // followed by: uint2 weights[units]; WarpScratch scratch[kFusedWarps]
 };
 
@@ -171,6 +175,81 @@ static __device__ __noinline__ void gather_features(const __half* __restrict__ t
         }
         reinterpret_cast<__half2*>(row)[l0] = __floats2half2_rn(acc[0].x, acc[0].y);
         if (l0 + 1 < L) reinterpret_cast<__half2*>(row)[l0 + 1] = __floats2half2_rn(acc[1].x, acc[1].y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather_fast: the hot-path gather. The density, palette and semantic grids of the model share ONE geometry (same
+// level table), so the 8 corner indices and trilinear weights of a level are computed once; with the density and
+// palette tables interleaved entry by entry (pnerf_palette_field::table_sigma_palette, EW = 2) one 8-byte load per
+// corner fetches both grids' features: half the loads and half the L2 sectors of two separate gathers.
+// Requires every level to wrap with a mask (FusedSmem::fast_wrap, true for every table GridEncoder can construct:
+// hashed levels hold 2^log2T entries, dense levels fit); the generic gather_features above stays as the fallback.
+// Address arithmetic is one mad.wide.u32 per load (32-bit entry index against a per-level 64-bit base).
+// Out-of-range samples produce zero features like the reference kernel (gridencoder.cu:118-130).
+//   EW: 32-bit words per table entry (1: one F=2 fp16 table, 2: two interleaved tables); rows[e] receives table e.
+//   LV: levels per iteration (LV x 8 loads in flight per lane).
+// ------------------------------------------------------------------------------------------------
+template <int EW>
+__device__ __forceinline__ void ldg_entry(uint64_t base, uint32_t idx, uint32_t (&v)[EW]) {
+    uint64_t addr;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "n"(EW * 4), "l"(base));
+    if (EW == 1) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v[0]) : "l"(addr));
+    else asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[EW - 1]) : "l"(addr));
+}
+
+template <int EW, int LV>
+__device__ __forceinline__ void gather_fast(const void* __restrict__ table, const LevelParams* __restrict__ lp,
+                                            float u, float v, float w, bool in_range, uint32_t* const (&rows)[EW]) {
+    static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
+    u = fminf(fmaxf(u, 0.f), 1.f); v = fminf(fmaxf(v, 0.f), 1.f); w = fminf(fmaxf(w, 0.f), 1.f);   // keeps the loads in bounds
+#pragma unroll 1
+    for (int l0 = 0; l0 < 16; l0 += LV) {
+        uint32_t val[LV][8][EW];
+        float wt[LV][8];
+#pragma unroll
+        for (int j = 0; j < LV; j++) {
+            const LevelParams& p = lp[l0 + j];
+            const float px = fmaf(u, p.scale, 0.5f), py = fmaf(v, p.scale, 0.5f), pz = fmaf(w, p.scale, 0.5f);
+            const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+            const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+            const float rx = px - (float)gx, ry = py - (float)gy, rz = pz - (float)gz;
+            const float wx[2] = {1 - rx, rx}, wy[2] = {1 - ry, ry}, wz[2] = {1 - rz, rz};
+            const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};   // (wx*wy)*wz: the reference's order
+#pragma unroll
+            for (int c = 0; c < 8; c++) wt[j][c] = wxy[c & 3] * wz[c >> 2];
+            uint32_t idx[8];
+            if (p.use_hash) {
+                const uint32_t hx1 = gx + 1, hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
+                const uint32_t hy1 = hy0 + 2654435761u, hz1 = hz0 + 805459861u;
+                const uint32_t yz[4] = {hy0 ^ hz0, hy1 ^ hz0, hy0 ^ hz1, hy1 ^ hz1};
+#pragma unroll
+                for (int c = 0; c < 8; c++) idx[c] = (((c & 1) ? hx1 : gx) ^ yz[c >> 1]) & p.mask;
+            } else {
+                const uint32_t ix0 = gx * p.stride[0], iy0 = gy * p.stride[1], iz0 = gz * p.stride[2];
+                const uint32_t yz[4] = {iy0 + iz0, iy0 + p.stride[1] + iz0, iy0 + iz0 + p.stride[2],
+                                        iy0 + p.stride[1] + iz0 + p.stride[2]};
+#pragma unroll
+                for (int c = 0; c < 8; c++) idx[c] = (((c & 1) ? ix0 + p.stride[0] : ix0) + yz[c >> 1]) & p.mask;
+            }
+            const uint64_t base = (uint64_t)(uintptr_t)table + (uint64_t)p.offset * (uint32_t)(EW * 4);
+#pragma unroll
+            for (int c = 0; c < 8; c++) ldg_entry<EW>(base, idx[c], val[j][c]);
+        }
+#pragma unroll
+        for (int j = 0; j < LV; j++) {
+#pragma unroll
+            for (int e = 0; e < EW; e++) {
+                float ax = 0.f, ay = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&val[j][c][e]));
+                    ax = fmaf(wt[j][c], h.x, ax);
+                    ay = fmaf(wt[j][c], h.y, ay);
+                }
+                rows[e][l0 + j] = in_range ? pack_h2(ax, ay) : 0u;
+            }
+        }
     }
 }
 

@@ -28,7 +28,7 @@ class PaletteField(ctypes.Structure):
                 ("wpack", c_void_p), ("head_bias", c_void_p), ("palette", c_void_p),
                 ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
                 ("S", c_float), ("bound", c_float), ("density_scale", c_float), ("offsets_weight", c_float),
-                ("view_dep_weight", c_float)]
+                ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p)]
 
 
 P, U, F = c_void_p, c_uint32, c_float
@@ -119,18 +119,21 @@ class FieldCache:
             t_sigma = m.encoder.embeddings.detach().to(torch.float16).contiguous()
             t_pal = m.encoder_palette.embeddings.detach().to(torch.float16).contiguous()
             t_clip = m.encoder_clip.embeddings.detach().to(torch.float16).contiguous() if m.opt.pred_clip else None
+            # density + palette tables interleaved per entry: one 8-byte gather serves both grids (same geometry)
+            t_pair = torch.stack((t_sigma, t_pal), dim=1).contiguous()
             wpack, bias = pack_weights(m)
             palette = m.basis_color.detach().float().clamp(0, 1).contiguous()
             offsets = m.encoder.offsets.contiguous()
         f = PaletteField()
         f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
+        f.table_sigma_palette = ptr(t_pair)
         f.offsets, f.wpack, f.head_bias, f.palette = ptr(offsets), ptr(wpack), ptr(bias), ptr(palette)
         f.L, f.H = m.encoder.num_levels, m.encoder.base_resolution
         f.pred_clip, f.clip_dim = int(bool(m.opt.pred_clip)), m.opt.clip_dim
         f.S = float(np.float32(np.log2(m.encoder.per_level_scale)))
         f.bound, f.density_scale = float(m.bound), float(m.density_scale)
         f.offsets_weight, f.view_dep_weight = float(m.offsets_weight), float(m.view_dep_weight)
-        self.keep = (t_sigma, t_pal, t_clip, wpack, bias, palette, offsets)  # keep the device buffers alive
+        self.keep = (t_sigma, t_pal, t_clip, t_pair, wpack, bias, palette, offsets)  # keep the device buffers alive
         self.field, self.key = f, key
         return f
 
