@@ -114,6 +114,49 @@ struct Marcher {
 
 
 // ------------------------------------------------------------------------------------------------
+// Lattice window: lane i receives t_i = t_start advanced i times by the (serial, fp32) step, i < nvalid (>= 1).
+// Constant step (dt_gamma == 0, every Blender config): inside one binade fl(t + dt) = t + dq ulps with a constant
+// integer dq (dt rounded to the binade's ulp; round-half-even ties and binade crossings excluded), so the lattice
+// points are consecutive-integer-spaced BIT PATTERNS and lane i gets its point in O(1). The window is accepted
+// only if every lane verifies t_i == fl(t_{i-1} + dt) with a real fp32 add, i.e. it is the reference's serial
+// sequence by construction; otherwise (tie, crossing at lane 1, dt_gamma > 0) the serial prefix is used.
+// All 32 lanes must call it with the same t_start.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lattice_window(const Marcher& m, float t_start, uint32_t lane, float& t, uint32_t& nvalid) {
+    const uint32_t dbits = __float_as_uint(m.dt_min);
+    t = t_start;
+    nvalid = 32;
+    bool fast = false;
+    if (m.dt_gamma == 0.f) {
+        const uint32_t tb = __float_as_uint(t_start);
+        const int shift = (int)((tb >> 23) & 0xffu) - (int)((dbits >> 23) & 0xffu);
+        if (shift >= 1 && shift <= 23 && (tb >> 23) != 0u && (tb >> 23) < 0xffu) {
+            const uint32_t md = (dbits & 0x7fffffu) | 0x800000u;
+            const uint32_t rem = md & ((1u << shift) - 1u), half = 1u << (shift - 1);
+            const uint32_t dq = (md >> shift) + (rem > half ? 1u : 0u);
+            const uint32_t bi = tb + lane * dq;
+            const bool wv = bi < ((tb | 0x7fffffu) + 1u);            // still inside t_start's binade
+            const float ti = __uint_as_float(bi);
+            const float pa = __shfl_up_sync(0xffffffffu, ti + m.dt_min, 1);
+            const bool ok = (lane == 0) || !wv || (pa == ti);
+            const uint32_t wmask = __ballot_sync(0xffffffffu, wv);
+            if (rem != half && dq != 0u && __all_sync(0xffffffffu, ok)) {
+                fast = true;
+                nvalid = __popc(wmask);                               // >= 1 (lane 0 is always inside)
+                t = wv ? ti : t_start;
+            }
+        }
+    }
+    if (!fast) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < 31; i++) {
+            const float tn = t + m.step_size(t);
+            if (i < lane) t = tn;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Warp-cooperative walk of ONE ray (all 32 lanes call it with the same ray). The reference walks the lattice
 // t_{k+1} = t_k + clamp(t_k * dt_gamma, dt_min, dt_max) serially, probing a point, then either emitting a sample
 // or skipping to the first lattice point past the empty voxel. Here a window of 32 consecutive lattice points is
@@ -131,44 +174,10 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
     float t_start = t0;
     float last_t = t0;  // end of the previous sample (start of the real-delta interval)
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t dbits = __float_as_uint(m.dt_min);
     while (t_start < far && count < budget) {
-        // ---- lattice window: lane i holds t_i = t_start advanced i times by the (serial, fp32) step ----
-        // Constant step (dt_gamma == 0, every Blender config): inside one binade fl(t + dt) = t + dq ulps with a constant
-        // integer dq (dt rounded to the binade's ulp; round-half-even ties and binade crossings excluded), so the lattice
-        // points are consecutive-integer-spaced BIT PATTERNS and lane i gets its point in O(1). The window is accepted
-        // only if every lane verifies t_i == fl(t_{i-1} + dt) with a real fp32 add, i.e. it is the reference's serial
-        // sequence by construction; otherwise (tie, crossing at lane 1, dt_gamma > 0) the serial prefix is used.
-        float t = t_start;
-        uint32_t nvalid = 32;
-        bool fast = false;
-        if (m.dt_gamma == 0.f) {
-            const uint32_t tb = __float_as_uint(t_start);
-            const int shift = (int)((tb >> 23) & 0xffu) - (int)((dbits >> 23) & 0xffu);
-            if (shift >= 1 && shift <= 23 && (tb >> 23) != 0u && (tb >> 23) < 0xffu) {
-                const uint32_t md = (dbits & 0x7fffffu) | 0x800000u;
-                const uint32_t rem = md & ((1u << shift) - 1u), half = 1u << (shift - 1);
-                const uint32_t dq = (md >> shift) + (rem > half ? 1u : 0u);
-                const uint32_t bi = tb + lane * dq;
-                const bool wv = bi < ((tb | 0x7fffffu) + 1u);            // still inside t_start's binade
-                const float ti = __uint_as_float(bi);
-                const float pa = __shfl_up_sync(0xffffffffu, ti + m.dt_min, 1);
-                const bool ok = (lane == 0) || !wv || (pa == ti);
-                const uint32_t wmask = __ballot_sync(0xffffffffu, wv);
-                if (rem != half && dq != 0u && __all_sync(0xffffffffu, ok)) {
-                    fast = true;
-                    nvalid = __popc(wmask);                               // >= 1 (lane 0 is always inside)
-                    t = wv ? ti : t_start;
-                }
-            }
-        }
-        if (!fast) {
-#pragma unroll 1
-            for (uint32_t i = 0; i < 31; i++) {
-                const float tn = t + m.step_size(t);
-                if (i < lane) t = tn;
-            }
-        }
+        float t;
+        uint32_t nvalid;
+        lattice_window(m, t_start, lane, t, nvalid);
         const bool wv = lane < nvalid;
         const float t_after = t + m.step_size(t);                 // lattice point following this lane's
         const bool inside = wv && t < far;
