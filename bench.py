@@ -215,6 +215,22 @@ def main():
     e2e = {"value": world * N_RAYS / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 2 * N_RAYS * 12,
            "d2h_bytes_per_step": N_RAYS * 12, "ms_per_step": ms_e2e}
 
+    # ---- e2e from the camera pose: 64 B pose H2D -> pnerf_get_rays -> render -> D2H image ------------
+    import math
+    from palettenerf_b200.nerf.utils import get_rays
+    pose_pin = S.lookat_pose(S.LEGO["radius"], 35.0 + 45.0 * rank)[None].contiguous().pin_memory()
+    focal = 0.5 * VIEW / math.tan(0.5 * S.LEGO["camera_angle_x"])
+    intr = [focal, focal, VIEW / 2, VIEW / 2]
+
+    def e2e_pose_step():
+        r = get_rays(pose_pin.to(dev, non_blocking=True), intr, VIEW, VIEW, N=-1)
+        out = render(r["rays_o"][0], r["rays_d"][0])
+        img_host.copy_(out["image"].view(-1, 3), non_blocking=True)
+    ms_pose, _, _ = timed(e2e_pose_step, args.steps, args.warmup)
+    e2e["from_pose"] = {"value": world * N_RAYS / (ms_pose / 1e3), "ms_per_step": ms_pose, "h2d_bytes_per_step": 64,
+                        "d2h_bytes_per_step": N_RAYS * 12,
+                        "note": "rays generated on the device by pnerf_get_rays from the pinned-host camera pose"}
+
     # ---- roofline of the dominant kernel of the step (CUDA events around each C-ABI launch, timed region) ---------
     # pnerf_palette_render_fused = pre-pass + 2 ordering kernels + the persistent k_render_fused (>= 97 % of the call,
     # profiles/r01_launches_bench_render_*.csv). It is the fused march -> hash-grid gather -> MLP -> blend -> composite

@@ -281,6 +281,29 @@ PNERF_API int pnerf_grid_encode_backward_counted(const void* grad, const float* 
                                                  uint32_t gridtype, int align_corners, int dtype, int grad_layout,
                                                  const int32_t* count_dev, float bound, void* stream);
 
+/* pnerf_grid_encode_backward for an fp16 gradient with D = 3, C = 2, accumulated in an fp32 workspace
+ * (replaces kernel_grid_backward<half> with its atomicAdd(__half2*), ref gridencoder/src/gridencoder.cu:226-313):
+ * the reductions go to `workspace` ([n_entries, 2] fp32, contents ignored, zeroed here) as red.global.add.v2.f32 --
+ * measured faster on B200's L2 than the packed f16x2 reduction, and each table entry is rounded to fp16 once instead of
+ * once per contribution -- then grad_embeddings (fp16 [n_entries, 2]) += workspace. n_entries = offsets[L], even. */
+PNERF_API int pnerf_grid_encode_backward_ws(const void* grad, const float* inputs, const int32_t* offsets,
+                                            void* grad_embeddings, float* workspace, uint64_t n_entries, uint32_t B,
+                                            uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                            int grad_layout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ray generation  (ref: get_rays, nerf/utils.py:52-151, the arithmetic at :132-149)
+ * poses [B,4,4] row-major camera-to-world, intrinsics fx fy cx cy, image H x W.
+ * inds : int64 pixel indices (row * W + col), element (b, n) at inds[b * inds_batch_stride + n] (stride 0 = one [N]
+ *        list shared by the batch, as the reference's `inds.expand([B, N])`); NULL = all H*W pixels in order (N = H*W).
+ * Writes rays_o, rays_d [B,N,3] (rays_d normalised and rotated; rays_o materialised, the reference returns a view).
+ * nears/fars (both or neither, [B,N]) additionally receive near_far_from_aabb(rays_o, rays_d, aabb, min_near)
+ * (ref: raymarching.cu:95-148) computed on the direction in registers.
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                             const int64_t* inds, uint64_t inds_batch_stride, uint32_t N, uint32_t B, float* rays_o,
+                             float* rays_d, const float* aabb, float min_near, float* nears, float* fars, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

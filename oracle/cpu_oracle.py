@@ -329,3 +329,33 @@ def freq_encode(inputs, degree):
         out.append(np.sin(x * 2.0 ** f))
         out.append(np.sin(x * 2.0 ** f + np.float32(np.pi / 2)))
     return np.concatenate(out, axis=-1)
+
+
+# ---------------------------------------------------------------- ray generation (numpy) ----------------------
+def get_rays(poses, intrinsics, H, W, inds=None):
+    """get_rays, nerf/utils.py:52-151, the arithmetic after the pixel indices are drawn (:69-71, :132-149), float32:
+    i = col + 0.5, j = row + 0.5; directions = ((i-cx)/fx, (j-cy)/fy, 1) / norm; rays_d = directions @ R^T;
+    rays_o = poses[:, :3, 3] broadcast. inds: int [B, N] / [N] (row * W + col) or None = all pixels in order.
+    Returns rays_o, rays_d [B, N, 3] float32."""
+    poses = np.asarray(poses, np.float32).reshape(-1, 4, 4)
+    B = poses.shape[0]
+    fx, fy, cx, cy = (np.float32(v) for v in intrinsics)
+    if inds is None:
+        inds = np.arange(H * W, dtype=np.int64)
+    inds = np.broadcast_to(np.asarray(inds, np.int64).reshape(-1, np.asarray(inds).shape[-1]), (B, np.asarray(inds).shape[-1]))
+    i = (inds % W).astype(np.float32) + np.float32(0.5)
+    j = (inds // W).astype(np.float32) + np.float32(0.5)
+    xs = (i - cx) / fx
+    ys = (j - cy) / fy
+    zs = np.ones_like(xs)
+    nrm = np.sqrt(xs * xs + ys * ys + zs * zs).astype(np.float32)
+    d = np.stack([xs / nrm, ys / nrm, zs / nrm], axis=-1).astype(np.float32)
+    R = poses[:, :3, :3]
+    rays_d = np.zeros((B, d.shape[1], 3), np.float32)
+    for k in range(3):   # accumulate in index order, float32
+        acc = d[..., 0] * R[:, None, k, 0]
+        acc = (acc + d[..., 1] * R[:, None, k, 1]).astype(np.float32)
+        acc = (acc + d[..., 2] * R[:, None, k, 2]).astype(np.float32)
+        rays_d[..., k] = acc
+    rays_o = np.broadcast_to(poses[:, None, :3, 3], rays_d.shape).astype(np.float32).copy()
+    return rays_o, rays_d

@@ -47,6 +47,8 @@ _SIGS = {
     "pnerf_composite_rays_flex": [U, U, U, F, P, P, P, P, P, P, P, P],
     "pnerf_grid_encode_forward": [P, P, P, P, U, U, U, U, F, U, P, U, I, I, I, P],
     "pnerf_grid_encode_backward": [P, P, P, P, P, U, U, U, U, F, U, P, P, U, I, I, I, P],
+    "pnerf_grid_encode_backward_ws": [P, P, P, P, P, c_uint64, U, U, F, U, U, I, I, P],
+    "pnerf_get_rays": [P, F, F, F, F, U, U, P, c_uint64, U, U, P, P, P, F, P, P, P],
     "pnerf_sh_encode_forward": [P, P, U, U, U, P, P],
     "pnerf_sh_encode_backward": [P, P, U, U, U, P, P, P],
     "pnerf_freq_encode_forward": [P, U, U, U, U, P, P],
@@ -98,7 +100,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim and per-kernel CUDA-event timing)
-LAUNCHES = {"pnerf_march_rays_train": 3}
+LAUNCHES = {"pnerf_march_rays_train": 3, "pnerf_grid_encode_backward_ws": 2}
 launch_count = 0
 _profile = None  # when set: dict name -> [list of (start_event, end_event), units]
 

@@ -112,15 +112,26 @@ __device__ __forceinline__ float activate(float v) {
     return v;
 }
 
+// pack two activated accumulators. ReLU is applied to the packed pair (one HMNMX2 instead of two FMNMX):
+// round-to-nearest is monotonic and sign-preserving, so max(rn(x), 0) == rn(max(x, 0)) for every finite x.
+template <int ACT>
+__device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
+    if (ACT == ACT_RELU) {
+        const __half2 h = __hmax2(__floats2half2_rn(lo, hi), __float2half2_rn(0.f));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return pack_h2(activate<ACT>(lo), activate<ACT>(hi));
+}
+
 // accumulators of NT n-tiles -> A fragments of NT/2 k-steps (layout identity of mma.m16n8k16, no shuffles)
 template <int NT, int ACT>
 __device__ __forceinline__ void chain(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
 #pragma unroll
     for (int j = 0; j < NT / 2; j++) {
-        a[j][0] = pack_h2(activate<ACT>(c[2 * j][0]), activate<ACT>(c[2 * j][1]));
-        a[j][1] = pack_h2(activate<ACT>(c[2 * j][2]), activate<ACT>(c[2 * j][3]));
-        a[j][2] = pack_h2(activate<ACT>(c[2 * j + 1][0]), activate<ACT>(c[2 * j + 1][1]));
-        a[j][3] = pack_h2(activate<ACT>(c[2 * j + 1][2]), activate<ACT>(c[2 * j + 1][3]));
+        a[j][0] = pack_act<ACT>(c[2 * j][0], c[2 * j][1]);
+        a[j][1] = pack_act<ACT>(c[2 * j][2], c[2 * j][3]);
+        a[j][2] = pack_act<ACT>(c[2 * j + 1][0], c[2 * j + 1][1]);
+        a[j][3] = pack_act<ACT>(c[2 * j + 1][2], c[2 * j + 1][3]);
     }
 }
 

@@ -308,9 +308,11 @@ __global__ void __launch_bounds__(256) k_grid_bwd_d3c2(const T* __restrict__ gra
 // same-address contention that serialises the reference's atomics at those levels (4 920 entries receiving 8*B adds)
 // disappears; at the fine levels every point is its own run and the kernel degenerates to one reduction per corner.
 // Threads of a warp hold 16 levels x 2 segments: the [B, L*2] gradient row is read as a contiguous 64 B.
-template <typename T, int K>
-__global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ grad, const float* __restrict__ inputs,
-                                                       const int32_t* __restrict__ offsets, T* __restrict__ grad_grid,
+// TG = type of the incoming gradient, TA = type of the table the reductions go to (TA = float with TG = half: fp32
+// workspace, see pnerf_grid_encode_backward_ws).
+template <typename TG, typename TA, int K>
+__global__ void __launch_bounds__(256) k_grid_bwd_runs(const TG* __restrict__ grad, const float* __restrict__ inputs,
+                                                       const int32_t* __restrict__ offsets, TA* __restrict__ grad_grid,
                                                        uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
                                                        bool align_corners, bool layout_blc,
                                                        const int32_t* __restrict__ count_dev = nullptr, float bound = 0.f) {
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
         const uint32_t level = (uint32_t)(tid % L);
         const uint64_t b0 = (tid / L) * K;
         const LevelParams& p = lp[level];
-        T* gg = grad_grid + (size_t)p.offset * 2;
+        TA* gg = grad_grid + (size_t)p.offset * 2;
 
         bool have = false;
         uint32_t cur_cell[3] = {0, 0, 0}, cur_idx[8];
@@ -339,8 +341,8 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
                 x = (x + bound) / (2 * bound); y = (y + bound) / (2 * bound); z = (z + bound) / (2 * bound);
             }
             if ((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1)) continue;
-            const T* gp = layout_blc ? grad + (b * L + level) * 2 : grad + ((size_t)level * B + b) * 2;
-            const float2 g = Pair<T>::load(gp);
+            const TG* gp = layout_blc ? grad + (b * L + level) * 2 : grad + ((size_t)level * B + b) * 2;
+            const float2 g = Pair<TG>::load(gp);
             uint32_t idx[8], cell[3];
             float w[8];
             corner_setup(p, x, y, z, idx, w, align_corners, cell);
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
             if (!same) {
                 if (have) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+                    for (int c = 0; c < 8; c++) Pair<TA>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
                 }
 #pragma unroll
                 for (int c = 0; c < 8; c++) { cur_idx[c] = idx[c]; acc[c] = make_float2(w[c] * g.x, w[c] * g.y); }
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_runs(const T* __restrict__ gra
         }
         if (have) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) Pair<T>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
+            for (int c = 0; c < 8; c++) Pair<TA>::red(gg + (size_t)cur_idx[c] * 2, acc[c].x, acc[c].y);
         }
     }
 }
@@ -463,7 +465,7 @@ int grid_backward_t(const T* grad, const float* inputs, const int32_t* offsets, 
         if constexpr (!std::is_same<T, double>::value) {
             constexpr int K = 8;
             const uint64_t threads = ceil_div<uint64_t>(B, K) * L;
-            k_grid_bwd_runs<T, K><<<(uint32_t)ceil_div<uint64_t>(threads, 256), 256, 0, s>>>(
+            k_grid_bwd_runs<T, T, K><<<(uint32_t)ceil_div<uint64_t>(threads, 256), 256, 0, s>>>(
                 grad, inputs, offsets, grad_emb, B, L, S, H, gridtype, align, blc);
             done = true;
         }
@@ -483,6 +485,20 @@ int grid_backward_t(const T* grad, const float* inputs, const int32_t* offsets, 
         k_grid_input_bwd<T><<<ceil_div(B * D, 256u), 256, 0, s>>>(grad, dy_dx, grad_inputs, B, D, C, L, blc);
     }
     return check_launch("grid_encode_backward");
+}
+
+// grad_embeddings(fp16) += round(workspace(fp32)); 8 entries (4 pairs) per thread, 128-bit loads
+__global__ void __launch_bounds__(256) k_grid_fold_ws(const float4* __restrict__ ws, uint2* __restrict__ out, uint64_t n4) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = ld_stream4(ws + i);
+        uint2 o = out[i];
+        __half2 a = *reinterpret_cast<__half2*>(&o.x), b = *reinterpret_cast<__half2*>(&o.y);
+        a = __hadd2(a, __floats2half2_rn(v.x, v.y));
+        b = __hadd2(b, __floats2half2_rn(v.z, v.w));
+        o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+        out[i] = o;
+    }
 }
 
 }  // namespace pnerf
@@ -523,14 +539,36 @@ int pnerf_grid_encode_backward_counted(const void* grad, const float* inputs, co
     const uint64_t blocks = ceil_div<uint64_t>(threads, 256);
     const uint32_t grid = (uint32_t)(blocks < 8ull * kNumSMs ? blocks : 8ull * kNumSMs);   // grid-stride kernel
     if (dtype == PNERF_F32)
-        k_grid_bwd_runs<float, K><<<grid, 256, 0, s>>>((const float*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
+        k_grid_bwd_runs<float, float, K><<<grid, 256, 0, s>>>((const float*)grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H,
                                                       gridtype, al, blc, count_dev, bound);
     else if (dtype == PNERF_F16)
-        k_grid_bwd_runs<__half, K><<<grid, 256, 0, s>>>((const __half*)grad, inputs, offsets, (__half*)grad_embeddings, B, L, S,
+        k_grid_bwd_runs<__half, __half, K><<<grid, 256, 0, s>>>((const __half*)grad, inputs, offsets, (__half*)grad_embeddings, B, L, S,
                                                        H, gridtype, al, blc, count_dev, bound);
     else
         return PNERF_ERR_UNSUPPORTED;
     return check_launch("grid_encode_backward_counted");
+}
+
+int pnerf_grid_encode_backward_ws(const void* grad, const float* inputs, const int32_t* offsets, void* grad_embeddings,
+                                  float* workspace, uint64_t n_entries, uint32_t B, uint32_t L, float S, uint32_t H,
+                                  uint32_t gridtype, int align_corners, int grad_layout, void* stream) {
+    if (B == 0) return PNERF_OK;
+    PNERF_REQUIRE(grad && inputs && offsets && grad_embeddings && workspace && n_entries > 0);
+    PNERF_REQUIRE((n_entries % 2) == 0);   // 2 entries (4 floats) per 128-bit access; GridEncoder pads levels to 8 entries
+    PNERF_REQUIRE(gridtype <= 1 && (grad_layout == PNERF_LAYOUT_LBC || grad_layout == PNERF_LAYOUT_BLC));
+    if (L < 1 || L > (uint32_t)kMaxLevels) return PNERF_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool blc = grad_layout == PNERF_LAYOUT_BLC, al = align_corners != 0;
+    if (cudaMemsetAsync(workspace, 0, n_entries * 2 * sizeof(float), s) != cudaSuccess) return check_launch("grid_encode_backward_ws");
+    constexpr int K = 8;
+    const uint64_t threads = ceil_div<uint64_t>(B, K) * L;
+    k_grid_bwd_runs<__half, float, K><<<(uint32_t)ceil_div<uint64_t>(threads, 256), 256, 0, s>>>(
+        (const __half*)grad, inputs, offsets, workspace, B, L, S, H, gridtype, al, blc);
+    const uint64_t n4 = n_entries / 2;
+    const uint64_t blocks = ceil_div<uint64_t>(n4, 256);
+    k_grid_fold_ws<<<(uint32_t)(blocks < 16ull * kNumSMs ? blocks : 16ull * kNumSMs), 256, 0, s>>>(
+        (const float4*)workspace, (uint2*)grad_embeddings, n4);
+    return check_launch("grid_encode_backward_ws");
 }
 
 int pnerf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,

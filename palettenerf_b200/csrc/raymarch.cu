@@ -12,6 +12,7 @@
 //   - packbits reads 2x float4 per byte, morton/near-far read and write through coalesced vector accesses.
 #include "common.cuh"
 #include "march_common.cuh"
+#include "ray_common.cuh"
 
 namespace pnerf {
 
@@ -25,28 +26,10 @@ __global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ rays
     if (n >= N) return;
     const float ox = rays_o[n * 3 + 0], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
     const float dx = rays_d[n * 3 + 0], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
-    const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
-    const float flt_max = 3.402823466e+38f;
-
-    float near = (aabb[0] - ox) * rdx, far = (aabb[3] - ox) * rdx;
-    if (near > far) { float s = near; near = far; far = s; }
-    float near_y = (aabb[1] - oy) * rdy, far_y = (aabb[4] - oy) * rdy;
-    if (near_y > far_y) { float s = near_y; near_y = far_y; far_y = s; }
-    bool miss = (near > far_y) || (near_y > far);
-    if (!miss) {
-        if (near_y > near) near = near_y;
-        if (far_y < far) far = far_y;
-        float near_z = (aabb[2] - oz) * rdz, far_z = (aabb[5] - oz) * rdz;
-        if (near_z > far_z) { float s = near_z; near_z = far_z; far_z = s; }
-        miss = (near > far_z) || (near_z > far);
-        if (!miss) {
-            if (near_z > near) near = near_z;
-            if (far_z < far) far = far_z;
-            if (near < min_near) near = min_near;
-        }
-    }
-    nears[n] = miss ? flt_max : near;
-    fars[n] = miss ? flt_max : far;
+    float near, far;
+    slab_near_far(ox, oy, oz, dx, dy, dz, aabb, min_near, near, far);
+    nears[n] = near;
+    fars[n] = far;
 }
 
 // ------------------------------------------------------------------------------------------------

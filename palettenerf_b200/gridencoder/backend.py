@@ -34,6 +34,12 @@ class _Backend:
         _check(inputs, embeddings, offsets, grad, grad_embeddings, dy_dx, grad_inputs)
         if grad.dtype != grad_embeddings.dtype or not grad.is_contiguous() or not grad_embeddings.is_contiguous():
             raise RuntimeError("grad / grad_embeddings must be contiguous and of one dtype")
+        if grad.dtype == torch.float16 and D == 3 and C == 2 and grad_embeddings.numel() % 4 == 0 and dy_dx is None:
+            # fp16 table: reduce into an fp32 workspace (red.global.add.v2.f32) and fold it into grad_embeddings once
+            ws = torch.empty(grad_embeddings.numel(), dtype=torch.float32, device=grad.device)
+            call("pnerf_grid_encode_backward_ws", ptr(grad), ptr(inputs), ptr(offsets), ptr(grad_embeddings), ptr(ws),
+                 grad_embeddings.shape[0], B, L_, float(S), H, gridtype, int(bool(align_corners)), _layout, stream())
+            return
         call("pnerf_grid_encode_backward", ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), B,
              D, C, L_, float(S), H, ptr(dy_dx), ptr(grad_inputs), gridtype, int(bool(align_corners)),
              dtype_id(grad.dtype), _layout, stream())

@@ -12,6 +12,9 @@ into this repository) and its outputs are committed as fixtures:
               reference file (the module itself runs CUDA code at import time)
   offsets     gridencoder.GridEncoder.__init__      (gridencoder/grid.py:91-129, the level-offset table)
   trunc_exp   activation.trunc_exp                  (activation.py:4-17, forward + backward)
+  get_rays    nerf/utils.py::get_rays               (:52-151) with custom_meshgrid (:34-40) — the two function statements
+              are exec'd from the reference file (the module imports tensorboardX / trimesh / mcubes / lpips, absent
+              here); every sampling mode: full image, random pixels, patches, random_size pairs, error-map sampling
   histogram   _palette_func.compute_RGB_histogram   (palette/src/bindings.cpp:52-91, host code) through the reference
               extension compiled by oracle/build_ref.py into oracle/_ref/
 
@@ -48,6 +51,45 @@ def _class_from_source(path, cls):
     ns = {"torch": torch, "nn": torch.nn, "np": np}
     exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns[cls]
+
+
+def _functions_from_source(path, names, ns):
+    """exec top-level function statements of a reference file (in place, nothing copied)"""
+    tree = ast.parse(open(path).read())
+    nodes = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def _golden_get_rays(out):
+    """the reference's get_rays run on the CPU with seeded torch RNG; inputs and outputs become fixtures"""
+    from packaging import version as pver
+    ns = {"torch": torch, "pver": pver, "np": np}
+    (get_rays,) = _functions_from_source(os.path.join(REF, "nerf", "utils.py"), ["get_rays"],
+                                         dict(ns, **{"custom_meshgrid": _functions_from_source(
+                                             os.path.join(REF, "nerf", "utils.py"), ["custom_meshgrid"], ns)[0]}))
+    g = torch.Generator().manual_seed(7)
+    H, W = 37, 53
+    # two cameras: rotation from a QR factorisation (a proper orthonormal frame), translation O(3)
+    poses = torch.eye(4).repeat(2, 1, 1)
+    for b in range(2):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        poses[b, :3, :3] = q
+        poses[b, :3, 3] = 3.0 * torch.randn(3, generator=g)
+    intr = np.array([61.7, 59.3, W / 2 + 0.25, H / 2 - 0.5], np.float32)
+    out["rays_poses"], out["rays_intrinsics"], out["rays_HW"] = poses.numpy(), intr, np.array([H, W])
+    err = torch.rand(2, 128 * 128, generator=g) + 1e-3
+    cases = {"full": dict(N=-1), "rand": dict(N=64), "patch": dict(N=64, patch_size=4), "pair": dict(N=64, random_size=3),
+             "err": dict(N=64, error_map=err)}
+    for name, kw in cases.items():
+        torch.manual_seed(11)
+        r = get_rays(poses, intr, H, W, **kw)
+        out[f"rays_{name}_inds"] = r["inds"].contiguous().numpy()
+        out[f"rays_{name}_o"] = r["rays_o"].contiguous().numpy()
+        out[f"rays_{name}_d"] = r["rays_d"].contiguous().numpy()
+        if "inds_coarse" in r:
+            out[f"rays_{name}_inds_coarse"] = r["inds_coarse"].numpy()
+    out["rays_error_map"] = err.numpy()
 
 
 def main():
@@ -105,6 +147,9 @@ def main():
         bw, bc = pf.compute_RGB_histogram(colors.reshape(-1).copy(), weights, bpc)   # numpy in / numpy out
         out[f"hist_bin_weights_b{bpc}"] = np.asarray(bw)
         out[f"hist_bin_centers_b{bpc}"] = np.asarray(bc)
+
+    # ---- ray generation ----
+    _golden_get_rays(out)
 
     path = os.path.join(HERE, "ref_python.npz")
     np.savez_compressed(path, **out)
