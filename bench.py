@@ -185,6 +185,7 @@ def main():
         if profile:
             L.profile_start()
         l0 = L.launch_count
+        torch.cuda.nvtx.range_push("timed")     # ncu --nvtx --nvtx-include "timed/" lists exactly the timed region
         for _ in range(steps):
             flush.fill_(1)  # L2 flush between timed iterations (not timed)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -192,6 +193,7 @@ def main():
             fn()
             b.record()
             evs.append((a, b))
+        torch.cuda.nvtx.range_pop()
         barrier()
         prof = L.profile_stop() if profile else None
         ms = sum(a.elapsed_time(b) for a, b in evs) / steps

@@ -82,6 +82,25 @@ PNERF_API int pnerf_march_rays_train(const float* rays_o, const float* rays_d, c
                                      float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
                                      const float* noises, void* stream);
 
+/* pnerf_march_rays_train with workspaces: ONE walk of the occupancy grid instead of the reference's two
+ * (raymarching.cu:358-409 counts, :421-482 walks again to write). Same outputs, bit for bit.
+ *   t_list   [N, max_steps] fp32 scratch (contents ignored): the counting walk records the ray parameter of every
+ *            sample; the write pass turns the list into xyzs / dirs / deltas without touching the grid again.
+ *   occ_aabb [6] or NULL: bounds of the occupied cells from pnerf_occupied_bounds for THIS grid; the counting walk
+ *            stops where the ray leaves them instead of marching the empty tail up to `far` (no lattice point behind
+ *            that exit can fall into an occupied cell, so the samples are unchanged). */
+PNERF_API int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                        float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                        uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                                        float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                        float* t_list, const float* occ_aabb, void* stream);
+
+/* occ_aabb[6] (device) = (lo xyz, hi xyz): world-space bounds of every occupied cell of the C cascades of `bitfield`
+ * ([C*H^3/8] bytes, Morton order, as packbits writes it), padded by one cell; a side reaching the scene bound is
+ * +-FLT_MAX; an empty grid gives lo > hi. One small single-CTA kernel; recompute when the bitfield changes. */
+PNERF_API int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float* occ_aabb,
+                                    void* stream);
+
 /* ref: raymarching.cu:504-580,647-655 */
 PNERF_API int pnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
                                                  const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
@@ -208,14 +227,17 @@ PNERF_API int pnerf_palette_field_forward(const float* xyzs, const float* dirs, 
  * (4 counters + a 32-bucket histogram + 32 cursors used to order the rays longest-first):
  * on return queue[1] = number of samples shaded, queue[2] = number of rays with at least one sample,
  * queue[3] = number of 32-sample tiles evaluated (queue[1] / (32 queue[3]) = tile fill).
- * hit_list (int32) is a [2N] scratch buffer (ordered hit list + samples per ray), t_first, t_last (fp32) are [N]. */
+ * hit_list (int32) is a [2N] scratch buffer (ordered hit list + samples per ray), t_first, t_last (fp32) are [N].
+ * occ_aabb (optional, may be NULL): pnerf_occupied_bounds of `bitfield`; the ray pre-pass then stops each walk at the
+ * ray's exit from the occupied bounds (same samples; rays that miss the bounds are not walked at all). */
 PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
                                          const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
                                          uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
                                          const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                                          float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
                                          float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue,
-                                         int32_t* hit_list, float* t_first, float* t_last, void* stream);
+                                         int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb,
+                                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fused palette field for TRAINING (new entry points; they replace the field evaluation of the training branch,

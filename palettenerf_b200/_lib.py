@@ -37,6 +37,8 @@ _SIGS = {
     "pnerf_morton3D_invert": [P, U, P, P],
     "pnerf_packbits": [P, U, F, P, P],
     "pnerf_march_rays_train": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P],
+    "pnerf_march_rays_train_ws": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P, P, P],
+    "pnerf_occupied_bounds": [P, U, U, F, P, P],
     "pnerf_composite_rays_train_forward": [P, P, P, P, U, U, F, P, P, P, P],
     "pnerf_composite_rays_train_backward": [P, P, P, P, P, P, P, P, U, U, F, P, P, P],
     "pnerf_composite_rays_flex_train_forward": [P, P, P, P, U, U, U, F, P, P],
@@ -100,7 +102,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim and per-kernel CUDA-event timing)
-LAUNCHES = {"pnerf_march_rays_train": 3, "pnerf_grid_encode_backward_ws": 2}
+LAUNCHES = {"pnerf_march_rays_train": 3, "pnerf_march_rays_train_ws": 3, "pnerf_grid_encode_backward_ws": 2}
 launch_count = 0
 _profile = None  # when set: dict name -> [list of (start_event, end_event), units]
 

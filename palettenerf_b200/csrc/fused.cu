@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
                                                      uint32_t N, uint32_t C, uint32_t H, uint32_t max_steps, float bound,
                                                      float dt_gamma, int32_t* __restrict__ hit_list,
                                                      int32_t* __restrict__ ray_count, float* __restrict__ t_first,
-                                                     float* __restrict__ t_last, unsigned int* __restrict__ queue) {
+                                                     float* __restrict__ t_last, unsigned int* __restrict__ queue,
+                                                     const float* __restrict__ occ) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     bool hit = false;
@@ -319,7 +320,10 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
         // 984-986), which is NOT always bit-identical to the marcher's own t (the subtraction rounds when the sample
         // lies beyond 2x the restart point). The persistent kernel performs the same walk, so t_first / t_last are
         // exact lattice points of it.
-        const float far = fars[n];
+        // occ (optional): bounds of the occupied cells; behind the ray's exit from them no lattice point is occupied, so
+        // the walk stops there (a ray that misses them — most of an object-centred view — does not walk at all)
+        float far = fars[n];
+        if (occ) far = fminf(far, m.occupied_exit(occ));
         float tc = nears[n];
         float t = tc;
         if (noises) t += m.step_size(t) * noises[n];
@@ -826,7 +830,7 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
                                          const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                                          float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
                                          float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue,
-                                         int32_t* hit_list, float* t_first, float* t_last, void* stream) {
+                                         int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
     PNERF_REQUIRE(hit_list && t_first && t_last);
@@ -847,7 +851,7 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* ray_count = hit_list + N;       // second half of the scratch: samples per ray
     k_ray_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, N, C, Hgrid, max_steps,
-                                                    field->bound, dt_gamma, hit_list, ray_count, t_first, t_last, queue);
+                                                    field->bound, dt_gamma, hit_list, ray_count, t_first, t_last, queue, occ_aabb);
     k_lpt_offsets<<<1, 32, 0, s>>>(queue);
     k_lpt_scatter<<<ceil_div(N, 256u), 256, 0, s>>>(ray_count, N, hit_list, queue);
     const bool clip_on = field->pred_clip != 0;

@@ -67,11 +67,45 @@ struct Marcher {
 
     // Classify lattice point t: returns true if (x,y,z) is an occupied sample; otherwise `tt` receives the ray
     // parameter at which the ray leaves the empty voxel (ref: raymarching.cu:364-403). Does not advance t.
-    __device__ __forceinline__ bool probe_point(float t, float& x, float& y, float& z, float& dt, float& tt) const {
+    // sample position and step at ray parameter t (ref: raymarching.cu:366-371); ONE definition, so the list-driven
+    // writer (k_march_train_emit) produces the bits the walk produced
+    __device__ __forceinline__ void position(float t, float& x, float& y, float& z, float& dt) const {
         x = clampf(ox + t * dx, -bound, bound);
         y = clampf(oy + t * dy, -bound, bound);
         z = clampf(oz + t * dz, -bound, bound);
         dt = step_size(t);
+    }
+
+    // first lattice point of a training ray (ref: raymarching.cu:352-355: t = near; t += clamp(t * dt_gamma, ..) * noise)
+    __device__ __forceinline__ float first_t(float near, float noise) const {
+        float t = near;
+        t += step_size(t) * noise;
+        return t;
+    }
+
+    // Ray parameter at which the ray leaves the box `occ` = world bounds of every occupied cell, padded by one cell
+    // (pnerf_occupied_bounds). Behind it no lattice point can fall into an occupied cell, so a walk may stop there
+    // instead of at `far`: the samples found are the same, the empty tail behind the object is not marched.
+    // A ray that misses the box gets -1 (no samples at all).
+    __device__ __forceinline__ float occupied_exit(const float* __restrict__ occ) const {
+        float t_in = -3.402823466e+38f, t_out = 3.402823466e+38f;
+        const float o[3] = {ox, oy, oz}, rd[3] = {rdx, rdy, rdz}, d[3] = {dx, dy, dz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float lo = occ[k], hi = occ[3 + k];
+            if (d[k] == 0.f) {
+                if (o[k] < lo || o[k] > hi) return -1.f;
+            } else {
+                const float a = (lo - o[k]) * rd[k], b = (hi - o[k]) * rd[k];
+                t_in = fmaxf(t_in, fminf(a, b));
+                t_out = fminf(t_out, fmaxf(a, b));
+            }
+        }
+        return (t_in <= t_out) ? t_out : -1.f;
+    }
+
+    __device__ __forceinline__ bool probe_point(float t, float& x, float& y, float& z, float& dt, float& tt) const {
+        position(t, x, y, z, dt);
 
         // cascade from position and from step size (ref: raymarching.cu:45-57)
         const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
@@ -166,10 +200,11 @@ __device__ __forceinline__ void lattice_window(const Marcher& m, float t_start, 
 //   WRITE = false: returns the sample count (<= budget)
 //   WRITE = true : additionally writes xyz / dir / (dt, real delta) of sample k to row (k) of the output pointers
 // ------------------------------------------------------------------------------------------------
+//   t_list (optional): receives the ray parameter t of sample k at t_list[k] (the list-driven writer needs nothing else)
 template <bool WRITE>
 __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float far, uint32_t budget, uint32_t lane,
                                               float* __restrict__ xyzs, float* __restrict__ dirs,
-                                              float* __restrict__ deltas) {
+                                              float* __restrict__ deltas, float* __restrict__ t_list = nullptr) {
     uint32_t count = 0;
     float t_start = t0;
     float last_t = t0;  // end of the previous sample (start of the real-delta interval)
@@ -224,6 +259,7 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
                 reinterpret_cast<float2*>(deltas)[k] = make_float2(dt, t_after - lt);
             }
         }
+        if (!WRITE && t_list && ((take >> lane) & 1u)) t_list[count + __popc(take & lt_mask)] = t;
         if (take) {
             const int top = 31 - __clz(take);
             last_t = __shfl_sync(0xffffffffu, t_after, top);

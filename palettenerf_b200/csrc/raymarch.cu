@@ -119,14 +119,18 @@ __global__ void __launch_bounds__(256) k_march_train_count(const float* __restri
                                                            uint32_t H, const float* __restrict__ nears,
                                                            const float* __restrict__ fars,
                                                            const float* __restrict__ noises,
-                                                           int32_t* __restrict__ rays) {
+                                                           int32_t* __restrict__ rays,
+                                                           float* __restrict__ t_list = nullptr,
+                                                           const float* __restrict__ occ = nullptr) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (n >= N) return;
     Marcher m;
     m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
-    float t = nears[n];
-    t += m.step_size(t) * noises[n];
-    const uint32_t num_steps = warp_walk<false>(m, t, fars[n], max_steps, lane, nullptr, nullptr, nullptr);
+    const float t = m.first_t(nears[n], noises[n]);
+    float far = fars[n];
+    if (occ) far = fminf(far, m.occupied_exit(occ));     // -1 for a ray that misses every occupied cell: no walk at all
+    const uint32_t num_steps = warp_walk<false>(m, t, far, max_steps, lane, nullptr, nullptr, nullptr,
+                                                t_list ? t_list + (size_t)n * max_steps : nullptr);
     if (lane == 0) {
         rays[n * 3 + 0] = (int32_t)n;
         rays[n * 3 + 2] = (int32_t)num_steps;
@@ -194,10 +198,96 @@ __global__ void __launch_bounds__(256) k_march_train_write(const float* __restri
     if (num_steps == 0 || offset + num_steps > M) return;   // ref: raymarching.cu:418-419
     Marcher m;
     m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, grid);
-    float t = nears[n];
-    t += m.step_size(t) * noises[n];
+    const float t = m.first_t(nears[n], noises[n]);
     warp_walk<true>(m, t, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3,
                     deltas + (size_t)offset * 2);
+}
+
+// pass 3, list-driven: pass 1 left the ray parameter of every sample in t_list[n][0..count); the samples are produced
+// from that list without touching the occupancy grid again. Lane k handles samples k, k+32, ...: position and step from
+// Marcher::position (the expressions of the walk), real delta = (t_k + dt_k) - (t_{k-1} + dt_{k-1}) (first sample:
+// - first lattice point), exactly what warp_walk<true> writes.
+__global__ void __launch_bounds__(256) k_march_train_emit(const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, float bound, float dt_gamma,
+                                                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                          uint32_t M, const float* __restrict__ nears,
+                                                          const float* __restrict__ noises,
+                                                          const int32_t* __restrict__ rays,
+                                                          const float* __restrict__ t_list, float* __restrict__ xyzs,
+                                                          float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t num_steps = (uint32_t)rays[n * 3 + 2], offset = (uint32_t)rays[n * 3 + 1];
+    if (num_steps == 0 || offset + num_steps > M) return;   // ref: raymarching.cu:418-419
+    Marcher m;
+    m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, nullptr);
+    const float t0 = m.first_t(nears[n], noises[n]);
+    const float* tl = t_list + (size_t)n * max_steps;
+    float* px = xyzs + (size_t)offset * 3;
+    float* pd = dirs + (size_t)offset * 3;
+    float2* pl = reinterpret_cast<float2*>(deltas) + offset;
+    for (uint32_t k = lane; k < num_steps; k += 32) {
+        const float t = tl[k];
+        float prev_end = t0;
+        if (k) { const float tp = tl[k - 1]; prev_end = tp + m.step_size(tp); }
+        float x, y, z, dt;
+        m.position(t, x, y, z, dt);
+        const float t_after = t + dt;
+        px[(size_t)k * 3 + 0] = x; px[(size_t)k * 3 + 1] = y; px[(size_t)k * 3 + 2] = z;
+        pd[(size_t)k * 3 + 0] = m.dx; pd[(size_t)k * 3 + 1] = m.dy; pd[(size_t)k * 3 + 2] = m.dz;
+        pl[k] = make_float2(dt, t_after - prev_end);
+    }
+}
+
+// world-space bounds of the occupied cells of all cascades, padded by one cell (single CTA: 512 KiB of bitfield).
+// One byte of the bitfield = 8 cells with consecutive Morton codes = one 2x2x2 block; a block with any bit set counts
+// as occupied. A side that reaches the scene bound is opened (+-FLT_MAX): positions are clamped to the bound
+// (raymarching.cu:366-368), so "beyond the bound" does not imply "outside the cell". occ[6] = (lo xyz, hi xyz);
+// an empty grid yields lo > hi (every ray misses).
+__global__ void __launch_bounds__(1024) k_occupied_bounds(const uint8_t* __restrict__ bitfield, uint32_t C, uint32_t H,
+                                                          float bound, float* __restrict__ occ) {
+    const float big = 3.402823466e+38f;
+    float lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+    const uint32_t bytes_per_level = H * H * H / 8, total = C * bytes_per_level;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(bitfield);
+    for (uint32_t w = threadIdx.x; w < total / 4; w += blockDim.x) {
+        const uint32_t v = __ldg(words + w);
+        if (!v) continue;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            if (!((v >> (8 * j)) & 0xffu)) continue;
+            const uint32_t byte = w * 4 + j, level = byte / bytes_per_level;
+            const uint32_t code = (byte - level * bytes_per_level) * 8;
+            const uint32_t c[3] = {compact3(code), compact3(code >> 1), compact3(code >> 2)};
+            const float mb = fminf(scalbnf(1.0f, (int)level), bound);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                lo[k] = fminf(lo[k], (((float)c[k] - 1.0f) / (float)H * 2 - 1) * mb);
+                hi[k] = fmaxf(hi[k], (((float)c[k] + 3.0f) / (float)H * 2 - 1) * mb);
+            }
+        }
+    }
+    __shared__ float red[6][32];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if (lane == 0) { red[k][wid] = lo[k]; red[3 + k][wid] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const bool is_lo = threadIdx.x < 3;
+        float v = is_lo ? big : -big;
+        for (uint32_t i = 0; i < blockDim.x / 32; i++) v = is_lo ? fminf(v, red[threadIdx.x][i]) : fmaxf(v, red[threadIdx.x][i]);
+        const float cell = fminf(scalbnf(1.0f, (int)C - 1), bound) * 2 / (float)H;   // coarsest cell
+        if (is_lo && v <= -bound + cell) v = -big;
+        if (!is_lo && v >= bound - cell) v = big;
+        occ[threadIdx.x] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,6 +410,30 @@ int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8
     k_march_train_write<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                         nears, fars, noises, rays, xyzs, dirs, deltas);
     return check_launch("march_rays_train");
+}
+
+int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float* occ_aabb, void* stream) {
+    PNERF_REQUIRE(bitfield && occ_aabb && C >= 1 && C <= 16 && H >= 2 && bound > 0.f);
+    if (H > 1024 || ((uint64_t)H * H * H) % 32 != 0) return PNERF_ERR_UNSUPPORTED;
+    k_occupied_bounds<<<1, 1024, 0, (cudaStream_t)stream>>>(bitfield, C, H, bound, occ_aabb);
+    return check_launch("occupied_bounds");
+}
+
+int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                              const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                              const float* noises, float* t_list, const float* occ_aabb, void* stream) {
+    if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter && noises && t_list);
+    PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
+    if (H > 1024) return PNERF_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_march_train_count<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                        fars, noises, rays, t_list, occ_aabb);
+    k_march_train_scan<<<1, 1024, 0, s>>>(rays, N, counter);
+    k_march_train_emit<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, noises,
+                                                       rays, t_list, xyzs, dirs, deltas);
+    return check_launch("march_rays_train_ws");
 }
 
 int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,

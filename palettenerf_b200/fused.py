@@ -33,7 +33,7 @@ class PaletteField(ctypes.Structure):
 
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
-L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_fused"] = 4  # pre-pass + 2 ordering kernels + persistent kernel
 
 
@@ -179,11 +179,14 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
     aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
+    from .raymarching.raymarching import occupied_bounds
+    occ = occupied_bounds(model.density_bitfield, model.cascade, model.grid_size, model.bound) \
+        if (model.grid_size ** 3) % 32 == 0 else None
     L.call("pnerf_palette_render_fused", ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises),
            ptr(model.density_bitfield), N, model.cascade, model.grid_size, max_steps, float(dt_gamma), float(T_thresh),
            ctypes.addressof(f), ptr(acc["weights_sum"]), ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"),
            aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"), aux("unscaled_basis_rgb"),
            ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), ptr(hit_list), ptr(t_first), ptr(t_last),
-           stream())
+           ptr(occ), stream())
     acc["_queue"] = queue   # [hit-list cursor, samples shaded, rays with samples, tiles evaluated]; read lazily (no sync here)
     return acc

@@ -1,6 +1,8 @@
 """`_backend` for raymarching: the reference's pybind11 module surface (raymarching/src/bindings.cpp:5-23), same
 function names and argument order, bound to the C ABI of libpnerf_b200.so. Tensors are caller-allocated CUDA
 tensors; nothing here allocates or synchronises."""
+import torch
+
 from .. import _lib as L
 from .._lib import ptr, stream, call, require_cuda
 
@@ -37,6 +39,24 @@ class _Backend:
         require_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter, noises)
         call("pnerf_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
              ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), stream())
+
+    @staticmethod
+    def march_rays_train_ws(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
+                            rays, counter, noises, t_list, occ_aabb):
+        """one-walk variant (not in the reference): t_list [N, max_steps] scratch, occ_aabb [6] from occupied_bounds or None"""
+        require_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter, noises, t_list, occ_aabb)
+        if t_list.numel() < N * max_steps or t_list.dtype != torch.float32:
+            raise RuntimeError("t_list must hold N * max_steps floats")
+        call("pnerf_march_rays_train_ws", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
+             ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), ptr(t_list),
+             ptr(occ_aabb), stream())
+
+    @staticmethod
+    def occupied_bounds(bitfield, C, H, bound, occ_aabb):
+        require_cuda(bitfield, occ_aabb)
+        if bitfield.numel() < C * H * H * H // 8 or occ_aabb.numel() < 6 or occ_aabb.dtype != torch.float32:
+            raise RuntimeError("occupied_bounds: bitfield [C*H^3/8] uint8, occ_aabb [6] float32")
+        call("pnerf_occupied_bounds", ptr(bitfield), C, H, float(bound), ptr(occ_aabb), stream())
 
     @staticmethod
     def composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image):

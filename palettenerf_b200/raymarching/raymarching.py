@@ -97,6 +97,26 @@ class _packbits(Function):
 packbits = _packbits.apply
 
 
+_OCC_CACHE = {}          # (data_ptr, device) -> (tensor version, C, H, bound, occ_aabb)
+T_LIST_MAX_BYTES = 256 << 20
+
+
+def occupied_bounds(density_bitfield, C, H, bound):
+    """[6] world-space bounds of the occupied cells (pnerf_occupied_bounds), cached until the bitfield tensor is
+    written again (torch bumps `_version` on every in-place write, e.g. packbits into the same buffer)."""
+    key = (density_bitfield.data_ptr(), str(density_bitfield.device))
+    tag = (density_bitfield._version, C, H, float(bound))
+    hit = _OCC_CACHE.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    occ = torch.empty(6, dtype=torch.float32, device=density_bitfield.device)
+    _backend.occupied_bounds(density_bitfield, C, H, bound, occ)
+    if len(_OCC_CACHE) > 64:
+        _OCC_CACHE.clear()
+    _OCC_CACHE[key] = (tag, occ)
+    return occ
+
+
 class _march_rays_train(Function):
     @staticmethod
     @_fwd32
@@ -128,8 +148,18 @@ class _march_rays_train(Function):
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         noises = torch.rand(N, dtype=dt, device=dev) if perturb else torch.zeros(N, dtype=dt, device=dev)
-        _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
-                                  xyzs, dirs, deltas, rays, step_counter, noises)
+        # (a backend with only the reference's surface, e.g. the reference's own extension swapped in by the perf test,
+        # takes the two-walk entry point)
+        if hasattr(_backend, "march_rays_train_ws") and N * max_steps * 4 <= T_LIST_MAX_BYTES and (H * H * H) % 32 == 0:
+            # one walk of the grid: the counting pass records the sample parameters (scratch) and stops at the occupied bounds
+            from ..arena import ARENA
+            t_list = ARENA.get("march_t_list", (N * max_steps,), torch.float32, dev)
+            occ = occupied_bounds(density_bitfield, C, H, bound)
+            _backend.march_rays_train_ws(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
+                                         xyzs, dirs, deltas, rays, step_counter, noises, t_list, occ)
+        else:
+            _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
+                                      xyzs, dirs, deltas, rays, step_counter, noises)
         if static:
             return xyzs, dirs, deltas, rays
         if force_all_rays or mean_count <= 0:

@@ -9,6 +9,7 @@ from conftest import load_ref
 from palettenerf_b200 import synthetic as S
 from palettenerf_b200.raymarching.backend import _backend as B
 import palettenerf_b200.raymarching as rm
+from palettenerf_b200.raymarching.raymarching import occupied_bounds as _occupied_bounds
 
 pytestmark = pytest.mark.gpu
 
@@ -87,6 +88,11 @@ def test_march_rays_train_bit_exact_vs_oracle_and_reference(cuda, scene, cfg):
         return xyzs.cpu().numpy(), dirs.cpu().numpy(), deltas.cpu().numpy(), rays.cpu().numpy(), counter.cpu().numpy()
 
     x, dr, dl, rays, cnt = run(B)
+    # the one-walk schedule (t-list + occupied bounds, pnerf_march_rays_train_ws) must give the same bits
+    for use_occ in (False, True):
+        got = run(_WsBackend(use_occ, cuda))
+        for a, b in zip(got, (x, dr, dl, rays, cnt)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"one-walk march differs (occupied bounds: {use_occ})"
     ox, odr, odl, orays, ocnt = oracle.march_rays_train(o.numpy(), d.numpy(), bitfield.numpy(), bound, cfg["dt_gamma"],
                                                         cfg["max_steps"], C, H, M, nears, fars, noises.numpy())
     assert np.array_equal(cnt, ocnt) and cnt[1] == N and cnt[0] == rays[:, 2].sum()
@@ -106,6 +112,94 @@ def test_march_rays_train_bit_exact_vs_oracle_and_reference(cuda, scene, cfg):
             for a, b in ((x, rx), (dr, rdr), (dl, rdl)):
                 ga, gb = _gather_samples(a, ns, M), _gather_samples(b, rs, M)
                 assert np.array_equal(ga.view(np.uint32), gb.view(np.uint32))
+
+
+class _WsBackend:
+    """pnerf_march_rays_train_ws behind the reference's march_rays_train signature"""
+
+    def __init__(self, use_occ, dev):
+        self.use_occ, self.dev = use_occ, dev
+
+    def march_rays_train(self, o, d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays,
+                         counter, noises):
+        t_list = torch.full((N * max_steps,), float("nan"), device=self.dev)
+        occ = None
+        if self.use_occ:
+            occ = torch.empty(6, device=self.dev)
+            B.occupied_bounds(grid, C, H, bound, occ)
+        B.march_rays_train_ws(o, d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays,
+                              counter, noises, t_list, occ)
+
+
+def _np_occupied_bounds(bitfield, C, H, bound):
+    """numpy restatement of k_occupied_bounds (2x2x2 blocks, one cell of padding, sides at the bound opened)"""
+    big = np.float32(3.402823466e+38)
+    lo, hi = np.full(3, big, np.float32), np.full(3, -big, np.float32)
+    per = H ** 3 // 8
+    for level in range(C):
+        nz = np.nonzero(bitfield[level * per:(level + 1) * per])[0].astype(np.uint32)
+        if nz.size == 0:
+            continue
+        c = oracle.morton3D_invert((nz * 8).astype(np.int32)).astype(np.float32)
+        mb = np.float32(min(2.0 ** level, bound))
+        lo = np.minimum(lo, ((((c - 1) / np.float32(H)) * 2 - 1) * mb).min(axis=0))
+        hi = np.maximum(hi, ((((c + 3) / np.float32(H)) * 2 - 1) * mb).max(axis=0))
+    cell = np.float32(min(2.0 ** (C - 1), bound) * 2 / H)
+    lo = np.where(lo <= -np.float32(bound) + cell, -big, lo)
+    hi = np.where(hi >= np.float32(bound) - cell, big, hi)
+    return np.concatenate([lo, hi]).astype(np.float32)
+
+
+def test_occupied_bounds_vs_numpy(cuda, scene):
+    bf = scene["bitfield"]
+    occ = torch.empty(6, device=cuda)
+    B.occupied_bounds(bf.to(cuda), 2, 128, 2.0, occ)
+    exp = _np_occupied_bounds(bf.numpy(), 2, 128, 2.0)
+    assert np.allclose(occ.cpu().numpy(), exp, rtol=1e-6, atol=1e-6)
+    assert (occ[:3] < -0.2).all() and (occ[3:] > 0.2).all() and (occ.abs() < 1.0).all()   # lego-shaped solid, well inside
+    # empty grid: lo > hi on every axis, and the wrapper cache follows in-place writes of the bitfield
+    z = torch.zeros_like(bf).to(cuda)
+    o1 = _occupied_bounds(z, 2, 128, 2.0)
+    assert (o1[:3] > o1[3:]).all()
+    z[12345] = 255
+    o2 = _occupied_bounds(z, 2, 128, 2.0)
+    assert (o2[:3] < o2[3:]).all() and o2 is not o1
+
+
+@pytest.mark.parametrize("seed,dt_gamma", [(0, 0.0), (1, 1.0 / 128), (2, 0.0)])
+def test_one_walk_march_on_scattered_occupancy_touching_the_bound(cuda, seed, dt_gamma):
+    """adversarial grid: sparse random cells in both cascades INCLUDING the faces of the scene bound (where positions are
+    clamped) — the occupied-bounds clip and the t-list writer must not change a single bit of the march"""
+    g = torch.Generator().manual_seed(seed)
+    H, C, bound = 128, 2, 2.0
+    bf = torch.zeros(C * H ** 3 // 8, dtype=torch.uint8)
+    idx = torch.randint(0, bf.numel(), (400,), generator=g)
+    bf[idx] = torch.randint(1, 256, (400,), generator=g).to(torch.uint8)
+    if seed == 2:   # cluster only: tight bounds, most of every ray is tail
+        bf.zero_()
+        coords = torch.randint(60, 70, (300, 3), generator=g).int()
+        codes = torch.from_numpy(oracle.morton3D(coords.numpy())).long()
+        bf[codes // 8] = 255
+    o, d = _rays(64, az=75.0)
+    N = o.shape[0]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = oracle.near_far_from_aabb(o.numpy(), d.numpy(), aabb, 0.05)
+    noises = torch.rand(N, generator=g)
+    M = N * 256
+
+    def run(backend):
+        xyzs = torch.zeros(M, 3, device=cuda); dirs = torch.zeros(M, 3, device=cuda); deltas = torch.zeros(M, 2, device=cuda)
+        rays = torch.empty(N, 3, dtype=torch.int32, device=cuda); counter = torch.zeros(2, dtype=torch.int32, device=cuda)
+        backend.march_rays_train(o.to(cuda), d.to(cuda), bf.to(cuda), bound, dt_gamma, 1024, N, C, H, M,
+                                 torch.from_numpy(nears).to(cuda), torch.from_numpy(fars).to(cuda), xyzs, dirs, deltas, rays,
+                                 counter, noises.to(cuda))
+        return [t.cpu().numpy() for t in (xyzs, dirs, deltas, rays, counter)]
+
+    base = run(B)
+    assert base[4][0] > 0
+    for use_occ in (False, True):
+        for a, b in zip(run(_WsBackend(use_occ, cuda)), base):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 def test_march_rays_train_overflow_drops_rays_like_reference(cuda, scene):
