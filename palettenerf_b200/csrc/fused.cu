@@ -25,7 +25,14 @@
 #include "fused_common.cuh"
 
 #ifndef PNERF_GATHER_LV
-#define PNERF_GATHER_LV 1     // levels per gather iteration (x 2 tables x 8 corners loads in flight per lane)
+#define PNERF_GATHER_LV 2     // levels per gather iteration (x 8 corners x 8 B loads in flight per lane); A/B on B200 at
+                              // 800x800: LV 1 7.47 ms, LV 2 7.30 ms, LV 4 7.99 ms per view (profiles/README.md)
+#endif
+
+#ifdef PNERF_TILE_UNROLL
+#define PNERF_TILE_LOOP _Pragma("unroll")
+#else
+#define PNERF_TILE_LOOP _Pragma("unroll 1")
 #endif
 
 namespace pnerf {
@@ -56,7 +63,7 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
         gather_features((const __half*)f.table_sigma, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
     }
     __syncwarp();
-#pragma unroll 1
+PNERF_TILE_LOOP
     for (int t = 0; t < 2; t++) {
         uint32_t a2[2][4];
         ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
@@ -98,7 +105,7 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
         for (int i = 0; i < 8; i++) reinterpret_cast<__half2*>(ws.feat[lane])[i] = __floats2half2_rn(sh[2 * i], sh[2 * i + 1]);
     }
     __syncwarp();
-#pragma unroll 1
+PNERF_TILE_LOOP
     for (int t = 0; t < 2; t++) {
         uint32_t a2[2][4];
         ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
@@ -126,7 +133,7 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
         gather_features((const __half*)f.table_palette, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
     }
     __syncwarp();
-#pragma unroll 1
+PNERF_TILE_LOOP
     for (int t = 0; t < 2; t++) {
         uint32_t a3[3][4];
         ldmatrix_a(a3[0], &ws.feat[0][0], 16 * t, 0, lane);
@@ -158,7 +165,7 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
             gather_features((const __half*)f.table_clip, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
         }
         __syncwarp();
-#pragma unroll 1
+PNERF_TILE_LOOP
         for (int t = 0; t < 2; t++) {
             uint32_t a2[2][4];
             ldmatrix_a(a2[0], &ws.feat[0][0], 16 * t, 0, lane);
@@ -299,6 +306,39 @@ constexpr int kLptBuckets = 32;          // buckets of 16 samples; rays with > 4
 constexpr int kQueueHist = 4, kQueueCursor = 4 + kLptBuckets;
 __device__ __forceinline__ uint32_t lpt_bucket(uint32_t count) { return min((uint32_t)kLptBuckets - 1u, (count - 1u) >> 4); }
 
+// candidates: rays that hit the scene box and (when the occupied bounds are known) the bounds of the occupied cells —
+// 21 % of an object-centred 800x800 view. They are compacted (warp-aggregated append, cursor in queue[0]) so that the
+// thread-per-ray walk of the pre-pass runs on full warps; every other ray gets ray_count = 0 here.
+__global__ void __launch_bounds__(256) k_ray_candidates(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                        const float* __restrict__ nears, const float* __restrict__ fars,
+                                                        uint32_t N, const float* __restrict__ occ,
+                                                        int32_t* __restrict__ cand, int32_t* __restrict__ ray_count,
+                                                        unsigned int* __restrict__ queue) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    bool keep = false;
+    if (n < N) {
+        ray_count[n] = 0;
+        const float near = nears[n], far = fars[n];
+        keep = near < far;
+        if (keep && occ) {
+            const float ox = rays_o[(size_t)n * 3], oy = rays_o[(size_t)n * 3 + 1], oz = rays_o[(size_t)n * 3 + 2];
+            const float dx = rays_d[(size_t)n * 3], dy = rays_d[(size_t)n * 3 + 1], dz = rays_d[(size_t)n * 3 + 2];
+            Marcher m;
+            m.ox = ox; m.oy = oy; m.oz = oz; m.dx = dx; m.dy = dy; m.dz = dz;
+            m.rdx = 1 / dx; m.rdy = 1 / dy; m.rdz = 1 / dz;
+            keep = near < m.occupied_exit(occ);
+        }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+    if (mask) {
+        uint32_t base = 0;
+        const uint32_t leader = __ffs(mask) - 1;
+        if (lane == leader) base = atomicAdd(queue, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) cand[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)n;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                      const float* __restrict__ nears, const float* __restrict__ fars,
                                                      const float* __restrict__ noises, const uint8_t* __restrict__ bitfield,
@@ -307,12 +347,16 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
                                                      int32_t* __restrict__ ray_count, float* __restrict__ t_first,
                                                      float* __restrict__ t_last, unsigned int* __restrict__ queue,
                                                      const float* __restrict__ occ) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    // thread i walks candidate i (k_ray_candidates; the list occupies the front of hit_list until k_lpt_scatter
+    // overwrites it with the ordered hit list)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
+    const bool work = i < min(N, queue[0]);
+    const uint32_t n = work ? (uint32_t)hit_list[i] : 0u;
     bool hit = false;
     float tf = 0.f, tl = 0.f;
     uint32_t count = 0;
-    if (n < N) {
+    if (work) {
         Marcher m;
         m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, bitfield);
         // The walk below is the reference's inference schedule with n_step = 1: after every sample the march
@@ -349,7 +393,7 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
     __shared__ unsigned int hist_s[kLptBuckets];
     if (threadIdx.x < kLptBuckets) hist_s[threadIdx.x] = 0u;
     __syncthreads();
-    if (n < N) {
+    if (work) {
         ray_count[n] = (int32_t)count;
         if (hit) {
             t_first[n] = tf;
@@ -359,7 +403,7 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
     }
     __syncthreads();
     if (threadIdx.x < kLptBuckets && hist_s[threadIdx.x]) atomicAdd(queue + kQueueHist + threadIdx.x, hist_s[threadIdx.x]);
-    (void)lane; (void)hit_list;
+    (void)lane;
 }
 
 // one warp: descending exclusive scan of the bucket histogram -> per-bucket write cursors; total -> queue[2]
@@ -373,7 +417,10 @@ __global__ void k_lpt_offsets(unsigned int* __restrict__ queue) {
         if (lane + o < 32) suffix += v;
     }
     queue[kQueueCursor + lane] = suffix - h;      // rays in longer buckets come first
-    if (lane == 0) queue[2] = suffix;             // number of rays with at least one sample
+    if (lane == 0) {
+        queue[2] = suffix;                        // number of rays with at least one sample
+        queue[0] = 0u;                            // was the candidate cursor of the pre-pass; now the hit-list cursor
+    }
 }
 
 __global__ void __launch_bounds__(256) k_lpt_scatter(const int32_t* __restrict__ ray_count, uint32_t N,
@@ -850,6 +897,7 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
     a.hit_list = hit_list; a.t_first = t_first; a.t_last = t_last;
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* ray_count = hit_list + N;       // second half of the scratch: samples per ray
+    k_ray_candidates<<<ceil_div(N, 256u), 256, 0, s>>>(rays_o, rays_d, nears, fars, N, occ_aabb, hit_list, ray_count, queue);
     k_ray_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, N, C, Hgrid, max_steps,
                                                     field->bound, dt_gamma, hit_list, ray_count, t_first, t_last, queue, occ_aabb);
     k_lpt_offsets<<<1, 32, 0, s>>>(queue);

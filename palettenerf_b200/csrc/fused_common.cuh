@@ -88,6 +88,20 @@ __device__ __forceinline__ void ldmatrix_a(uint32_t (&a)[4], const __half* tile,
 template <int KS, int NT>
 __device__ __forceinline__ void mma_layer(const uint2* __restrict__ w, const uint32_t (&a)[KS][4], float (&c)[NT][4],
                                           int lane) {
+#ifdef PNERF_MMA_KS_OUTER
+    // k-step outer: consecutive MMAs go to different accumulators (no back-to-back dependent HMMAs); every accumulator
+    // still sums its k-steps in the order 0..KS-1, so the result is bit-identical to the n-tile-outer order
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            const uint2 b = w[(nt * KS + ks) * 32 + lane];
+            mma16816(c[nt], a[ks], b.x, b.y);
+        }
+    }
+#else
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
         c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
@@ -97,6 +111,7 @@ __device__ __forceinline__ void mma_layer(const uint2* __restrict__ w, const uin
             mma16816(c[nt], a[ks], b.x, b.y);
         }
     }
+#endif
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {

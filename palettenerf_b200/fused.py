@@ -34,7 +34,7 @@ class PaletteField(ctypes.Structure):
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
 L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
-L.LAUNCHES["pnerf_palette_render_fused"] = 4  # pre-pass + 2 ordering kernels + persistent kernel
+L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 ordering kernels + persistent kernel
 
 
 def _frag(W, n_pad, k_pad):

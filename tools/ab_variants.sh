@@ -1,7 +1,10 @@
-python -m pytest tests/test_fused_gpu.py tests/test_render_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/ab_pytest.log
-for v in main w12_lv2 w16_lv1 w16_lv2; do
+#!/bin/bash
+# A/B of library variants built with PNERF_LIB_OUT / PNERF_EXTRA_NVCC_FLAGS (palettenerf_b200/build.py):
+# usage (under gpurun): bash tools/ab_variants.sh <variant> [<variant> ...]   ("main" = the in-tree library)
+mkdir -p gpurun_out
+for v in "$@"; do
   if [ $v = main ]; then lib=palettenerf_b200/libpnerf_b200.so; else lib=palettenerf_b200/variants/lib_$v.so; fi
-  PNERF_LIB=$PWD/$lib python bench.py --no-extras --steps 5 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  PNERF_LIB=$PWD/$lib python bench.py --no-extras --steps 10 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<P
 import json
 try:
@@ -10,4 +13,3 @@ try:
 except Exception as e: print("$v failed", e)
 P
 done
-cat gpurun_out/ab_pytest.log

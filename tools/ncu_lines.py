@@ -6,7 +6,11 @@ import csv, io, re, subprocess, sys, collections, os, tempfile
 def main(rep, obj, kern, top=45):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # a report with several kernels prints one table per kernel: NCU_TABLE picks it (0-based, default the first)
+    heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    which = int(os.environ.get("NCU_TABLE", "0"))
+    hi = heads[which]
+    rows = rows[: heads[which + 1]] if which + 1 < len(heads) else rows
     hdr = rows[hi]
     ia, ie, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
