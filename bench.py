@@ -283,7 +283,10 @@ def main():
             "frac": hg["fwd_f16_eff_gbs"] / hbm_peak, "hbm_only_gbs": hg["fwd_f16_hbm_gbs"],
             "traffic": _ncu_traffic("k_grid_fwd_d3c2_f16"),
             "algorithmic": "588 B/point (12 xyz + 16 levels x 8 corners x 4 B gathered + 64 out) x 2^22 points; the table is "
-                           "L2-resident, compulsory HBM bytes are 76 B/point (hbm_only_gbs)"}
+                           "L2-resident, compulsory HBM bytes are 76 B/point (hbm_only_gbs)",
+            "ncu": _ncu_entry("k_grid_fwd_d3c2_f16"),
+            "note": "random points: every gather instruction touches 32 different sectors, the kernel sits on the L1/TEX "
+                    "pipe (ncu l1tex throughput, see the ncu entry) with L2 close behind, not on HBM"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and "cpu" in sections:
@@ -304,6 +307,16 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ncu_entry(kernel):
+    """the committed ncu figures of `kernel` (profiles/traffic.json) or None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        e = json.load(open(p)).get(kernel)
+        return {k: v for k, v in e.items() if k != "source"} if e else None
+    except Exception:
+        return None
 
 
 def _ncu_traffic(kernel):
