@@ -72,7 +72,13 @@ class GradBucket:
             flat[off:off + k].copy_(p.grad.reshape(-1))
             off += k
         # the flag rides in the same bucket; it is summed, so any rank's inf makes it non-zero everywhere
-        flat[off] = 0.0 if found_inf is None else float(found_inf)
+        # (device-side writes only: a Python scalar assignment is a host->device copy, which a CUDA-graph capture rejects)
+        if found_inf is None:
+            flat[off:off + 1].zero_()
+        elif torch.is_tensor(found_inf):
+            flat[off:off + 1].copy_(found_inf.reshape(1).to(torch.float32))
+        else:
+            flat[off:off + 1].fill_(float(found_inf))
         if ws > 1:
             dist.all_reduce(flat, group=group)
         flag = flat[off].clone()

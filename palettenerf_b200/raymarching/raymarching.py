@@ -6,6 +6,8 @@ Same twelve callables with the same positional signatures, dtypes and in-place c
     atomicAdd race) — `rays[i] == (i, offset_i, count_i)`;
   * no torch.cuda.empty_cache() after marching (raymarching.py:231) — it only defeats the caching allocator.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
@@ -97,23 +99,30 @@ class _packbits(Function):
 packbits = _packbits.apply
 
 
-_OCC_CACHE = {}          # (data_ptr, device) -> (tensor version, C, H, bound, occ_aabb)
+_OCC_CACHE = {}          # data_ptr -> (weakref to the bitfield tensor, (version, C, H, bound), occ_aabb)
 T_LIST_MAX_BYTES = 256 << 20
 
 
 def occupied_bounds(density_bitfield, C, H, bound):
-    """[6] world-space bounds of the occupied cells (pnerf_occupied_bounds), cached until the bitfield tensor is
-    written again (torch bumps `_version` on every in-place write, e.g. packbits into the same buffer)."""
-    key = (density_bitfield.data_ptr(), str(density_bitfield.device))
+    """[6] world-space bounds of the occupied cells (pnerf_occupied_bounds), cached per bitfield TENSOR OBJECT until it is
+    written again (torch bumps `_version` on every in-place write, e.g. packbits into the same buffer). The entry holds
+    a weak reference: a different tensor that happens to reuse the address of a freed one never hits."""
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the kernel is recorded: every replay recomputes the bounds from the live bitfield
+        # (a cached tensor would go stale when the density grid is refreshed between replays)
+        occ = torch.empty(6, dtype=torch.float32, device=density_bitfield.device)
+        _backend.occupied_bounds(density_bitfield, C, H, bound, occ)
+        return occ
+    key = density_bitfield.data_ptr()
     tag = (density_bitfield._version, C, H, float(bound))
     hit = _OCC_CACHE.get(key)
-    if hit is not None and hit[0] == tag:
-        return hit[1]
+    if hit is not None and hit[0]() is density_bitfield and hit[1] == tag:
+        return hit[2]
     occ = torch.empty(6, dtype=torch.float32, device=density_bitfield.device)
     _backend.occupied_bounds(density_bitfield, C, H, bound, occ)
     if len(_OCC_CACHE) > 64:
         _OCC_CACHE.clear()
-    _OCC_CACHE[key] = (tag, occ)
+    _OCC_CACHE[key] = (weakref.ref(density_bitfield), tag, occ)
     return occ
 
 
