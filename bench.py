@@ -123,6 +123,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
     ap.add_argument("--sections", default="hashgrid,train,mip360,cpu",
                     help="extra sections to run (comma list of hashgrid,train,mip360,cpu)")
+    ap.add_argument("--torch-loss", action="store_true", help="training sections: the loss as torch tensor expressions "
+                    "instead of palette_loss (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
     ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
@@ -267,7 +269,7 @@ def main():
     if "train" in sections:
         try:
             extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush,
-                                      use_graph=not args.no_graph))
+                                      use_graph=not args.no_graph, torch_loss=args.torch_loss))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if "mip360" in sections:
@@ -372,7 +374,7 @@ def bench_hashgrid(torch, dev, L, hbm_peak, flush):
     return {"hashgrid": res}
 
 
-def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True):
+def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True, torch_loss=False):
     """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
     GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1.
     The step (static-capacity march, fused field fwd/bwd/wgrad, one-pass compositor, loss, all-reduce, GradScaler, fused
@@ -389,9 +391,15 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
     gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
 
+    from palettenerf_b200.palette.losses import palette_loss
+
     def loss_fn(out):
-        return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
-            + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+        # PaletteTrainer.train_step's loss (palette/utils.py:486-567: rgb + direct rgb + the three regularisers with the
+        # reference's default lambdas) in one kernel; the palette term is off (lambda_palette = 0 until basis colours unfreeze)
+        if torch_loss:
+            return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
+                + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+        return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1)[0]
 
     step_fn = make_palette_train_step(model, opt, scaler, o, d, loss_fn, bucket=bucket)
     mode = "eager"
@@ -421,6 +429,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
                       "optimizer": "Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler",
+                      "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
 
@@ -469,10 +478,10 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
     gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=g)
     feat = torch.randn(1, TRAIN_RAYS, 16, device=dev, generator=g)
 
+    from palettenerf_b200.palette.losses import palette_loss
+
     def loss_fn(out):
-        return ((out["image"] - gt) ** 2).mean() + ((out["direct_rgb"] - gt) ** 2).mean() \
-            + ((out["clip_feat"] - feat) ** 2).mean() \
-            + 2e-4 * out["omega_sparsity"].mean() + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean()
+        return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1, gt_clip_feat=feat)[0]
     step_fn = make_palette_train_step(tm, opt, scaler, to, td, loss_fn, render_kwargs=dict(dt_gamma=DTG))
     gs = GraphedStep(step_fn, warmup=3)
     for _ in range(3):

@@ -95,9 +95,11 @@ PNERF_API int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d
                                         float* deltas, int32_t* rays, int32_t* counter, const float* noises,
                                         float* t_list, const float* occ_aabb, void* stream);
 
-/* occ_aabb[6] (device) = (lo xyz, hi xyz): world-space bounds of every occupied cell of the C cascades of `bitfield`
+/* occ_aabb[0..6) (device) = (lo xyz, hi xyz): world-space bounds of every occupied cell of the C cascades of `bitfield`
  * ([C*H^3/8] bytes, Morton order, as packbits writes it), padded by one cell; a side reaching the scene bound is
- * +-FLT_MAX; an empty grid gives lo > hi. One small single-CTA kernel; recompute when the bitfield changes. */
+ * +-FLT_MAX; an empty grid gives lo > hi. The buffer must hold pnerf_occupied_bounds_floats() floats (the tail is
+ * scratch for the per-CTA partial bounds). Two small launches; recompute when the bitfield changes. */
+PNERF_API uint32_t pnerf_occupied_bounds_floats(void);
 PNERF_API int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float* occ_aabb,
                                     void* stream);
 
@@ -325,6 +327,40 @@ PNERF_API int pnerf_grid_encode_backward_ws(const void* grad, const float* input
 PNERF_API int pnerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                              const int64_t* inds, uint64_t inds_batch_stride, uint32_t N, uint32_t B, float* rays_o,
                              float* rays_d, const float* aabb, float min_near, float* nears, float* fars, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * per-ray losses of the palette training step  (ref: PaletteTrainer.train_step, palette/utils.py:486-567)
+ * One pass over the inputs computes the gradient of every input (for an upstream gradient of 1) and per-CTA partial
+ * sums; a second tiny launch reduces them in a fixed order to the loss and its terms (deterministic).
+ *   image, direct_rgb, gt_rgb [N,3]; maps [N, stride] = the renderer's channel-composite output, whose columns hold the
+ *   regulariser maps (col_sparsity / col_offsets / col_view_dep / col_smooth: one column each), the semantic feature
+ *   (col_clip .. +clip_dim, with gt_clip [N,clip_dim]) and the blending weights (col_basis .. +num_basis, with
+ *   gt_weights [N,num_basis]); a column index of -1 switches the term off. basis_color / basis_color_origin
+ *   [num_basis,3] (NULL: no palette term).
+ *   terms [10] = total, rgb, direct, clip, sparsity, offsets, view_dep, smooth, weight, palette (lambda-weighted, as
+ *   the reference's loss_dict); per_ray [N] (optional) = mean_c (image - gt)^2, the error-map quantity (:590).
+ *   g_image, g_direct [N,3], g_maps [N, stride] (every column written; zero where no term reads), g_basis_color.
+ * pnerf_scale_buffers: b_i[0..n_i) *= *scale (device scalar) for up to four buffers, one launch (the loss backward).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pnerf_palette_loss_args {
+    const float* image; const float* direct_rgb; const float* gt_rgb;
+    const float* maps; uint32_t stride;
+    int32_t col_sparsity, col_offsets, col_view_dep, col_smooth, col_clip, col_basis;
+    uint32_t clip_dim, num_basis;
+    const float* gt_clip; const float* gt_weights;
+    const float* basis_color; const float* basis_color_origin;
+    float lambda_sparsity, lambda_offsets, lambda_view_dep, lambda_smooth, lambda_weight, lambda_palette;
+    uint32_t N;
+    float* terms; float* per_ray;
+    float* g_image; float* g_direct; float* g_maps; float* g_basis_color;
+    float* partials;   /* scratch, pnerf_palette_loss_partials(N) floats, contents ignored */
+} pnerf_palette_loss_args;
+
+PNERF_API uint32_t pnerf_palette_loss_partials(uint32_t N);
+
+PNERF_API int pnerf_palette_loss(const pnerf_palette_loss_args* args, void* stream);
+PNERF_API int pnerf_scale_buffers(float* b0, uint32_t n0, float* b1, uint32_t n1, float* b2, uint32_t n2, float* b3,
+                                  uint32_t n3, const float* scale, void* stream);
 
 #ifdef __cplusplus
 }

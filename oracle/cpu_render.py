@@ -238,3 +238,33 @@ def train_forward_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=1
     maps = O.composite_rays_flex_train_forward(sig, buf.numpy(), deltas, rays, T_thresh)
     return dict(image=image + (1 - ws)[:, None] * bg_color, depth=np.clip(depth - nears, 0, None) / (fars - nears),
                 weights_sum=ws, maps=maps, n_samples=int(counter[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-ray losses of the palette training step (TEST INFRASTRUCTURE; restates palette/utils.py:486-567 in torch)
+# ---------------------------------------------------------------------------------------------------------------
+def palette_train_loss(outputs, gt_rgb, lambda_sparsity=0.0, lambda_offsets=0.0, lambda_view_dep=0.0, lambda_smooth=0.0,
+                       gt_clip_feat=None, gt_weights=None, lambda_weight=0.0, basis_color=None, basis_color_origin=None,
+                       lambda_palette=0.0):
+    """PaletteTrainer.train_step after model.render, expression by expression (criterion = MSELoss(reduction='none'),
+    palette/utils.py:334): returns (loss, loss_dict, per_ray) where per_ray is `loss` before the final .mean() minus the
+    broadcast scalar terms, i.e. the rgb error the error map stores. Parity of this restatement is unpinned by the
+    reference (the trainer cannot be imported here: tensorboardX / lpips / torch_ema are absent) — it is arithmetic on
+    [N]-sized tensors, checked against autograd."""
+    pred_rgb = outputs["image"]
+    loss = ((pred_rgb - gt_rgb) ** 2).mean(-1)                                   # :486  [B, N]
+    per_ray = loss.detach().clone()
+    d = {}
+    d["direct"] = ((outputs["direct_rgb"] - gt_rgb) ** 2).mean()                 # :487
+    d["clip_feat"] = ((outputs["clip_feat"] - gt_clip_feat) ** 2).mean() if gt_clip_feat is not None else 0.0   # :490-492
+    d["sparsity"] = lambda_sparsity * outputs["omega_sparsity"].mean()           # :521-522, 546
+    d["offsets"] = lambda_offsets * outputs["offsets_norm"].mean()               # :524-525, 549
+    d["view_dep"] = lambda_view_dep * outputs["view_dep_norm"].mean()            # :527-528, 552
+    d["smooth"] = lambda_smooth * outputs["smooth_norm"].mean() if lambda_smooth != 0.0 else 0.0   # :538-542, 555
+    d["weight"] = lambda_weight * ((gt_weights - outputs["basis_acc"]) ** 2).mean() if gt_weights is not None else 0.0  # :532-536
+    d["palette"] = lambda_palette * ((basis_color - basis_color_origin) ** 2).sum(dim=-1).mean() \
+        if basis_color is not None else 0.0                                      # :544, 561
+    for k in ("sparsity", "offsets", "view_dep", "smooth", "palette", "weight", "direct", "clip_feat"):   # order of :546-571
+        loss = loss + d[k]
+    d["rgb"] = per_ray.mean()
+    return loss.mean(), d, per_ray                                               # :598

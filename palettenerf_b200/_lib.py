@@ -102,7 +102,8 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim and per-kernel CUDA-event timing)
-LAUNCHES = {"pnerf_march_rays_train": 3, "pnerf_march_rays_train_ws": 3, "pnerf_grid_encode_backward_ws": 2}
+LAUNCHES = {"pnerf_march_rays_train": 3, "pnerf_march_rays_train_ws": 3, "pnerf_grid_encode_backward_ws": 2,
+            "pnerf_occupied_bounds": 2}
 launch_count = 0
 _profile = None  # when set: dict name -> [list of (start_event, end_event), units]
 

@@ -239,18 +239,21 @@ __global__ void __launch_bounds__(256) k_march_train_emit(const float* __restric
     }
 }
 
-// world-space bounds of the occupied cells of all cascades, padded by one cell (single CTA: 512 KiB of bitfield).
+// world-space bounds of the occupied cells of all cascades, padded by one cell. Two launches: kOccBlocks CTAs scan the
+// bitfield (512 KiB at C = 2, H = 128) and leave per-CTA bounds in the scratch part of occ; one CTA reduces them.
 // One byte of the bitfield = 8 cells with consecutive Morton codes = one 2x2x2 block; a block with any bit set counts
 // as occupied. A side that reaches the scene bound is opened (+-FLT_MAX): positions are clamped to the bound
-// (raymarching.cu:366-368), so "beyond the bound" does not imply "outside the cell". occ[6] = (lo xyz, hi xyz);
-// an empty grid yields lo > hi (every ray misses).
-__global__ void __launch_bounds__(1024) k_occupied_bounds(const uint8_t* __restrict__ bitfield, uint32_t C, uint32_t H,
-                                                          float bound, float* __restrict__ occ) {
+// (raymarching.cu:366-368), so "beyond the bound" does not imply "outside the cell". occ[0..6) = (lo xyz, hi xyz);
+// an empty grid yields lo > hi (every ray misses). occ[6 .. 6 + 6 kOccBlocks) is scratch.
+constexpr int kOccBlocks = kNumSMs;
+
+__global__ void __launch_bounds__(256) k_occupied_bounds_scan(const uint8_t* __restrict__ bitfield, uint32_t C, uint32_t H,
+                                                               float bound, float* __restrict__ occ) {
     const float big = 3.402823466e+38f;
     float lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
     const uint32_t bytes_per_level = H * H * H / 8, total = C * bytes_per_level;
     const uint32_t* words = reinterpret_cast<const uint32_t*>(bitfield);
-    for (uint32_t w = threadIdx.x; w < total / 4; w += blockDim.x) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total / 4; w += gridDim.x * blockDim.x) {
         const uint32_t v = __ldg(words + w);
         if (!v) continue;
 #pragma unroll
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(1024) k_occupied_bounds(const uint8_t* __restr
             }
         }
     }
-    __shared__ float red[6][32];
+    __shared__ float red[6][8];
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -283,10 +286,30 @@ __global__ void __launch_bounds__(1024) k_occupied_bounds(const uint8_t* __restr
         const bool is_lo = threadIdx.x < 3;
         float v = is_lo ? big : -big;
         for (uint32_t i = 0; i < blockDim.x / 32; i++) v = is_lo ? fminf(v, red[threadIdx.x][i]) : fmaxf(v, red[threadIdx.x][i]);
+        occ[6 + blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(192) k_occupied_bounds_finish(uint32_t C, uint32_t H, float bound, uint32_t blocks,
+                                                                 float* __restrict__ occ) {
+    const float big = 3.402823466e+38f;
+    const uint32_t lane = threadIdx.x & 31u, k = threadIdx.x >> 5;     // warp k reduces component k
+    const bool is_lo = k < 3;
+    float v = is_lo ? big : -big;
+    for (uint32_t b = lane; b < blocks; b += 32) {
+        const float p = occ[6 + b * 6 + k];
+        v = is_lo ? fminf(v, p) : fmaxf(v, p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float q = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_lo ? fminf(v, q) : fmaxf(v, q);
+    }
+    if (lane == 0) {
         const float cell = fminf(scalbnf(1.0f, (int)C - 1), bound) * 2 / (float)H;   // coarsest cell
         if (is_lo && v <= -bound + cell) v = -big;
         if (!is_lo && v >= bound - cell) v = big;
-        occ[threadIdx.x] = v;
+        occ[k] = v;
     }
 }
 
@@ -412,10 +435,13 @@ int pnerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8
     return check_launch("march_rays_train");
 }
 
+uint32_t pnerf_occupied_bounds_floats(void) { return 6u + 6u * (uint32_t)kOccBlocks; }
+
 int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float* occ_aabb, void* stream) {
     PNERF_REQUIRE(bitfield && occ_aabb && C >= 1 && C <= 16 && H >= 2 && bound > 0.f);
     if (H > 1024 || ((uint64_t)H * H * H) % 32 != 0) return PNERF_ERR_UNSUPPORTED;
-    k_occupied_bounds<<<1, 1024, 0, (cudaStream_t)stream>>>(bitfield, C, H, bound, occ_aabb);
+    k_occupied_bounds_scan<<<kOccBlocks, 256, 0, (cudaStream_t)stream>>>(bitfield, C, H, bound, occ_aabb);
+    k_occupied_bounds_finish<<<1, 192, 0, (cudaStream_t)stream>>>(C, H, bound, kOccBlocks, occ_aabb);
     return check_launch("occupied_bounds");
 }
 

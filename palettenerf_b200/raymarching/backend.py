@@ -1,10 +1,16 @@
 """`_backend` for raymarching: the reference's pybind11 module surface (raymarching/src/bindings.cpp:5-23), same
 function names and argument order, bound to the C ABI of libpnerf_b200.so. Tensors are caller-allocated CUDA
 tensors; nothing here allocates or synchronises."""
+import ctypes
+
 import torch
 
 from .. import _lib as L
 from .._lib import ptr, stream, call, require_cuda
+
+
+L.lib.pnerf_occupied_bounds_floats.restype = ctypes.c_uint32
+OCC_FLOATS = int(L.lib.pnerf_occupied_bounds_floats())
 
 
 class _Backend:
@@ -54,8 +60,8 @@ class _Backend:
     @staticmethod
     def occupied_bounds(bitfield, C, H, bound, occ_aabb):
         require_cuda(bitfield, occ_aabb)
-        if bitfield.numel() < C * H * H * H // 8 or occ_aabb.numel() < 6 or occ_aabb.dtype != torch.float32:
-            raise RuntimeError("occupied_bounds: bitfield [C*H^3/8] uint8, occ_aabb [6] float32")
+        if bitfield.numel() < C * H * H * H // 8 or occ_aabb.numel() < OCC_FLOATS or occ_aabb.dtype != torch.float32:
+            raise RuntimeError(f"occupied_bounds: bitfield [C*H^3/8] uint8, occ_aabb [{OCC_FLOATS}] float32 (6 bounds + scratch)")
         call("pnerf_occupied_bounds", ptr(bitfield), C, H, float(bound), ptr(occ_aabb), stream())
 
     @staticmethod

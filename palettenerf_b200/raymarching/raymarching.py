@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
-from .backend import _backend
+from .backend import _backend, OCC_FLOATS
 
 __all__ = ["near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
            "composite_rays_train", "composite_rays_flex_train", "march_rays", "composite_rays", "composite_rays_flex",
@@ -110,7 +110,7 @@ def occupied_bounds(density_bitfield, C, H, bound):
     if torch.cuda.is_current_stream_capturing():
         # inside a CUDA-graph capture the kernel is recorded: every replay recomputes the bounds from the live bitfield
         # (a cached tensor would go stale when the density grid is refreshed between replays)
-        occ = torch.empty(6, dtype=torch.float32, device=density_bitfield.device)
+        occ = torch.empty(OCC_FLOATS, dtype=torch.float32, device=density_bitfield.device)
         _backend.occupied_bounds(density_bitfield, C, H, bound, occ)
         return occ
     key = density_bitfield.data_ptr()
@@ -118,7 +118,7 @@ def occupied_bounds(density_bitfield, C, H, bound):
     hit = _OCC_CACHE.get(key)
     if hit is not None and hit[0]() is density_bitfield and hit[1] == tag:
         return hit[2]
-    occ = torch.empty(6, dtype=torch.float32, device=density_bitfield.device)
+    occ = torch.empty(OCC_FLOATS, dtype=torch.float32, device=density_bitfield.device)
     _backend.occupied_bounds(density_bitfield, C, H, bound, occ)
     if len(_OCC_CACHE) > 64:
         _OCC_CACHE.clear()

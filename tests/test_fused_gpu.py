@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+import oracle
 from oracle import cpu_render
 from palettenerf_b200 import fused, synthetic as S
 
@@ -123,3 +124,35 @@ def test_fused_render_early_termination_and_step_budget(cuda):
     assert q[1] < 0.25 * 17664 * (32 * 32) / (24 * 24)                  # far fewer samples than the unterminated march
     assert np.abs(fus["weights_sum"].cpu().numpy() - ref["weights_sum"]).max() < 1e-2
     assert np.abs(fus["image"][0].cpu().numpy() - ref["image"]).max() < 1e-2
+
+
+def test_fused_render_follows_in_place_bitfield_updates(cuda):
+    """the ray walks are clipped at the bounds of the occupied cells, cached per bitfield tensor: an in-place update of
+    `density_bitfield` (what update_extra_state does) must invalidate them — the fused render after the update equals
+    the loop schedule (no clip anywhere on that path) on the updated grid, and its sample count changes accordingly"""
+    m = S.build_palette_model(cuda, seed=3, pred_clip=False, table_scale=0.5)
+    m.eval()
+    o, d = S.camera_rays(40, 40)
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+
+    def both():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            f = m.render(o, d, staged=True, bg_color=1, perturb=False, gui_mode=True, fused=True)
+            n = int(m._last_queue[1].item())
+            l = m.render(o, d, staged=True, bg_color=1, perturb=False, gui_mode=True, fused=False)
+        return f, l, n
+
+    f0, l0, n0 = both()
+    assert (f0["image"] - l0["image"]).abs().max().item() < 2e-3
+    # grow the occupancy far outside the old bounds, in place: a slab of cascade-0 cells near +x
+    H = m.grid_size
+    coords = torch.stack(torch.meshgrid(torch.arange(118, 124), torch.arange(40, 90), torch.arange(40, 90), indexing="ij"), -1)
+    codes = torch.from_numpy(oracle.morton3D(coords.reshape(-1, 3).int().numpy())).long().to(cuda)
+    bf = m.density_bitfield
+    for b in range(8):      # index_put with duplicates is not an OR: set one bit plane at a time
+        sel = codes[(codes % 8) == b] // 8
+        bf[sel] = bf[sel] | (1 << b)
+    f1, l1, n1 = both()
+    assert n1 > n0, "the new cells lie outside the old occupied bounds: a stale clip would not see them"
+    assert (f1["image"] - l1["image"]).abs().max().item() < 2e-3
+    assert (f1["weights_sum"] - l1["weights_sum"]).abs().max().item() < 2e-3

@@ -7,7 +7,7 @@ import torch
 import oracle
 from conftest import load_ref
 from palettenerf_b200 import synthetic as S
-from palettenerf_b200.raymarching.backend import _backend as B
+from palettenerf_b200.raymarching.backend import _backend as B, OCC_FLOATS
 import palettenerf_b200.raymarching as rm
 from palettenerf_b200.raymarching.raymarching import occupied_bounds as _occupied_bounds
 
@@ -125,7 +125,7 @@ class _WsBackend:
         t_list = torch.full((N * max_steps,), float("nan"), device=self.dev)
         occ = None
         if self.use_occ:
-            occ = torch.empty(6, device=self.dev)
+            occ = torch.empty(OCC_FLOATS, device=self.dev)
             B.occupied_bounds(grid, C, H, bound, occ)
         B.march_rays_train_ws(o, d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays,
                               counter, noises, t_list, occ)
@@ -152,18 +152,19 @@ def _np_occupied_bounds(bitfield, C, H, bound):
 
 def test_occupied_bounds_vs_numpy(cuda, scene):
     bf = scene["bitfield"]
-    occ = torch.empty(6, device=cuda)
+    occ = torch.empty(OCC_FLOATS, device=cuda)
     B.occupied_bounds(bf.to(cuda), 2, 128, 2.0, occ)
+    occ = occ[:6]
     exp = _np_occupied_bounds(bf.numpy(), 2, 128, 2.0)
     assert np.allclose(occ.cpu().numpy(), exp, rtol=1e-6, atol=1e-6)
     assert (occ[:3] < -0.2).all() and (occ[3:] > 0.2).all() and (occ.abs() < 1.0).all()   # lego-shaped solid, well inside
     # empty grid: lo > hi on every axis, and the wrapper cache follows in-place writes of the bitfield
     z = torch.zeros_like(bf).to(cuda)
     o1 = _occupied_bounds(z, 2, 128, 2.0)
-    assert (o1[:3] > o1[3:]).all()
+    assert (o1[:3] > o1[3:6]).all()
     z[12345] = 255
     o2 = _occupied_bounds(z, 2, 128, 2.0)
-    assert (o2[:3] < o2[3:]).all() and o2 is not o1
+    assert (o2[:3] < o2[3:6]).all() and o2 is not o1
 
 
 @pytest.mark.parametrize("seed,dt_gamma", [(0, 0.0), (1, 1.0 / 128), (2, 0.0)])

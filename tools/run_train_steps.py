@@ -19,7 +19,10 @@ gt = torch.rand(1, 4096, 3, device=dev)
 step = make_palette_train_step(model, opt, scaler, o, d, lambda out: ((out["image"] - gt) ** 2).mean()
                                + ((out["direct_rgb"] - gt) ** 2).mean() + 2e-4 * out["omega_sparsity"].mean()
                                + 0.03 * out["offsets_norm"].mean() + 0.1 * out["view_dep_norm"].mean())
-for _ in range(n):
+for i in range(n):
+    if i == n - 1:
+        torch.cuda.nvtx.range_push("laststep")   # ncu --nvtx --nvtx-include "laststep/": the launches of ONE warm step
     step()
+torch.cuda.nvtx.range_pop()
 torch.cuda.synchronize()
 print("samples:", int(model.step_counter[(model.local_step - 1) % 16, 0].item()), "schedule:", model._last_train_schedule)
