@@ -125,6 +125,8 @@ def main():
                     help="extra sections to run (comma list of hashgrid,train,mip360,cpu)")
     ap.add_argument("--torch-loss", action="store_true", help="training sections: the loss as torch tensor expressions "
                     "instead of palette_loss (A/B)")
+    ap.add_argument("--torch-adam", action="store_true", help="training sections: torch.optim.Adam(fused, capturable) "
+                    "instead of palettenerf_b200.optim.FusedAdam (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
     ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
@@ -269,7 +271,7 @@ def main():
     if "train" in sections:
         try:
             extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush,
-                                      use_graph=not args.no_graph, torch_loss=args.torch_loss))
+                                      use_graph=not args.no_graph, torch_loss=args.torch_loss, torch_adam=args.torch_adam))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if "mip360" in sections:
@@ -374,7 +376,16 @@ def bench_hashgrid(torch, dev, L, hbm_peak, flush):
     return {"hashgrid": res}
 
 
-def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True, torch_loss=False):
+def _adam(torch, params, torch_adam):
+    if torch_adam:
+        return torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True), \
+            "torch Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler"
+    from palettenerf_b200.optim import FusedAdam
+    return FusedAdam(params, betas=(0.9, 0.99), eps=1e-15), "FusedAdam(0.9,0.99,1e-15: pnerf_adam_step)+GradScaler"
+
+
+def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True, torch_loss=False,
+                torch_adam=False):
     """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
     GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1.
     The step (static-capacity march, fused field fwd/bwd/wgrad, one-pass compositor, loss, all-reduce, GradScaler, fused
@@ -383,7 +394,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     from palettenerf_b200.graphs import GraphedStep, make_palette_train_step
     model = S.build_palette_model(dev, seed=0, pred_clip=False)
     model.train()
-    opt = torch.optim.Adam(model.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    opt, opt_name = _adam(torch, model.get_params(1e-2), torch_adam)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda")
     bucket = GradBucket(params) if world > 1 else None
@@ -428,7 +439,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
-                      "optimizer": "Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler",
+                      "optimizer": opt_name,
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
@@ -470,7 +481,7 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
     tm = S.build_palette_model(dev, seed=0, pred_clip=True, ground=True, scene_scale=1.5)
     tm.min_near = 0.05
     tm.train()
-    opt = torch.optim.Adam(tm.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    opt, _ = _adam(torch, tm.get_params(1e-2), False)
     scaler = torch.amp.GradScaler("cuda")
     to, td = S.training_rays(TRAIN_RAYS, H=Hm, W=Wm, seed=rank)
     to, td = to.to(dev)[None].contiguous(), td.to(dev)[None].contiguous()

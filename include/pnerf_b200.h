@@ -362,6 +362,26 @@ PNERF_API int pnerf_palette_loss(const pnerf_palette_loss_args* args, void* stre
 PNERF_API int pnerf_scale_buffers(float* b0, uint32_t n0, float* b1, uint32_t n1, float* b2, uint32_t n2, float* b3,
                                   uint32_t n3, const float* scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adam step of up to PNERF_ADAM_MAX_TENSORS fp32 tensors in one launch  (ref: the optimizer the
+ * trainers build, palette/utils.py:719-724 + main_palette.py: optim.Adam(params, betas=(0.9, 0.99), eps=1e-15), stepped
+ * through torch.cuda.amp.GradScaler). torch's fused-optimizer contract: gradients are divided by *grad_scale (device
+ * scalar, may be NULL) on the fly; *found_inf != 0 (device scalar, may be NULL) skips the whole step incl. the step
+ * counters. `step` (device float per tensor) holds the number of updates done so far and is advanced here.
+ * lr_dev (optional device scalar) overrides lr (a learning-rate schedule inside a captured CUDA graph).
+ * Non-amsgrad, maximize = false, L2 weight decay added to the gradient (torch.optim.Adam semantics).
+ * ---------------------------------------------------------------------------------------------- */
+#define PNERF_ADAM_MAX_TENSORS 32
+typedef struct pnerf_adam_tensor {
+    float* p; const float* g; float* m; float* v;   /* parameter, gradient, exp_avg, exp_avg_sq : [n] fp32 */
+    const float* step;                              /* device scalar, advanced by the call               */
+    uint64_t n;
+} pnerf_adam_tensor;
+
+PNERF_API int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, float lr, const float* lr_dev, float beta1,
+                              float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -597,241 +597,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
     if (lane == 0 && shaded) { atomicAdd(a.queue + 1, shaded); atomicAdd(a.queue + 3, rounds); }
 }
 
-// ------------------------------------------------------------------------------------------------
-// kernel 3: persistent fused renderer, one RAY per WARP (lane = one of 32 consecutive samples of the ray)
-//
-// k_render_fused above gives every lane its own ray, so the 32 samples a warp shades lie anywhere in the volume: each
-// of the 128 corner loads per sample tile touches 32 different 128-byte lines, and the L1 pipeline (one line per
-// cycle per SM) becomes the bound. Here the 32 samples of a tile are CONSECUTIVE samples of ONE ray (spacing
-// 2*sqrt(3)/1024 ~ 1/1200 of the unit cube): on the coarse half of the level pyramid they share cells and lines, so a
-// corner load needs 1-10 lines instead of 32, and its sectors are reused by the neighbouring corners.
-//   * march: the warp generates windows of 32 lattice points (lattice_window: the reference's serial fp32 sequence),
-//     classifies them in parallel and replays the serial walk of the reference's inference schedule with n_step = 1
-//     (march one sample from rays_t, composite, rays_t += real delta; raymarching.cu:936-1010, 1051-1110) warp-uniformly,
-//     run by run, until 32 samples are collected or the ray ends. Same lattice, same samples as k_ray_prepass.
-//   * composite: transmittance by an exclusive product scan of (1 - alpha) across the lanes; the termination rule of
-//     the reference (stop after the first sample whose incoming T < T_thresh) is a ballot; the weighted channels are
-//     staged in the warp's output tile and lane c sums channel c over the samples in ray order — the accumulators of
-//     the whole ray live in ONE register per lane (two with the auxiliary maps) and are written once when the ray retires.
-// ------------------------------------------------------------------------------------------------
-constexpr int kClipStride = kClipMax + 1;   // floats per staged semantic-feature row (odd: conflict-free)
-static_assert(32 * kClipStride * 4 <= (int)sizeof(((WarpScratch*)nullptr)->feat), "clip staging must fit the feature tile");
-static_assert(5 + kAuxCh <= kOutStride, "channel staging must fit the output tile");
-
-// output element of channel c for ray 0, and the per-ray stride (in floats); NULL if the channel does not exist
-template <bool AUX>
-__device__ __forceinline__ void channel_slot(const RenderArgs& a, int c, float*& p, uint32_t& stride) {
-    p = nullptr; stride = 0;
-    if (c == 0) { p = a.weights_sum; stride = 1; }
-    else if (c == 1) { p = a.depth; stride = 1; }
-    else if (c < 5) { p = a.image + (c - 2); stride = 3; }
-    else if (AUX) {
-        if (c < 8) { p = a.direct_rgb + (c - 5); stride = 3; }
-        else if (c < 11) { p = a.view_dep_rgb + (c - 8); stride = 3; }
-        else if (c < 11 + kNB) { p = a.basis_acc + (c - 11); stride = kNB; }
-        else if (c < 11 + kNB + kNB * 3) { p = a.basis_rgb + (c - 11 - kNB); stride = kNB * 3; }
-        else if (c < 5 + kAuxCh) { p = a.unscaled_basis_rgb + (c - 11 - kNB - kNB * 3); stride = kNB * 3; }
-    }
-}
-
-template <bool CLIP, bool AUX>
-__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_rays(RenderArgs a, pnerf_palette_field f) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem* sm = reinterpret_cast<FusedSmem*>(smem_raw);
-    uint2* wts = reinterpret_cast<uint2*>(smem_raw + ((sizeof(FusedSmem) + 15) & ~(size_t)15));
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(wts + (f.pred_clip ? kWUnitsClip : kWUnitsNoClip));
-    fused_prologue(f, sm, wts);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpScratch& ws = scratch[wid];
-    float* const clip_stage = reinterpret_cast<float*>(&ws.feat[0][0]);
-    constexpr uint32_t FULL = 0xffffffffu;
-    constexpr int NC = AUX ? 5 + kAuxCh : 5;      // channels accumulated per ray (besides the semantic feature)
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    float *out0, *out1;
-    uint32_t stride0, stride1;
-    channel_slot<AUX>(a, lane, out0, stride0);
-    channel_slot<AUX>(a, lane + 32, out1, stride1);
-    const bool clip_on = CLIP && a.clip_feat != nullptr;
-
-    const uint32_t n_hit = a.queue[2];
-    uint32_t shaded = 0, rounds = 0;              // warp-uniform
-    for (;;) {
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(a.queue, 1u);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= n_hit) break;
-        const uint32_t ray = (uint32_t)a.hit_list[slot];
-        // warp-uniform ray state (see k_ray_prepass for the schedule)
-        float tc = a.nears[ray];        // the compositor's ray parameter (rays_t of the reference)
-        float mark = tc;                // start of the current real-delta interval (last_t of the reference's march call)
-        if (a.noises) {
-            const float dt_min = 2 * 1.7320508075688772f / a.max_steps;
-            const float dt_max = 2 * 1.7320508075688772f * (1u << (a.C - 1)) / a.Hgrid;
-            mark += clampf(tc * a.dt_gamma, dt_min, dt_max) * a.noises[ray];
-        }
-        float t_cur = a.t_first[ray];   // next lattice point to probe
-        const float t_end = a.t_last[ray];
-        uint32_t count = 0;
-        float T = 1.f;                  // transmittance in front of the next sample
-        float acc0 = 0.f, acc1 = 0.f, accc = 0.f;
-        bool ray_done = false;
-        while (!ray_done) {
-            // ---- collect up to 32 consecutive samples of the ray into the staging rows ----
-            uint32_t filled = 0;
-            float ddx, ddy, ddz;
-            {
-                Marcher m;
-                m.init(a.rays_o + (size_t)ray * 3, a.rays_d + (size_t)ray * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid,
-                       a.bitfield);
-                ddx = m.dx; ddy = m.dy; ddz = m.dz;
-                while (filled < 32 && !ray_done) {
-                    float t;
-                    uint32_t nvalid;
-                    lattice_window(m, t_cur, (uint32_t)lane, t, nvalid);
-                    const bool wv = (uint32_t)lane < nvalid;
-                    const float t_after = t + m.step_size(t);
-                    const bool inside = wv && t <= t_end;
-                    float x = 0.f, y = 0.f, z = 0.f, dt = 0.f, tt = 0.f;
-                    bool occ = false;
-                    if (inside) occ = m.probe_point(t, x, y, z, dt, tt);
-                    const uint32_t in_mask = __ballot_sync(FULL, inside);
-                    const uint32_t occ_mask = __ballot_sync(FULL, occ);
-                    uint32_t take = 0, cur = 0;
-                    float my_tc = 0.f;
-                    bool restart = false;
-                    float t_next = 0.f;
-                    while (cur < nvalid) {
-                        if (!((in_mask >> cur) & 1u)) { ray_done = true; break; }          // past the last occupied point
-                        const float t_c = __shfl_sync(FULL, t, cur);
-                        if ((occ_mask >> cur) & 1u) {
-                            const uint32_t got = __popc(take);
-                            if (count + got >= a.max_steps) { ray_done = true; break; }   // sample budget of the ray
-                            if (filled + got >= 32u) { restart = true; t_next = t_c; break; }   // tile full
-                            const uint32_t room = min(32u - filled - got, a.max_steps - count - got);
-                            if (mark == t_c && tc == t_c) {
-                                // gap-free run: tc + ((t + dt) - tc) == fl(t + dt) exactly, the lattice continues
-                                const uint32_t inv = ~(occ_mask >> cur);
-                                const uint32_t run = min(inv ? (uint32_t)(__ffs(inv) - 1) : 32u, room);
-                                const uint32_t bits = (run >= 32u ? FULL : ((1u << run) - 1u)) << cur;
-                                take |= bits;
-                                if ((bits >> lane) & 1u) my_tc = t_after;
-                                cur += run;
-                                tc = mark = __shfl_sync(FULL, t_after, cur - 1);
-                            } else {
-                                // first sample behind a gap: the real delta spans the gap, and rays_t may round off the lattice
-                                const float ta = __shfl_sync(FULL, t_after, cur);
-                                const float tcn = tc + (ta - mark);
-                                take |= 1u << cur;
-                                if ((uint32_t)lane == cur) my_tc = tcn;
-                                tc = mark = tcn;
-                                if (tcn == ta) { cur++; }
-                                else { restart = true; t_next = tcn; break; }
-                            }
-                        } else {
-                            // empty voxel: skip to the first lattice point at / behind its exit face
-                            const float tt_cur = __shfl_sync(FULL, tt, cur);
-                            const uint32_t above = (cur >= 31u) ? 0u : (FULL << (cur + 1));
-                            const uint32_t ge = __ballot_sync(FULL, wv && t >= tt_cur) & above;
-                            if (ge) {
-                                cur = __ffs(ge) - 1;
-                            } else {
-                                float tn = __shfl_sync(FULL, t, nvalid - 1);
-                                do { tn += m.step_size(tn); } while (tn < tt_cur);
-                                restart = true; t_next = tn;
-                                break;
-                            }
-                        }
-                    }
-                    if (!restart && !ray_done) t_next = __shfl_sync(FULL, t_after, nvalid - 1);   // walked off the window
-                    t_cur = t_next;
-                    if ((take >> lane) & 1u) {
-                        float* row = ws.out[filled + __popc(take & lt_mask)];
-                        row[0] = x; row[1] = y; row[2] = z; row[3] = dt; row[4] = my_tc;
-                    }
-                    filled += __popc(take);
-                    count += __popc(take);
-                }
-            }
-            if (filled == 0) break;
-            __syncwarp();
-            const bool sample = (uint32_t)lane < filled;
-            const float x = ws.out[lane][0], y = ws.out[lane][1], z = ws.out[lane][2], dt = ws.out[lane][3], tcs = ws.out[lane][4];
-            __syncwarp();
-
-            // ---- shade the tile ----
-            rounds++;
-            FieldOut o;
-            eval_field<CLIP>(f, *sm, wts, ws, sample ? x : 0.f, sample ? y : 0.f, sample ? z : 0.f, ddx, ddy, ddz, sample, lane, o);
-
-            // ---- composite (ref: raymarching.cu:1051-1110) ----
-            float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
-            blend(f, *sm, o, rgb, basis_rgb, unscaled);
-            const float alpha = sample ? 1.0f - __expf(-(f.density_scale * o.sigma) * dt) : 0.f;
-            float p = 1.0f - alpha;                        // inclusive product scan of (1 - alpha)
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const float v = __shfl_up_sync(FULL, p, s);
-                if (lane >= s) p *= v;
-            }
-            float pex = __shfl_up_sync(FULL, p, 1);
-            if (lane == 0) pex = 1.f;
-            const float Tpre = T * pex;                     // transmittance in front of this lane's sample
-            const uint32_t term = __ballot_sync(FULL, sample && Tpre < a.T_thresh);
-            const uint32_t kstar = term ? (uint32_t)(__ffs(term) - 1) : 31u;     // the terminating sample is accumulated
-            const bool incl = sample && (uint32_t)lane <= kstar;
-            const float wgt = incl ? alpha * Tpre : 0.f;
-            const uint32_t nincl = min(filled, kstar + 1u);
-            shaded += nincl;
-            T *= __shfl_sync(FULL, p, nincl - 1);
-            if (term) ray_done = true;
-
-            float* row = ws.out[lane];
-            row[0] = wgt; row[1] = wgt * tcs;
-#pragma unroll
-            for (int c = 0; c < 3; c++) row[2 + c] = wgt * rgb[c];
-            if (AUX) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    row[5 + c] = wgt * (o.diffuse[c] + o.view_dep[c]);
-                    row[8 + c] = wgt * o.view_dep[c];
-                }
-#pragma unroll
-                for (int k = 0; k < kNB; k++) row[11 + k] = wgt * o.omega[k];
-#pragma unroll
-                for (int k = 0; k < kNB * 3; k++) {
-                    row[11 + kNB + k] = wgt * basis_rgb[k];
-                    row[11 + kNB + kNB * 3 + k] = wgt * unscaled[k];
-                }
-            }
-            if (clip_on) {
-#pragma unroll
-                for (int k = 0; k < kClipMax; k++) clip_stage[lane * kClipStride + k] = wgt * o.clip[k];
-            }
-            __syncwarp();
-            // lane c sums channel c over the tile's samples, in ray order
-            float s0 = 0.f, s1 = 0.f, sc = 0.f;
-            if (lane < NC) {
-#pragma unroll 4
-                for (uint32_t r = 0; r < nincl; r++) s0 += ws.out[r][lane];
-            }
-            if (AUX && lane + 32 < NC) {
-#pragma unroll 4
-                for (uint32_t r = 0; r < nincl; r++) s1 += ws.out[r][lane + 32];
-            }
-            if (clip_on && lane < kClipMax) {
-#pragma unroll 4
-                for (uint32_t r = 0; r < nincl; r++) sc += clip_stage[r * kClipStride + lane];
-            }
-            acc0 += s0; acc1 += s1; accc += sc;
-            __syncwarp();
-        }
-        // ---- retire the ray: every channel is written once ----
-        if (out0) out0[(size_t)ray * stride0] = acc0;
-        if (AUX && out1) out1[(size_t)ray * stride1] = acc1;
-        if (clip_on && (uint32_t)lane < f.clip_dim) a.clip_feat[(size_t)ray * f.clip_dim + lane] = accc;
-    }
-    if (lane == 0 && shaded) { atomicAdd(a.queue + 1, shaded); atomicAdd(a.queue + 3, rounds); }
-}
+// (A warp-per-ray variant of this kernel — lane = one of 32 consecutive samples of ONE ray, so that the corner loads of
+// the coarse levels share cache lines — was drafted in round 1 and is in the history (commit 15cc783); it is not part
+// of the build until it is finished and measured.)
 
 }  // namespace pnerf
 

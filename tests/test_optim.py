@@ -1,0 +1,125 @@
+"""FusedAdam (the optimizer of ref palette/utils.py:719-724) vs torch.optim.Adam on the same
+parameters and gradients: fp32, |a - b| <= 2e-6 |b| + 2e-8 on the parameters after several steps (2e-8 = 2e-6 of one
+lr-sized update; torch's own fused and foreach Adam differ by the same order), exact agreement on skipped steps and step
+counters, state_dict interchange."""
+import pytest
+import torch
+
+
+def _close(a, b, rel=2e-6, abs_=2e-8):
+    return bool(((a - b).abs() <= rel * b.abs() + abs_).all())
+
+
+def test_fused_adam_needs_cuda():
+    from palettenerf_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdam([p], lr=1e-2).step()
+    with pytest.raises(RuntimeError):
+        FusedAdam([p], amsgrad=True)
+
+
+def _params(dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(1 << 16, 2), (64, 32), (16, 64), (3,), (4, 3), (1000003,), (5,)]     # unaligned / odd sizes included
+    return [torch.randn(*s, generator=g).to(dev) for s in shapes]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam(cuda, wd):
+    from palettenerf_b200.optim import FusedAdam
+    base = _params(cuda)
+    pa = [torch.nn.Parameter(t.clone()) for t in base]
+    pb = [torch.nn.Parameter(t.clone()) for t in base]
+    kw = dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=wd)          # the reference's Adam
+    ref = torch.optim.Adam(pb, **kw)
+    opt = FusedAdam(pa, **kw)
+    g = torch.Generator().manual_seed(1)
+    for it in range(6):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(cuda) * (10.0 ** (it - 3))
+            if it == 2 and a.dim() == 2:
+                gr[0] = 0.0                                                     # untouched entries: g = 0
+            a.grad, b.grad = gr.clone(), gr.clone()
+        pa[-1].grad = None if it == 4 else pa[-1].grad                          # a parameter without a gradient is skipped
+        pb[-1].grad = None if it == 4 else pb[-1].grad
+        opt.step(); ref.step()
+    for a, b in zip(pa, pb):
+        assert _close(a, b), (a - b).abs().max().item()
+    for a, b in zip(pa, pb):
+        sa, sb = opt.state[a], ref.state[b]
+        assert float(sa["step"]) == float(sb["step"])
+        # moments: relative to the largest entry (an exp_avg entry can cancel to ~0 from O(10) gradients)
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert _close(sa[k], sb[k], 2e-6, 2e-6 * sb[k].abs().max().item()), k
+
+
+@pytest.mark.gpu
+def test_fused_adam_with_grad_scaler_skips_on_inf_and_interchanges_state(cuda):
+    from palettenerf_b200.optim import FusedAdam
+    base = _params(cuda, seed=2)[:4]
+    pa = [torch.nn.Parameter(t.clone()) for t in base]
+    pb = [torch.nn.Parameter(t.clone()) for t in base]
+    kw = dict(lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+    opt, ref = FusedAdam(pa, **kw), torch.optim.Adam(pb, fused=True, capturable=True, **kw)
+    sa, sb = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    g = torch.Generator().manual_seed(3)
+    for it in range(5):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(cuda) * 1024.0 * (0.5 if it > 2 else 1.0)   # scale halves after the skip
+            if it == 2 and a is pa[0]:
+                gr.view(-1)[7] = float("inf")
+            a.grad, b.grad = gr.clone(), gr.clone()
+        before = [a.detach().clone() for a in pa]
+        sa.scale(torch.ones((), device=cuda)); sb.scale(torch.ones((), device=cuda))   # lazy-initialises the scalers
+        sa.step(opt); sa.update()
+        sb.step(ref); sb.update()
+        if it == 2:
+            assert all(torch.equal(x, y) for x, y in zip(before, pa))          # skipped on the device
+            assert float(opt.state[pa[0]]["step"]) == 2.0
+    assert sa.get_scale() == sb.get_scale() == 512.0
+    for a, b in zip(pa, pb):
+        assert _close(a, b), (a - b).abs().max().item()
+        assert float(opt.state[a]["step"]) == float(ref.state[b]["step"]) == 4.0
+    # state interchange: torch -> FusedAdam and back
+    opt2 = FusedAdam(pa, **kw)
+    opt2.load_state_dict(ref.state_dict())
+    ref2 = torch.optim.Adam(pb, fused=True, capturable=True, **kw)
+    ref2.load_state_dict(opt.state_dict())
+    for a, b in zip(pa, pb):
+        gr = torch.randn(a.shape, generator=g).to(cuda)
+        a.grad, b.grad = gr.clone(), gr.clone()
+    opt2.step(); ref2.step()
+    for a, b in zip(pa, pb):
+        assert _close(a, b, 4e-6, 4e-8), (a - b).abs().max().item()
+
+
+@pytest.mark.gpu
+def test_fused_adam_in_a_cuda_graph_with_device_lr(cuda):
+    from palettenerf_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.randn(4097, device=cuda))
+    q = torch.nn.Parameter(p.detach().clone())
+    lr = torch.tensor(1e-2, device=cuda)
+    opt = FusedAdam([p], lr=lr, betas=(0.9, 0.99), eps=1e-15)
+    ref = torch.optim.Adam([q], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    grad = torch.randn(4097, device=cuda)
+    p.grad = grad.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        opt.step()                                # state allocation outside the capture
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    q.grad = grad.clone(); ref.step()            # the eager step; the captured one only runs on replay
+    for k in range(3):
+        lr.fill_(1e-2 * 0.5 ** (k + 1))           # the schedule reaches the captured kernel through device memory
+        graph.replay()
+        for gq in ref.param_groups:
+            gq["lr"] = 1e-2 * 0.5 ** (k + 1)
+        ref.step()
+    assert float(opt.state[p]["step"]) == 4.0
+    assert _close(p, q, 4e-6, 4e-8), (p - q).abs().max().item()
