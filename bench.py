@@ -436,10 +436,25 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     barrier()
     m = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
     ms = max_over_ranks(sum(ts) / len(ts))
+    # the optimizer alone (HBM stream: 16 B read + 12 B written per element with a gradient), same events / L2 flush
+    adam = None
+    if not torch_adam:
+        n_el = sum(p.numel() for p in params if p.grad is not None)
+        tt = []
+        for _ in range(10):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            L.profile_start()                    # CUDA events around the C-ABI call itself (not around Python's step())
+            opt.step()
+            pr = L.profile_stop()
+            tt.append(pr["pnerf_adam_step"][0] / max(1, pr["pnerf_adam_step"][1]))
+        ams = sum(tt) / len(tt)
+        adam = {"ms": ams, "elements": n_el, "gbs": 28.0 * n_el / (ams / 1e3) / 1e9,
+                "algorithmic": "28 B/element (p, g, m, v read; p, m, v written), all tensors of the step in one launch"}
     return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
-                      "optimizer": opt_name,
+                      "optimizer": opt_name, "adam_alone": adam,
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 

@@ -44,10 +44,16 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ A
 #pragma unroll 1
     while (ti + 1 < a.count && blockIdx.x >= a.first_block[ti + 1]) ti++;
     const pnerf_adam_tensor& T = a.t[ti];
-    const double t = (double)__ldg(T.step) + 1.0;
-    const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
-    const float step_size = (float)((double)lr / (1.0 - pow((double)a.beta1, t)));
-    const float rsqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a.beta2, t)));
+    // bias corrections in double like torch; one lane per warp evaluates the two pow() (the FP64 pipe is narrow)
+    float step_size = 0.f, rsqrt_bc2 = 0.f;
+    if ((threadIdx.x & 31) == 0) {
+        const double t = (double)__ldg(T.step) + 1.0;
+        const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
+        step_size = (float)((double)lr / (1.0 - pow((double)a.beta1, t)));
+        rsqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a.beta2, t)));
+    }
+    step_size = __shfl_sync(0xffffffffu, step_size, 0);
+    rsqrt_bc2 = __shfl_sync(0xffffffffu, rsqrt_bc2, 0);
     const float inv_scale = a.grad_scale ? 1.0f / __ldg(a.grad_scale) : 1.0f;
     const uint64_t base = (uint64_t)(blockIdx.x - a.first_block[ti]) * kAdamPerBlock;
     const uint64_t n = T.n;
