@@ -390,20 +390,17 @@ __global__ void __launch_bounds__(128) k_ray_prepass(const float* __restrict__ r
     // list is written bucket by bucket, longest first. A lane of the persistent kernel keeps a ray until it ends, so with
     // pixel order the last rays pulled from the queue decide when a warp finishes (tile fill 0.80 at 800x800); with the
     // longest rays first the tail consists of the shortest ones.
-    __shared__ unsigned int hist_s[kLptBuckets];
-    if (threadIdx.x < kLptBuckets) hist_s[threadIdx.x] = 0u;
-    __syncthreads();
+    // (warp-aggregated global atomics, no CTA barrier: a warp retires as soon as its own rays are walked)
     if (work) {
         ray_count[n] = (int32_t)count;
         if (hit) {
             t_first[n] = tf;
             t_last[n] = tl;
-            atomicAdd(&hist_s[lpt_bucket(count)], 1u);
         }
     }
-    __syncthreads();
-    if (threadIdx.x < kLptBuckets && hist_s[threadIdx.x]) atomicAdd(queue + kQueueHist + threadIdx.x, hist_s[threadIdx.x]);
-    (void)lane;
+    const uint32_t key = hit ? lpt_bucket(count) : (uint32_t)kLptBuckets + lane;     // misses: a key nobody shares
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (hit && lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(queue + kQueueHist + key, (unsigned int)__popc(peers));
 }
 
 // one warp: descending exclusive scan of the bucket histogram -> per-bucket write cursors; total -> queue[2]

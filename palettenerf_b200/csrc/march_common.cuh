@@ -40,7 +40,8 @@ __device__ __forceinline__ int frexp_exponent(float v) {
 struct Marcher {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
     float bound, dt_gamma, dt_min, dt_max;
-    float rH, Hf, halfH, Hm1, H3f, Cm1;
+    float rH, Hf, halfH, Hm1, H3f, rbound;
+    int Ci1;
     const uint8_t* __restrict__ grid;
 
     __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d, float bound_,
@@ -59,7 +60,8 @@ struct Marcher {
         halfH = 0.5f * Hf;  // exact; (0.5 * v * H) in double rounds once, same as v * halfH in float
         Hm1 = (float)(H - 1);
         H3f = (float)(H * H * H);
-        Cm1 = (float)C - 1.0f;
+        Ci1 = (int)C - 1;
+        rbound = 1 / bound_;
         grid = grid_;
     }
 
@@ -108,13 +110,16 @@ struct Marcher {
         position(t, x, y, z, dt);
 
         // cascade from position and from step size (ref: raymarching.cu:45-57)
+        // (integer clamps: the reference clamps the exponents as floats, fminf(C-1, fmaxf(0, e)) — same integers)
         const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-        const int lp = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(mx)));
-        const int ld = (int)fminf(Cm1, fmaxf(0.0f, (float)frexp_exponent(dt * Hf * 0.5f)));
-        const int level = max(lp, ld);
+        const int level = min(max(max(frexp_exponent(mx), frexp_exponent(dt * Hf * 0.5f)), 0), Ci1);
 
-        const float mip_bound = fminf(scalbnf(1.0f, level), bound);
-        const float mip_rbound = 1 / mip_bound;
+        // mip_bound = min(2^level, bound) and its reciprocal without scalbnf / a division: 2^level and 2^-level are
+        // exponent-field constructions (exact), and 1 / bound is the same correctly-rounded quotient computed once
+        const float pow2 = __int_as_float((127 + level) << 23);
+        const bool capped = pow2 > bound;
+        const float mip_bound = capped ? bound : pow2;
+        const float mip_rbound = capped ? rbound : __int_as_float((127 - level) << 23);
 
         const int nx = (int)clampf((x * mip_rbound + 1) * halfH, 0.0f, Hm1);
         const int ny = (int)clampf((y * mip_rbound + 1) * halfH, 0.0f, Hm1);
@@ -139,10 +144,22 @@ struct Marcher {
     __device__ __forceinline__ bool probe(float& t, float& x, float& y, float& z, float& dt) const {
         float tt;
         if (probe_point(t, x, y, z, dt, tt)) return true;
-        do {
-            t += step_size(t);
-        } while (t < tt);
+        t = advance_past(t, tt);
         return false;
+    }
+
+    // first lattice point at or behind tt: the reference's `do { t += clamp(t * dt_gamma, dt_min, dt_max); } while (t < tt)`
+    // (raymarching.cu:399-402). With dt_gamma == 0 (every Blender config) the step is the same constant in every
+    // iteration — clamp(+0, dt_min, dt_max) — so the loop is one dependent FADD per lattice point instead of
+    // FMUL + FMNMX + FMNMX + FADD; the sequence of sums, hence the result, is bit-identical.
+    __device__ __forceinline__ float advance_past(float t, float tt) const {
+        if (dt_gamma == 0.f) {
+            const float s = clampf(0.f, dt_min, dt_max);
+            do { t += s; } while (t < tt);
+        } else {
+            do { t += step_size(t); } while (t < tt);
+        }
+        return t;
     }
 };
 
@@ -238,9 +255,7 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
                 if (ge) {
                     cur = __ffs(ge) - 1;
                 } else {   // the empty voxel extends past the window: keep stepping from the last lattice point
-                    float tn = __shfl_sync(0xffffffffu, t, nvalid - 1);
-                    do { tn += m.step_size(tn); } while (tn < tt_cur);
-                    t_jump = tn;
+                    t_jump = m.advance_past(__shfl_sync(0xffffffffu, t, nvalid - 1), tt_cur);
                     jumped = true;
                     break;
                 }
