@@ -235,9 +235,10 @@ __device__ __forceinline__ void fused_prologue(const pnerf_palette_field& f, Fus
     __syncthreads();
 }
 
-__host__ __device__ constexpr size_t fused_smem_bytes(bool clip, bool aux) {
+__host__ __device__ constexpr size_t fused_smem_bytes(bool clip, bool aux, bool clip_acc = false) {
     return sizeof(FusedSmem) + (size_t)(clip ? kWUnitsClip : kWUnitsNoClip) * sizeof(uint2) +
-           sizeof(WarpScratch) * kFusedWarps + (aux ? sizeof(WarpAux) * kFusedWarps : 0) + 16;
+           sizeof(WarpScratch) * kFusedWarps + (aux ? sizeof(WarpAux) * kFusedWarps : 0) +
+           (clip_acc ? sizeof(WarpClip) * kFusedWarps : 0) + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,9 +445,19 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
     WarpScratch& ws = scratch[wid];
     WarpAux* auxs = reinterpret_cast<WarpAux*>(scratch + kFusedWarps);
     float (*aux)[32] = AUX ? auxs[wid].acc : nullptr;
+    // semantic-feature accumulators of the lane's ray: shared memory (written to clip_feat once, when the ray retires)
+    WarpClip* clips = reinterpret_cast<WarpClip*>(reinterpret_cast<unsigned char*>(auxs) + (AUX ? sizeof(WarpAux) * kFusedWarps : 0));
+    const bool clip_on = CLIP && a.clip_feat != nullptr;
+    float (*cacc)[32] = clip_on ? clips[wid].acc : nullptr;
     const uint32_t lt_mask = (1u << lane) - 1u;
     // retire a ray: its accumulators go to global memory once
     auto retire = [&](uint32_t ray_, float wsum_, float dep_, float r_, float g_, float b_) {
+        if (CLIP && clip_on) {
+            float* pc = a.clip_feat + (size_t)ray_ * f.clip_dim;
+#pragma unroll
+            for (int k = 0; k < kClipMax; k++)
+                if (k < (int)f.clip_dim) pc[k] = cacc[k][lane];
+        }
         a.weights_sum[ray_] = wsum_; a.depth[ray_] = dep_;
         a.image[(size_t)ray_ * 3] = r_; a.image[(size_t)ray_ * 3 + 1] = g_; a.image[(size_t)ray_ * 3 + 2] = b_;
         if (AUX) {
@@ -511,6 +522,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
                         if (AUX) {
 #pragma unroll
                             for (int c = 0; c < kAuxCh; c++) aux[c][lane] = 0.f;
+                        }
+                        if (CLIP && clip_on) {
+#pragma unroll
+                            for (int k = 0; k < kClipMax; k++) cacc[k][lane] = 0.f;
                         }
                     }
                 }
@@ -578,9 +593,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
                     aux[6 + kNB + kNB * 3 + k][lane] += wgt * unscaled[k];
                 }
             }
-            if (CLIP && a.clip_feat) {
-                float* pc = a.clip_feat + (size_t)ray * f.clip_dim;
-                for (uint32_t k = 0; k < f.clip_dim; k++) pc[k] += wgt * o.clip[k];
+            if (CLIP && clip_on) {
+#pragma unroll
+                for (int k = 0; k < kClipMax; k++) cacc[k][lane] += wgt * o.clip[k];      // o.clip is zero beyond clip_dim
             }
             // early termination (the terminating sample is accumulated, like the reference) or sample budget used up
             if (T < a.T_thresh || count >= a.max_steps) {
@@ -668,7 +683,7 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
     k_lpt_offsets<<<1, 32, 0, s>>>(queue);
     k_lpt_scatter<<<ceil_div(N, 256u), 256, 0, s>>>(ray_count, N, hit_list, queue);
     const bool clip_on = field->pred_clip != 0;
-    const size_t smem = fused_smem_bytes(clip_on, aux);
+    const size_t smem = fused_smem_bytes(clip_on, aux, clip_on && clip_feat != nullptr);
     const uint32_t warps_needed = ceil_div(N, 32u);
     const uint32_t grid = min(ceil_div(warps_needed, (uint32_t)kFusedWarps), (uint32_t)kNumSMs);  // persistent: one CTA per SM
 #define PNERF_LAUNCH_RENDER(CL, AX)                                                                                   \

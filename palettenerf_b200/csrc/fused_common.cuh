@@ -54,6 +54,11 @@ struct WarpAux {
     float acc[kAuxCh][32];
 };
 
+// per-warp accumulators of the semantic-feature map (renderer with pred_clip): channel-major like WarpAux
+struct WarpClip {
+    float acc[kClipMax][32];
+};
+
 struct FusedSmem {
     LevelParams lp[kMaxLevels];
     float head_bias[16];
