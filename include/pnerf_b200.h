@@ -267,6 +267,10 @@ typedef struct pnerf_palette_train {
                                    min(M, *m_dev) samples and M is only the capacity of the buffers */
     uint32_t L, H, pred_clip, clip_dim;
     float S, bound, density_scale;
+    /* optional (may be NULL): density and palette tables interleaved entry by entry, fp16 [n_entries][2 tables][2]
+     * (one 8-byte load per lattice corner serves both grids); when it is given, table_sigma / table_palette may be NULL.
+     * The forward pass falls back to the separate tables if a level does not wrap with a mask. */
+    const void* table_sigma_palette;
 } pnerf_palette_train;
 
 PNERF_API uint64_t pnerf_palette_train_xbuf_bytes(uint32_t M, uint32_t pred_clip);

@@ -127,6 +127,7 @@ __device__ __forceinline__ void store_denc(float* __restrict__ d_enc, uint32_t s
 struct TrainSmem {
     LevelParams lp[kMaxLevels];
     float palette[kNB * 3];
+    uint32_t fast_wrap;   // every level wraps with a mask (see FusedSmem::fast_wrap)
     // followed by: uint2 weights[...]; per-warp scratch
 };
 
@@ -143,6 +144,8 @@ k_field_train_fwd(const float* __restrict__ xyzs, const float* __restrict__ dirs
     constexpr int kWU = CLIP ? kWUnitsClip : kWUnitsNoClip;
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(wts + kWU);
     if (threadIdx.x < f.L) make_level(sm->lp[threadIdx.x], threadIdx.x, f.offsets, f.S, f.H, 3, 0, false);
+    const int slow = __syncthreads_or(threadIdx.x < f.L && sm->lp[threadIdx.x].mask == 0u);
+    if (threadIdx.x == 0) sm->fast_wrap = slow ? 0u : 1u;
     if (threadIdx.x < kNB * 3) sm->palette[threadIdx.x] = f.palette[threadIdx.x];
     {
         const uint4* src = reinterpret_cast<const uint4*>(f.wfwd);
@@ -171,7 +174,18 @@ k_field_train_fwd(const float* __restrict__ xyzs, const float* __restrict__ dirs
         uint32_t* carry = reinterpret_cast<uint32_t*>(&ws.out[lane][O_CLIP]);   // [t][6], see fused.cu::eval_field
 
         // ---- phase 1: density grid -> sigma net -> geo; geo -> diffuse net ----
-        gather_features((const __half*)f.table_sigma, sm->lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        // The palette grid shares the density grid's geometry: with the two tables interleaved entry by entry
+        // (table_sigma_palette) both are read here with ONE set of corner indices and one 8-byte load per corner; the
+        // palette features wait (fp16 pairs) in this lane's output row, columns O_OFFRAD.. that phase 3 writes last
+        // (same scheme as fused.cu::eval_field).
+        uint32_t* park = reinterpret_cast<uint32_t*>(&ws.out[lane][O_OFFRAD]);   // 16 words
+        const bool paired = sm->fast_wrap && f.table_sigma_palette != nullptr && f.L == 16;     // warp-uniform
+        if (paired) {
+            uint32_t* const rows[2] = {reinterpret_cast<uint32_t*>(ws.feat[lane]), park};
+            gather_fast<2, 2>(f.table_sigma_palette, sm->lp, u, v, w, in_range, rows);
+        } else {
+            gather_features((const __half*)f.table_sigma, sm->lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        }
         __syncwarp();
 #pragma unroll 1
         for (int t = 0; t < 2; t++) {
@@ -248,7 +262,12 @@ k_field_train_fwd(const float* __restrict__ xyzs, const float* __restrict__ dirs
         __syncwarp();
 
         // ---- phase 3: palette grid ++ diffuse(detached) -> basis net -> heads (bias folded into column 15) ----
-        gather_features((const __half*)f.table_palette, sm->lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        if (paired) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) reinterpret_cast<uint32_t*>(ws.feat[lane])[i] = park[i];
+        } else {
+            gather_features((const __half*)f.table_palette, sm->lp, f.L, u, v, w, in_range, ws.feat[lane]);
+        }
         __syncwarp();
 #pragma unroll 1
         for (int t = 0; t < 2; t++) {
@@ -663,7 +682,8 @@ uint32_t pnerf_palette_train_wfwd_units(uint32_t pred_clip) { return pred_clip ?
 uint32_t pnerf_palette_train_wbwd_units(uint32_t pred_clip) { return pred_clip ? kTUnitsClip : kTUnitsNoClip; }
 
 static int train_args_ok(const pnerf_palette_train* p) {
-    if (!p || !p->table_sigma || !p->table_palette || !p->offsets || !p->wfwd || !p->wbwd || !p->palette) return PNERF_ERR_INVALID_ARG;
+    if (!p || !p->offsets || !p->wfwd || !p->wbwd || !p->palette) return PNERF_ERR_INVALID_ARG;
+    if (!p->table_sigma_palette && (!p->table_sigma || !p->table_palette)) return PNERF_ERR_INVALID_ARG;
     if (p->pred_clip && !p->table_clip) return PNERF_ERR_INVALID_ARG;
     if (p->L != 16 || p->clip_dim > (uint32_t)kClipMax) return PNERF_ERR_UNSUPPORTED;
     return PNERF_OK;

@@ -28,7 +28,7 @@ class PaletteTrain(ctypes.Structure):
     _fields_ = [("table_sigma", c_void_p), ("table_palette", c_void_p), ("table_clip", c_void_p), ("offsets", c_void_p),
                 ("wfwd", c_void_p), ("wbwd", c_void_p), ("palette", c_void_p), ("m_dev", c_void_p),
                 ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
-                ("S", c_float), ("bound", c_float), ("density_scale", c_float)]
+                ("S", c_float), ("bound", c_float), ("density_scale", c_float), ("table_sigma_palette", c_void_p)]
 
 
 P, U = c_void_p, c_uint32
@@ -157,6 +157,24 @@ class _Tables:
             self.c[name] = hit
         return hit[1]
 
+    def pair(self, sigma_p, palette_p, refresh_palette):
+        """density + palette tables interleaved per entry, fp16 [n, 2, 2] (one 8-byte gather per lattice corner serves
+        both grids). The buffer is persistent: the frozen density half is written when that parameter changes, the
+        trained palette half on every call (one strided fp32 -> fp16 copy, the conversion the step needs anyway)."""
+        key_s = (sigma_p._version, sigma_p.data_ptr())
+        key_p = (palette_p._version, palette_p.data_ptr())
+        hit = self.c.get("pair")
+        if hit is None or hit[2].shape[0] != sigma_p.shape[0] or hit[2].device != sigma_p.device:
+            hit = [None, None, torch.empty(sigma_p.shape[0], 2, 2, dtype=torch.float16, device=sigma_p.device)]
+            self.c["pair"] = hit
+        if hit[0] != key_s:
+            hit[2][:, 0, :].copy_(sigma_p.detach())
+            hit[0] = key_s
+        if refresh_palette or hit[1] != key_p:
+            hit[2][:, 1, :].copy_(palette_p.detach())
+            hit[1] = key_p
+        return hit[2]
+
 
 def _state(model):
     st = getattr(model, "_fused_train_state", None)
@@ -193,13 +211,20 @@ class _TrainField(Function):
         flat = torch.cat([w.detach().reshape(-1).float() for w in weights] + [st["zero"]])
         blob = flat[st["index"]].to(torch.float16)
         tabs = st["tables"]
-        t_sigma = tabs.get("sigma", model.encoder.embeddings)
-        t_pal = tabs.get("palette", emb_palette, always=emb_palette.requires_grad)
+        sig = model.encoder.embeddings
+        if sig.shape == emb_palette.shape and sig.shape[1] == 2:
+            t_pair = tabs.pair(sig, emb_palette, refresh_palette=emb_palette.requires_grad)
+            t_sigma = t_pal = None
+        else:
+            t_pair = None
+            t_sigma = tabs.get("sigma", sig)
+            t_pal = tabs.get("palette", emb_palette, always=emb_palette.requires_grad)
         t_clip = tabs.get("clip", emb_clip, always=emb_clip.requires_grad) if pc else None
         pal = palette.detach().float().contiguous()
         offsets = model.encoder.offsets
         f = PaletteTrain()
         f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
+        f.table_sigma_palette = ptr(t_pair)
         f.offsets, f.palette = ptr(offsets), ptr(pal)
         f.wfwd, f.wbwd = blob.data_ptr(), blob.data_ptr() + 2 * st["n_fwd"]
         f.m_dev = ptr(count)
@@ -215,7 +240,7 @@ class _TrainField(Function):
         sigma, rgb, flex = new("sigma", M), new("rgb", M, 3), new("flex", M, nflex)
         L.call("pnerf_palette_train_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(xbuf), ptr(sigma), ptr(rgb),
                ptr(flex), stream())
-        ctx.keep = (f, blob, t_sigma, t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count)
+        ctx.keep = (f, blob, (t_sigma, t_pair), t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count)
         ctx.model, ctx.M, ctx.n_weights = model, M, len(weights)
         ctx.need_palette = palette.requires_grad
         ctx.mark_non_differentiable(sigma)
