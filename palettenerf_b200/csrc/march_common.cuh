@@ -245,9 +245,14 @@ __device__ __forceinline__ uint32_t warp_walk(const Marcher& m, float t0, float 
         while (cur < nvalid) {
             if (!((in_mask >> cur) & 1u)) { finished = true; break; }            // t >= far
             if ((occ_mask >> cur) & 1u) {
-                if (count + __popc(take) >= budget) { finished = true; break; }   // sample budget (max_steps / num_steps)
-                take |= 1u << cur;
-                cur++;
+                // a run of consecutive occupied points is taken in one step (the serial walk would visit them one by
+                // one: same points, same order), cut at the sample budget (max_steps / num_steps)
+                const uint32_t room = budget - (count + __popc(take));
+                if (room == 0u) { finished = true; break; }
+                const uint32_t inv = ~(occ_mask >> cur);
+                const uint32_t run = min(inv ? (uint32_t)(__ffs(inv) - 1) : 32u, room);      // >= 1; occupied => inside the window
+                take |= (run >= 32u ? 0xffffffffu : ((1u << run) - 1u)) << cur;
+                cur += run;
             } else {
                 const float tt_cur = __shfl_sync(0xffffffffu, tt, cur);
                 const uint32_t above = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
