@@ -127,9 +127,18 @@ def test_raymarch_composite_vs_reference_kernels(cuda, flush, scene):
     counter = torch.zeros(2, dtype=torch.int32, device=cuda)
     noises = torch.rand(n, device=cuda)
 
+    from palettenerf_b200.raymarching.backend import OCC_FLOATS
+    t_list = torch.empty(n * 1024, device=cuda)
+    occ = torch.empty(OCC_FLOATS, device=cuda)
+    B.occupied_bounds(bitfield, 2, 128, 2.0, occ)        # once per bitfield version (cached by the wrapper)
+
     def march(be):
         counter.zero_()
-        be.march_rays_train(to, td, bitfield, 2.0, 0.0, 1024, n, 2, 128, M, tn, tf, xyzs, dirs, deltas, rays, counter, noises)
+        if be is B:    # the entry point the drop-in wrapper uses: one grid walk, clipped at the occupied bounds
+            be.march_rays_train_ws(to, td, bitfield, 2.0, 0.0, 1024, n, 2, 128, M, tn, tf, xyzs, dirs, deltas, rays, counter,
+                                   noises, t_list, occ)
+        else:
+            be.march_rays_train(to, td, bitfield, 2.0, 0.0, 1024, n, 2, 128, M, tn, tf, xyzs, dirs, deltas, rays, counter, noises)
     _record("march_rays_train_4096", _time(lambda: march(ref), flush=flush), _time(lambda: march(B), flush=flush))
     march(B)
     m = int(counter[0].item())
@@ -239,11 +248,24 @@ def test_end_to_end_reference_schedule_on_reference_kernels_vs_fused(cuda, flush
     del m1, o1, s1
     # new path, the whole step replayed from ONE CUDA graph (static shapes, no host sync: palettenerf_b200/graphs.py)
     from palettenerf_b200.graphs import GraphedStep
+    # (with this repository's fused loss and optimizer: palette/losses.py, optim.py)
+    from palettenerf_b200.optim import FusedAdam
+    from palettenerf_b200.palette.losses import palette_loss
     m3 = S.build_palette_model(cuda, seed=0, pred_clip=False)
     m3.train()
-    o3 = torch.optim.Adam(m3.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+    o3 = FusedAdam(m3.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
     s3 = torch.amp.GradScaler("cuda")
-    g = GraphedStep(lambda: step(m3, o3, s3, None), warmup=3)
+
+    def step3():
+        o3.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = m3.render(to[None], td[None], staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0,
+                            max_steps=1024)
+            loss = palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1)[0]
+        s3.scale(loss).backward()
+        s3.step(o3)
+        s3.update()
+    g = GraphedStep(step3, warmup=3)
     graph_ms = _time(g.replay, iters=10, warm=3, flush=flush)
     # eager launches are bound by the host (Python + ~60 launches per step), which varies from box to box: recorded, not
     # asserted. The product path is the graph replay below.
