@@ -25,7 +25,7 @@ const char* pnerf_status_string(int status) {
 
 const char* pnerf_last_cuda_error(void) { return pnerf::g_last_err; }
 
-int pnerf_abi_version(void) { return 1; }
+int pnerf_abi_version(void) { return 2; }   // 2: occ_aabb argument of pnerf_palette_render_fused, workspace entry points, loss / Adam / get_rays
 
 const char* pnerf_build_arch(void) { return "sm_100a"; }
 

@@ -53,24 +53,32 @@ class GradBucket:
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         self.flat = None
+        self._sizes, self._views = None, []
 
     def _live(self):
         return [p for p in self.params if p.grad is not None]
 
     def all_reduce(self, found_inf=None, average=True, group=None):
-        """sums (or averages) gradients across ranks in place; returns the global found-inf flag (max over ranks)"""
+        """sums (or averages) gradients across ranks; returns the global found-inf flag (max over ranks).
+        Pack = ONE multi-tensor copy into the flat bucket; after the collective every `p.grad` IS its slice of the bucket
+        (re-pointed, not copied back), so the per-step cost besides the all-reduce is one 50 MB copy and one scaling
+        kernel instead of ~40 small launches. The bucket is therefore owned by the gradients until the next backward."""
         ws, _ = world()
         live = self._live()
-        n = sum(p.grad.numel() for p in live) + 1
+        sizes = [p.grad.numel() for p in live]
+        n = sum(sizes) + 1
         dev = live[0].grad.device if live else torch.device("cpu")
-        if self.flat is None or self.flat.numel() != n or self.flat.device != dev:
+        if self.flat is None or self.flat.numel() != n or self.flat.device != dev or self._sizes != sizes:
             self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        flat = self.flat
-        off = 0
-        for p in live:
-            k = p.grad.numel()
-            flat[off:off + k].copy_(p.grad.reshape(-1))
-            off += k
+            self._sizes = sizes
+            self._views, off = [], 0
+            for k in sizes:
+                self._views.append(self.flat[off:off + k])
+                off += k
+        flat, off = self.flat, n - 1
+        srcs = [p.grad.reshape(-1) for p in live]
+        if any(s.data_ptr() != v.data_ptr() for s, v in zip(srcs, self._views)):   # (already in place: nothing to pack)
+            torch._foreach_copy_(self._views, srcs)
         # the flag rides in the same bucket; it is summed, so any rank's inf makes it non-zero everywhere
         # (device-side writes only: a Python scalar assignment is a host->device copy, which a CUDA-graph capture rejects)
         if found_inf is None:
@@ -83,12 +91,9 @@ class GradBucket:
             dist.all_reduce(flat, group=group)
         flag = flat[off].clone()
         if average and ws > 1:
-            flat[:off].div_(ws)
-        off = 0
-        for p in live:
-            k = p.grad.numel()
-            p.grad.copy_(flat[off:off + k].view_as(p.grad))
-            off += k
+            flat[:off].mul_(1.0 / ws)
+        for p, v in zip(live, self._views):
+            p.grad = v.view_as(p.grad)
         return flag
 
     def signature(self):
