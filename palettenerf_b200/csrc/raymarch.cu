@@ -75,29 +75,36 @@ __global__ void __launch_bounds__(256) k_morton3D_invert(const int32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// packbits (ref: raymarching.cu:271-292): one thread packs 4 bytes = 32 cells = 8 x float4 loads,
-// coalesced 128-bit streaming reads, 32-bit stores.
+// packbits (ref: raymarching.cu:271-292). One WARP packs 128 bytes = 1024 cells: in each of 8 steps the lanes read 32
+// consecutive float4 (512 contiguous bytes per load instruction), turn them into 4-bit nibbles, and three xor-shuffles
+// OR the nibbles of 8 neighbouring lanes into a 32-bit word; every lane keeps one of the 32 words and the warp stores
+// them into one 128-byte line. Ragged tails and unaligned pointers take the byte-per-thread path.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid, uint32_t N, float thresh,
                                                   uint8_t* __restrict__ bitfield) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit word index
-    const uint32_t n0 = w * 4;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n0 = warp * 128;                         // first byte of this warp's chunk
     if (n0 >= N) return;
-    if (n0 + 4 <= N && ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) &&
-        ((reinterpret_cast<uintptr_t>(bitfield) & 3u) == 0)) {
-        const float4* g4 = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
-        uint32_t bits = 0;
+    const bool fast = n0 + 128 <= N && ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(bitfield) & 3u) == 0);
+    if (fast) {
+        const float4* g4 = reinterpret_cast<const float4*>(grid) + (size_t)warp * 256;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = ld_stream4(g4 + i * 32 + lane);
+        uint32_t mine = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float4 v = ld_stream4(g4 + i);
-            bits |= (v.x > thresh ? 1u : 0u) << (4 * i + 0);
-            bits |= (v.y > thresh ? 1u : 0u) << (4 * i + 1);
-            bits |= (v.z > thresh ? 1u : 0u) << (4 * i + 2);
-            bits |= (v.w > thresh ? 1u : 0u) << (4 * i + 3);
+            uint32_t w = ((v[i].x > thresh ? 1u : 0u) | (v[i].y > thresh ? 2u : 0u) | (v[i].z > thresh ? 4u : 0u) |
+                          (v[i].w > thresh ? 8u : 0u)) << ((lane & 7u) * 4);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);        // word (4 i + lane / 8) of the chunk, in all 8 lanes of the group
+            if ((lane & 7u) == (uint32_t)i) mine = w;
         }
-        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+        reinterpret_cast<uint32_t*>(bitfield)[(size_t)warp * 32 + (lane & 7u) * 4 + (lane >> 3)] = mine;
     } else {
-        for (uint32_t n = n0; n < N && n < n0 + 4; n++) {
+        for (uint32_t n = n0 + lane; n < N && n < n0 + 128; n += 32) {
             uint8_t bits = 0;
             for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (uint8_t)(1u << i) : 0;
             bitfield[n] = bits;
@@ -413,8 +420,8 @@ int pnerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, v
 int pnerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(grid && bitfield);
-    const uint32_t words = ceil_div(N, 4u);
-    k_packbits<<<ceil_div(words, 256u), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+    const uint32_t warps = ceil_div(N, 128u);
+    k_packbits<<<ceil_div(warps, 8u), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
     return check_launch("packbits");
 }
 
