@@ -127,6 +127,8 @@ def main():
                     "instead of palette_loss (A/B)")
     ap.add_argument("--torch-adam", action="store_true", help="training sections: torch.optim.Adam(fused, capturable) "
                     "instead of palettenerf_b200.optim.FusedAdam (A/B)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1 training: dist.all_reduce (NCCL) for the gradient "
+                    "bucket instead of pnerf_peer_allreduce over symmetric memory (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gui-mode", action="store_true", help="skip the five debug maps (reference gui_mode=True)")
     ap.add_argument("--fused", type=int, default=-1, help="-1 auto, 0 compatibility loop, 1 fused schedule")
@@ -271,7 +273,8 @@ def main():
     if "train" in sections:
         try:
             extras.update(bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush,
-                                      use_graph=not args.no_graph, torch_loss=args.torch_loss, torch_adam=args.torch_adam))
+                                      use_graph=not args.no_graph, torch_loss=args.torch_loss, torch_adam=args.torch_adam,
+                                      nccl_allreduce=args.nccl_allreduce))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if "mip360" in sections:
@@ -385,7 +388,7 @@ def _adam(torch, params, torch_adam):
 
 
 def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True, torch_loss=False,
-                torch_adam=False):
+                torch_adam=False, nccl_allreduce=False):
     """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
     GradScaler; ray-batch data parallel with ONE all-reduce over a flat gradient bucket when N > 1.
     The step (static-capacity march, fused field fwd/bwd/wgrad, one-pass compositor, loss, all-reduce, GradScaler, fused
@@ -397,7 +400,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     opt, opt_name = _adam(torch, model.get_params(1e-2), torch_adam)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda")
-    bucket = GradBucket(params) if world > 1 else None
+    bucket = GradBucket(params, peer=not nccl_allreduce) if world > 1 else None
     o, d = S.training_rays(TRAIN_RAYS, seed=rank)
     o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
     gt = torch.rand(1, TRAIN_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
@@ -455,6 +458,8 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
                       "optimizer": opt_name, "adam_alone": adam,
+                      "allreduce": None if world == 1 else ("nccl all_reduce" if nccl_allreduce or bucket._pm is None
+                                                            else "pnerf_peer_allreduce (two-shot over NVLink peer memory)"),
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 

@@ -386,6 +386,18 @@ PNERF_API int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, 
                               float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * gradient all-reduce over NVLink peer memory (no reference counterpart: the reference is single-GPU)
+ * peer_ptrs: HOST array of `world` device addresses, entry p = the bucket of rank p mapped into this process
+ * (symmetric memory / CUDA IPC), each holding n floats, n a multiple of 4 * world. Two-shot: this rank sums slice
+ * `rank` of every bucket in rank order, multiplies by `scale` (1/world to average) and stores the result into slice
+ * `rank` of every bucket. The caller provides a cross-GPU barrier before (all buckets written) and after (all slices
+ * delivered) the call; the kernel itself does not synchronise.
+ * ---------------------------------------------------------------------------------------------- */
+#define PNERF_PEER_MAX 8
+PNERF_API int pnerf_peer_allreduce(const uint64_t* peer_ptrs, uint32_t world, uint32_t rank, uint64_t n, float scale,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,13 +47,48 @@ def gather_maps(local, n_rays, shard, group=None):
     return full
 
 
-class GradBucket:
-    """ONE flat fp32 all-reduce per step for all trainable gradients (+ the found-inf flag of the loss scaler)."""
+class PeerMemory:
+    """the flat bucket as SYMMETRIC memory: every rank of the box maps every other rank's bucket (torch's
+    `_symmetric_memory`: CUDA VMM / IPC handles exchanged once at rendezvous), so the all-reduce is our own kernel over
+    NVLink loads and stores (csrc/peer.cu::pnerf_peer_allreduce) between two cross-GPU barriers of the same handle."""
 
-    def __init__(self, params):
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("peer all-reduce: at most 8 ranks (one NVSwitch box)")
+        pad = 4 * self.world
+        self.n = (n_floats + pad - 1) // pad * pad
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:   # noqa: BLE001  (newer torch enables every group implicitly)
+            pass
+        self.buf = symm.empty(self.n, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        import ctypes
+        self._ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+
+    def all_reduce_(self, average):
+        import ctypes
+        from . import _lib as L
+        self.handle.barrier(channel=0)                      # every rank's gradients are in its bucket
+        L.call("pnerf_peer_allreduce", ctypes.addressof(self._ptrs), self.world, self.rank, self.n,
+               (1.0 / self.world) if average else 1.0, L.stream())
+        self.handle.barrier(channel=1)                      # every slice has been delivered to every rank
+
+
+class GradBucket:
+    """ONE flat fp32 all-reduce per step for all trainable gradients (+ the found-inf flag of the loss scaler).
+    peer=True: the bucket lives in symmetric memory and the all-reduce is `pnerf_peer_allreduce` over NVLink peer
+    memory (CUDA, one box, <= 8 ranks); otherwise (and on CPU / gloo) `dist.all_reduce`."""
+
+    def __init__(self, params, peer=False):
         self.params = [p for p in params if p.requires_grad]
         self.flat = None
         self._sizes, self._views = None, []
+        self.peer, self._pm = bool(peer), None
 
     def _live(self):
         return [p for p in self.params if p.grad is not None]
@@ -68,8 +103,13 @@ class GradBucket:
         sizes = [p.grad.numel() for p in live]
         n = sum(sizes) + 1
         dev = live[0].grad.device if live else torch.device("cpu")
-        if self.flat is None or self.flat.numel() != n or self.flat.device != dev or self._sizes != sizes:
-            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        if self.flat is None or self._sizes != sizes or self.flat.device != dev:
+            if self.peer and ws > 1 and dev.type == "cuda":
+                self._pm = PeerMemory(n, dev, group)
+                self.flat = self._pm.buf[:n]
+            else:
+                self._pm = None
+                self.flat = torch.empty(n, dtype=torch.float32, device=dev)
             self._sizes = sizes
             self._views, off = [], 0
             for k in sizes:
@@ -87,11 +127,13 @@ class GradBucket:
             flat[off:off + 1].copy_(found_inf.reshape(1).to(torch.float32))
         else:
             flat[off:off + 1].fill_(float(found_inf))
-        if ws > 1:
+        if ws > 1 and self._pm is not None:
+            self._pm.all_reduce_(average)              # averaging is folded into the reduction kernel
+        elif ws > 1:
             dist.all_reduce(flat, group=group)
+            if average:
+                flat[:off].mul_(1.0 / ws)
         flag = flat[off].clone()
-        if average and ws > 1:
-            flat[:off].mul_(1.0 / ws)
         for p, v in zip(live, self._views):
             p.grad = v.view_as(p.grad)
         return flag
