@@ -104,11 +104,16 @@ class GradBucket:
         n = sum(sizes) + 1
         dev = live[0].grad.device if live else torch.device("cpu")
         if self.flat is None or self._sizes != sizes or self.flat.device != dev:
+            self._pm = None
             if self.peer and ws > 1 and dev.type == "cuda":
-                self._pm = PeerMemory(n, dev, group)
+                try:
+                    self._pm = PeerMemory(n, dev, group)
+                except Exception as e:   # noqa: BLE001  (no symmetric memory on this box / build: the NCCL path still works)
+                    import warnings
+                    warnings.warn(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using dist.all_reduce")
+            if self._pm is not None:
                 self.flat = self._pm.buf[:n]
             else:
-                self._pm = None
                 self.flat = torch.empty(n, dtype=torch.float32, device=dev)
             self._sizes = sizes
             self._views, off = [], 0
