@@ -240,7 +240,7 @@ def main():
                         "note": "rays generated on the device by pnerf_get_rays from the pinned-host camera pose"}
 
     # ---- roofline of the dominant kernel of the step (CUDA events around each C-ABI launch, timed region) ---------
-    # pnerf_palette_render_fused = pre-pass + 2 ordering kernels + the persistent k_render_fused (>= 97 % of the call,
+    # pnerf_palette_render_fused = candidates + pre-pass + 2 ordering kernels + the persistent k_render_fused (92 % of the call,
     # profiles/r01_launches_bench_render_*.csv). It is the fused march -> hash-grid gather -> MLP -> blend -> composite
     # kernel; SURVEY §8(d) puts the MLP on the tensor roofline (36 094 FLOP per sample without the semantic branch).
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
@@ -261,7 +261,7 @@ def main():
         ach = FLOP_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e12
         roofline.update(achieved=ach, frac=ach / tf_peak,
                         note="the kernel is bound by the latency of its L2-resident hash-table gathers, not by the tensor pipe "
-                             "(ncu: tensor pipe 12 % active, DRAM 0.03 %); see l2_gather and profiles/",
+                             "(ncu: tensor pipe 22 % active, L1/TEX pipe 81 %, issue slots 49 %, DRAM 0.07 %); see l2_gather and profiles/",
                         l2_gather={"achieved_gbs": GATHER_B_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e9,
                                    "algorithmic": f"{GATHER_B_PER_SAMPLE} B gathered per sample (2 tables x 16 levels x 8 corners x 4 B)",
                                    "hbm_peak_gbs_for_scale": hbm_peak})
