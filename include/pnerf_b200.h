@@ -241,6 +241,12 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
                                          int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb,
                                          void* stream);
 
+/* measurement hook for bench.py's roofline: with timing enabled, pnerf_palette_render_fused brackets its persistent
+ * kernel (k_render_fused, not the pre-pass / ordering launches) with an event pair on the launch stream;
+ * pnerf_render_kernel_last_ms() synchronises on it and returns the duration of the last launch (-1 if none). */
+PNERF_API void pnerf_render_kernel_timing(int enable);
+PNERF_API float pnerf_render_kernel_last_ms(void);
+
 /* ------------------------------------------------------------------------------------------------
  * fused palette field for TRAINING (new entry points; they replace the field evaluation of the training branch,
  * ref: palette/renderer.py:322-359 + palette/network.py:156-280, and its autograd graph)

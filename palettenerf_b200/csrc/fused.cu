@@ -617,6 +617,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_render_fused(RenderArgs
 
 using namespace pnerf;
 
+// measurement hook (off by default; not thread-safe, meant for the single-threaded benchmark)
+static bool g_render_timing = false, g_render_timed = false;
+static cudaEvent_t g_render_ev[2] = {nullptr, nullptr};
+
 extern "C" {
 
 /* fused field: xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (may be NULL), omega [M,4], off_rad [M,13],
@@ -692,10 +696,26 @@ int pnerf_palette_render_fused(const float* rays_o, const float* rays_d, const f
         if (e != cudaSuccess) { set_last_cuda_error(e, "render_fused attr"); return PNERF_ERR_CUDA; }                 \
         k_render_fused<CL, AX><<<grid, kFusedWarps * 32, smem, s>>>(a, *field);                                       \
     } while (0)
+    // optional timing of the persistent kernel alone (bench.py's roofline): an event pair on the launch stream
+    if (g_render_timing) {
+        if (!g_render_ev[0]) { cudaEventCreate(&g_render_ev[0]); cudaEventCreate(&g_render_ev[1]); }
+        cudaEventRecord(g_render_ev[0], s);
+    }
     if (clip_on) { if (aux) PNERF_LAUNCH_RENDER(true, true); else PNERF_LAUNCH_RENDER(true, false); }
     else { if (aux) PNERF_LAUNCH_RENDER(false, true); else PNERF_LAUNCH_RENDER(false, false); }
 #undef PNERF_LAUNCH_RENDER
+    if (g_render_timing) { cudaEventRecord(g_render_ev[1], s); g_render_timed = true; }
     return check_launch("palette_render_fused");
+}
+
+void pnerf_render_kernel_timing(int enable) { g_render_timing = enable != 0; g_render_timed = false; }
+
+float pnerf_render_kernel_last_ms(void) {
+    if (!g_render_timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(g_render_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, g_render_ev[0], g_render_ev[1]) != cudaSuccess)
+        return -1.0f;
+    return ms;
 }
 
 }  // extern "C"
