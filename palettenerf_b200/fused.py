@@ -169,12 +169,18 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     f = _cache(model).get()
     N, dev = rays_o.shape[0], rays_o.device
     nb, cd = model.num_basis, model.opt.clip_dim
-    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-    acc = {"weights_sum": z(N), "depth": z(N), "image": z(N, 3), "clip_feat": z(N, cd)}
+    # every accumulator (and the queue counters) is a view of ONE zero-filled buffer: one fill launch per view instead of ten
+    shapes = {"weights_sum": (N,), "depth": (N,), "image": (N, 3), "clip_feat": (N, cd)}
     if not gui_mode:
-        acc.update(direct_rgb=z(N, 3), view_dep_rgb=z(N, 3), basis_acc=z(N, nb), basis_rgb=z(N, 3 * nb),
-                   unscaled_basis_rgb=z(N, 3 * nb))
-    queue = torch.zeros(68, dtype=torch.int32, device=dev)   # 4 counters + 32-bucket histogram + 32 cursors
+        shapes.update(direct_rgb=(N, 3), view_dep_rgb=(N, 3), basis_acc=(N, nb), basis_rgb=(N, 3 * nb),
+                      unscaled_basis_rgb=(N, 3 * nb))
+    sizes = {k: int(np.prod(v)) for k, v in shapes.items()}
+    flat = torch.zeros(sum(sizes.values()) + 68, dtype=torch.float32, device=dev)
+    acc, off = {}, 0
+    for k, shp in shapes.items():
+        acc[k] = flat[off:off + sizes[k]].view(*shp)
+        off += sizes[k]
+    queue = flat[off:off + 68].view(torch.int32)             # 4 counters + 32-bucket histogram + 32 cursors
     hit_list = torch.empty(2 * N, dtype=torch.int32, device=dev)   # ordered hit list + samples per ray
     t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
