@@ -393,6 +393,22 @@ PNERF_API int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, 
                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * per-ray epilogue of run_cuda  (ref: palette/renderer.py:399-429, 525-551; nerf/renderer.py:335-343)
+ *   depth_n = clamp(depth - near, 0) / (far - near) (depth_n NULL: skipped); image_out = image + (1 - weights_sum) bg;
+ *   direct_out = direct + (1 - weights_sum) bg (direct_out NULL: skipped). `direct` rows are direct_stride floats apart
+ *   (3 columns of a wider tensor are read in place). bg: [3] (bg_stride 0) or per ray [N,3] (bg_stride 3).
+ * backward: g_weights_sum = -sum_c bg_c (g_image_c + g_direct_c) (either gradient may be NULL = zero);
+ *   g_direct_full (optional) [N, stride] = zeros with g_direct in columns [col, col+3). d image = g_image unchanged.
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_render_tail_forward(uint32_t N, const float* depth, const float* nears, const float* fars,
+                                        const float* image, const float* weights_sum, const float* direct,
+                                        uint32_t direct_stride, const float* bg, uint32_t bg_stride, float* depth_n,
+                                        float* image_out, float* direct_out, void* stream);
+PNERF_API int pnerf_render_tail_backward(uint32_t N, const float* g_image, const float* g_direct, const float* bg,
+                                         uint32_t bg_stride, uint32_t stride, uint32_t col, float* g_weights_sum,
+                                         float* g_direct_full, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * gradient all-reduce over NVLink peer memory (no reference counterpart: the reference is single-GPU)
  * peer_ptrs: HOST array of `world` device addresses, entry p = the bucket of rank p mapped into this process
  * (symmetric memory / CUDA IPC), each holding n floats, n a multiple of 4 * world. Two-shot: this rank sums slice

@@ -12,7 +12,10 @@ import math
 import numpy as np
 import torch
 import torch.nn as nn
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd import Function
 
+from .. import _lib as _L
 from .. import raymarching
 
 
@@ -160,6 +163,70 @@ def mix_background(image, weights_sum, bg_color):
 
 def normalise_depth(depth, nears, fars):
     return torch.clamp(depth - nears, min=0) / (fars - nears)
+
+
+class _RenderTail(Function):
+    """depth normalisation + background mixing of run_cuda's epilogue in one launch (csrc/tail.cu); backward in one."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, depth, nears, fars, image, weights_sum, bg, maps, col_direct):
+        N = weights_sum.shape[0]
+        dev = image.device
+        image, weights_sum = image.contiguous(), weights_sum.contiguous()
+        depth_n = torch.empty(N, dtype=torch.float32, device=dev)
+        image_out = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        direct_out = torch.empty(N, 3, dtype=torch.float32, device=dev) if maps is not None else None
+        bg_stride = 0 if bg.numel() == 3 else 3
+        stride = maps.shape[1] if maps is not None else 0
+        _L.call("pnerf_render_tail_forward", N, _L.ptr(depth.contiguous()), _L.ptr(nears.contiguous()), _L.ptr(fars.contiguous()),
+                _L.ptr(image), _L.ptr(weights_sum), None if maps is None else maps.data_ptr() + 4 * col_direct, stride,
+                _L.ptr(bg), bg_stride, _L.ptr(depth_n), _L.ptr(image_out), _L.ptr(direct_out), _L.stream())
+        ctx.save_for_backward(bg)
+        ctx.dims = (N, bg_stride, stride, col_direct, maps is not None)
+        ctx.mark_non_differentiable(depth_n)      # the compositors ignore d depth (raymarching.py:275), so does this
+        if maps is None:
+            return depth_n, image_out
+        return depth_n, image_out, direct_out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, _g_depth, g_image, g_direct=None):
+        (bg,) = ctx.saved_tensors
+        N, bg_stride, stride, col, has_maps = ctx.dims
+        dev = bg.device
+        g_image = None if g_image is None else g_image.contiguous().float()
+        g_direct = None if g_direct is None else g_direct.contiguous().float()
+        g_ws = torch.empty(N, dtype=torch.float32, device=dev)
+        g_maps = torch.empty(N, stride, dtype=torch.float32, device=dev) if has_maps else None
+        _L.call("pnerf_render_tail_backward", N, _L.ptr(g_image), _L.ptr(g_direct), _L.ptr(bg), bg_stride, stride, col,
+                _L.ptr(g_ws), _L.ptr(g_maps), _L.stream())
+        return None, None, None, g_image, g_ws, None, g_maps, None
+
+
+_BG_CACHE = {}
+
+
+def render_tail(depth, nears, fars, image, weights_sum, bg_color, maps=None, col_direct=0):
+    """-> (depth_n [N], image [N,3], direct [N,3] | None): normalise_depth + mix_background (twice with `maps`, whose
+    columns [col_direct, col_direct+3) hold the un-mixed direct colour). One kernel when everything is a plain fp32 CUDA
+    tensor and the background is a constant / per-ray colour without gradient; the tensor expressions otherwise."""
+    N = weights_sum.shape[0]
+    bg = bg_color
+    if not torch.is_tensor(bg):
+        key = (float(bg), str(image.device))
+        bg = _BG_CACHE.get(key)
+        if bg is None:
+            bg = _BG_CACHE[key] = torch.full((3,), float(bg_color), dtype=torch.float32, device=image.device)
+    ok = (image.is_cuda and image.dtype == torch.float32 and weights_sum.dtype == torch.float32 and N > 0
+          and not bg.requires_grad and bg.is_cuda and bg.numel() in (3, 3 * N)
+          and (maps is None or (maps.dim() == 2 and maps.is_contiguous() and maps.dtype == torch.float32)))
+    if not ok:
+        direct = None if maps is None else mix_background(maps[..., col_direct:col_direct + 3], weights_sum, bg_color)
+        return normalise_depth(depth, nears, fars), mix_background(image, weights_sum, bg_color), direct
+    bg = bg.detach().to(torch.float32).contiguous()
+    out = _RenderTail.apply(depth, nears, fars, image, weights_sum, bg, maps, col_direct)
+    return (out[0], out[1], out[2]) if maps is not None else (out[0], out[1], None)
 
 
 class NeRFRenderer(nn.Module, OccupancyState):

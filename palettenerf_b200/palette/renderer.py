@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import raymarching
-from ..nerf.renderer import OccupancyState, mix_background, normalise_depth
+from ..nerf.renderer import OccupancyState, mix_background, normalise_depth, render_tail  # noqa: F401
 from .backend import rgb_to_hsv, hsv_to_rgb
 
 
@@ -226,16 +226,18 @@ class PaletteRenderer(nn.Module, OccupancyState):
             # all auxiliary channels ride through ONE n-channel composite: [M, 13 + clip_dim + Nb]
             maps = raymarching.composite_rays_flex_train(sigmas, channels, deltas, rays, T_thresh)
 
+        # depth normalisation + both background mixes: one launch forward, one backward (csrc/tail.cu)
+        depth_n, image_mixed, direct_mixed = render_tail(depth, nears, fars, image, weights_sum, bg_color, maps, 7)
         out = {
-            "depth": normalise_depth(depth, nears, fars).view(*prefix),
-            "image": mix_background(image, weights_sum, bg_color).view(*prefix, 3),
+            "depth": depth_n.view(*prefix),
+            "image": image_mixed.view(*prefix, 3),
             "weights_sum": weights_sum,
             "omega_sparsity": maps[..., 0:1].view(*prefix),
             "view_dep_norm": maps[..., 1:2].view(*prefix),
             "offsets_norm": maps[..., 2:3].view(*prefix),
             "smooth_norm": maps[..., 3:4].view(*prefix),
             "view_dep_rgb": maps[..., 4:7].view(*prefix, 3),
-            "direct_rgb": mix_background(maps[..., 7:10], weights_sum, bg_color).view(*prefix, 3),
+            "direct_rgb": direct_mixed.view(*prefix, 3),
             "diffuse_rgb": maps[..., 10:13].view(*prefix, 3),
             "clip_feat": maps[..., 13:13 + cd].view(*prefix, cd),
             "basis_acc": maps[..., 13 + cd:13 + cd + nb].view(*prefix, nb),
@@ -326,15 +328,17 @@ class PaletteRenderer(nn.Module, OccupancyState):
         self._last_schedule = "fused" if use_fused else "loop"
         self._last_queue = acc.get("_queue")
         ws = acc["weights_sum"]
+        depth_n, image_mixed, direct_mixed = render_tail(acc["depth"], nears, fars, acc["image"], ws, bg_color,
+                                                         None if gui_mode else acc["direct_rgb"], 0)
         out = {
-            "depth": normalise_depth(acc["depth"], nears, fars).view(*prefix),
-            "depth_origin": acc["depth"].clone().view(*prefix),
-            "image": mix_background(acc["image"], ws, bg_color).view(*prefix, 3),
+            "depth": depth_n.view(*prefix),
+            "depth_origin": acc["depth"].view(*prefix),     # the accumulator itself (nothing writes it afterwards)
+            "image": image_mixed.view(*prefix, 3),
             "weights_sum": ws,
             "clip_feat": acc["clip_feat"].view(*prefix, cd),
         }
         if not gui_mode:
-            out["direct_rgb"] = mix_background(acc["direct_rgb"], ws, bg_color).view(*prefix, 3)
+            out["direct_rgb"] = direct_mixed.view(*prefix, 3)
             out["view_dep_rgb"] = acc["view_dep_rgb"].view(*prefix, 3)
             out["basis_rgb"] = acc["basis_rgb"].view(*prefix, nb * 3)
             out["unscaled_basis_rgb"] = acc["unscaled_basis_rgb"].view(*prefix, nb * 3)

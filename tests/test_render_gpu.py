@@ -89,3 +89,35 @@ def test_nerf_stage_model_and_density_grid_update(cuda):
     m.mark_untrained_grid(pose, (277.8, 277.8, 100.0, 100.0))
     frac = (m.density_grid < 0).float().mean().item()
     assert 0.05 < frac < 0.999
+
+
+@pytest.mark.parametrize("bg_kind", ["scalar", "rgb", "per_ray"])
+@pytest.mark.parametrize("with_maps", [True, False])
+def test_render_tail_matches_tensor_expressions(cuda, bg_kind, with_maps):
+    """csrc/tail.cu (depth normalisation + background mixing, ref palette/renderer.py:399-429) vs the torch expressions it
+    replaces: values exact to 1 ulp-level (same fp32 operations, fma contraction aside: 1e-6), gradients likewise"""
+    from palettenerf_b200.nerf.renderer import mix_background, normalise_depth, render_tail
+    N = 5001
+    g = torch.Generator(device=cuda).manual_seed(3)
+    r = lambda *s: torch.rand(*s, device=cuda, generator=g)  # noqa: E731
+    nears, fars = r(N) + 0.2, r(N) + 2.0
+    depth = r(N) * 3
+    bg = {"scalar": 1, "rgb": r(3), "per_ray": r(N, 3)}[bg_kind]
+    image0, ws0, maps0 = r(N, 3), r(N), r(N, 33)
+    res = []
+    for fused_tail in (True, False):
+        image, ws, maps = image0.clone().requires_grad_(True), ws0.clone().requires_grad_(True), maps0.clone().requires_grad_(True)
+        if fused_tail:
+            d, im, di = render_tail(depth, nears, fars, image, ws, bg, maps if with_maps else None, 7)
+        else:
+            d, im = normalise_depth(depth, nears, fars), mix_background(image, ws, bg)
+            di = mix_background(maps[..., 7:10], ws, bg) if with_maps else None
+        w_im, w_di = torch.linspace(0.5, 1.5, N * 3, device=cuda).view(N, 3), torch.linspace(-1, 1, N * 3, device=cuda).view(N, 3)
+        loss = (im * w_im).sum() + ((di * w_di).sum() if with_maps else 0.0) + (maps ** 2).sum() * 0.01
+        loss.backward()
+        res.append((d, im, di, image.grad, ws.grad, maps.grad))
+    for a, b in zip(*res):
+        if a is None:
+            assert b is None
+            continue
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
