@@ -290,8 +290,8 @@ class NeRFRenderer(nn.Module, OccupancyState):
             else:
                 weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
                 _, _, err_map = raymarching.composite_rays_train(sigmas, err, deltas, rays, T_thresh)
-                image = mix_background(image, weights_sum, bg_color).view(*prefix, 3)
-                depth = normalise_depth(depth, nears, fars).view(*prefix)
+                depth, image, _ = render_tail(depth, nears, fars, image, weights_sum, bg_color)
+                image, depth = image.view(*prefix, 3), depth.view(*prefix)
                 rgb_norm = err_map.mean(dim=-1).view(*prefix)
         else:
             weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -313,8 +313,8 @@ class NeRFRenderer(nn.Module, OccupancyState):
                                            weights_sum, depth, image, T_thresh)
                 rays_alive = rays_alive[rays_alive >= 0]
                 step += n_step
-            image = mix_background(image, weights_sum, bg_color).view(*prefix, 3)
-            depth = normalise_depth(depth, nears, fars).view(*prefix)
+            depth, image, _ = render_tail(depth, nears, fars, image, weights_sum, bg_color)
+            image, depth = image.view(*prefix, 3), depth.view(*prefix)
             rgb_norm = torch.zeros_like(image[..., 0])
 
         return {"depth": depth, "image": image, "rgb_norm": rgb_norm, "weights_sum": weights_sum}
