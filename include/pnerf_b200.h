@@ -386,6 +386,12 @@ typedef struct pnerf_adam_tensor {
     float* p; const float* g; float* m; float* v;   /* parameter, gradient, exp_avg, exp_avg_sq : [n] fp32 */
     const float* step;                              /* device scalar, advanced by the call               */
     uint64_t n;
+    /* optional fp16 mirror of the updated parameter, written in the same pass: elements (2e, 2e+1) go as one half2 to
+     * (char*)mirror + e * mirror_stride (n even, mirror 4-byte aligned, stride a multiple of 4). The fused training
+     * field reads the trained hash table through such a copy (interleaved with the frozen density table: stride 8), so
+     * the separate fp32 -> fp16 refresh pass over the table disappears. NULL: no mirror. */
+    void* mirror;
+    uint64_t mirror_stride;
 } pnerf_adam_tensor;
 
 PNERF_API int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, float lr, const float* lr_dev, float beta1,

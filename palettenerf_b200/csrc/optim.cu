@@ -75,11 +75,17 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ A
             *reinterpret_cast<float4*>(T.p + i) = p;
             *reinterpret_cast<float4*>(T.m + i) = m;
             *reinterpret_cast<float4*>(T.v + i) = v;
+            if (T.mirror) {
+                char* mp = reinterpret_cast<char*>(T.mirror) + (i >> 1) * T.mirror_stride;
+                *reinterpret_cast<__half2*>(mp) = __floats2half2_rn(p.x, p.y);
+                *reinterpret_cast<__half2*>(mp + T.mirror_stride) = __floats2half2_rn(p.z, p.w);
+            }
         } else {
             for (uint64_t j = i; j < n && j < i + 4; j++) {
                 float p = T.p[j], m = T.m[j], v = T.v[j];
                 adam_one(p, T.g[j], m, v, inv_scale, a.weight_decay, a.beta1, a.beta2, step_size, rsqrt_bc2, a.eps);
                 T.p[j] = p; T.m[j] = m; T.v[j] = v;
+                if (T.mirror) reinterpret_cast<__half*>(reinterpret_cast<char*>(T.mirror) + (j >> 1) * T.mirror_stride)[j & 1] = __float2half_rn(p);
             }
         }
     }
@@ -106,6 +112,9 @@ int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, float lr, 
     uint64_t blocks = 0;
     for (uint32_t i = 0; i < count; i++) {
         PNERF_REQUIRE(tensors[i].p && tensors[i].g && tensors[i].m && tensors[i].v && tensors[i].step);
+        if (tensors[i].mirror)
+            PNERF_REQUIRE((tensors[i].n & 1) == 0 && (reinterpret_cast<uintptr_t>(tensors[i].mirror) & 3) == 0 &&
+                          tensors[i].mirror_stride >= 4 && (tensors[i].mirror_stride & 3) == 0);
         a.t[i] = tensors[i];
         a.first_block[i] = (uint32_t)blocks;
         blocks += ceil_div<uint64_t>(tensors[i].n, kAdamPerBlock);

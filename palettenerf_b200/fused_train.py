@@ -152,6 +152,16 @@ class _Tables:
         contain the conversion no matter what the cache looked like at capture time)"""
         key = (p._version, p.data_ptr())
         hit = self.c.get(name)
+        if always and hit is not None and hit[1].shape == p.shape:
+            # a trained table: FusedAdam keeps this fp16 copy current in its own pass (pnerf_adam_tensor.mirror, contiguous
+            # half2 entries: offset 0, 4 bytes per entry) and records the parameter version it did that for
+            mir = getattr(p, "_pnerf_half_mirror", None)
+            if mir is not None and mir[0] is hit[1] and getattr(p, "_pnerf_mirror_version", None) == p._version:
+                return hit[1]
+            hit[1].copy_(p.detach())                  # same buffer every step (stable address for the mirror / a graph)
+            p._pnerf_half_mirror, p._pnerf_mirror_version = (hit[1], 0, 4), None
+            self.c[name] = (key, hit[1])
+            return hit[1]
         if always or hit is None or hit[0] != key:
             hit = (key, p.detach().to(torch.float16).contiguous())
             self.c[name] = hit
@@ -170,6 +180,15 @@ class _Tables:
         if hit[0] != key_s:
             hit[2][:, 0, :].copy_(sigma_p.detach())
             hit[0] = key_s
+        # FusedAdam writes fp16(p) into this buffer in its own pass (pnerf_adam_tensor.mirror) and records the parameter
+        # version it did that for: then there is nothing to refresh
+        mir = getattr(palette_p, "_pnerf_half_mirror", None)
+        if mir is None or mir[0] is not hit[2]:
+            palette_p._pnerf_half_mirror = (hit[2], 4, 8)      # (buffer, byte offset of the palette slot, bytes per entry)
+            palette_p._pnerf_mirror_version = None
+        if getattr(palette_p, "_pnerf_mirror_version", None) == palette_p._version and hit[1] is not None:
+            hit[1] = key_p
+            return hit[2]
         if refresh_palette or hit[1] != key_p:
             hit[2][:, 1, :].copy_(palette_p.detach())
             hit[1] = key_p

@@ -21,7 +21,8 @@ from ._lib import ptr, stream
 
 
 class _AdamTensor(ctypes.Structure):
-    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("step", c_void_p), ("n", c_uint64)]
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("step", c_void_p), ("n", c_uint64),
+                ("mirror", c_void_p), ("mirror_stride", c_uint64)]
 
 
 MAX_TENSORS = 32
@@ -91,9 +92,20 @@ class FusedAdam(torch.optim.Optimizer):
             for i in range(0, len(todo), MAX_TENSORS):
                 chunk = todo[i:i + MAX_TENSORS]
                 arr = (_AdamTensor * len(chunk))()
+                mirrored = []
                 for k, (p, g, m, v, s) in enumerate(chunk):
                     arr[k].p, arr[k].g, arr[k].m, arr[k].v, arr[k].step, arr[k].n = ptr(p), ptr(g), ptr(m), ptr(v), ptr(s), p.numel()
+                    # fp16 mirror registered on the parameter (fused_train: the interleaved table the forward kernel reads)
+                    mir = getattr(p, "_pnerf_half_mirror", None)
+                    if mir is not None and mir[0].device == p.device and p.numel() % 2 == 0:
+                        arr[k].mirror, arr[k].mirror_stride = mir[0].data_ptr() + mir[1], mir[2]
+                        mirrored.append(p)
                 L.call("pnerf_adam_step", ctypes.addressof(arr), len(chunk), 0.0 if lr_dev is not None else float(lr),
                        ptr(lr_dev), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), ptr(grad_scale),
                        ptr(found_inf), stream())
+                # the kernel writes through raw pointers: tell autograd / version-keyed caches (fused.FieldCache, the fp16
+                # table copies) that the tensors changed, as an in-place torch op would
+                torch.autograd.graph.increment_version([t for tup in chunk for t in (tup[0], tup[2], tup[3], tup[4])])
+                for p in mirrored:        # the mirror holds fp16(p) for exactly this version of p
+                    p._pnerf_mirror_version = p._version
         return loss

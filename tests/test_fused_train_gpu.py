@@ -213,3 +213,45 @@ def test_cuda_graph_captured_step_matches_eager_steps(cuda):
     for (n1, p1), (_, p2) in zip(m_graph.named_parameters(), m_eager.named_parameters()):
         if p1.requires_grad and p1.numel() < 100000:
             assert torch.allclose(p1, p2, rtol=5e-2, atol=5e-3), n1
+
+
+def test_fused_adam_mirror_trains_like_torch_adam_with_table_refresh(cuda):
+    """FusedAdam writes the fp16 copy of the trained hash table (the interleaved table the forward kernel reads) in its own
+    pass; torch's Adam leaves that to the per-step refresh copy. Same model, same rays: the two must train alike — eager and
+    from a CUDA graph (whose capture then contains no refresh copy at all) — and the mirror must equal fp16(parameter)."""
+    from palettenerf_b200.graphs import GraphedStep, make_palette_train_step
+    from palettenerf_b200.optim import FusedAdam
+    from palettenerf_b200.palette.losses import palette_loss
+    o, d = S.training_rays(512, seed=5)
+    o, d = o.to(cuda)[None].contiguous(), d.to(cuda)[None].contiguous()
+    gt = torch.rand(1, 512, 3, device=cuda, generator=torch.Generator(device=cuda).manual_seed(2))
+
+    def make(fused_adam):
+        m = S.build_palette_model(cuda, seed=8, pred_clip=False, table_scale=0.3)
+        m.train()
+        params = m.get_params(1e-2)
+        opt = FusedAdam(params, betas=(0.9, 0.99), eps=1e-15) if fused_adam else \
+            torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+        sc = torch.amp.GradScaler("cuda", init_scale=1024.0)
+        return m, make_palette_train_step(m, opt, sc, o, d, lambda out: palette_loss(out, gt, 2e-4, 0.03, 0.1)[0],
+                                          render_kwargs=dict(perturb=False))
+
+    m_ref, step_ref = make(False)
+    m_new, step_new = make(True)
+    m_gr, step_gr = make(True)
+    l_ref = [float(step_ref()) for _ in range(6)]
+    l_new = [float(step_new()) for _ in range(6)]
+    g = GraphedStep(step_gr, warmup=2)
+    l_gr = [float(g.replay()) for _ in range(4)]
+    np.testing.assert_allclose(l_new, l_ref, rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(l_gr, l_ref[2:], rtol=2e-3, atol=1e-5)
+    assert l_new[-1] < l_new[0]
+    for m in (m_new, m_gr):
+        p = m.encoder_palette.embeddings
+        buf, off, stride = p._pnerf_half_mirror
+        assert p._pnerf_mirror_version == p._version and (off, stride) == (4, 8)
+        assert torch.equal(buf[:, 1, :], p.detach().to(torch.float16))          # the mirror IS fp16(parameter)
+        assert torch.equal(buf[:, 0, :], m.encoder.embeddings.detach().to(torch.float16))
+    for (n1, p1), (_, p2) in zip(m_new.named_parameters(), m_ref.named_parameters()):
+        if p1.requires_grad and p1.numel() < 100000:
+            assert torch.allclose(p1, p2, rtol=5e-2, atol=5e-3), n1

@@ -123,3 +123,16 @@ def test_fused_adam_in_a_cuda_graph_with_device_lr(cuda):
         ref.step()
     assert float(opt.state[p]["step"]) == 4.0
     assert _close(p, q, 4e-6, 4e-8), (p - q).abs().max().item()
+
+
+@pytest.mark.gpu
+def test_fused_adam_bumps_tensor_versions(cuda):
+    """the kernel writes parameters through raw pointers; version-keyed caches (the renderer's fp16 table copies) rely on
+    `_version` changing like it does for torch's in-place optimizers"""
+    from palettenerf_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.randn(1000, device=cuda))
+    opt = FusedAdam([p], lr=1e-2)
+    p.grad = torch.randn(1000, device=cuda)
+    v0 = p._version
+    opt.step()
+    assert p._version > v0
