@@ -10,7 +10,7 @@
 //
 // Arithmetic = torch's (aten/src/ATen/native/cuda/fused_adam_utils.cuh, non-amsgrad, maximize = false):
 //   g = grad / grad_scale (+ weight_decay * p);  m = lerp(m, g, 1 - beta1);  v = beta2 * v + (1 - beta2) g^2
-//   p -= (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = step + 1   (bias corrections in double)
+//   p -= (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = step + 1
 #include "common.cuh"
 
 namespace pnerf {
@@ -44,16 +44,13 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ A
 #pragma unroll 1
     while (ti + 1 < a.count && blockIdx.x >= a.first_block[ti + 1]) ti++;
     const pnerf_adam_tensor& T = a.t[ti];
-    // bias corrections in double like torch; one lane per warp evaluates the two pow() (the FP64 pipe is narrow)
-    float step_size = 0.f, rsqrt_bc2 = 0.f;
-    if ((threadIdx.x & 31) == 0) {
-        const double t = (double)__ldg(T.step) + 1.0;
-        const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
-        step_size = (float)((double)lr / (1.0 - pow((double)a.beta1, t)));
-        rsqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a.beta2, t)));
-    }
-    step_size = __shfl_sync(0xffffffffu, step_size, 0);
-    rsqrt_bc2 = __shfl_sync(0xffffffffu, rsqrt_bc2, 0);
+    // bias corrections 1 - beta^t = -expm1(t log beta): fp32 expm1f / logf keep the relative error of the correction at a
+    // few 1e-7 even for t = 1 (where 1 - 0.99 cancels), without the double-precision pow() torch uses (a long serial
+    // prologue in front of every warp's first load; measured: 97 -> 92 us for the 12.7 M-element step)
+    const float t = __ldg(T.step) + 1.0f;
+    const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
+    const float step_size = lr / (-expm1f(t * logf(a.beta1)));
+    const float rsqrt_bc2 = 1.0f / sqrtf(-expm1f(t * logf(a.beta2)));
     const float inv_scale = a.grad_scale ? 1.0f / __ldg(a.grad_scale) : 1.0f;
     const uint64_t base = (uint64_t)(blockIdx.x - a.first_block[ti]) * kAdamPerBlock;
     const uint64_t n = T.n;
