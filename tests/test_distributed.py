@@ -88,3 +88,26 @@ def test_data_parallel_bucket_sharded_render_and_density_merge_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(ws, port, ret), nprocs=ws, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_grad_bucket_single_process_semantics():
+    """world size 1 (no process group): pack once, gradients re-pointed at the bucket, flag forms, repeated calls"""
+    import torch
+    from palettenerf_b200.distributed import GradBucket
+    ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+    ps[2].requires_grad_(False)
+    b = GradBucket(ps)
+    for step in range(3):
+        ps[0].grad, ps[1].grad = torch.full((5, 3), 1.0 + step), torch.arange(7.0) * (step + 1)
+        want0, want1 = ps[0].grad.clone(), ps[1].grad.clone()
+        flag = b.all_reduce(found_inf=torch.tensor(float(step == 1)), average=True)
+        assert float(flag) == float(step == 1)
+        assert torch.equal(ps[0].grad, want0) and torch.equal(ps[1].grad, want1)
+        assert ps[0].grad.shape == (5, 3) and ps[0].grad.data_ptr() == b.flat.data_ptr()            # a view of the bucket
+        assert ps[1].grad.data_ptr() == b.flat[15:].data_ptr() and b.flat.numel() == 15 + 7 + 1
+    assert b.signature() == [(5, 3), (7,)]
+    # a parameter that stops receiving gradients changes the layout: the bucket is rebuilt
+    ps[1].grad = None
+    ps[0].grad = torch.ones(5, 3)
+    b.all_reduce()
+    assert b.flat.numel() == 16 and b.signature() == [(5, 3)]
