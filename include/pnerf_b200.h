@@ -103,6 +103,14 @@ PNERF_API uint32_t pnerf_occupied_bounds_floats(void);
 PNERF_API int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float* occ_aabb,
                                     void* stream);
 
+/* NeRFRenderer.mark_untrained_grid (ref: nerf/renderer.py:395-465) as one kernel: poses [B,4,4] row-major camera-to-world,
+ * intrinsics fx fy cx cy; density_grid [C, H^3] (Morton order) receives -1 in every cell that no camera sees or that a
+ * seeing camera has closer than min_near (filter_close_point: also cells within min_near of any camera centre).
+ * n_marked (optional device counter, += number of cells marked). B = 0 marks everything. */
+PNERF_API int pnerf_mark_untrained_grid(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t C,
+                                        uint32_t H, float bound, float min_near, int filter_close_point,
+                                        float* density_grid, uint32_t* n_marked, void* stream);
+
 /* ref: raymarching.cu:504-580,647-655 */
 PNERF_API int pnerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
                                                  const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,

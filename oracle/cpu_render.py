@@ -268,3 +268,54 @@ def palette_train_loss(outputs, gt_rgb, lambda_sparsity=0.0, lambda_offsets=0.0,
         loss = loss + d[k]
     d["rgb"] = per_ray.mean()
     return loss.mean(), d, per_ray                                               # :598
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mark_untrained_grid (TEST INFRASTRUCTURE; restates NeRFRenderer.mark_untrained_grid, nerf/renderer.py:395-465)
+# ---------------------------------------------------------------------------------------------------------------
+def mark_untrained_grid(density_grid, poses, intrinsic, cascade, grid_size, bound, min_near, filter_close_point=False,
+                        cam_chunk=16, margin=False):
+    """-> (new density grid [C, H^3] in Morton order, fp64 decision margins or None). The reference's tensor program
+    (:421-456) on the CPU in float64, cell by cell in chunks: world = (2 c/(H-1) - 1)(bound_k - bound_k/H) (:427, :431-434),
+    cam = (world - t) @ R (:443-444), the three frustum tests (:447-450), the min_near tests (:452-453), count /
+    too_close accumulation over all cameras (:455-458) and the final marking (:462-463).
+    margin=True additionally returns, per cell, the smallest |lhs - rhs| over every comparison made for it: cells whose
+    margin is below fp32 resolution may legitimately flip between an fp32 and an fp64 evaluation."""
+    import oracle
+    H = grid_size
+    fx, fy, cx, cy = (float(v) for v in intrinsic)
+    poses = torch.as_tensor(poses, dtype=torch.float64).reshape(-1, 4, 4)
+    g = torch.arange(H, dtype=torch.int32)
+    coords = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    indices = torch.from_numpy(oracle.morton3D(coords.numpy())).long()
+    unit = 2 * coords.double() / (H - 1) - 1
+    out = density_grid.clone()
+    margins = torch.full((cascade, H ** 3), float("inf"), dtype=torch.float64) if margin else None
+    for cas in range(cascade):
+        b = min(2 ** cas, bound)
+        half = b / H
+        world = unit * (b - half)
+        count = torch.zeros(H ** 3, dtype=torch.int64)
+        close = torch.zeros(H ** 3, dtype=torch.int64)
+        mg = torch.full((H ** 3,), float("inf"), dtype=torch.float64)
+        for h in range(0, poses.shape[0], cam_chunk):
+            R, t = poses[h:h + cam_chunk, :3, :3], poses[h:h + cam_chunk, :3, 3]
+            cam = (world.unsqueeze(0) - t.unsqueeze(1)) @ R
+            z = cam[..., 2]
+            lim_x, lim_y = cx / fx * z + half * 2, cy / fy * z + half * 2
+            vis = (z > 0) & (cam[..., 0].abs() < lim_x) & (cam[..., 1].abs() < lim_y)
+            count += vis.sum(0)
+            close += (vis & (z < min_near)).sum(0)
+            if filter_close_point:
+                close += (cam.norm(dim=-1) < min_near).sum(0)
+            if margin:
+                m = torch.minimum(z.abs(), torch.minimum((cam[..., 0].abs() - lim_x).abs(), (cam[..., 1].abs() - lim_y).abs()))
+                m = torch.minimum(m, (z - min_near).abs())
+                if filter_close_point:
+                    m = torch.minimum(m, (cam.norm(dim=-1) - min_near).abs())
+                mg = torch.minimum(mg, m.min(0).values)
+        mark = (count * (close == 0)) == 0
+        out[cas, indices[mark]] = -1
+        if margin:
+            margins[cas, indices] = mg
+    return out, margins

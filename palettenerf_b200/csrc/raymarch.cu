@@ -321,6 +321,62 @@ __global__ void __launch_bounds__(192) k_occupied_bounds_finish(uint32_t C, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// mark_untrained_grid (ref: NeRFRenderer.mark_untrained_grid, nerf/renderer.py:395-465): a cell that no
+// training camera sees, or that lies closer than min_near to a camera that sees it (optionally: closer than min_near to
+// any camera centre), gets density -1 and never sets an occupancy bit. The reference walks a 5-deep Python loop of
+// batched matmuls over 64^3 blocks x cascades x 64-camera chunks; here one thread owns one (cascade, cell) and loops over
+// the cameras, which are staged in shared memory 64 at a time (12 floats each). Same expressions in fp32:
+//   world = (2 c / (H-1) - 1) * (bound_k - bound_k / H);  cam = (world - t) R  (row vector times the c2w rotation)
+//   seen  = z > 0 && |x| < cx/fx z + 2 half && |y| < cy/fy z + 2 half;  close = seen && z < min_near
+// ------------------------------------------------------------------------------------------------
+constexpr int kMarkCams = 64;
+
+__global__ void __launch_bounds__(256) k_mark_untrained(const float* __restrict__ poses, uint32_t B, float cxfx, float cyfy,
+                                                        uint32_t C, uint32_t H, float bound, float min_near,
+                                                        int filter_close_point, float* __restrict__ density_grid,
+                                                        unsigned int* __restrict__ n_marked) {
+    __shared__ float cam[kMarkCams][12];
+    const uint32_t H3 = H * H * H;
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x, cas = blockIdx.y;
+    const bool live = cell < H3;
+    const float b = fminf(scalbnf(1.0f, (int)cas), bound), half = b / (float)H;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (live) {
+        const uint32_t x = compact3(cell), y = compact3(cell >> 1), z = compact3(cell >> 2);     // density_grid is in Morton order
+        const float s = b - half, hm1 = (float)(H - 1);
+        wx = (2 * (float)x / hm1 - 1) * s; wy = (2 * (float)y / hm1 - 1) * s; wz = (2 * (float)z / hm1 - 1) * s;
+    }
+    uint32_t seen = 0, close = 0;
+    for (uint32_t c0 = 0; c0 < B; c0 += kMarkCams) {
+        const uint32_t nc = min((uint32_t)kMarkCams, B - c0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nc * 12; i += blockDim.x) {
+            const uint32_t k = i / 12, e = i - k * 12;          // rows 0..2 of the 4x4 pose: R[r][0..2], t[r]
+            cam[k][e] = poses[(size_t)(c0 + k) * 16 + (e >> 2) * 4 + (e & 3)];
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (uint32_t k = 0; k < nc; k++) {
+            const float* P = cam[k];
+            const float dx = wx - P[3], dy = wy - P[7], dz = wz - P[11];
+            const float cx_ = dx * P[0] + dy * P[4] + dz * P[8];
+            const float cy_ = dx * P[1] + dy * P[5] + dz * P[9];
+            const float cz_ = dx * P[2] + dy * P[6] + dz * P[10];
+            const bool vis = cz_ > 0 && fabsf(cx_) < cxfx * cz_ + half * 2 && fabsf(cy_) < cyfy * cz_ + half * 2;
+            seen += vis ? 1u : 0u;
+            close += (vis && cz_ < min_near) ? 1u : 0u;
+            if (filter_close_point) close += (sqrtf(cx_ * cx_ + cy_ * cy_ + cz_ * cz_) < min_near) ? 1u : 0u;
+        }
+    }
+    const bool mark = live && (seen == 0u || close != 0u);
+    if (mark) density_grid[(size_t)cas * H3 + cell] = -1.0f;
+    if (n_marked) {
+        const uint32_t m = __popc(__ballot_sync(0xffffffffu, mark));
+        if ((threadIdx.x & 31u) == 0 && m) atomicAdd(n_marked, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // inference march (ref: raymarching.cu:907-1011)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_march_rays(uint32_t n_alive, uint32_t n_step,
@@ -467,6 +523,17 @@ int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const ui
     k_march_train_emit<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, noises,
                                                        rays, t_list, xyzs, dirs, deltas);
     return check_launch("march_rays_train_ws");
+}
+
+int pnerf_mark_untrained_grid(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t C, uint32_t H,
+                              float bound, float min_near, int filter_close_point, float* density_grid,
+                              uint32_t* n_marked, void* stream) {
+    PNERF_REQUIRE(density_grid && (B == 0 || poses) && C >= 1 && C <= 16 && H >= 2 && fx != 0.f && fy != 0.f && bound > 0.f);
+    if (H > 1024) return PNERF_ERR_UNSUPPORTED;
+    const dim3 grid(ceil_div(H * H * H, 256u), C, 1);
+    k_mark_untrained<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, B, cx / fx, cy / fy, C, H, bound, min_near,
+                                                            filter_close_point, density_grid, n_marked);
+    return check_launch("mark_untrained_grid");
 }
 
 int pnerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,

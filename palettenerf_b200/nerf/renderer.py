@@ -81,38 +81,25 @@ class OccupancyState:
     # -- density grid maintenance (ref: nerf/renderer.py:395-561) -----------------------------------------
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """cells seen by no training camera (or closer than min_near to one) get density -1 and never set a bit"""
+        """cells seen by no training camera (or closer than min_near to one) get density -1 and never set a bit.
+        One kernel over (cascade, cell) with the cameras staged in shared memory (csrc/raymarch.cu::k_mark_untrained)
+        instead of the reference's 5-deep Python loop (nerf/renderer.py:395-465); `S` (its chunk size) is ignored."""
         if not self.cuda_ray:
             return
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
         dev = self.density_bitfield.device
-        poses = poses.to(dev)
-        fx, fy, cx, cy = intrinsic
-        coords, indices = self._cells(dev)
-        unit = 2 * coords.float() / (self.grid_size - 1) - 1
-        seen = torch.zeros_like(self.density_grid)
-        near_cam = torch.zeros_like(self.density_grid)
-        chunk = 128 ** 3 // 8
-        for cas in range(self.cascade):
-            b, half = self._cascade_extent(cas)
-            for c0 in range(0, unit.shape[0], chunk):
-                world = (unit[c0:c0 + chunk] * (b - half)).unsqueeze(0)
-                ind = indices[c0:c0 + chunk]
-                for h in range(0, poses.shape[0], S):
-                    R, t = poses[h:h + S, :3, :3], poses[h:h + S, :3, 3]
-                    cam = (world - t.unsqueeze(1)) @ R
-                    front = cam[..., 2] > 0
-                    in_x = cam[..., 0].abs() < cx / fx * cam[..., 2] + half * 2
-                    in_y = cam[..., 1].abs() < cy / fy * cam[..., 2] + half * 2
-                    vis = front & in_x & in_y
-                    seen[cas, ind] += vis.sum(0)
-                    near_cam[cas, ind] += (vis & (cam[..., 2] < self.min_near)).sum(0)
-                    if getattr(self, "filter_close_point", False):
-                        near_cam[cas, ind] += (cam.norm(dim=-1) < self.min_near).sum(0)
-        seen = seen * (near_cam == 0)
-        self.density_grid[seen == 0] = -1
-        print(f"[mark untrained grid] {(seen == 0).sum()} from {self.grid_size ** 3 * self.cascade}")
+        _L.require_cuda(self.density_grid)
+        poses = poses.to(dev).to(torch.float32).reshape(-1, 4, 4).contiguous()
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        if not self.density_grid.is_contiguous():
+            raise RuntimeError("density_grid must be contiguous")
+        n_marked = torch.zeros(1, dtype=torch.int32, device=dev)
+        _L.call("pnerf_mark_untrained_grid", _L.ptr(poses), poses.shape[0], fx, fy, cx, cy, self.cascade, self.grid_size,
+                float(self.bound), float(self.min_near), int(bool(getattr(self, "filter_close_point", False))),
+                _L.ptr(self.density_grid), _L.ptr(n_marked), _L.stream())
+        torch.autograd.graph.increment_version(self.density_grid)     # written through a raw pointer
+        print(f"[mark untrained grid] {int(n_marked.item())} from {self.grid_size ** 3 * self.cascade}")
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):

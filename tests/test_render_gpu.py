@@ -121,3 +121,37 @@ def test_render_tail_matches_tensor_expressions(cuda, bg_kind, with_maps):
             assert b is None
             continue
         assert (a - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("filter_close", [False, True])
+def test_mark_untrained_grid_kernel_vs_oracle(cuda, filter_close):
+    """pnerf_mark_untrained_grid (one kernel) vs the fp64 restatement of the reference's 5-deep loop (nerf/renderer.py:
+    395-465). Index work: every cell whose decision is not within fp32 rounding of a comparison threshold must agree
+    exactly; the kernel must also agree with itself when the cameras arrive in another order."""
+    import math
+    from oracle import cpu_render
+    from palettenerf_b200.nerf.network import NeRFNetwork
+    H, C, bound, min_near = 32, 2, 2.0, 0.35
+    m = NeRFNetwork(bound=bound, cuda_ray=True, min_near=min_near, filter_close_point=filter_close).to(cuda)
+    m.grid_size, m.cascade = H, C
+    m.density_grid = torch.zeros(C, H ** 3, device=cuda)
+    poses = torch.stack([S.lookat_pose(r, az) for r, az in ((3.2, 10.0), (3.2, 130.0), (1.2, 250.0), (0.5, 40.0))] +
+                        [S.lookat_pose(2.5, 15.0 * k) for k in range(70)])          # > 64 cameras: two shared-memory chunks
+    f = 0.5 * 100 / math.tan(0.5 * 0.69)
+    intr = [f, f, 50.0, 50.0]
+    m.mark_untrained_grid(poses.numpy(), intr)
+    got = m.density_grid.cpu()
+    ref, margin = cpu_render.mark_untrained_grid(torch.zeros(C, H ** 3), poses, intr, C, H, bound, min_near, filter_close,
+                                                 margin=True)
+    decided = margin > 1e-4                      # fp32 evaluation of O(1) camera coordinates: safe margin
+    assert decided.float().mean().item() > 0.99
+    assert torch.equal(got[decided], ref[decided])
+    n_marked = int((got == -1).sum())
+    assert 0 < n_marked < C * H ** 3 and abs(n_marked - int((ref == -1).sum())) <= int((~decided).sum())
+    # camera order does not matter; B = 0 marks everything
+    m.density_grid = torch.zeros(C, H ** 3, device=cuda)
+    m.mark_untrained_grid(poses.flip(0).contiguous(), intr)
+    assert torch.equal(m.density_grid.cpu(), got)
+    m.density_grid = torch.zeros(C, H ** 3, device=cuda)
+    m.mark_untrained_grid(poses[:0], intr)
+    assert bool((m.density_grid == -1).all())
