@@ -24,41 +24,58 @@ def custom_meshgrid(*args):
     return torch.meshgrid(*args, indexing="ij")
 
 
+# Pixel-index sampling. The four modes of the reference (nerf/utils.py:76-124) as separate samplers; each makes the
+# reference's torch RNG calls in the reference's order (a seeded run draws the same pixels), everything else is this
+# module's own arrangement. Every sampler returns flat pixel ids `row * W + col` of shape [B, N].
+def _rand(hi, n, device, lo=0):
+    return torch.randint(lo, hi, size=[n], device=device)
+
+
+def _sample_patches(B, H, W, N, p, device):
+    """N // p^2 random p x p patches (top-left corners drawn first along rows, then along columns); ref :79-95"""
+    k = N // (p * p)
+    rows, cols = _rand(H - p, k, device), _rand(W - p, k, device)
+    dr, dc = custom_meshgrid(torch.arange(p, device=device), torch.arange(p, device=device))
+    pix = (rows[:, None] + dr.reshape(1, -1)) * W + (cols[:, None] + dc.reshape(1, -1))      # [k, p^2]
+    return pix.reshape(-1).expand([B, N])      # as in the reference, N must be a multiple of p^2
+
+
+def _sample_pairs(B, H, W, N, r, device):
+    """N/2 random pixels followed by one neighbour each within +-r (clamped to the image); ref :96-110"""
+    assert N % 2 == 0
+    k = N // 2
+    rows, cols = _rand(H, k, device), _rand(W, k, device)
+    d_rows, d_cols = _rand(r, k, device, lo=-r), _rand(r, k, device, lo=-r)
+    first = rows * W + cols
+    second = (rows + d_rows).clamp(0, H - 1) * W + (cols + d_cols).clamp(0, W - 1)
+    return torch.cat([first, second]).expand([B, N])
+
+
+def _sample_uniform(B, H, W, N, device):
+    """N pixels with replacement; ref :111-113"""
+    return _rand(H * W, N, device).expand([B, N])
+
+
+def _sample_error_map(B, H, W, N, error_map, device):
+    """N cells of the 128 x 128 error map without replacement, then a uniform pixel inside each cell; ref :114-126"""
+    coarse = torch.multinomial(error_map.to(device), N, replacement=False)       # [B, N]
+    cell_h, cell_w = H / 128, W / 128
+    rows = ((coarse // 128) * cell_h + torch.rand(B, N, device=device) * cell_h).long().clamp(max=H - 1)
+    cols = ((coarse % 128) * cell_w + torch.rand(B, N, device=device) * cell_w).long().clamp(max=W - 1)
+    return rows * W + cols, coarse
+
+
 def _draw_indices(B, H, W, N, error_map, patch_size, random_size, device):
-    """pixel-index sampling of the reference, call for call (nerf/utils.py:76-124)"""
+    """mode dispatch in the reference's precedence: patches, then neighbour pairs, then uniform / error-map sampling"""
     extra = {}
     if patch_size > 1:
-        num_patch = N // (patch_size ** 2)
-        inds_x = torch.randint(0, H - patch_size, size=[num_patch], device=device)
-        inds_y = torch.randint(0, W - patch_size, size=[num_patch], device=device)
-        inds = torch.stack([inds_x, inds_y], dim=-1)
-        pi, pj = custom_meshgrid(torch.arange(patch_size, device=device), torch.arange(patch_size, device=device))
-        offsets = torch.stack([pi.reshape(-1), pj.reshape(-1)], dim=-1)
-        inds = (inds.unsqueeze(1) + offsets.unsqueeze(0)).view(-1, 2)
-        inds = inds[:, 0] * W + inds[:, 1]
-        # note: N is not updated when patch_size**2 does not divide it; the reference's expand([B, N]) raises then too
-        inds = inds.expand([B, N])
+        inds = _sample_patches(B, H, W, N, patch_size, device)
     elif random_size > 0:
-        assert N % 2 == 0
-        num_patch = N // 2
-        inds_x = torch.randint(0, H, size=[num_patch], device=device)
-        inds_y = torch.randint(0, W, size=[num_patch], device=device)
-        inds = torch.stack([inds_x, inds_y], dim=-1)
-        off_x = torch.randint(-random_size, random_size, size=[num_patch], device=device)
-        off_y = torch.randint(-random_size, random_size, size=[num_patch], device=device)
-        diff = torch.stack([(inds_x + off_x).clamp(0, H - 1), (inds_y + off_y).clamp(0, W - 1)], dim=-1)
-        inds = torch.cat([inds, diff], dim=0)
-        inds = (inds[:, 0] * W + inds[:, 1]).expand([B, N])
+        inds = _sample_pairs(B, H, W, N, random_size, device)
     elif error_map is None:
-        inds = torch.randint(0, H * W, size=[N], device=device).expand([B, N])
+        inds = _sample_uniform(B, H, W, N, device)
     else:
-        inds_coarse = torch.multinomial(error_map.to(device), N, replacement=False)   # [B, N] in [0, 128*128)
-        inds_x, inds_y = inds_coarse // 128, inds_coarse % 128
-        sx, sy = H / 128, W / 128
-        inds_x = (inds_x * sx + torch.rand(B, N, device=device) * sx).long().clamp(max=H - 1)
-        inds_y = (inds_y * sy + torch.rand(B, N, device=device) * sy).long().clamp(max=W - 1)
-        inds = inds_x * W + inds_y
-        extra["inds_coarse"] = inds_coarse
+        inds, extra["inds_coarse"] = _sample_error_map(B, H, W, N, error_map, device)
     return inds, extra
 
 

@@ -106,3 +106,20 @@ def test_cuda_get_rays_full_view_with_fused_near_far(cuda):
     # empty
     e = rays_from_indices(poses, intr, H, W, inds[:, :0])
     assert e[0].shape == (3, 0, 3)
+
+
+@pytest.mark.parametrize("case", ["rand", "patch", "pair", "err"])
+def test_index_sampling_draws_the_reference_pixels(gp, case):
+    """host logic (CPU): with the same torch seed the samplers make the reference's RNG calls in the reference's order, so
+    they draw exactly the pixels the reference's get_rays drew when the fixtures were generated (CPU generator, seed 11)"""
+    import torch
+    from palettenerf_b200.nerf import utils as U
+    H, W = (int(v) for v in gp["rays_HW"])
+    kw = {"rand": {}, "patch": dict(patch_size=4), "pair": dict(random_size=3),
+          "err": dict(error_map=torch.from_numpy(gp["rays_error_map"]))}[case]
+    torch.manual_seed(11)
+    inds, extra = U._draw_indices(2, H, W, 64, kw.get("error_map"), kw.get("patch_size", 1), kw.get("random_size", 0),
+                                  torch.device("cpu"))
+    assert np.array_equal(inds.contiguous().numpy(), gp[f"rays_{case}_inds"])
+    if case == "err":
+        assert np.array_equal(extra["inds_coarse"].numpy(), gp["rays_err_inds_coarse"])
