@@ -9,7 +9,15 @@
                              upsample_steps=0 (main_palette.py:33-34) — BASELINE config 1 (the "reference PyTorch path")
   * render_cuda_ray        — the cuda_ray inference schedule of palette/renderer.py:430-552 driven by the C oracle kernels
   * train_forward_cuda_ray — the cuda_ray training branch of palette/renderer.py:322-429 on the C oracle kernels
+  * region_edit / stylize  — RegionEdit.forward / Stylizer.forward, palette/renderer.py:121-147, 166-183
+  * random_palette_params  — a random-init state_dict of the architecture built WITHOUT the product package (bench.py's
+                             reference arm must not map libpnerf_b200.so)
 All take a `params` dict = the model's state_dict (numpy or torch CPU tensors, fp32).
+
+PARITY PINNING: palette_forward, blend, render_cuda_ray (incl. RegionEdit / Stylizer), train_forward_cuda_ray (incl. the
+smooth-loss branch) and palette_train_loss are checked against outputs of the REFERENCE ITSELF — its unmodified Python on
+its own CUDA kernels, run on a B200 by tests/golden/make_golden_palette.py -> tests/golden/ref_palette.npz — in
+tests/test_golden_palette.py (fp32 reference run: <= 5e-5; the reference's fp16-autocast run: <= 1e-3).
 """
 import math
 
@@ -111,15 +119,53 @@ def nerf_forward(params, x, d, bound, per_level_scale):
     return sigma, rgb
 
 
-def blend(params, omega, offsets_radiance, view_dep, num_basis=4):
+def blend(params, omega, offsets_radiance, view_dep, num_basis=4, offsets_weight=1.0, view_dep_weight=1.0, edit=None,
+          xyzs=None, clip=None):
     """palette/renderer.py:470-494: -> rgbs [M,3], basis_rgb [M,Nb,3], unscaled_basis_rgb [M,Nb,3]"""
     M = omega.shape[0]
     offsets = offsets_radiance[..., :-1].reshape(M, num_basis, 3)
     radiance = offsets_radiance[..., -1:].reshape(M, 1, 1)
     palette = _t(params["basis_color"]).float()[None].clamp(0, 1)
-    final = F.softplus(radiance) * (palette + offsets)
+    final = F.softplus(radiance) * (palette + offsets_weight * offsets)          # :477
+    if edit is not None:
+        final = region_edit(edit, final, xyzs, clip)                              # :481-482
     basis_rgb = omega.reshape(M, num_basis, 1) * final
-    return basis_rgb.sum(dim=-2) + view_dep, basis_rgb, (palette + offsets)
+    return basis_rgb.sum(dim=-2) + view_dep_weight * view_dep, basis_rgb, (palette + offsets)
+
+
+def region_edit(edit, rgbs, xyz=None, clip_feat=None):
+    """RegionEdit.forward, palette/renderer.py:121-147. edit: dict(delta_hsv [Nb,3], mean_xyz [3]|None, mean_clip [cd]|None,
+    std_xyz, std_clip, weight_mode). rgbs [M,Nb,3] -> [M,Nb,3]"""
+    rgbs = _t(rgbs).float()
+    M, nb, _ = rgbs.shape
+    hsv = torch.from_numpy(O.rgb_to_hsv(rgbs.reshape(-1, 3).numpy())).reshape(M, nb, 3)
+    dh = _t(edit["delta_hsv"]).float()
+    weight = torch.ones(M, 1)
+    if xyz is not None and edit.get("mean_xyz") is not None:
+        weight = weight * torch.exp(-((_t(xyz).float() - _t(edit["mean_xyz"]).float()[None]) ** 2.).sum(-1, keepdim=True)
+                                    / edit.get("std_xyz", 1))
+    if clip_feat is not None and edit.get("mean_clip") is not None:
+        weight = weight * torch.exp(-((_t(clip_feat).float() - _t(edit["mean_clip"]).float()[None]) ** 2.).sum(-1, keepdim=True)
+                                    / edit.get("std_clip", 1))
+    new = torch.stack([torch.fmod(hsv[..., 0] + dh[..., 0] + 360, 360), torch.clip(hsv[..., 1] * dh[..., 1], 0),
+                       torch.clip(hsv[..., 2] * dh[..., 2], 0)], dim=-1)
+    rgb_new = torch.from_numpy(O.hsv_to_rgb(new.reshape(-1, 3).numpy())).reshape(M, nb, 3)
+    if edit.get("weight_mode"):
+        return weight[..., None].repeat(1, nb, 3)
+    return torch.lerp(rgbs, rgb_new, weight[..., None])
+
+
+def stylize(sty, radiance, omega, palette, offsets, view_dep=None):
+    """Stylizer.forward, palette/renderer.py:166-183. sty: dict(dI [Nb], dP [1,Nb,3], ddelta [Nb,3,3])"""
+    nb = omega.shape[-1] if omega.dim() == 2 else omega.shape[-2]
+    radiance, omega = _t(radiance).float().reshape(-1, 1, 1), _t(omega).float().reshape(-1, nb, 1)
+    palette = _t(palette).float().reshape(-1, nb, 3) + _t(sty["dP"]).float()
+    offsets = torch.einsum("npi,pij->npj", _t(offsets).float().reshape(-1, nb, 3), _t(sty["ddelta"]).float())
+    gain = (F.softplus(radiance).repeat(1, nb, 1) + _t(sty["dI"]).float()[None, :, None]).clamp(0)
+    rgbs = (omega * (gain * (palette + offsets)).clamp(0, 1)).sum(dim=-2)
+    if view_dep is not None:
+        rgbs = rgbs + _t(view_dep).float()
+    return rgbs
 
 
 def render_sampler(params, rays_o, rays_d, bound=2.0, min_near=0.2, per_level_scale=2 ** (8 / 15), num_steps=512,
@@ -155,8 +201,11 @@ def render_sampler(params, rays_o, rays_d, bound=2.0, min_near=0.2, per_level_sc
 
 def render_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min_near=0.2, per_level_scale=2 ** (8 / 15),
                     dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, pred_clip=False, bg_color=1.0, gui_mode=False,
-                    density_scale=1.0, num_basis=4, clip_dim=16):
-    """palette/renderer.py:430-552 (inference schedule incl. n_step growth and alive-list compaction), oracle kernels"""
+                    density_scale=1.0, num_basis=4, clip_dim=16, edit=None, stylizer=None, offsets_weight=1.0,
+                    view_dep_weight=1.0):
+    """palette/renderer.py:430-552 (inference schedule incl. n_step growth and alive-list compaction), oracle kernels.
+    edit: dict(delta_hsv, mean_xyz, mean_clip, std_xyz, std_clip) -> RegionEdit (:481-482); stylizer: dict(dI, dP, ddelta)
+    -> Stylizer replaces the blend (:474-475)"""
     rays_o = np.ascontiguousarray(_t(rays_o).float().reshape(-1, 3).numpy())
     rays_d = np.ascontiguousarray(_t(rays_d).float().reshape(-1, 3).numpy())
     N = rays_o.shape[0]
@@ -183,9 +232,15 @@ def render_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min
         n_samples += int((deltas[:, 0] > 0).sum())
         sigma, clip, omega, off_rad, view_dep, diffuse = palette_forward(params, xyzs, dirs, bound, per_level_scale, pred_clip,
                                                                          clip_dim)
-        rgbs, basis_rgb, unscaled = blend(params, omega, off_rad, view_dep, num_basis)
+        if stylizer is not None:
+            rgbs = stylize(stylizer, off_rad[..., -1:], omega, _t(params["basis_color"]).float()[None].clamp(0, 1),
+                           off_rad[..., :-1].reshape(M, num_basis, 3), view_dep)
+            basis_rgb = unscaled = None
+        else:
+            rgbs, basis_rgb, unscaled = blend(params, omega, off_rad, view_dep, num_basis, offsets_weight=offsets_weight,
+                                              view_dep_weight=view_dep_weight, edit=edit, xyzs=_t(xyzs).float(), clip=clip)
         sig = (density_scale * sigma).numpy()
-        if not gui_mode:
+        if not gui_mode and basis_rgb is not None:
             for name, val in (("direct_rgb", diffuse + view_dep), ("view_dep_rgb", view_dep), ("basis_acc", omega),
                               ("basis_rgb", basis_rgb.reshape(M, -1)),
                               ("unscaled_basis_rgb", unscaled.expand(M, num_basis, 3).reshape(M, -1))):
@@ -209,8 +264,10 @@ def render_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min
 
 def train_forward_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=128, min_near=0.2,
                            per_level_scale=2 ** (8 / 15), dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, pred_clip=False,
-                           bg_color=1.0, density_scale=1.0, num_basis=4, clip_dim=16, noises=None):
-    """palette/renderer.py:322-429 forward (no smooth loss), oracle kernels; returns the result maps + sample count"""
+                           bg_color=1.0, density_scale=1.0, num_basis=4, clip_dim=16, noises=None, smooth=False,
+                           jitter_fn=None, smooth_sigma_xyz=0.005, smooth_sigma_color=0.2, smooth_sigma_clip=0.0):
+    """palette/renderer.py:322-429 forward, oracle kernels; returns the result maps + sample count.
+    smooth=True: the smooth-loss branch (:360-381); jitter_fn(xyzs) -> U[0,1) noise [M,3] stands for torch.rand_like"""
     rays_o = np.ascontiguousarray(_t(rays_o).float().reshape(-1, 3).numpy())
     rays_d = np.ascontiguousarray(_t(rays_d).float().reshape(-1, 3).numpy())
     N = rays_o.shape[0]
@@ -233,7 +290,19 @@ def train_forward_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=1
     sparsity = omega.sum(-1, keepdim=True) / ((omega ** 2).sum(-1, keepdim=True) + 1e-6) - 1
     offsets_norm = (offsets ** 2).sum(-1).sum(-1, keepdim=True)
     view_dep_norm = (view_dep ** 2).sum(-1, keepdim=True)
-    buf = torch.cat([sparsity, view_dep_norm, offsets_norm, torch.zeros_like(sparsity), view_dep, diffuse + view_dep, diffuse,
+    smooth_norm = torch.zeros_like(sparsity)
+    if smooth:
+        x = torch.from_numpy(np.ascontiguousarray(xyzs))
+        xj = (x + jitter_fn(x) * bound * 0.03).clamp(-bound, bound)                                          # :362
+        _, clip_j, omega_j, _, _, diffuse_j = palette_forward(params, xj, dirs, bound, per_level_scale, pred_clip, clip_dim)
+        k_xyz = (x - xj).norm(dim=-1, keepdim=True) ** 2 / bound ** 2 / smooth_sigma_xyz                      # :368
+        k_rgb = (diffuse - diffuse_j).norm(dim=-1, keepdim=True) ** 2 / smooth_sigma_color                   # :369
+        k_clip = (clip - clip_j).norm(dim=-1, keepdim=True) / smooth_sigma_clip if (pred_clip and smooth_sigma_clip > 0) else 0
+        gate = torch.exp(-k_xyz - k_rgb - k_clip)                                                             # :375
+        smooth_norm = ((omega_j - omega) ** 2).sum(dim=-1, keepdim=True) * gate                               # :376
+        if pred_clip:
+            smooth_norm = smooth_norm + ((clip_j - clip) ** 2).sum(dim=-1, keepdim=True) * gate               # :378
+    buf = torch.cat([sparsity, view_dep_norm, offsets_norm, smooth_norm, view_dep, diffuse + view_dep, diffuse,
                      clip, omega], dim=-1)
     maps = O.composite_rays_flex_train_forward(sig, buf.numpy(), deltas, rays, T_thresh)
     return dict(image=image + (1 - ws)[:, None] * bg_color, depth=np.clip(depth - nears, 0, None) / (fars - nears),
@@ -248,9 +317,8 @@ def palette_train_loss(outputs, gt_rgb, lambda_sparsity=0.0, lambda_offsets=0.0,
                        lambda_palette=0.0):
     """PaletteTrainer.train_step after model.render, expression by expression (criterion = MSELoss(reduction='none'),
     palette/utils.py:334): returns (loss, loss_dict, per_ray) where per_ray is `loss` before the final .mean() minus the
-    broadcast scalar terms, i.e. the rgb error the error map stores. Parity of this restatement is unpinned by the
-    reference (the trainer cannot be imported here: tensorboardX / lpips / torch_ema are absent) — it is arithmetic on
-    [N]-sized tensors, checked against autograd."""
+    broadcast scalar terms, i.e. the rgb error the error map stores. Pinned against the reference's own train_step
+    (tests/golden/ref_palette.npz: loss and every loss_dict entry, tests/test_golden_palette.py)."""
     pred_rgb = outputs["image"]
     loss = ((pred_rgb - gt_rgb) ** 2).mean(-1)                                   # :486  [B, N]
     per_ray = loss.detach().clone()
@@ -319,3 +387,37 @@ def mark_untrained_grid(density_grid, poses, intrinsic, cascade, grid_size, boun
         if margin:
             margins[cas, indices] = mg
     return out, margins
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# random-init parameters of the palette architecture, built without the product package (bench.py reference arm)
+# ---------------------------------------------------------------------------------------------------------------
+def random_palette_params(seed=0, pred_clip=False, bound=2.0, num_basis=4, clip_dim=16):
+    """state_dict-shaped dict: nn.Linear default init U(-1/sqrt(in), 1/sqrt(in)) (kaiming_uniform with
+    a = sqrt(5)), hash tables U(-1e-4, 1e-4) (gridencoder/grid.py:131-133), basis_color 0.5"""
+    g = torch.Generator().manual_seed(seed)
+    per_level_scale = float(np.exp2(np.log2(2048 * bound / 16) / 15))
+    offsets = O.grid_offsets(3, 16, 16, 19, per_level_scale)
+    n = int(offsets[-1])
+
+    def lin(o, i):
+        b = 1.0 / math.sqrt(i)
+        return (torch.rand(o, i, generator=g) * 2 - 1) * b
+
+    def table():
+        return (torch.rand(n, 2, generator=g) * 2 - 1) * 1e-4
+    p = {}
+    for name in ("encoder", "encoder_palette", "encoder_clip"):
+        p[f"{name}.embeddings"] = table()
+        p[f"{name}.offsets"] = torch.as_tensor(np.asarray(offsets, dtype=np.int32))
+    p["sigma_net.0.weight"], p["sigma_net.1.weight"] = lin(64, 32), lin(16, 64)
+    p["color_net.0.weight"], p["color_net.1.weight"], p["color_net.2.weight"] = lin(64, 31), lin(64, 64), lin(3, 64)
+    p["diff_net.0.weight"], p["diff_net.1.weight"], p["diff_net.2.weight"] = lin(64, 15), lin(64, 64), lin(3, 64)
+    p["basis_net.0.weight"], p["basis_net.1.weight"] = lin(64, 35), lin(15, 64)
+    p["offsets_radiance_net.weight"] = lin(3 * num_basis + 1, 15)
+    p["offsets_radiance_net.bias"] = (torch.rand(3 * num_basis + 1, generator=g) * 2 - 1) / math.sqrt(15)
+    p["omega_net.0.weight"] = lin(num_basis, 15)
+    if pred_clip:
+        p["clip_net.0.weight"], p["clip_net.1.weight"] = lin(64, 32), lin(clip_dim, 64)
+    p["basis_color"] = torch.full((num_basis, 3), 0.5)
+    return p, per_level_scale

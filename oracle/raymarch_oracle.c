@@ -5,9 +5,10 @@
  * checker. The product path (palettenerf_b200/) never links or calls this file.
  *
  * PARITY STATUS: the reference holds no golden vectors / known-answer tests for this path, so this
- * restatement is pinned against the reference ITSELF: tests/test_ref_parity.py runs the reference's own CUDA
- * kernels (oracle/_ref, built from /root/reference by oracle/build_ref.py) side by side with this oracle and with
- * the new kernels on the GPU box, and tests/golden/ holds outputs of this oracle that were cross-checked that way.
+ * restatement is pinned against the reference ITSELF: tests/test_golden.py checks it against outputs of the reference's
+ * own CUDA kernels (tests/golden/ref_kernels.npz, written on a B200 by tests/golden/make_golden_gpu.py from oracle/_ref,
+ * which oracle/build_ref.py compiles from /root/reference), and tests/test_raymarching_gpu.py / test_composite_gpu.py run
+ * those kernels side by side with this oracle and the new kernels on the GPU box.
  *
  * Every function cites the reference lines it follows (paths under the reference repo). fp32 arithmetic is written
  * with explicit fmaf() wherever nvcc's default -fmad=true contracts a*b+c in the reference kernels, and this file is

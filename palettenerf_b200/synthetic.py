@@ -138,3 +138,18 @@ def build_palette_model(device="cuda", seed=0, pred_clip=False, table_scale=None
         model.mean_density = grid.clamp(min=0).mean().item()
         model.density_bitfield.copy_(packbits_np(grid, min(model.mean_density, LEGO["density_thresh"])))
     return model.to(device)
+
+
+def build_nerf_model(device="cuda", seed=0, table_scale=None, ground=False, scene_scale=1.0):
+    """random-init stage-1 NeRFNetwork (torch.manual_seed(seed)) on the same synthetic occupancy grid"""
+    from .nerf.network import NeRFNetwork
+    torch.manual_seed(seed)
+    model = NeRFNetwork(bound=LEGO["bound"], cuda_ray=True, min_near=LEGO["min_near"], density_thresh=LEGO["density_thresh"])
+    with torch.no_grad():
+        if table_scale is not None:
+            model.encoder.embeddings.uniform_(-table_scale, table_scale)
+        grid = density_grid(LEGO["bound"], LEGO["cascade"], LEGO["grid_size"], scale=scene_scale, ground=ground)
+        model.density_grid.copy_(grid)
+        model.mean_density = grid.clamp(min=0).mean().item()
+        model.density_bitfield.copy_(packbits_np(grid, min(model.mean_density, LEGO["density_thresh"])))
+    return model.to(device)
