@@ -76,18 +76,28 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's PyTorch-only CPU path (restated in oracle/cpu_render.py)
 # -------------------------------------------------------------------------------------------------------------------
+def _scene_module():
+    """palettenerf_b200/synthetic.py (pure torch / numpy scene + camera helpers) loaded BY PATH: the reference arm must not
+    import the product package, whose field modules map libpnerf_b200.so into the process"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_pnerf_scene", os.path.join(ROOT, "palettenerf_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from oracle import cpu_render
-    from palettenerf_b200 import synthetic as S
+    S = _scene_module()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample_rays = 1024
-    model = S.build_palette_model("cpu", seed=0, pred_clip=False)
-    params = {k: v.detach() for k, v in model.state_dict().items()}
+    params, _ = cpu_render.random_palette_params(seed=0, pred_clip=False)     # no product code in this process
+    assert not any("libpnerf_b200" in l for l in open("/proc/self/maps")), "reference arm mapped the product library"
     g = torch.Generator().manual_seed(0)
     times = []
     for it in range(args.warmup + args.steps):
@@ -105,7 +115,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "palette-mode inference render 800x800 lego-shaped, 4 palettes (BASELINE config 3), "
-                                   "rendered by the reference's PyTorch-only CPU path on a bounded sample"},
+                                   "SAMPLED: each step renders 1024 random pixels of the view with the reference's PyTorch-only "
+                                   "CPU path (oracle port); the product library is not loaded in this process"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -259,7 +270,9 @@ def main():
     FLOP_PER_SAMPLE = 36094                          # palette field without clip, forward
     GATHER_B_PER_SAMPLE = 2 * 16 * 8 * 4             # two fp16 F=2 tables, 16 levels, 8 corners
     roofline = {"bound": "tensor", "achieved": None, "peak": tf_peak, "unit": "TFLOP/s", "frac": None,
-                "traffic": _ncu_traffic("k_render_fused"), "kernel": top[0] + " (k_render_fused)", "kernel_ms": kernel_ms, "call_ms": call_ms,
+                "traffic": _ncu_traffic("k_render_fused"), "traffic_source": "profiles/traffic.json (ncu --set full capture of this "
+                "kernel, committed; not measured in this run)",
+                "kernel": top[0] + " (k_render_fused)", "kernel_ms": kernel_ms, "call_ms": call_ms,
                 "peak_kind": peak_kind + " (bf16 dense, burst; fp16 assumed equal)",
                 "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {samples_per_step} samples per launch",
                 "kernel_time_share_of_own_kernels": shares}
@@ -539,26 +552,23 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
 
 
 def bench_cpu_baseline(S):
-    """the oracle's restatement of the reference's PyTorch-only CPU path, timed on this box's host cores on a bounded
-    sample of the same 800x800 view (reported baseline, not the optimisation target)"""
+    """BASELINE config 1 in full: ONE 200x200 view (40 000 rays x 512 samples = 20.5 M samples) of the same scene through the
+    oracle's restatement of the reference's PyTorch-only CPU path, on this box's host cores: one small
+    warm-up, one timed repetition (about 20 s; a reported baseline, not the optimisation target)"""
     import torch
     from oracle import cpu_render
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = S.build_palette_model("cpu", seed=0, pred_clip=False)
-    params = {k: v.detach() for k, v in model.state_dict().items()}
-    n = 1024
-    inds = torch.randint(0, N_RAYS, (n,), generator=torch.Generator().manual_seed(0))
-    o, d = S.camera_rays(VIEW, VIEW, inds=inds)
-    cpu_render.render_sampler(params, o[:256], d[:256], num_steps=512)  # warm-up
+    params, _ = cpu_render.random_palette_params(seed=0, pred_clip=False)
+    side = 200
+    o, d = S.camera_rays(side, side)
+    cpu_render.render_sampler(params, o[:512], d[:512], num_steps=512)  # warm-up
     t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        cpu_render.render_sampler(params, o, d, num_steps=512)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} random pixels of the 800x800 view, 512 uniform samples/ray (NeRFRenderer.run sampler), torch fp32, "
-                      f"{reps} repetitions after one warm-up"}
+    cpu_render.render_sampler(params, o, d, num_steps=512)
+    dt = time.perf_counter() - t0
+    return {"value": side * side / dt, "unit": "rays/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"the whole {side}x{side} view of BASELINE config 1 (40 000 rays x 512 uniform samples, NeRFRenderer.run "
+                      "sampler in 4096-ray chunks, palette field + blend), torch fp32, one repetition after a 512-ray warm-up"}
 
 
 if __name__ == "__main__":

@@ -88,12 +88,15 @@ PNERF_API int pnerf_march_rays_train(const float* rays_o, const float* rays_d, c
  *            sample; the write pass turns the list into xyzs / dirs / deltas without touching the grid again.
  *   occ_aabb [6] or NULL: bounds of the occupied cells from pnerf_occupied_bounds for THIS grid; the counting walk
  *            stops where the ray leaves them instead of marching the empty tail up to `far` (no lattice point behind
- *            that exit can fall into an occupied cell, so the samples are unchanged). */
+ *            that exit can fall into an occupied cell, so the samples are unchanged).
+ *   valid_rows [1] int32 or NULL: receives the number of leading rows of xyzs / dirs / deltas that were written. Rows are
+ *            handed out in ray order, so this is min(counter[0], offset of the first ray with offset + num_steps > M):
+ *            a caller that does not zero-fill the buffers (static-capacity training step) must stop reading there. */
 PNERF_API int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                         float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                         uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
                                         float* deltas, int32_t* rays, int32_t* counter, const float* noises,
-                                        float* t_list, const float* occ_aabb, void* stream);
+                                        float* t_list, const float* occ_aabb, int32_t* valid_rows, void* stream);
 
 /* occ_aabb[0..6) (device) = (lo xyz, hi xyz): world-space bounds of every occupied cell of the C cascades of `bitfield`
  * ([C*H^3/8] bytes, Morton order, as packbits writes it), padded by one cell; a side reaching the scene bound is

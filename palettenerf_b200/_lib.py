@@ -37,7 +37,7 @@ _SIGS = {
     "pnerf_morton3D_invert": [P, U, P, P],
     "pnerf_packbits": [P, U, F, P, P],
     "pnerf_march_rays_train": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P],
-    "pnerf_march_rays_train_ws": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P, P, P],
+    "pnerf_march_rays_train_ws": [P, P, P, F, F, U, U, U, U, U, P, P, P, P, P, P, P, P, P, P, P, P],
     "pnerf_occupied_bounds": [P, U, U, F, P, P],
     "pnerf_mark_untrained_grid": [P, U, F, F, F, F, U, U, F, F, I, P, P, P],
     "pnerf_composite_rays_train_forward": [P, P, P, P, U, U, F, P, P, P, P],

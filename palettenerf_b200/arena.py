@@ -4,7 +4,9 @@ The fused training path allocates the same large, data-independent buffers every
 reference's 4096 x 1024 sample capacity, per-layer gradients, per-sample channels ...). Going through torch's caching
 allocator for them fragments its pools when the host runs ahead of the device (large blocks get split for smaller
 requests, the next step needs fresh cudaMallocs: measured 7-30 ms spikes per step and 50 GB reserved). The arena keeps one
-tensor per (name, shape, dtype, device) and hands it out again as soon as nobody else references it — neither Python
+tensor per (name, dtype, device) — of the shape last asked for under that name: a request with another shape (the sample
+capacity follows `mean_count`, which changes at every density-grid refresh) drops the pooled buffers of the old shape, so
+the arena never holds more than the live working set — and hands it out again as soon as nobody else references it — neither Python
 (the caller's variables, ctx attributes) nor C++ (autograd saved tensors, views sharing the storage).
 All users run on one stream at a time (eager: the current stream; CUDA graph: the capture stream), so reuse is
 stream-ordered like torch's own allocator.
@@ -27,12 +29,16 @@ class Arena:
         self.pool = {}
 
     def get(self, name, shape, dtype, device):
-        key = (name, tuple(int(s) for s in shape), dtype, str(device))
-        lst = self.pool.setdefault(key, [])
+        key = (name, dtype, str(device))
+        shape = tuple(int(s) for s in shape)
+        entry = self.pool.get(key)
+        if entry is None or entry[0] != shape:
+            entry = self.pool[key] = (shape, [])        # buffers of the previous shape are released (freed once unreferenced)
+        lst = entry[1]
         for t in lst:
             if _free(t):
                 return t
-        t = torch.empty(key[1], dtype=dtype, device=device)
+        t = torch.empty(shape, dtype=dtype, device=device)
         lst.append(t)
         return t
 
@@ -40,7 +46,7 @@ class Arena:
         self.pool.clear()
 
     def bytes(self):
-        return sum(t.numel() * t.element_size() for lst in self.pool.values() for t in lst)
+        return sum(t.numel() * t.element_size() for _, lst in self.pool.values() for t in lst)
 
 
 ARENA = Arena()

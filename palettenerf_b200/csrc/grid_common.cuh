@@ -35,8 +35,10 @@ __device__ __forceinline__ void make_level(LevelParams& p, uint32_t level, const
     p.use_hash = (gridtype == 0 && stride > p.size) ? 1u : 0u;
     p.mask = ((p.size & (p.size - 1)) == 0) ? (p.size - 1) : 0u;
     // dense level whose full (res+1)^D lattice fits the table: every index is < stride <= size, so the reference's
-    // `index % hashmap_size` (gridencoder.cu:71) is the identity and the integer division can be dropped
-    if (!p.use_hash && stride <= p.size && D <= 5 && p.stride[D - 1] != 0) p.mask = 0xffffffffu;
+    // `index % hashmap_size` (gridencoder.cu:71) is the identity and the integer division can be dropped.
+    // NOT with align_corners: the stride multiplier is `resolution` there while an input of exactly 1.0 on an integer
+    // scale reaches lattice coordinate `resolution` (pos_grid + 1), so an index can exceed stride — keep the modulo.
+    if (!align_corners && !p.use_hash && stride <= p.size && D <= 5 && p.stride[D - 1] != 0) p.mask = 0xffffffffu;
 }
 
 __device__ __forceinline__ uint32_t wrap_index(uint32_t index, const LevelParams& p) {

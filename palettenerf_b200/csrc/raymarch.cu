@@ -145,10 +145,13 @@ __global__ void __launch_bounds__(256) k_march_train_count(const float* __restri
 }
 
 // pass 2: single-CTA exclusive scan of the counts in ray order. 1024 threads, each owns a contiguous run.
+// valid (optional): number of leading rows that will be written = min(total, offset of the first ray that does not fit M)
 __global__ void __launch_bounds__(1024) k_march_train_scan(int32_t* __restrict__ rays, uint32_t N,
-                                                           int32_t* __restrict__ counter) {
+                                                           int32_t* __restrict__ counter, uint32_t M = 0,
+                                                           int32_t* __restrict__ valid = nullptr) {
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t base_s;
+    __shared__ uint32_t base_s, first_bad_s, total_s;
+    if (threadIdx.x == 0) first_bad_s = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t per = ceil_div(N, 1024u);
     const uint32_t lo = min(N, tid * per), hi = min(N, lo + per);
@@ -175,16 +178,24 @@ __global__ void __launch_bounds__(1024) k_march_train_scan(int32_t* __restrict__
         if (lane == 31) {
             // counter[0] accumulates the grand total, counter[1] the ray count (ref: raymarching.cu:408-409)
             base_s = (uint32_t)counter[0];
+            total_s = base_s + winc;
             counter[0] = (int32_t)(base_s + winc);
             counter[1] += (int32_t)N;
         }
     }
     __syncthreads();
     uint32_t off = base_s + warp_tot[wid] + (inc - sum);
+    uint32_t bad = 0xffffffffu;
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t c = (uint32_t)rays[i * 3 + 2];
         rays[i * 3 + 1] = (int32_t)off;
+        if (c && off + c > M) bad = min(bad, off);          // this ray (and every later one) writes nothing
         off += c;
+    }
+    if (valid) {
+        if (bad != 0xffffffffu) atomicMin(&first_bad_s, bad);
+        __syncthreads();
+        if (tid == 0) *valid = (int32_t)min(min(first_bad_s, total_s), M);
     }
 }
 
@@ -511,7 +522,7 @@ int pnerf_occupied_bounds(const uint8_t* bitfield, uint32_t C, uint32_t H, float
 int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                               const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
-                              const float* noises, float* t_list, const float* occ_aabb, void* stream) {
+                              const float* noises, float* t_list, const float* occ_aabb, int32_t* valid_rows, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter && noises && t_list);
     PNERF_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1);
@@ -519,7 +530,7 @@ int pnerf_march_rays_train_ws(const float* rays_o, const float* rays_d, const ui
     cudaStream_t s = (cudaStream_t)stream;
     k_march_train_count<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
                                                         fars, noises, rays, t_list, occ_aabb);
-    k_march_train_scan<<<1, 1024, 0, s>>>(rays, N, counter);
+    k_march_train_scan<<<1, 1024, 0, s>>>(rays, N, counter, M, valid_rows);
     k_march_train_emit<<<ceil_div(N, 8u), 256, 0, s>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, noises,
                                                        rays, t_list, xyzs, dirs, deltas);
     return check_launch("march_rays_train_ws");

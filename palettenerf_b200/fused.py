@@ -7,7 +7,8 @@ folded into the packing:
     color_net.0  [64,31]  -> K=32 : 0..15 SH, 16 -> zero (logit), 17..31 geo
     basis_net.0  [64,35]  -> K=48 : 0..31 palette grid, 32..34 diffuse, rest zero
     heads                 -> K=16, N=24 : rows 0..12 offsets_radiance_net.weight, rows 13..16 omega_net.0.weight
-Nothing here computes on the CPU at render time; the cache is rebuilt only when a parameter's version counter moves.
+Nothing here computes on the CPU at render time; FieldCache re-packs tables and weights on the device (see its docstring
+for the freshness policy).
 """
 import ctypes
 from ctypes import c_float, c_uint32, c_void_p
@@ -96,46 +97,81 @@ def supported(model):
 
 
 class FieldCache:
-    """device-resident fp16 tables + packed weights of one model, refreshed when parameters change"""
+    """device-resident fp16 tables + packed weights of one model for the inference kernels.
+
+    Freshness: the default (`model.fused_weights_static` unset / False) re-packs on EVERY call — three strided
+    fp32->fp16 table copies into persistent buffers (144 MB of HBM traffic, ~30 us) and one gather of the ~20 k MLP
+    weights. A version key alone is not enough: `param.data.copy_()` — what torch_ema's store / copy_to / restore do
+    around every evaluate() of the reference trainer (nerf/utils.py:934-944), and what checkpoint loading or GUI edits
+    may do — does not bump `Parameter._version`, so a cache keyed on it would render EMA weights after restore().
+    `model.fused_weights_static = True` opts into the version key (interactive viewers that never write through .data).
+    All buffers keep their addresses, so the C struct is built once."""
 
     def __init__(self, model):
         self.model = model
         self.key = None
-        self.keep = None
+        self.buf = None
         self.field = None
 
     def _version_key(self):
         m = self.model
         ps = list(m.parameters())
-        return tuple(p._version for p in ps) + (m.density_scale, m.offsets_weight, m.view_dep_weight,
-                                                id(m.basis_color), m.encoder.embeddings.device)
+        return tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps) + (m.density_scale, m.offsets_weight,
+                                                                                 m.view_dep_weight, id(m.basis_color))
 
-    def get(self):
-        key = self._version_key()
-        if key == self.key:
-            return self.field
+    def _allocate(self):
+        from . import fused_train
         m = self.model
-        with torch.no_grad():
-            t_sigma = m.encoder.embeddings.detach().to(torch.float16).contiguous()
-            t_pal = m.encoder_palette.embeddings.detach().to(torch.float16).contiguous()
-            t_clip = m.encoder_clip.embeddings.detach().to(torch.float16).contiguous() if m.opt.pred_clip else None
-            # density + palette tables interleaved per entry: one 8-byte gather serves both grids (same geometry)
-            t_pair = torch.stack((t_sigma, t_pal), dim=1).contiguous()
-            wpack, bias = pack_weights(m)
-            palette = m.basis_color.detach().float().clamp(0, 1).contiguous()
-            offsets = m.encoder.offsets.contiguous()
+        st = fused_train._state(m)
+        dev = m.encoder.embeddings.device
+        n = m.encoder.embeddings.shape[0]
+        self.buf = dict(
+            pair=torch.empty(n, 2, 2, dtype=torch.float16, device=dev),
+            clip=torch.empty(n, 2, dtype=torch.float16, device=dev) if m.opt.pred_clip else None,
+            wpack=torch.empty(st["n_fwd"], dtype=torch.float16, device=dev),
+            bias=torch.zeros(16, dtype=torch.float32, device=dev),
+            palette=torch.empty(m.num_basis, 3, dtype=torch.float32, device=dev),
+            offsets=m.encoder.offsets.contiguous(), index=st["index"][:st["n_fwd"]], names=st["names"], zero=st["zero"],
+            device=dev)
+        b = self.buf
         f = PaletteField()
-        f.table_sigma, f.table_palette, f.table_clip = ptr(t_sigma), ptr(t_pal), ptr(t_clip)
-        f.table_sigma_palette = ptr(t_pair)
-        f.offsets, f.wpack, f.head_bias, f.palette = ptr(offsets), ptr(wpack), ptr(bias), ptr(palette)
+        # the kernels read both grids through the interleaved table; the separate-table pointers are kept non-NULL for the
+        # ABI's argument check only (every table GridEncoder can build takes the interleaved fast path)
+        f.table_sigma = f.table_palette = f.table_sigma_palette = ptr(b["pair"])
+        f.table_clip = ptr(b["clip"])
+        f.offsets, f.wpack, f.head_bias, f.palette = ptr(b["offsets"]), ptr(b["wpack"]), ptr(b["bias"]), ptr(b["palette"])
         f.L, f.H = m.encoder.num_levels, m.encoder.base_resolution
         f.pred_clip, f.clip_dim = int(bool(m.opt.pred_clip)), m.opt.clip_dim
         f.S = float(np.float32(np.log2(m.encoder.per_level_scale)))
+        self.field = f
+
+    def get(self):
+        m = self.model
+        if self.buf is None or self.buf["device"] != m.encoder.embeddings.device:
+            self._allocate()
+            self.key = None
+        f, b = self.field, self.buf
         f.bound, f.density_scale = float(m.bound), float(m.density_scale)
         f.offsets_weight, f.view_dep_weight = float(m.offsets_weight), float(m.view_dep_weight)
-        self.keep = (t_sigma, t_pal, t_clip, t_pair, wpack, bias, palette, offsets)  # keep the device buffers alive
-        self.field, self.key = f, key
+        if getattr(m, "fused_weights_static", False):
+            key = self._version_key()
+            if key == self.key:
+                return f
+            self.key = key
+        with torch.no_grad():
+            b["pair"][:, 0, :].copy_(m.encoder.embeddings.detach())
+            b["pair"][:, 1, :].copy_(m.encoder_palette.embeddings.detach())
+            if b["clip"] is not None:
+                b["clip"].copy_(m.encoder_clip.embeddings.detach())
+            sd = dict(m.named_parameters())
+            flat = torch.cat([sd[n].detach().reshape(-1).float() for n in b["names"]] + [b["zero"]])
+            b["wpack"].copy_(flat[b["index"]])
+            b["bias"][0:13].copy_(m.offsets_radiance_net.bias.detach())
+            b["palette"].copy_(m.basis_color.detach().float().clamp(0, 1))
         return f
+
+    def invalidate(self):
+        self.key = None
 
 
 def _cache(model):

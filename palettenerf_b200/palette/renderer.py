@@ -208,10 +208,11 @@ class PaletteRenderer(nn.Module, OccupancyState):
             from .. import fused_train
             if self.require_smooth_loss:
                 raise RuntimeError("the fused training field does not cover the smooth-loss branch")
-            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+            xyzs, dirs, deltas, rays, valid = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
                 self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, True)
-            sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0], count=counter[0:1])
+            # `valid` (not counter[0]): when the capacity overflows, rows behind the first dropped ray are uninitialised
+            sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0], count=valid)
             if channels.shape[1] == 33:
                 weights_sum, depth, image, maps = fused_train.composite(sigmas, rgbs, channels, deltas, rays, T_thresh)
             else:

@@ -48,14 +48,15 @@ class _Backend:
 
     @staticmethod
     def march_rays_train_ws(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
-                            rays, counter, noises, t_list, occ_aabb):
-        """one-walk variant (not in the reference): t_list [N, max_steps] scratch, occ_aabb [6] from occupied_bounds or None"""
-        require_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter, noises, t_list, occ_aabb)
+                            rays, counter, noises, t_list, occ_aabb, valid_rows=None):
+        """one-walk variant (not in the reference): t_list [N, max_steps] scratch, occ_aabb [6] from occupied_bounds or None,
+        valid_rows: optional int32 [1] receiving the number of leading sample rows that were written"""
+        require_cuda(rays_o, rays_d, grid, nears, fars, xyzs, dirs, deltas, rays, counter, noises, t_list, occ_aabb, valid_rows)
         if t_list.numel() < N * max_steps or t_list.dtype != torch.float32:
             raise RuntimeError("t_list must hold N * max_steps floats")
         call("pnerf_march_rays_train_ws", ptr(rays_o), ptr(rays_d), ptr(grid), bound, dt_gamma, max_steps, N, C, H, M,
              ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), ptr(t_list),
-             ptr(occ_aabb), stream())
+             ptr(occ_aabb), ptr(valid_rows), stream())
 
     @staticmethod
     def occupied_bounds(bitfield, C, H, bound, occ_aabb):

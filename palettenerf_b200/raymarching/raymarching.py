@@ -92,7 +92,12 @@ class _packbits(Function):
         N = C * H3 // 8
         if bitfield is None:
             bitfield = torch.empty(N, dtype=torch.uint8, device=grid.device)
+            _backend.packbits(grid, N, thresh, bitfield)
+            return bitfield
+        # in-place convention of the reference (packbits(grid, thresh, bitfield), keep using `bitfield`): the kernel writes
+        # through a raw pointer, so tell autograd / the version counter — occupied_bounds() caches per bitfield version
         _backend.packbits(grid, N, thresh, bitfield)
+        ctx.mark_dirty(bitfield)
         return bitfield
 
 
@@ -105,8 +110,9 @@ T_LIST_MAX_BYTES = 256 << 20
 
 def occupied_bounds(density_bitfield, C, H, bound):
     """[6] world-space bounds of the occupied cells (pnerf_occupied_bounds), cached per bitfield TENSOR OBJECT until it is
-    written again (torch bumps `_version` on every in-place write, e.g. packbits into the same buffer). The entry holds
-    a weak reference: a different tensor that happens to reuse the address of a freed one never hits."""
+    written again: torch bumps `_version` on every in-place write, and packbits() into an existing buffer marks it dirty
+    itself (its kernel writes through a raw pointer). The entry holds a weak reference: a different tensor that happens to
+    reuse the address of a freed one never hits."""
     if torch.cuda.is_current_stream_capturing():
         # inside a CUDA-graph capture the kernel is recorded: every replay recomputes the bounds from the live bitfield
         # (a cached tensor would go stale when the density grid is refreshed between replays)
@@ -132,8 +138,11 @@ class _march_rays_train(Function):
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
                 perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, static=False):
         """`static=True` (not in the reference): return the full-capacity buffers without reading the sample count back
-        (no D2H sync, shapes independent of the data -> CUDA-graph capturable); the count stays in step_counter[0] and
-        rows beyond it are uninitialised. Slot order is the deterministic ray order, so rows [0, count) are all valid."""
+        (no D2H sync, shapes independent of the data -> CUDA-graph capturable) plus a 5th output `valid` (int32 [1], device):
+        the number of leading rows that hold samples. Slot order is the deterministic ray order, so rows [0, valid) are all
+        written; when the total count (step_counter[0]) exceeds the capacity M, `valid` is the offset of the first ray that
+        did not fit (that ray and every later one write nothing, raymarching.cu:418-419) and rows >= valid are
+        UNINITIALISED — consumers must not read them."""
         rays_o = _cuda(rays_o).contiguous().view(-1, 3)
         rays_d = _cuda(rays_d).contiguous().view(-1, 3)
         density_bitfield = _cuda(density_bitfield).contiguous()
@@ -154,6 +163,7 @@ class _march_rays_train(Function):
             dirs = torch.zeros(M, 3, dtype=dt, device=dev)
             deltas = torch.zeros(M, 2, dtype=dt, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        valid = torch.empty(1, dtype=torch.int32, device=dev) if static else None
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         noises = torch.rand(N, dtype=dt, device=dev) if perturb else torch.zeros(N, dtype=dt, device=dev)
@@ -165,12 +175,15 @@ class _march_rays_train(Function):
             t_list = ARENA.get("march_t_list", (N * max_steps,), torch.float32, dev)
             occ = occupied_bounds(density_bitfield, C, H, bound)
             _backend.march_rays_train_ws(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
-                                         xyzs, dirs, deltas, rays, step_counter, noises, t_list, occ)
+                                         xyzs, dirs, deltas, rays, step_counter, noises, t_list, occ, valid)
         else:
+            if static:
+                raise RuntimeError("march_rays_train(static=True) needs the one-walk entry point (march_rays_train_ws)")
             _backend.march_rays_train(rays_o, rays_d, density_bitfield, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
                                       xyzs, dirs, deltas, rays, step_counter, noises)
         if static:
-            return xyzs, dirs, deltas, rays
+            ctx.mark_non_differentiable(valid)
+            return xyzs, dirs, deltas, rays, valid
         if force_all_rays or mean_count <= 0:
             m = step_counter[0].item()  # D2H sync, as in the reference (raymarching.py:224)
             if align > 0:

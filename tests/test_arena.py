@@ -8,7 +8,9 @@ from palettenerf_b200.arena import Arena
 
 
 def _n(A, name, shape):
-    return len(A.pool[(name, shape, torch.float32, "cpu")])
+    cur, lst = A.pool[(name, torch.float32, "cpu")]
+    assert cur == shape
+    return len(lst)
 
 
 def test_arena_reuses_only_unreferenced_buffers():
@@ -28,7 +30,7 @@ def test_arena_reuses_only_unreferenced_buffers():
     alias = A.get("x", (4,), torch.float32, "cpu").detach()         # the pattern used for autograd outputs
     e = A.get("x", (4,), torch.float32, "cpu")
     assert e.data_ptr() != alias.data_ptr()
-    assert A.bytes() == sum(t.numel() * 4 for t in A.pool[("x", (4,), torch.float32, "cpu")])
+    assert A.bytes() == sum(t.numel() * 4 for t in A.pool[("x", torch.float32, "cpu")][1])
 
 
 def test_arena_respects_autograd_lifetimes():
@@ -66,3 +68,17 @@ def test_arena_respects_autograd_lifetimes():
     o1 = Saved.apply(x)                      # graph alive -> a second forward must not clobber the first one's buffers
     o2 = Saved.apply(x)
     assert o1.data_ptr() != o2.data_ptr() and _n(A, "y", (3,)) == 2
+
+
+def test_arena_drops_buffers_of_a_previous_shape():
+    """the sample capacity follows mean_count, which changes at every density-grid refresh: buffers of the old capacity
+    must not pile up (round-1 advisor finding)"""
+    A = Arena()
+    for cap in (1000, 1200, 900, 1500):
+        t = A.get("xbuf", (cap, 8), torch.float32, "cpu")
+        assert t.shape == (cap, 8)
+        del t
+        assert A.bytes() == cap * 8 * 4                               # only the live shape is pooled
+    a = A.get("xbuf", (1500, 8), torch.float32, "cpu")
+    b = A.get("xbuf", (700, 8), torch.float32, "cpu")               # another shape while `a` is still held
+    assert a.shape == (1500, 8) and b.shape == (700, 8) and A.bytes() == 700 * 8 * 4

@@ -1,0 +1,393 @@
+"""GPU half of the reference-pinned parity: the CUDA path against tests/golden/ref_palette.npz (outputs of the
+reference's own Python on the reference's own kernels, see tests/test_golden_palette.py for the CPU half).
+
+Two CUDA paths are checked on every case:
+  * fp32, per-op schedule (no autocast): hash grid / SH kernels + torch fp32 MLPs + the compositor kernels
+  * fp16 autocast (`-O`): the FUSED kernels — persistent renderer, fused training field, fused loss
+Tolerances, two-sided, stated per block (north_star: 1e-5 fp32, 1e-3 fp16):
+  fp32 path vs the reference's fp32 run  : 5e-5 x max(1, |ref|_max)   (same arithmetic up to exp / sum reassociation)
+  fused fp16 path vs the reference's fp32: 1e-3 x max(1, |ref|_max)   on every composited map and per-sample output
+  fused fp16 path vs the reference's fp16: 1.5e-3 (both sides carry their own fp16 rounding)
+  gradients (fused fp16 vs reference fp32): relative L2 <= 2e-2, cosine >= 0.9995 per parameter
+Every comparison also lands in gpurun_out/parity_report.json (max error and the bar) when the directory exists.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import palette_cases as PC  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(HERE, "golden", "ref_palette.npz")
+REPORT = {}
+
+TOL_FP32 = 5e-5
+TOL_F16_VS_FP32 = 1e-3
+TOL_F16_VS_F16 = 1.5e-3
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module", params=list(PC.MODEL_CASES), ids=list(PC.MODEL_CASES))
+def case(request, cuda):
+    name = request.param
+    m = PC.build_model(name, cuda)
+    return name, PC.MODEL_CASES[name], m
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_report():
+    yield
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out) and REPORT:
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def _check(a, r, tol, what, rel=False):
+    a = a.detach().float().cpu().numpy().astype(np.float64).reshape(r.shape) if torch.is_tensor(a) else np.asarray(a, np.float64).reshape(r.shape)
+    err = np.abs(a - r)
+    if rel:
+        err = err / np.maximum(np.abs(r), 1e-3)
+        bar = tol
+    else:
+        bar = tol * max(1.0, float(np.abs(r).max()))
+    REPORT[what] = {"max_err": float(err.max()), "bar": float(bar), "ref_absmax": float(np.abs(r).max())}
+    assert err.max() <= bar, f"{what}: max err {err.max():.3e} > {bar:.3e}"
+
+
+FWD_NAMES = ["sigma", "clip", "omega", "offsets_radiance", "view_dep", "diffuse"]
+
+
+def test_field_forward_fp32_ops_and_fused_fp16(gold, case, cuda):
+    from palettenerf_b200 import fused
+    name, cfg, m = case
+    m.eval()
+    x, d = torch.from_numpy(gold[f"fwd_{name}_x"]).to(cuda), torch.from_numpy(gold[f"fwd_{name}_d"]).to(cuda)
+    with torch.no_grad():
+        res32 = m(x, d)
+    fus = fused.field_forward(m, x, d)
+    for n, a32, af in zip(FWD_NAMES, res32, fus):
+        rel = n == "sigma"
+        _check(a32, gold[f"fwd_{name}_fp32_{n}"], 2e-4 if rel else TOL_FP32, f"fwd/{name}/{n}/fp32ops_vs_ref32", rel)
+        _check(af, gold[f"fwd_{name}_fp32_{n}"], 2e-3 if rel else TOL_F16_VS_FP32, f"fwd/{name}/{n}/fused_vs_ref32", rel)
+        _check(af, gold[f"fwd_{name}_f16_{n}"], 2e-3 if rel else TOL_F16_VS_F16, f"fwd/{name}/{n}/fused_vs_ref16", rel)
+
+
+EVAL_KEYS = ["image", "depth", "depth_origin", "weights_sum", "clip_feat", "direct_rgb", "view_dep_rgb", "basis_rgb",
+             "unscaled_basis_rgb", "basis_acc"]
+
+
+def _render(m, o, d, fused, gui_mode=False):
+    kw = dict(staged=True, bg_color=1, perturb=False, gui_mode=gui_mode, **PC.RENDER_KW)
+    with torch.no_grad():
+        if fused:
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = m.render(o, d, **kw)
+            assert m._last_schedule == "fused"
+        else:
+            out = m.render(o, d, fused=False, **kw)
+    return out
+
+
+@pytest.mark.parametrize("ds", [1, 40])
+def test_run_cuda_inference_fp32_loop_and_fused_renderer(gold, case, cuda, ds):
+    name, cfg, m = case
+    m.eval()
+    m.density_scale = float(ds)
+    o, d = PC.eval_rays()
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    try:
+        loop, fus = _render(m, o, d, False), _render(m, o, d, True)
+    finally:
+        m.density_scale = 1.0
+    for k in EVAL_KEYS:
+        r32, r16 = gold[f"eval_{name}_ds{ds}_fp32_{k}"], gold[f"eval_{name}_ds{ds}_f16_{k}"]
+        _check(loop[k], r32, TOL_FP32, f"eval/{name}/ds{ds}/{k}/fp32loop_vs_ref32")
+        _check(fus[k], r32, TOL_F16_VS_FP32, f"eval/{name}/ds{ds}/{k}/fused_vs_ref32")
+        _check(fus[k], r16, TOL_F16_VS_F16, f"eval/{name}/ds{ds}/{k}/fused_vs_ref16")
+
+
+def _set_edit(m, gold, name, clip, cuda):
+    from palettenerf_b200.palette.renderer import RegionEdit
+    e = RegionEdit(m.opt)
+    e.delta_hsv = torch.from_numpy(gold[f"edit_{name}_delta_hsv"]).to(cuda)
+    e.update_cent(mean_xyz=torch.tensor([0.2, 0.1, 0.0], device=cuda),
+                  mean_clip=torch.linspace(-0.2, 0.2, 16, device=cuda) if clip else None)
+    e.update_std(std_xyz=0.15, std_clip=0.5)
+    return e
+
+
+def _set_stylizer(m, gold, name, cuda):
+    from palettenerf_b200.palette.renderer import Stylizer
+    s = Stylizer(m.opt).to(cuda)
+    with torch.no_grad():
+        s.dI.copy_(torch.tensor([0.1, -0.05, 0.2, 0.0]))
+        s.dP.copy_(torch.tensor([[[0.05, -0.1, 0.0], [0.1, 0.1, 0.1], [-0.2, 0.0, 0.05], [0.0, 0.15, -0.05]]]))
+        s.ddelta.copy_(torch.from_numpy(gold[f"style_{name}_ddelta"]))
+    return s
+
+
+def test_run_cuda_with_region_edit_and_stylizer(gold, case, cuda):
+    name, cfg, m = case
+    m.eval()
+    m.density_scale = 40.0
+    o, d = PC.eval_rays()
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    try:
+        m.edit = _set_edit(m, gold, name, cfg["pred_clip"], cuda)
+        loop = _render(m, o, d, False)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            auto = m.render(o, d, staged=True, bg_color=1, perturb=False, gui_mode=False, **PC.RENDER_KW)
+        sched_edit = m._last_schedule
+        m.edit = None
+        m.stylizer = _set_stylizer(m, gold, name, cuda)
+        sloop = _render(m, o, d, False, gui_mode=True)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            sauto = m.render(o, d, staged=True, bg_color=1, perturb=False, gui_mode=True, **PC.RENDER_KW)
+        sched_style = m._last_schedule
+    finally:
+        m.edit, m.stylizer, m.density_scale = None, None, 1.0
+    REPORT[f"edit/{name}/schedule_under_autocast"] = {"edit": sched_edit, "stylizer": sched_style}
+    for k in EVAL_KEYS:
+        # the reference's HSV kernels are compiled with -use_fast_math (palette/setup.py): 3e-4 on recoloured maps
+        _check(loop[k], gold[f"edit_{name}_fp32_{k}"], 3e-4, f"edit/{name}/{k}/fp32loop_vs_ref32")
+        _check(auto[k], gold[f"edit_{name}_fp32_{k}"], TOL_F16_VS_FP32, f"edit/{name}/{k}/autocast_vs_ref32")
+    for k in ["image", "depth", "weights_sum", "clip_feat"]:
+        _check(sloop[k], gold[f"style_{name}_fp32_{k}"], TOL_FP32, f"style/{name}/{k}/fp32loop_vs_ref32")
+        _check(sauto[k], gold[f"style_{name}_fp32_{k}"], TOL_F16_VS_FP32, f"style/{name}/{k}/autocast_vs_ref32")
+
+
+def test_region_edit_and_stylizer_modules(gold, cuda):
+    m = PC.build_model("clip", cuda)
+    e = _set_edit(m, gold, "clip", True, cuda)
+    t = lambda k: torch.from_numpy(gold[k]).to(cuda)  # noqa: E731
+    with torch.no_grad():
+        out = e(t("regionedit_in_final"), t("regionedit_in_xyz"), t("regionedit_in_clip"))
+        _check(out, gold["regionedit_out"], 3e-4, "module/RegionEdit.forward")
+        e.weight_mode = True
+        _check(e(t("regionedit_in_final"), t("regionedit_in_xyz"), t("regionedit_in_clip")), gold["regionedit_out_weight_mode"],
+               1e-6, "module/RegionEdit.forward/weight_mode")
+        s = _set_stylizer(m, gold, "clip", cuda)
+        M = gold["stylizer_in_radiance"].shape[0]
+        out = s(t("stylizer_in_radiance").reshape(M, 1, 1), t("stylizer_in_omega").reshape(M, 4, 1),
+                m.basis_color.detach().clamp(0, 1)[None], t("stylizer_in_offsets"), t("stylizer_in_view_dep"))
+        _check(out, gold["stylizer_out"], 2e-6, "module/Stylizer.forward")
+    # update_delta_hsv reproduces the delta the reference derived from the same palettes
+    e2 = _set_edit(m, gold, "clip", True, cuda)
+    e2.delta_hsv = torch.zeros(4, 3, device=cuda)
+    rgb_new = torch.tensor([[0.2, 0.7, 0.3], [0.25, 0.2, 0.3], [0.9, 0.6, 0.7], [0.1, 0.3, 0.8]], device=cuda)
+    e2.update_delta_hsv(m.basis_color.detach().clamp(0, 1), rgb_new)
+    _check(e2.delta_hsv, gold["edit_clip_delta_hsv"], 1e-4, "module/RegionEdit.update_delta_hsv")
+
+
+TRAIN_KEYS = ["image", "depth", "weights_sum", "omega_sparsity", "view_dep_norm", "offsets_norm", "smooth_norm", "view_dep_rgb",
+              "direct_rgb", "diffuse_rgb", "clip_feat", "basis_acc"]
+
+
+def _train_step(m, cfg, cuda, smooth, fused):
+    """one PaletteTrainer.train_step-equivalent on this repository's model -> (outputs, loss, terms, grads)"""
+    from palettenerf_b200.palette.losses import palette_loss, TERMS
+    m.train()
+    m.require_smooth_loss = bool(smooth)
+    o, d = PC.train_rays()
+    gt, feat = PC.train_targets(cfg["pred_clip"])
+    o, d, gt = o.to(cuda)[None], d.to(cuda)[None], gt.to(cuda)
+    feat = None if feat is None else feat.to(cuda)
+    for p in m.parameters():
+        p.grad = None
+    lam = PC.LAMBDAS
+    bc0 = (m.basis_color.detach() * 0.9 + 0.03)
+    with PC.FixedRandom(), torch.autocast("cuda", dtype=torch.float16, enabled=fused):
+        out = m.render(o, d, staged=False, bg_color=1, perturb=True, force_all_rays=True, fused=fused, **PC.RENDER_KW)
+        loss, terms, _ = palette_loss(out, gt, lambda_sparsity=lam["lambda_sparsity"], lambda_offsets=lam["lambda_offsets"],
+                                      lambda_view_dep=lam["lambda_view_dep"], lambda_smooth=lam["lambda_smooth"] if smooth else 0.0,
+                                      gt_clip_feat=feat, basis_color=m.basis_color, basis_color_origin=bc0,
+                                      lambda_palette=lam["lambda_palette"])
+    (loss * PC.GRAD_SCALE).backward()
+    grads = {n: p.grad.detach().float() / PC.GRAD_SCALE for n, p in m.named_parameters() if p.grad is not None}
+    m.require_smooth_loss = False
+    return out, loss, dict(zip(TERMS, terms.tolist())), grads, m._last_train_schedule
+
+
+@pytest.mark.parametrize("smooth", [0, 1])
+@pytest.mark.parametrize("fused", [False, True], ids=["fp32ops", "fused16"])
+def test_train_step_outputs_loss_and_gradients(gold, case, cuda, smooth, fused):
+    name, cfg, m = case
+    out, loss, terms, grads, sched = _train_step(m, cfg, cuda, smooth, fused)
+    tag = f"train_{name}_s{smooth}"
+    path = "fused16" if fused else "fp32ops"
+    REPORT[f"{tag}/{path}/schedule"] = sched
+    if fused:
+        assert sched == "fused", "under fp16 autocast the training step must take the fused kernels (smooth loss included)"
+    tol = TOL_F16_VS_FP32 if fused else TOL_FP32
+    for k in TRAIN_KEYS:
+        _check(out[k], gold[f"{tag}_fp32_{k}"], tol, f"{tag}/{k}/{path}_vs_ref32")
+        if fused:
+            _check(out[k], gold[f"{tag}_f16_{k}"], TOL_F16_VS_F16, f"{tag}/{k}/{path}_vs_ref16")
+    ref_loss = float(gold[f"{tag}_fp32_loss"])
+    REPORT[f"{tag}/loss/{path}"] = {"ours": float(loss), "ref32": ref_loss, "ref16": float(gold[f"{tag}_f16_loss"])}
+    assert abs(float(loss) - ref_loss) <= (1e-3 if fused else 2e-5) * max(1.0, abs(ref_loss))
+    for k_ref, k in (("loss_sparsity", "sparsity"), ("loss_offsets", "offsets"), ("loss_view_dep", "view_dep"),
+                     ("loss_smooth", "smooth"), ("loss_palette", "palette"), ("loss_direct", "direct")):
+        r = float(gold[f"{tag}_fp32_{k_ref}"])
+        assert abs(terms[k] - r) <= (1e-3 if fused else 2e-5) * max(1e-2, abs(r)) + 1e-7, (k, terms[k], r)
+    # gradients: every small parameter in full, sampled rows + norms of the hash-table gradients
+    checked = 0
+    for key in gold.files:
+        if not key.startswith(f"{tag}_fp32_grad"):
+            continue
+        kind, pname = key[len(f"{tag}_fp32_"):].split("_", 1)
+        r = gold[key].astype(np.float64)
+        if pname.startswith("basis_net"):
+            continue          # the reference computes these but never steps them (not in get_params); the fused path skips them
+        if kind == "gradnorm":
+            g = grads[pname].double()
+            ours = np.array([g.norm().item(), g.abs().sum().item(), float((g != 0).any(dim=1).sum().item())])
+            REPORT[f"{tag}/grad/{pname}/norms/{path}"] = {"ours": ours.tolist(), "ref": r.tolist()}
+            assert abs(ours[0] - r[0]) <= (2e-2 if fused else 1e-4) * r[0]
+            assert abs(ours[2] - r[2]) <= (0.002 * r[2] if fused else 0), "touched rows of the table gradient"
+            continue
+        if kind == "gradrows":
+            idx = PC.table_grad_indices(grads[pname].shape[0]).to(cuda)
+            a = grads[pname][idx].double().cpu().numpy().reshape(-1)
+        else:
+            a = grads[pname].double().cpu().numpy().reshape(-1)
+        r = r.reshape(-1)
+        if np.abs(r).max() == 0:
+            assert np.abs(a).max() <= 1e-12, pname
+            continue
+        rel = np.linalg.norm(a - r) / np.linalg.norm(r)
+        cos = float(np.dot(a, r) / (np.linalg.norm(a) * np.linalg.norm(r)))
+        REPORT[f"{tag}/grad/{pname}/{kind}/{path}"] = {"rel_l2": float(rel), "cos": cos}
+        assert rel <= (2e-2 if fused else 2e-4) and cos >= (0.9995 if fused else 0.999999), f"{pname}: rel {rel:.3e} cos {cos:.6f}"
+        checked += 1
+    assert checked >= 9
+
+
+def test_nerf_stage_forward_render_and_train(gold, cuda):
+    from palettenerf_b200 import synthetic as S
+    m = S.build_nerf_model(cuda, seed=4, table_scale=0.5)
+    m.eval()
+    x, d = torch.from_numpy(gold["nerf_fwd_x"]).to(cuda), torch.from_numpy(gold["nerf_fwd_d"]).to(cuda)
+    o, dd = PC.eval_rays()
+    o, dd = o.to(cuda)[None], dd.to(cuda)[None]
+    for prec, tol in (("fp32", TOL_FP32), ("f16", TOL_F16_VS_FP32)):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=prec == "f16"):
+            s, c = m(x, d)
+            _check(s, gold["nerf_fwd_fp32_sigma"], 2e-4 if prec == "fp32" else 2e-3, f"nerf/fwd/sigma/{prec}_vs_ref32", rel=True)
+            _check(c, gold["nerf_fwd_fp32_color"], tol, f"nerf/fwd/color/{prec}_vs_ref32")
+            for ds in (1, 40):
+                m.density_scale = float(ds)
+                out = m.render(o, dd, staged=True, bg_color=1, perturb=False, **PC.RENDER_KW)
+                for k in ("image", "depth", "weights_sum"):
+                    _check(out[k], gold[f"nerf_eval_ds{ds}_fp32_{k}"], tol, f"nerf/eval/ds{ds}/{k}/{prec}_vs_ref32")
+            m.density_scale = 1.0
+    m.train()
+    to, td = PC.train_rays()
+    gt, _ = PC.train_targets(False)
+    for prec, tol in (("fp32", TOL_FP32), ("f16", TOL_F16_VS_FP32)):
+        for p in m.parameters():
+            p.grad = None
+        with PC.FixedRandom(), torch.autocast("cuda", dtype=torch.float16, enabled=prec == "f16"):
+            out = m.render(to.to(cuda)[None], td.to(cuda)[None], rays_gt=gt.to(cuda), staged=False, bg_color=1, perturb=True,
+                           force_all_rays=True, **PC.RENDER_KW)
+            loss = ((out["image"] - gt.to(cuda)) ** 2).mean()
+        (loss * PC.GRAD_SCALE).backward()
+        for k in ("image", "depth", "weights_sum", "rgb_norm"):
+            _check(out[k], gold[f"nerf_train_fp32_{k}"], tol, f"nerf/train/{k}/{prec}_vs_ref32")
+        for n, p in m.named_parameters():
+            key = f"nerf_train_fp32_grad_{n}"
+            if key in gold.files:
+                a = (p.grad.detach().float() / PC.GRAD_SCALE).double().cpu().numpy().reshape(-1)
+                r = gold[key].astype(np.float64).reshape(-1)
+                rel = np.linalg.norm(a - r) / np.linalg.norm(r)
+                REPORT[f"nerf/train/grad/{n}/{prec}"] = {"rel_l2": float(rel)}
+                assert rel <= (2e-2 if prec == "f16" else 2e-4), (n, rel)
+
+
+def test_fused_train_survives_capacity_overflow_with_poisoned_scratch(cuda):
+    """round-1 advisor finding: with a sample capacity M below the total count, rows behind the first dropped ray are never
+    written; the fused step must not read them (NaN * 0 = NaN would poison every weight gradient)"""
+    from palettenerf_b200.arena import ARENA
+    m = PC.build_model("noclip", cuda)
+    m.train()
+    o, d = PC.train_rays()
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    kw = dict(staged=False, bg_color=1, perturb=False, dt_gamma=0.0, max_steps=1024)
+    with torch.autocast("cuda", dtype=torch.float16):
+        full = m.render(o, d, force_all_rays=True, **kw)
+    total = int(m.step_counter[(m.local_step - 1) % 16, 0].item())
+    m.mean_count = total // 2                                  # capacity = half of what the rays need
+    ARENA.clear()
+    for nm in ("march_xyzs", "march_dirs", "march_deltas"):
+        cap = m.mean_count + (128 - m.mean_count % 128)
+        ARENA.get(nm, (cap, 3 if nm != "march_deltas" else 2), torch.float32, cuda).fill_(float("nan"))
+    for p in m.parameters():
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = m.render(o, d, force_all_rays=False, **kw)
+        loss = ((out["image"] - 0.5) ** 2).mean() + out["omega_sparsity"].mean() + ((out["direct_rgb"] - 0.5) ** 2).mean()
+    assert m._last_train_schedule == "fused"
+    loss.backward()
+    assert torch.isfinite(loss)
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), n
+    kept = out["weights_sum"] > 0
+    assert kept.sum() > 10 and (~kept).sum() > 10             # some rays fit, the rest were dropped
+    # rays that fit render exactly what they render with unlimited capacity
+    assert torch.allclose(out["image"][0][kept], full["image"][0][kept], atol=1e-6)
+    m.mean_count = 0
+
+
+def test_packbits_in_place_invalidates_the_occupied_bounds_cache(cuda):
+    """round-1 advisor finding: packbits(grid, thresh, bitfield) writes through a raw pointer; the in-place convention of
+    the reference must still invalidate occupied_bounds()'s per-version cache"""
+    import palettenerf_b200.raymarching as rm
+    from palettenerf_b200.raymarching.raymarching import occupied_bounds
+    from palettenerf_b200 import synthetic as S
+    grid = S.density_grid().to(cuda)
+    bf = rm.packbits(grid, 10.0)
+    b0 = occupied_bounds(bf, 2, 128, 2.0)[:6].clone()
+    v0 = bf._version
+    grid2 = S.density_grid(scale=1.5).to(cuda)
+    ret = rm.packbits(grid2, 10.0, bf)                          # same tensor object, new contents
+    assert ret.data_ptr() == bf.data_ptr() and bf._version > v0
+    b1 = occupied_bounds(bf, 2, 128, 2.0)[:6]
+    assert (b1[3:] - b1[:3] > (b0[3:] - b0[:3]) * 1.2).all()   # the larger solid has larger bounds: not the cached ones
+
+
+def test_field_cache_follows_data_writes_that_do_not_bump_versions(cuda):
+    """round-1 advisor finding: torch_ema's copy_to / restore write through param.data.copy_ (no version bump); the fused
+    renderer must render the weights the module holds NOW"""
+    m = PC.build_model("noclip", cuda)
+    m.eval()
+    o, d = PC.eval_rays()
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    a = _render(m, o, d, True)["image"].clone()
+    saved = [p.detach().clone() for p in m.parameters()]
+    versions = [p._version for p in m.parameters()]
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2 and p.shape[0] <= 64:
+                p.data.copy_(p.data * 0.5)                      # "EMA weights"
+    assert versions == [p._version for p in m.parameters()]
+    b = _render(m, o, d, True)["image"].clone()
+    assert (a - b).abs().max().item() > 1e-2, "stale cache: the .data write was not seen"
+    ref = _render(m, o, d, False)["image"]
+    assert (b - ref).abs().max().item() < 2e-3
+    for p, s in zip(m.parameters(), saved):
+        p.data.copy_(s)                                         # "restore"
+    c = _render(m, o, d, True)["image"]
+    assert torch.equal(a, c)
