@@ -252,6 +252,25 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
                                          int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb,
                                          void* stream);
 
+/* Round-2 renderer: a warp owns ONE ray at a time (csrc/render_rays.cu): warp-cooperative lattice walk of the ray, tiles of
+ * 32 consecutive samples (lane = sample) through the fused field with lane-pair hash-grid gathers, warp-scan compositing,
+ * one writer per ray. Same arguments as pnerf_palette_render_fused up to the scratch:
+ *   queue     [8] u32, zero on entry; on return {ray cursor, samples shaded, rays with samples, 32-sample tiles, candidates}
+ *   cand      [N] int32 scratch (rays that can have samples)
+ *   t_scratch [pnerf_palette_render_rays_warps() * max_steps] fp32 scratch (per-warp sample lists)
+ * Requires field->table_sigma_palette (interleaved tables). Replaces palette/renderer.py:430-523. */
+PNERF_API uint32_t pnerf_palette_render_rays_warps(void);
+PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                                        const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C,
+                                        uint32_t Hgrid, uint32_t max_steps, float dt_gamma, float T_thresh,
+                                        const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
+                                        float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
+                                        float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, int32_t* cand,
+                                        float* t_scratch, const float* occ_aabb, void* stream);
+/* bench hook: CUDA-event pair around the persistent kernel of the last pnerf_palette_render_rays call (off by default) */
+PNERF_API void pnerf_render_rays_timing(int enable);
+PNERF_API float pnerf_render_rays_last_ms(void);
+
 /* measurement hook for bench.py's roofline: with timing enabled, pnerf_palette_render_fused brackets its persistent
  * kernel (k_render_fused, not the pre-pass / ordering launches) with an event pair on the launch stream;
  * pnerf_render_kernel_last_ms() synchronises on it and returns the duration of the last launch (-1 if none). */
@@ -301,7 +320,10 @@ PNERF_API int pnerf_palette_train_forward(const float* xyzs, const float* dirs, 
 PNERF_API int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train* p, const void* xbuf, void* ybuf,
                                            const float* grad_rgb, const float* grad_flex, const float* flex, float* d_enc,
                                            float* d_enc_clip, float* d_palette, void* stream);
-PNERF_API int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf,
+/* flags: bit 0 = pred_clip (the clip_net layers are present); bit 1 = also compute the weight gradients of basis_net,
+ * which the reference's optimizer never steps (palette/network.py:283-308 omits it from get_params) — off = those two
+ * slots of dwbuf are left untouched. */
+PNERF_API int pnerf_palette_train_wgrad(uint32_t M, uint32_t flags, const void* xbuf, const void* ybuf, float* dwbuf,
                                         const int32_t* m_dev, void* stream);
 
 /* ONE-pass compositor of the palette training step: composite_rays_train on (sigma, rgb) and composite_rays_flex_train

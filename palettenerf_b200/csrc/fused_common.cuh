@@ -284,6 +284,108 @@ __device__ __forceinline__ void gather_fast(const void* __restrict__ table, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// gather_coop: LANE-PAIR cooperative gather of one warp tile (32 samples).
+//
+// Why: a fully scattered warp-wide load costs the L1/TEX pipe one wavefront per distinct 128-byte line it touches
+// (round 1: 81 % L1/TEX pipe utilisation, 128 scattered 8-byte loads per sample). The two x-neighbour corners of a lattice
+// cell are ADJACENT table entries — dense levels: x has stride 1; hashed levels: the x prime is 1, so
+// idx(x+1) = idx(x) ^ 1 whenever x is even and differs only in the low bits otherwise — hence they share a 128-byte line
+// 15 times out of 16. Here a load instruction serves 16 samples x 2 x-corners: lanes 2p and 2p+1 fetch the x / x+1 corner
+// of the same (y, z) combination of sample p, so one instruction touches ~17 lines instead of 32; consecutive samples of
+// ONE ray (the renderer's and the training path's sample order) additionally share lines on the coarse levels.
+// Each lane accumulates its 4 (y, z) corners; one shuffle pair per (level, table) combines the two x halves; with two
+// interleaved tables lane 2p ends up owning table 0's feature and lane 2p+1 table 1's, so both keep busy.
+//
+// Interpolation arithmetic: weights (wx*wy)*wz in fp32 (the reference's order), rounded ONCE to fp16, then
+// fma.rn.f32.f16 (SASS FHFMA, new on sm_100): exact fp16 x fp16 products accumulated in fp32 — no fp16 -> fp32
+// conversion instructions at all. Error vs fp32 weights <= 2^-11 * sum|w_c v_c| per feature, the size of the final fp16
+// rounding of the feature itself (the reference accumulates all 8 terms in fp16, gridencoder.cu:142-165).
+//   row(e, s) -> uint32_t* : destination row (16 words, one per level) of table e, sample s
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f2h_bits(float v) {
+    uint16_t h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
+}
+// ax += lo(v) * w, ay += hi(v) * w  (v = packed half2 table entry, w = fp16 weight): two FHFMA
+__device__ __forceinline__ void fhfma2(float& ax, float& ay, uint32_t v, uint16_t w) {
+    asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %3, %0;\n\tfma.rn.f32.f16 %1, hi, %3, %1;\n\t}"
+        : "+f"(ax), "+f"(ay)
+        : "r"(v), "h"(w));
+}
+
+template <int EW, int LV, typename RowFn>
+__device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
+                                            float w, bool in_range, int lane, RowFn row) {
+    static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
+    u = fminf(fmaxf(u, 0.f), 1.f); v = fminf(fmaxf(v, 0.f), 1.f); w = fminf(fmaxf(w, 0.f), 1.f);   // keeps the loads in bounds
+    const uint32_t xsel = (uint32_t)lane & 1u;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int s = half * 16 + (lane >> 1);
+        const float us = __shfl_sync(0xffffffffu, u, s), vs = __shfl_sync(0xffffffffu, v, s), wsm = __shfl_sync(0xffffffffu, w, s);
+        const bool inr = __shfl_sync(0xffffffffu, (int)in_range, s) != 0;
+        uint32_t* const dst = row(EW == 2 ? (int)xsel : 0, s);
+#pragma unroll 1
+        for (int l0 = 0; l0 < 16; l0 += LV) {
+            uint32_t val[LV][4][EW];
+            uint16_t wt[LV][4];
+#pragma unroll
+            for (int j = 0; j < LV; j++) {
+                const LevelParams& p = lp[l0 + j];
+                const float px = fmaf(us, p.scale, 0.5f), py = fmaf(vs, p.scale, 0.5f), pz = fmaf(wsm, p.scale, 0.5f);
+                const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+                const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+                const float rx = px - fx0, ry = py - fy0, rz = pz - fz0;
+                const float wx = xsel ? rx : 1.f - rx;
+                const float wxy0 = wx * (1.f - ry), wxy1 = wx * ry;        // (wx*wy)*wz: the reference's order
+                wt[j][0] = f2h_bits(wxy0 * (1.f - rz)); wt[j][1] = f2h_bits(wxy1 * (1.f - rz));
+                wt[j][2] = f2h_bits(wxy0 * rz);         wt[j][3] = f2h_bits(wxy1 * rz);
+                uint32_t idx[4];
+                const uint32_t hx = gx + xsel;
+                if (p.use_hash) {
+                    const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
+                    const uint32_t hy1 = hy0 + 2654435761u, hz1 = hz0 + 805459861u;
+                    idx[0] = (hx ^ hy0 ^ hz0) & p.mask; idx[1] = (hx ^ hy1 ^ hz0) & p.mask;
+                    idx[2] = (hx ^ hy0 ^ hz1) & p.mask; idx[3] = (hx ^ hy1 ^ hz1) & p.mask;
+                } else {
+                    const uint32_t ix = hx * p.stride[0], iy0 = gy * p.stride[1], iz0 = gz * p.stride[2];
+                    const uint32_t iy1 = iy0 + p.stride[1], iz1 = iz0 + p.stride[2];
+                    idx[0] = (ix + iy0 + iz0) & p.mask; idx[1] = (ix + iy1 + iz0) & p.mask;
+                    idx[2] = (ix + iy0 + iz1) & p.mask; idx[3] = (ix + iy1 + iz1) & p.mask;
+                }
+                const uint64_t base = (uint64_t)(uintptr_t)table + (uint64_t)p.offset * (uint32_t)(EW * 4);
+#pragma unroll
+                for (int c = 0; c < 4; c++) ldg_entry<EW>(base, idx[c], val[j][c]);
+            }
+#pragma unroll
+            for (int j = 0; j < LV; j++) {
+                float acc[EW][2];
+#pragma unroll
+                for (int e = 0; e < EW; e++) {
+                    acc[e][0] = acc[e][1] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) fhfma2(acc[e][0], acc[e][1], val[j][c][e], wt[j][c]);
+                }
+                float rx_, ry_;
+                if (EW == 2) {
+                    // lane 2p keeps table 0 and receives the partner's table-0 half; lane 2p+1 the same for table 1
+                    const float sx = xsel ? acc[0][0] : acc[EW - 1][0], sy = xsel ? acc[0][1] : acc[EW - 1][1];
+                    const float mx = xsel ? acc[EW - 1][0] : acc[0][0], my = xsel ? acc[EW - 1][1] : acc[0][1];
+                    rx_ = mx + __shfl_xor_sync(0xffffffffu, sx, 1);
+                    ry_ = my + __shfl_xor_sync(0xffffffffu, sy, 1);
+                    dst[l0 + j] = inr ? pack_h2(rx_, ry_) : 0u;
+                } else {
+                    rx_ = acc[0][0] + __shfl_xor_sync(0xffffffffu, acc[0][0], 1);
+                    ry_ = acc[0][1] + __shfl_xor_sync(0xffffffffu, acc[0][1], 1);
+                    if (!xsel) dst[l0 + j] = inr ? pack_h2(rx_, ry_) : 0u;
+                }
+            }
+        }
+    }
+}
+
 // (Measured and rejected, profiles/README.md "gather variants": computing the corner indices once for the density and
 // palette grids — same geometry — and reading both tables with them cuts ~30 % of the gather's instructions but does not
 // speed the renderer up: the gather is bound by L1/L2 load latency, the index arithmetic hides under it, and the second

@@ -742,10 +742,12 @@ int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train* p, const
     return check_launch("palette_train_backward");
 }
 
-int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, const void* ybuf, float* dwbuf,
+int pnerf_palette_train_wgrad(uint32_t M, uint32_t flags, const void* xbuf, const void* ybuf, float* dwbuf,
                               const int32_t* m_dev, void* stream) {
     if (M == 0) return PNERF_OK;
     PNERF_REQUIRE(xbuf && ybuf && dwbuf);
+    const uint32_t pred_clip = flags & 1u;          // PNERF_TRAIN_WGRAD_CLIP
+    const bool basis = (flags & 2u) != 0;           // PNERF_TRAIN_WGRAD_BASIS_NET
     WJobs J;
     J.n = 0;
     add_job(J, YD0, 4, XD0, 1, DW_D0);
@@ -754,8 +756,11 @@ int pnerf_palette_train_wgrad(uint32_t M, uint32_t pred_clip, const void* xbuf, 
     add_job(J, YV0, 4, XV0, 2, DW_V0);
     add_job(J, YV1, 4, XV1, 4, DW_V1);
     add_job(J, YV2, 1, XV2, 4, DW_V2);
-    add_job(J, YB0, 4, XB0, 3, DW_B0);
-    add_job(J, YB1, 1, XB1, 4, DW_B1);
+    if (basis) {   // the reference never steps basis_net (absent from get_params, palette/network.py:283-308): its weight
+                   // gradients are computed on request only; their slots of dwbuf stay as the caller initialised them
+        add_job(J, YB0, 4, XB0, 3, DW_B0);
+        add_job(J, YB1, 1, XB1, 4, DW_B1);
+    }
     add_job(J, YH, 2, XH, 1, DW_H);
     if (pred_clip) {
         add_job(J, YC0, 4, XC0, 2, DW_C0);

@@ -36,6 +36,9 @@ P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
 L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 ordering kernels + persistent kernel
+L.register("pnerf_palette_render_rays", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.LAUNCHES["pnerf_palette_render_rays"] = 2   # candidate filter + the persistent warp-per-ray kernel
+L.lib.pnerf_palette_render_rays_warps.restype = c_uint32
 
 
 def _frag(W, n_pad, k_pad):
@@ -199,12 +202,30 @@ def field_forward(model, xyzs, dirs):
     return sigma, clip, omega, off_rad, view_dep, diffuse
 
 
+_T_SCRATCH = {}
+
+
+def _t_scratch(dev, max_steps):
+    """per-warp sample lists of the warp-per-ray renderer: [resident warps, max_steps] fp32, allocated once per device"""
+    key = (str(dev), int(max_steps))
+    t = _T_SCRATCH.get(key)
+    if t is None:
+        t = _T_SCRATCH[key] = torch.empty(int(L.lib.pnerf_palette_render_rays_warps()) * int(max_steps), dtype=torch.float32,
+                                          device=dev)
+    return t
+
+
+RENDER_KERNEL = __import__("os").environ.get("PNERF_RENDER_KERNEL", "lanes")    # "rays" (round 2) | "lanes" (round 1, A/B)
+
+
 @torch.no_grad()
-def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
-    """persistent fused renderer -> dict of accumulators like PaletteRenderer._infer_loop"""
+def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode, kernel=None):
+    """persistent fused renderer -> dict of accumulators like PaletteRenderer._infer_loop.
+    kernel: "rays" = warp-per-ray kernel (csrc/render_rays.cu, default), "lanes" = round 1's lane-per-ray kernel"""
     f = _cache(model).get()
     N, dev = rays_o.shape[0], rays_o.device
     nb, cd = model.num_basis, model.opt.clip_dim
+    kernel = kernel or RENDER_KERNEL
     # every accumulator (and the queue counters) is a view of ONE zero-filled buffer: one fill launch per view instead of ten
     shapes = {"weights_sum": (N,), "depth": (N,), "image": (N, 3), "clip_feat": (N, cd)}
     if not gui_mode:
@@ -216,19 +237,23 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     for k, shp in shapes.items():
         acc[k] = flat[off:off + sizes[k]].view(*shp)
         off += sizes[k]
-    queue = flat[off:off + 68].view(torch.int32)             # 4 counters + 32-bucket histogram + 32 cursors
-    hit_list = torch.empty(2 * N, dtype=torch.int32, device=dev)   # ordered hit list + samples per ray
-    t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
+    queue = flat[off:off + 68].view(torch.int32)             # counters (+ round 1's 32-bucket histogram and cursors)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
     aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
     from .raymarching.raymarching import occupied_bounds
     occ = occupied_bounds(model.density_bitfield, model.cascade, model.grid_size, model.bound) \
         if (model.grid_size ** 3) % 32 == 0 else None
-    L.call("pnerf_palette_render_fused", ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises),
-           ptr(model.density_bitfield), N, model.cascade, model.grid_size, max_steps, float(dt_gamma), float(T_thresh),
-           ctypes.addressof(f), ptr(acc["weights_sum"]), ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"),
-           aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"), aux("unscaled_basis_rgb"),
-           ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue), ptr(hit_list), ptr(t_first), ptr(t_last),
-           ptr(occ), stream())
-    acc["_queue"] = queue   # [hit-list cursor, samples shaded, rays with samples, tiles evaluated]; read lazily (no sync here)
+    common = (ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises), ptr(model.density_bitfield), N, model.cascade,
+              model.grid_size, max_steps, float(dt_gamma), float(T_thresh), ctypes.addressof(f), ptr(acc["weights_sum"]),
+              ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"), aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"),
+              aux("unscaled_basis_rgb"), ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue))
+    if kernel == "rays":
+        cand = torch.empty(N, dtype=torch.int32, device=dev)
+        L.call("pnerf_palette_render_rays", *common, ptr(cand), ptr(_t_scratch(dev, max_steps)), ptr(occ), stream())
+    else:
+        hit_list = torch.empty(2 * N, dtype=torch.int32, device=dev)   # ordered hit list + samples per ray
+        t_first, t_last = torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev)
+        L.call("pnerf_palette_render_fused", *common, ptr(hit_list), ptr(t_first), ptr(t_last), ptr(occ), stream())
+    acc["_queue"] = queue   # [ray cursor, samples shaded, rays with samples, tiles evaluated, ...]; read lazily (no sync here)
+    acc["_kernel"] = kernel
     return acc

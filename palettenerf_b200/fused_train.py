@@ -285,7 +285,11 @@ class _TrainField(Function):
         dw = torch.zeros(int(L.lib.pnerf_palette_train_dw_floats(int(pc))), dtype=torch.float32, device=dev)
         L.call("pnerf_palette_train_backward", M, ctypes.addressof(f), ptr(xbuf), ptr(ybuf), ptr(g_rgb), ptr(g_flex), ptr(flex),
                ptr(d_enc), ptr(d_enc_clip), ptr(d_pal), stream())
-        L.call("pnerf_palette_train_wgrad", M, int(pc), ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
+        # basis_net: the reference leaves it out of get_params (palette/network.py:283-308), so nothing ever steps it and its
+        # weight gradients are dead work; they are computed only when the model asks (`fused_basis_net_grad = True`),
+        # otherwise those parameters receive NO gradient (None) on this path
+        basis = bool(getattr(model, "fused_basis_net_grad", False))
+        L.call("pnerf_palette_train_wgrad", M, int(pc) | (2 if basis else 0), ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
         # hash-grid scatter of the feature gradients (run-length kernel, fp32 accumulation, [B, L*C] layout)
         from .gridencoder.backend import _backend as GB
         enc = model.encoder_palette
@@ -305,7 +309,7 @@ class _TrainField(Function):
         g_pal_tab = scatter(emb_pal, d_enc) if M > 0 else torch.zeros_like(emb_pal)
         g_clip_tab = (scatter(emb_clip, d_enc_clip) if M > 0 else torch.zeros_like(emb_clip)) if pc else None
         gw = dw_views(dw, pc, cd)
-        grads = [gw.get(n) for n in st["names"]]           # sigma_net.* -> None (constants of this stage)
+        grads = [None if (not basis and n.startswith("basis_net")) else gw.get(n) for n in st["names"]]   # sigma_net.* -> None
         return (None, None, None, None, d_pal, g_pal_tab, g_clip_tab, *grads)
 
 

@@ -191,6 +191,31 @@ class PaletteRenderer(nn.Module, OccupancyState):
                               clip_feat, w], dim=-1)
         return sigmas, rgbs, channels, weights_sum, depth, image
 
+    def _smooth_channels(self, fused_train, xyzs, dirs, palette, valid, channels):
+        """smooth-loss branch of the training field (ref: palette/renderer.py:360-381) on the fused kernels: a SECOND fused
+        forward on the jittered points (its backward runs through the same hand-written kernels: the reference lets the
+        gradient of smooth_norm flow into both evaluations), the gate / norm arithmetic as a handful of per-sample tensor
+        expressions, and the result replaces column 3 of the channel buffer the one-pass compositor consumes.
+        Rows beyond `valid` (static capacity) hold garbage on both sides and are never composited."""
+        nb, cd = self.num_basis, self.opt.clip_dim
+        b = self.bound
+        jitter = (xyzs + torch.rand_like(xyzs) * b * 0.03).clamp(-b, b)
+        _, _, ch_j = fused_train.field(self, jitter, dirs, palette, count=valid)
+        c0 = 13 + cd
+        omega, omega_j = channels[:, c0:c0 + nb], ch_j[:, c0:c0 + nb]
+        diffuse, diffuse_j = channels[:, 10:13], ch_j[:, 10:13]
+        clip, clip_j = channels[:, 13:c0], ch_j[:, 13:c0]
+        k_xyz = (xyzs - jitter).norm(dim=-1, keepdim=True) ** 2 / b ** 2 / self.opt.smooth_sigma_xyz
+        k_rgb = (diffuse - diffuse_j).norm(dim=-1, keepdim=True) ** 2 / self.opt.smooth_sigma_color
+        k_clip = 0
+        if self.opt.pred_clip and self.opt.smooth_sigma_clip > 0:
+            k_clip = (clip - clip_j).norm(dim=-1, keepdim=True) / self.opt.smooth_sigma_clip
+        gate = torch.exp(-k_xyz - k_rgb - k_clip).detach()
+        smooth = ((omega_j - omega) ** 2).sum(dim=-1, keepdim=True) * gate
+        if self.opt.pred_clip:
+            smooth = smooth + ((clip_j - clip) ** 2).sum(dim=-1, keepdim=True) * gate
+        return torch.cat([channels[:, :3], smooth, channels[:, 4:]], dim=1)
+
     # ------------------------------------------------------------------------------------------------
     def _train_branch(self, rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays, max_steps,
                       T_thresh, fused=None):
@@ -206,13 +231,13 @@ class PaletteRenderer(nn.Module, OccupancyState):
             # of the data -> the whole step can be captured in a CUDA graph); ONE forward kernel (hash grids + MLPs +
             # blend + regulariser channels) with a hand-written backward; ONE compositing pass for rgb + all channels.
             from .. import fused_train
-            if self.require_smooth_loss:
-                raise RuntimeError("the fused training field does not cover the smooth-loss branch")
             xyzs, dirs, deltas, rays, valid = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
                 self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, True)
             # `valid` (not counter[0]): when the capacity overflows, rows behind the first dropped ray are uninitialised
             sigmas, rgbs, channels = fused_train.field(self, xyzs, dirs, palette[0], count=valid)
+            if self.require_smooth_loss:
+                channels = self._smooth_channels(fused_train, xyzs, dirs, palette[0], valid, channels)
             if channels.shape[1] == 33:
                 weights_sum, depth, image, maps = fused_train.composite(sigmas, rgbs, channels, deltas, rays, T_thresh)
             else:
@@ -354,10 +379,9 @@ class PaletteRenderer(nn.Module, OccupancyState):
         return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None and fused.supported(self))
 
     def _fused_train_available(self):
-        """fused training field: same policy as inference, and only without the smooth-loss branch"""
+        """fused training field: same policy as inference (the smooth-loss branch included, see _smooth_channels)"""
         from .. import fused
-        return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None
-                and not self.require_smooth_loss and fused.supported(self))
+        return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None and fused.supported(self))
 
     def _infer_fused(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
         from .. import fused

@@ -85,6 +85,7 @@ def _grads(model, fn):
 def test_fused_train_backward_matches_torch_autograd(cuda, model):
     xyzs, dirs, _, _ = _samples(model, cuda, n_side=32)
     M = xyzs.shape[0]
+    model.fused_basis_net_grad = True        # off by default: the reference never steps basis_net (dead work)
     nflex = 13 + model.opt.clip_dim + 4
     g = torch.Generator(device=cuda).manual_seed(5)
     w_rgb = torch.randn(M, 3, device=cuda, generator=g)
@@ -120,6 +121,11 @@ def test_fused_train_backward_matches_torch_autograd(cuda, model):
         assert gt[n] is None or gt[n].abs().max().item() == 0, n
     if not model.opt.pred_clip:
         assert gf["encoder_clip.embeddings"] is None
+    model.fused_basis_net_grad = False
+    g0 = _grads(model, loss_fused)
+    assert g0["basis_net.0.weight"] is None and g0["basis_net.1.weight"] is None     # default: no gradient at all
+    assert torch.equal(g0["diff_net.1.weight"], gf["diff_net.1.weight"]) or \
+        torch.allclose(g0["diff_net.1.weight"], gf["diff_net.1.weight"], rtol=1e-4, atol=1e-7)
 
 
 def test_fused_train_ragged_and_empty(cuda, model):

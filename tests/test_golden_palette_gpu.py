@@ -256,7 +256,14 @@ def test_train_step_outputs_loss_and_gradients(gold, case, cuda, smooth, fused):
             ours = np.array([g.norm().item(), g.abs().sum().item(), float((g != 0).any(dim=1).sum().item())])
             REPORT[f"{tag}/grad/{pname}/norms/{path}"] = {"ours": ours.tolist(), "ref": r.tolist()}
             assert abs(ours[0] - r[0]) <= (2e-2 if fused else 1e-4) * r[0]
-            assert abs(ours[2] - r[2]) <= (0.002 * r[2] if fused else 0), "touched rows of the table gradient"
+            # rows of the table that receive a gradient: exact in fp32; the fp16 paths (the reference's own `-O` run
+            # included) flush the smallest contributions — the 1e-9-scale smooth-loss gradients of the jittered samples —
+            # so the fused count lies between the reference's fp16 and fp32 counts
+            r16 = gold[key.replace("_fp32_", "_f16_")][2]
+            if fused:
+                assert 0.998 * min(r16, r[2]) <= ours[2] <= 1.002 * r[2], ("touched rows", ours[2], r16, r[2])
+            else:
+                assert ours[2] == r[2], "touched rows of the table gradient"
             continue
         if kind == "gradrows":
             idx = PC.table_grad_indices(grads[pname].shape[0]).to(cuda)
