@@ -228,6 +228,9 @@ typedef struct pnerf_palette_field {
      * so that one 8-byte load fetches the features of both grids at a lattice corner (the two grids share their
      * geometry). The inference kernels prefer it; table_sigma / table_palette must still be valid. */
     const void* table_sigma_palette;
+    /* optional (may be NULL): the MLP weights as tcgen05 B operands — per layer fp16 [k-chunk][n][8] (K-major, no swizzle),
+     * pnerf_palette_tc_weight_bytes() bytes, palettenerf_b200/fused.py::tc_pack_index. Needed by the *_tc entry points. */
+    const void* wpack_tc;
 } pnerf_palette_field;
 
 /* xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (NULL unless pred_clip), omega [M,4], off_rad [M,13],
@@ -252,6 +255,13 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
                                          int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb,
                                          void* stream);
 
+/* Tensor-core (tcgen05 / TMEM) version of pnerf_palette_field_forward: a warpgroup evaluates 128 samples per tile, every
+ * dense layer is one tcgen05.mma chain (csrc/field_tc.cuh). Same arguments and results (fp16 operands, fp32 accumulation). */
+PNERF_API uint32_t pnerf_palette_tc_weight_bytes(uint32_t pred_clip);
+PNERF_API int pnerf_palette_field_forward_tc(const float* xyzs, const float* dirs, uint32_t M,
+                                             const pnerf_palette_field* field, float* sigma, float* clip, float* omega,
+                                             float* off_rad, float* view_dep, float* diffuse, void* stream);
+
 /* Round-2 renderer: a warp owns ONE ray at a time (csrc/render_rays.cu): warp-cooperative lattice walk of the ray, tiles of
  * 32 consecutive samples (lane = sample) through the fused field with lane-pair hash-grid gathers, warp-scan compositing,
  * one writer per ray. Same arguments as pnerf_palette_render_fused up to the scratch:
@@ -267,6 +277,23 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
                                         float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, int32_t* cand,
                                         float* t_scratch, const float* occ_aabb, void* stream);
+/* The same renderer with the field on the 5th-generation tensor cores (tcgen05.mma, activations and accumulators in TMEM;
+ * csrc/field_tc.cuh): a warpgroup shades 4 rays x 32 samples per tile. A thread-per-ray pre-pass records each candidate ray's
+ * occupied stretches (`runs`), so the persistent kernel never touches the occupancy grid.
+ *   runs      [N * pnerf_palette_render_tc_runs_bytes()] bytes scratch
+ *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32 scratch
+ * Needs field->wpack_tc and field->table_sigma_palette. Replaces palette/renderer.py:430-523. */
+PNERF_API uint32_t pnerf_palette_render_tc_warps(void);
+PNERF_API uint32_t pnerf_palette_render_tc_runs_bytes(void);
+PNERF_API int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                                      const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t Hgrid,
+                                      uint32_t max_steps, float dt_gamma, float T_thresh, const pnerf_palette_field* field,
+                                      float* weights_sum, float* depth, float* image, float* direct_rgb, float* view_dep_rgb,
+                                      float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb, float* clip_feat,
+                                      uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
+                                      void* stream);
+PNERF_API void pnerf_render_tc_timing(int enable);
+PNERF_API float pnerf_render_tc_last_ms(void);
 /* bench hook: CUDA-event pair around the persistent kernel of the last pnerf_palette_render_rays call (off by default) */
 PNERF_API void pnerf_render_rays_timing(int enable);
 PNERF_API float pnerf_render_rays_last_ms(void);

@@ -1,0 +1,495 @@
+// field_tc.cu — kernels built on the tcgen05 field (field_tc.cuh): the batch field evaluation and the warp-per-ray
+// persistent renderer with a 128-sample (4 rays x 32 samples) tensor-core tile per warpgroup.
+#include "field_tc.cuh"
+
+namespace pnerf {
+
+constexpr int kTcGroups = 4;                       // warpgroups per CTA (one CTA per SM): 16 warps, <= 128 registers/thread
+constexpr int kTcThreads = kTcGroups * 128;
+constexpr int kTcSharedBytes = (sizeof(TcShared) + 1023) & ~1023;
+
+__host__ __device__ constexpr size_t tc_smem_bytes(bool clip, size_t extra_per_warp = 0) {
+    return (size_t)kTcSharedBytes + (size_t)(clip ? kTcWBytesClip : kTcWBytesNoClip) +
+           (size_t)kTcGroups * (clip ? kTcGroupBytesClip : kTcGroupBytesNoClip) + extra_per_warp * kTcGroups * 4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch field evaluation (drop-in for PaletteNetwork.forward in eval mode), 128 samples per warpgroup tile
+// ------------------------------------------------------------------------------------------------
+template <bool CLIP>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_field_forward_tc(const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M, pnerf_palette_field f,
+                   float* __restrict__ sigma, float* __restrict__ clip, float* __restrict__ omega, float* __restrict__ off_rad,
+                   float* __restrict__ view_dep, float* __restrict__ diffuse) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcShared* sm = reinterpret_cast<TcShared*>(smem_raw);
+    unsigned char* wts = smem_raw + kTcSharedBytes;
+    unsigned char* groups = wts + (CLIP ? kTcWBytesClip : kTcWBytesNoClip);
+    constexpr int group_bytes = CLIP ? kTcGroupBytesClip : kTcGroupBytesNoClip;
+    tc_prologue<kTcGroups>(f, f.wpack_tc, sm, wts, groups, group_bytes);
+    TcGroup g = tc_make_group(sm, wts, groups, group_bytes);
+    const int lane = threadIdx.x & 31, gi = threadIdx.x >> 7;
+    const uint32_t n_tiles = ceil_div(M, 128u);
+    for (uint32_t tile = blockIdx.x * kTcGroups + gi; tile < n_tiles; tile += gridDim.x * kTcGroups) {
+        const uint32_t s = tile * 128 + (uint32_t)g.row;
+        const bool active = s < M;
+        float x = 0, y = 0, z = 0, dx = 0, dy = 0, dz = 1;
+        if (active) {
+            x = xyzs[(size_t)s * 3]; y = xyzs[(size_t)s * 3 + 1]; z = xyzs[(size_t)s * 3 + 2];
+            dx = dirs[(size_t)s * 3]; dy = dirs[(size_t)s * 3 + 1]; dz = dirs[(size_t)s * 3 + 2];
+        }
+        FieldOut o;
+        eval_field_tc<CLIP>(f, *sm, g, x, y, z, dx, dy, dz, active, lane, o);
+        if (active) {
+            sigma[s] = o.sigma;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { diffuse[(size_t)s * 3 + i] = o.diffuse[i]; view_dep[(size_t)s * 3 + i] = o.view_dep[i]; }
+#pragma unroll
+            for (int i = 0; i < 13; i++) off_rad[(size_t)s * 13 + i] = o.off_rad[i];
+#pragma unroll
+            for (int b = 0; b < kNB; b++) omega[(size_t)s * kNB + b] = o.omega[b];
+            if (CLIP && clip) {
+                for (uint32_t i = 0; i < f.clip_dim; i++) clip[(size_t)s * f.clip_dim + i] = o.clip[i];
+            }
+        }
+    }
+    tc_epilogue_cta<kTcGroups>(sm);
+}
+
+}  // namespace pnerf
+
+using namespace pnerf;
+
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = kNumSMs;
+    }
+    return sms;
+}
+
+extern "C" {
+
+uint32_t pnerf_palette_tc_weight_bytes(uint32_t pred_clip) { return pred_clip ? kTcWBytesClip : kTcWBytesNoClip; }
+
+/* tensor-core (tcgen05) version of pnerf_palette_field_forward: same arguments; needs field->wpack_tc (weight image of
+ * palettenerf_b200/fused.py::tc_pack_index) and field->table_sigma_palette (interleaved tables). */
+int pnerf_palette_field_forward_tc(const float* xyzs, const float* dirs, uint32_t M, const pnerf_palette_field* field,
+                                   float* sigma, float* clip, float* omega, float* off_rad, float* view_dep, float* diffuse,
+                                   void* stream) {
+    if (M == 0) return PNERF_OK;
+    PNERF_REQUIRE(xyzs && dirs && field && sigma && omega && off_rad && view_dep && diffuse);
+    PNERF_REQUIRE(field->table_sigma_palette && field->offsets && field->wpack_tc && field->head_bias && field->palette);
+    if (field->L != 16 || field->clip_dim > (uint32_t)kClipMax) return PNERF_ERR_UNSUPPORTED;
+    if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool clip_on = field->pred_clip != 0;
+    const size_t smem = tc_smem_bytes(clip_on);
+    const uint32_t grid = min(ceil_div(ceil_div(M, 128u), (uint32_t)kTcGroups), (uint32_t)sm_count());
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[clip_on]) {
+        cudaError_t e = clip_on ? cudaFuncSetAttribute(k_field_forward_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(k_field_forward_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_cuda_error(e, "field_forward_tc attr"); return PNERF_ERR_CUDA; }
+        attr_done[clip_on] = true;
+    }
+    if (clip_on) k_field_forward_tc<true><<<grid, kTcThreads, smem, s>>>(xyzs, dirs, M, *field, sigma, clip, omega, off_rad, view_dep, diffuse);
+    else k_field_forward_tc<false><<<grid, kTcThreads, smem, s>>>(xyzs, dirs, M, *field, sigma, nullptr, omega, off_rad, view_dep, diffuse);
+    return check_launch("palette_field_forward_tc");
+}
+
+}  // extern "C"
+
+// =================================================================================================================
+// warp-per-ray persistent renderer on the tensor-core field
+// =================================================================================================================
+namespace pnerf {
+
+constexpr int kMaxRuns = 6;                         // occupied stretches of a ray recorded by the pre-pass
+
+// Pre-pass record of one candidate ray: the maximal runs of consecutive occupied lattice points of the reference's walk.
+// The lattice inside a run is t_{k+1} = fl(t_k + dt): the renderer regenerates it bit for bit (lattice_window), so a run is
+// (first ray parameter, number of points). Rays with more than kMaxRuns runs are walked by the renderer itself.
+struct RayRuns {
+    uint32_t count;                                 // samples of the ray (0: nothing to render)
+    uint32_t n_runs;                                // kMaxRuns + 1 = overflow
+    float t_start[kMaxRuns];
+    uint32_t n[kMaxRuns];
+    float t0;                                       // first lattice point of the walk (== nears (+ noise step))
+    uint32_t pad;
+};
+
+struct RaysTcArgs {
+    const float* rays_o; const float* rays_d; const float* nears; const float* fars; const float* noises;
+    const uint8_t* bitfield;
+    const float* occ;
+    uint32_t N, C, Hgrid, max_steps;
+    float dt_gamma, T_thresh;
+    float* weights_sum; float* depth; float* image;
+    float* direct_rgb; float* view_dep_rgb; float* basis_acc; float* basis_rgb; float* unscaled_basis_rgb;
+    float* clip_feat;
+    unsigned int* queue;                            // [8]: ray cursor, samples shaded, rays with samples, tiles, candidates
+    const int32_t* cand;                            // [N] candidate ray ids
+    const RayRuns* runs;                            // [N] indexed by candidate slot
+    float* t_scratch;                               // [warps, max_steps]
+};
+
+enum { QT_CURSOR = 0, QT_SAMPLES = 1, QT_RAYS = 2, QT_TILES = 3, QT_CAND = 4 };
+
+__global__ void __launch_bounds__(256) k_tc_candidates(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                       const float* __restrict__ nears, const float* __restrict__ fars,
+                                                       uint32_t N, const float* __restrict__ occ, int32_t* __restrict__ cand,
+                                                       unsigned int* __restrict__ queue) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    bool keep = false;
+    if (n < N) {
+        const float near = nears[n], far = fars[n];
+        keep = near < far;
+        if (keep && occ) {
+            Marcher m;
+            m.ox = rays_o[(size_t)n * 3]; m.oy = rays_o[(size_t)n * 3 + 1]; m.oz = rays_o[(size_t)n * 3 + 2];
+            m.dx = rays_d[(size_t)n * 3]; m.dy = rays_d[(size_t)n * 3 + 1]; m.dz = rays_d[(size_t)n * 3 + 2];
+            m.rdx = 1 / m.dx; m.rdy = 1 / m.dy; m.rdz = 1 / m.dz;
+            keep = near < m.occupied_exit(occ);
+        }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+    if (mask) {
+        uint32_t base = 0;
+        const uint32_t leader = __ffs(mask) - 1;
+        if (lane == leader) base = atomicAdd(queue + QT_CAND, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) cand[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)n;
+    }
+}
+
+// thread per candidate ray: the reference's serial walk (raymarching.cu:351-403 with n_step unbounded), recording runs
+__global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                    const float* __restrict__ nears, const float* __restrict__ fars,
+                                                    const float* __restrict__ noises, const uint8_t* __restrict__ bitfield,
+                                                    uint32_t C, uint32_t H, uint32_t max_steps, float bound, float dt_gamma,
+                                                    const int32_t* __restrict__ cand, const unsigned int* __restrict__ queue,
+                                                    const float* __restrict__ occ, RayRuns* __restrict__ runs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= queue[QT_CAND]) return;
+    const uint32_t n = (uint32_t)cand[i];
+    Marcher m;
+    m.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H, bitfield);
+    float far = fars[n];
+    if (occ) far = fminf(far, m.occupied_exit(occ));
+    float t = m.first_t(nears[n], noises ? noises[n] : 0.f);
+    RayRuns rr;
+    rr.t0 = t; rr.count = 0; rr.n_runs = 0; rr.pad = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxRuns; k++) { rr.t_start[k] = 0.f; rr.n[k] = 0; }
+    uint32_t count = 0, n_runs = 0, run_n = 0;
+    float run_t = 0.f, x, y, z, dt;
+    bool in_run = false;
+    while (t < far && count < max_steps) {
+        if (m.probe(t, x, y, z, dt)) {
+            if (!in_run) { in_run = true; run_t = t; run_n = 0; }
+            run_n++;
+            count++;
+            t += dt;
+        } else if (in_run) {          // probe() advanced t past the empty voxel: the run is closed
+            in_run = false;
+            if (n_runs < (uint32_t)kMaxRuns) {
+#pragma unroll
+                for (int k = 0; k < kMaxRuns; k++)
+                    if (k == (int)n_runs) { rr.t_start[k] = run_t; rr.n[k] = run_n; }
+            }
+            n_runs++;
+        }
+    }
+    if (in_run) {
+        if (n_runs < (uint32_t)kMaxRuns) {
+#pragma unroll
+            for (int k = 0; k < kMaxRuns; k++)
+                if (k == (int)n_runs) { rr.t_start[k] = run_t; rr.n[k] = run_n; }
+        }
+        n_runs++;
+    }
+    rr.count = count;
+    rr.n_runs = min(n_runs, (uint32_t)kMaxRuns + 1u);
+    runs[i] = rr;
+}
+
+constexpr int kRedStride = 33;                      // floats per channel row of the reduction scratch (conflict-free both ways)
+
+__host__ __device__ constexpr size_t tc_render_smem(bool clip) { return tc_smem_bytes(clip); }
+
+template <bool CLIP, bool AUX>
+__global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, pnerf_palette_field f) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcShared* sm = reinterpret_cast<TcShared*>(smem_raw);
+    unsigned char* wts = smem_raw + kTcSharedBytes;
+    unsigned char* groups = wts + (CLIP ? kTcWBytesClip : kTcWBytesNoClip);
+    constexpr int group_bytes = CLIP ? kTcGroupBytesClip : kTcGroupBytesNoClip;
+    static_assert(kAuxCh * kRedStride * 4 <= group_bytes / 4, "per-warp reduction scratch must fit a quarter of the group's regions");
+    tc_prologue<kTcGroups>(f, f.wpack_tc, sm, wts, groups, group_bytes);
+    TcGroup g = tc_make_group(sm, wts, groups, group_bytes);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gi = wid >> 2, wig = wid & 3;
+    // after the field of a tile is complete the group's input regions are dead until the next gather: a quarter of them is
+    // this warp's scratch for the per-tile channel reduction
+    float* const red = reinterpret_cast<float*>(g.smem + wig * (group_bytes / 4));
+    float* const t_list = a.t_scratch + (size_t)(blockIdx.x * (kTcGroups * 4) + wid) * a.max_steps;
+    const bool clip_on = CLIP && a.clip_feat != nullptr;
+    const uint32_t n_cand = a.queue[QT_CAND];
+    const float dt_min = 2 * 1.7320508075688772f / a.max_steps;
+    const float dt_max = 2 * 1.7320508075688772f * (1u << (a.C - 1)) / a.Hgrid;
+    uint32_t shaded = 0, tiles = 0, hit_rays = 0;
+
+    // per-warp ray state (warp-uniform unless noted)
+    bool has_ray = false, exhausted = false;
+    uint32_t ray = 0, count = 0, done = 0;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t0 = 0.f;
+    float T_run = 1.f;
+    float wsum = 0.f, dep = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;   // ray totals (warp-uniform)
+    float acc_lo = 0.f, acc_hi = 0.f, acc_clip = 0.f;      // per-LANE: totals of aux channel `lane`, `lane + 32`, clip channel `lane`
+
+    for (;;) {
+        // ---- every warp makes sure it has a ray with samples left ----
+        while (!has_ray && !exhausted) {
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(a.queue + QT_CURSOR, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot >= n_cand) { exhausted = true; break; }
+            const RayRuns* rr = a.runs + slot;
+            count = rr->count;
+            if (count == 0) continue;
+            ray = (uint32_t)a.cand[slot];
+            Marcher m;
+            m.init(a.rays_o + (size_t)ray * 3, a.rays_d + (size_t)ray * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid, a.bitfield);
+            const uint32_t n_runs = rr->n_runs;
+            t0 = rr->t0;
+            if (n_runs > (uint32_t)kMaxRuns) {          // too many stretches for the record: walk the ray here
+                float far = a.fars[ray];
+                if (a.occ) far = fminf(far, m.occupied_exit(a.occ));
+                count = warp_walk<false>(m, t0, far, a.max_steps, (uint32_t)lane, nullptr, nullptr, nullptr, t_list);
+            } else {
+                uint32_t pos = 0;
+                for (uint32_t r = 0; r < n_runs; r++) {
+                    float ts = rr->t_start[r];
+                    uint32_t left = rr->n[r];
+                    while (left > 0) {
+                        float t;
+                        uint32_t nvalid;
+                        lattice_window(m, ts, (uint32_t)lane, t, nvalid);
+                        const uint32_t nv = min(nvalid, left);
+                        if ((uint32_t)lane < nv) t_list[pos + lane] = t;
+                        pos += nv;
+                        left -= nv;
+                        ts = __shfl_sync(0xffffffffu, t + m.step_size(t), nv - 1);
+                    }
+                }
+            }
+            __syncwarp();
+            ox = m.ox; oy = m.oy; oz = m.oz; dx = m.dx; dy = m.dy; dz = m.dz;
+            has_ray = true; done = 0; T_run = 1.f;
+            wsum = dep = cr = cg = cb = 0.f;
+            acc_lo = acc_hi = acc_clip = 0.f;
+            hit_rays++;
+        }
+        // ---- group vote: the field is evaluated while any warp of the group has a tile ----
+        if (lane == 0) sm->flags[gi][wig] = has_ray ? 1u : 0u;
+        tc::group_bar(g.bar_id, 128);
+        const uint32_t any = sm->flags[gi][0] | sm->flags[gi][1] | sm->flags[gi][2] | sm->flags[gi][3];
+        if (!any) break;
+
+        // ---- this warp's tile: 32 consecutive samples of its ray ----
+        const uint32_t k = done + (uint32_t)lane;
+        const bool active = has_ray && k < count;
+        const float t = active ? t_list[k] : t0;
+        const float x = clampf(ox + t * dx, -f.bound, f.bound);
+        const float y = clampf(oy + t * dy, -f.bound, f.bound);
+        const float z = clampf(oz + t * dz, -f.bound, f.bound);
+        const float dt = clampf(t * a.dt_gamma, dt_min, dt_max);
+        const float t_end = t + dt;
+        FieldOut o;
+        eval_field_tc<CLIP>(f, *sm, g, x, y, z, active ? dx : 0.f, active ? dy : 0.f, active ? dz : 1.f, active, lane, o);
+        if (!has_ray) continue;                         // (warp-uniform) idle warp of a busy group
+        tiles++;
+
+        // ---- front-to-back compositing of the tile (ref: raymarching.cu:1051-1110 per sample) ----
+        const float alpha = active ? 1.0f - fast_exp(-(f.density_scale * o.sigma) * dt) : 0.f;
+        float incl = 1.0f - alpha;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, ofs);
+            if (lane >= ofs) incl *= up;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float T = T_run * excl;
+        const uint32_t term = __ballot_sync(0xffffffffu, active && T < a.T_thresh);
+        const int last = term ? (__ffs(term) - 1) : 31;
+        const bool use = active && lane <= last;
+        const float wgt = use ? alpha * T : 0.f;
+        shaded += __popc(__ballot_sync(0xffffffffu, use));
+        {
+            float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
+            const float sp = softplusf_(o.off_rad[12]);
+            rgb[0] = rgb[1] = rgb[2] = 0.f;
+#pragma unroll
+            for (int b = 0; b < kNB; b++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float off = o.off_rad[b * 3 + c];
+                    unscaled[b * 3 + c] = sm->palette[b * 3 + c] + off;
+                    basis_rgb[b * 3 + c] = o.omega[b] * (sp * (sm->palette[b * 3 + c] + f.offsets_weight * off));
+                    rgb[c] += basis_rgb[b * 3 + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
+            wsum += warp_sum(wgt);
+            dep += warp_sum(wgt * t_end);
+            cr += warp_sum(wgt * rgb[0]); cg += warp_sum(wgt * rgb[1]); cb += warp_sum(wgt * rgb[2]);
+            if (AUX) {
+                // channel-major scratch red[c][lane]; the column sums below run with lane = channel
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    red[c * kRedStride + lane] = wgt * (o.diffuse[c] + o.view_dep[c]);
+                    red[(3 + c) * kRedStride + lane] = wgt * o.view_dep[c];
+                }
+#pragma unroll
+                for (int q = 0; q < kNB; q++) red[(6 + q) * kRedStride + lane] = wgt * o.omega[q];
+#pragma unroll
+                for (int q = 0; q < kNB * 3; q++) {
+                    red[(6 + kNB + q) * kRedStride + lane] = wgt * basis_rgb[q];
+                    red[(6 + kNB + kNB * 3 + q) * kRedStride + lane] = wgt * unscaled[q];
+                }
+            }
+        }
+        if (AUX) {
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; q++) s0 += red[lane * kRedStride + q];
+            if (lane + 32 < kAuxCh) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) s1 += red[(lane + 32) * kRedStride + q];
+            }
+            acc_lo += s0; acc_hi += s1;
+        }
+        if (CLIP && clip_on) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kClipMax; q++) red[q * kRedStride + lane] = wgt * o.clip[q];
+            __syncwarp();
+            if (lane < kClipMax) {
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < 32; q++) s += red[lane * kRedStride + q];
+                acc_clip += s;
+            }
+        }
+        __syncwarp();
+        done += 32;
+        T_run *= __shfl_sync(0xffffffffu, incl, 31);
+        if (term || done >= count) {
+            // ---- retire: one writer per value; lane = auxiliary channel ----
+            if (lane == 0) {
+                a.weights_sum[ray] = wsum; a.depth[ray] = dep;
+                a.image[(size_t)ray * 3] = cr; a.image[(size_t)ray * 3 + 1] = cg; a.image[(size_t)ray * 3 + 2] = cb;
+            }
+            if (AUX) {
+                auto dst_of = [&](int c) -> float* {       // 0-2 direct, 3-5 view_dep, 6-9 basis_acc, 10-21 basis_rgb, 22-33 unscaled
+                    if (c < 3) return a.direct_rgb + (size_t)ray * 3 + c;
+                    if (c < 6) return a.view_dep_rgb + (size_t)ray * 3 + (c - 3);
+                    if (c < 6 + kNB) return a.basis_acc + (size_t)ray * kNB + (c - 6);
+                    if (c < 6 + kNB + kNB * 3) return a.basis_rgb + (size_t)ray * kNB * 3 + (c - 6 - kNB);
+                    return a.unscaled_basis_rgb + (size_t)ray * kNB * 3 + (c - 6 - kNB - kNB * 3);
+                };
+                *dst_of(lane) = acc_lo;
+                if (lane + 32 < kAuxCh) *dst_of(lane + 32) = acc_hi;
+            }
+            if (CLIP && clip_on && lane < (int)f.clip_dim) a.clip_feat[(size_t)ray * f.clip_dim + lane] = acc_clip;
+            has_ray = false;
+        }
+    }
+    if (lane == 0 && tiles) {
+        atomicAdd(a.queue + QT_SAMPLES, shaded);
+        atomicAdd(a.queue + QT_RAYS, hit_rays);
+        atomicAdd(a.queue + QT_TILES, tiles);
+    }
+    tc_epilogue_cta<kTcGroups>(sm);
+}
+
+}  // namespace pnerf
+
+static bool g_tc_timing = false, g_tc_timed = false;
+static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
+
+extern "C" {
+
+uint32_t pnerf_palette_render_tc_warps(void) { return (uint32_t)sm_count() * (uint32_t)(kTcGroups * 4); }
+uint32_t pnerf_palette_render_tc_runs_bytes(void) { return (uint32_t)sizeof(RayRuns); }
+
+/* Tensor-core warp-per-ray renderer (csrc/field_tc.cu): like pnerf_palette_render_rays, with the field on tcgen05 / TMEM and
+ * a thread-per-ray pre-pass that records each ray's occupied stretches.
+ *   queue [8] u32 zero on entry; cand [N] int32; runs [N * pnerf_palette_render_tc_runs_bytes()] bytes;
+ *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32. Needs field->wpack_tc and field->table_sigma_palette. */
+int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const float* nears, const float* fars, const float* noises,
+                            const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t Hgrid, uint32_t max_steps, float dt_gamma,
+                            float T_thresh, const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
+                            float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb,
+                            float* clip_feat, uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
+                            void* stream) {
+    if (N == 0) return PNERF_OK;
+    PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
+    PNERF_REQUIRE(cand && runs && t_scratch);
+    PNERF_REQUIRE(field->table_sigma_palette && field->offsets && field->wpack_tc && field->head_bias && field->palette);
+    PNERF_REQUIRE(C >= 1 && C <= 16 && Hgrid >= 1 && max_steps >= 1);
+    if (field->L != 16 || field->clip_dim > (uint32_t)kClipMax || Hgrid > 1024) return PNERF_ERR_UNSUPPORTED;
+    if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
+    const bool aux = direct_rgb != nullptr;
+    if (aux) PNERF_REQUIRE(view_dep_rgb && basis_acc && basis_rgb && unscaled_basis_rgb);
+    RaysTcArgs a;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.nears = nears; a.fars = fars; a.noises = noises; a.bitfield = bitfield; a.occ = occ_aabb;
+    a.N = N; a.C = C; a.Hgrid = Hgrid; a.max_steps = max_steps; a.dt_gamma = dt_gamma; a.T_thresh = T_thresh;
+    a.weights_sum = weights_sum; a.depth = depth; a.image = image;
+    a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
+    a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue; a.cand = cand;
+    a.runs = (const RayRuns*)runs; a.t_scratch = t_scratch;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_tc_candidates<<<ceil_div(N, 256u), 256, 0, s>>>(rays_o, rays_d, nears, fars, N, occ_aabb, cand, queue);
+    k_tc_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, C, Hgrid, max_steps, field->bound,
+                                                   dt_gamma, cand, queue, occ_aabb, (RayRuns*)runs);
+    const bool clip_on = field->pred_clip != 0;
+    const size_t smem = tc_render_smem(clip_on);
+    const uint32_t grid = (uint32_t)sm_count();
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+#define PNERF_LAUNCH_TC(CL, AX)                                                                                          \
+    do {                                                                                                                \
+        if (!attr_done[CL][AX]) {                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<CL, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 (int)tc_render_smem(CL));                                              \
+            if (e != cudaSuccess) { set_last_cuda_error(e, "render_tc attr"); return PNERF_ERR_CUDA; }                  \
+            attr_done[CL][AX] = true;                                                                                   \
+        }                                                                                                               \
+        k_render_rays_tc<CL, AX><<<grid, kTcThreads, smem, s>>>(a, *field);                                             \
+    } while (0)
+    if (g_tc_timing) {
+        if (!g_tc_ev[0]) { cudaEventCreate(&g_tc_ev[0]); cudaEventCreate(&g_tc_ev[1]); }
+        cudaEventRecord(g_tc_ev[0], s);
+    }
+    if (clip_on) { if (aux) PNERF_LAUNCH_TC(true, true); else PNERF_LAUNCH_TC(true, false); }
+    else { if (aux) PNERF_LAUNCH_TC(false, true); else PNERF_LAUNCH_TC(false, false); }
+#undef PNERF_LAUNCH_TC
+    if (g_tc_timing) { cudaEventRecord(g_tc_ev[1], s); g_tc_timed = true; }
+    return check_launch("palette_render_tc");
+}
+
+void pnerf_render_tc_timing(int enable) { g_tc_timing = enable != 0; g_tc_timed = false; }
+
+float pnerf_render_tc_last_ms(void) {
+    if (!g_tc_timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(g_tc_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, g_tc_ev[0], g_tc_ev[1]) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+}  // extern "C"

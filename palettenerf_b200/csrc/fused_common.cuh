@@ -11,6 +11,10 @@
 
 namespace pnerf {
 
+#ifndef PNERF_COOP_LV
+#define PNERF_COOP_LV 4       // levels per iteration of the lane-pair gather (x 4 corners x 8 B loads in flight per lane)
+#endif
+
 constexpr int kNB = 4;            // palette bases supported by the fused path (reference default, main_palette.py:99)
 constexpr int kClipMax = 16;      // semantic feature width supported by the fused path (main_palette.py:76)
 #ifndef PNERF_FUSED_WARPS
@@ -124,11 +128,24 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// exp(v) as ONE multiply + ONE MUFU.EX2 (ex2.approx.ftz: 2 ulp, denormal results flush to zero). __expf() spends ~6 more
+// instructions per value on scaling denormal results, which no consumer here can tell from zero.
+__device__ __forceinline__ float fast_exp(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 enum Act { ACT_NONE, ACT_RELU, ACT_ELU };
 template <int ACT>
 __device__ __forceinline__ float activate(float v) {
     if (ACT == ACT_RELU) return fmaxf(v, 0.f);
-    if (ACT == ACT_ELU) return v > 0.f ? v : (__expf(v) - 1.0f);
+    if (ACT == ACT_ELU) return v > 0.f ? v : (fast_exp(v) - 1.0f);
     return v;
 }
 
@@ -168,8 +185,10 @@ __device__ __forceinline__ void store_out(float (*out)[kOutStride], int row0, in
     }
 }
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
-__device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : log1pf(__expf(v)); }  // torch threshold 20
+__device__ __forceinline__ float sigmoidf_(float v) { return fast_rcp(1.0f + fast_exp(-v)); }
+// torch threshold 20; log(1 + e^v) instead of log1p(e^v): the absolute error is < 6e-8 (the consumers add 0.05 / multiply
+// an O(1) colour), at a quarter of the instructions
+__device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : __logf(1.0f + fast_exp(v)); }
 
 // ------------------------------------------------------------------------------------------------
 // hash-grid gather of one sample (this lane) into its fp16 feature row
@@ -301,7 +320,7 @@ __device__ __forceinline__ void gather_fast(const void* __restrict__ table, cons
 // fma.rn.f32.f16 (SASS FHFMA, new on sm_100): exact fp16 x fp16 products accumulated in fp32 — no fp16 -> fp32
 // conversion instructions at all. Error vs fp32 weights <= 2^-11 * sum|w_c v_c| per feature, the size of the final fp16
 // rounding of the feature itself (the reference accumulates all 8 terms in fp16, gridencoder.cu:142-165).
-//   row(e, s) -> uint32_t* : destination row (16 words, one per level) of table e, sample s
+//   st(e, s, l0, words[LV]) : stores the packed fp16 feature pairs of table e, sample s, levels l0 .. l0 + LV - 1
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint16_t f2h_bits(float v) {
     uint16_t h;
@@ -315,9 +334,9 @@ __device__ __forceinline__ void fhfma2(float& ax, float& ay, uint32_t v, uint16_
         : "r"(v), "h"(w));
 }
 
-template <int EW, int LV, typename RowFn>
+template <int EW, int LV, typename StoreFn>
 __device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
-                                            float w, bool in_range, int lane, RowFn row) {
+                                            float w, bool in_range, int lane, StoreFn st) {
     static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
     u = fminf(fmaxf(u, 0.f), 1.f); v = fminf(fmaxf(v, 0.f), 1.f); w = fminf(fmaxf(w, 0.f), 1.f);   // keeps the loads in bounds
     const uint32_t xsel = (uint32_t)lane & 1u;
@@ -326,7 +345,6 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
         const int s = half * 16 + (lane >> 1);
         const float us = __shfl_sync(0xffffffffu, u, s), vs = __shfl_sync(0xffffffffu, v, s), wsm = __shfl_sync(0xffffffffu, w, s);
         const bool inr = __shfl_sync(0xffffffffu, (int)in_range, s) != 0;
-        uint32_t* const dst = row(EW == 2 ? (int)xsel : 0, s);
 #pragma unroll 1
         for (int l0 = 0; l0 < 16; l0 += LV) {
             uint32_t val[LV][4][EW];
@@ -359,6 +377,7 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
 #pragma unroll
                 for (int c = 0; c < 4; c++) ldg_entry<EW>(base, idx[c], val[j][c]);
             }
+            uint32_t words[LV];
 #pragma unroll
             for (int j = 0; j < LV; j++) {
                 float acc[EW][2];
@@ -375,13 +394,13 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
                     const float mx = xsel ? acc[EW - 1][0] : acc[0][0], my = xsel ? acc[EW - 1][1] : acc[0][1];
                     rx_ = mx + __shfl_xor_sync(0xffffffffu, sx, 1);
                     ry_ = my + __shfl_xor_sync(0xffffffffu, sy, 1);
-                    dst[l0 + j] = inr ? pack_h2(rx_, ry_) : 0u;
                 } else {
                     rx_ = acc[0][0] + __shfl_xor_sync(0xffffffffu, acc[0][0], 1);
                     ry_ = acc[0][1] + __shfl_xor_sync(0xffffffffu, acc[0][1], 1);
-                    if (!xsel) dst[l0 + j] = inr ? pack_h2(rx_, ry_) : 0u;
                 }
+                words[j] = inr ? pack_h2(rx_, ry_) : 0u;
             }
+            if (EW == 2 || !xsel) st(EW == 2 ? (int)xsel : 0, s, l0, words);
         }
     }
 }

@@ -9,10 +9,6 @@
                               // 800x800: LV 1 7.47 ms, LV 2 7.30 ms, LV 4 7.99 ms per view (profiles/README.md)
 #endif
 
-#ifndef PNERF_COOP_LV
-#define PNERF_COOP_LV 4       // levels per iteration of the lane-pair gather (x 4 corners x 8 B loads in flight per lane)
-#endif
-
 #ifdef PNERF_TILE_UNROLL
 #define PNERF_TILE_LOOP _Pragma("unroll")
 #else
@@ -43,10 +39,12 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
     uint32_t* park = reinterpret_cast<uint32_t*>(&ws.out[lane][O_OFFRAD]);   // 16 words
     const bool paired = COOP || (sm.fast_wrap && f.table_sigma_palette != nullptr);      // warp-uniform
     if (COOP) {
-        auto row = [&ws](int e, int s) {
-            return e == 0 ? reinterpret_cast<uint32_t*>(ws.feat[s]) : reinterpret_cast<uint32_t*>(&ws.out[s][O_OFFRAD]);
+        auto st = [&ws](int e, int s, int l0, const uint32_t (&words)[PNERF_COOP_LV]) {
+            uint32_t* dst = e == 0 ? reinterpret_cast<uint32_t*>(ws.feat[s]) : reinterpret_cast<uint32_t*>(&ws.out[s][O_OFFRAD]);
+#pragma unroll
+            for (int j = 0; j < PNERF_COOP_LV; j++) dst[l0 + j] = words[j];
         };
-        gather_coop<2, PNERF_COOP_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, row);
+        gather_coop<2, PNERF_COOP_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
     } else if (paired) {
         uint32_t* const rows[2] = {reinterpret_cast<uint32_t*>(ws.feat[lane]), park};
         gather_fast<2, PNERF_GATHER_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, rows);
@@ -150,8 +148,11 @@ PNERF_TILE_LOOP
     // ---------------- phase 4 (optional): semantic grid -> clip net ----------------
     if (CLIP) {
         if (COOP) {
-            auto row = [&ws](int, int s) { return reinterpret_cast<uint32_t*>(ws.feat[s]); };
-            gather_coop<1, PNERF_COOP_LV>(f.table_clip, sm.lp, u, v, w, in_range, lane, row);
+            auto st = [&ws](int, int s, int l0, const uint32_t (&words)[PNERF_COOP_LV]) {
+#pragma unroll
+                for (int j = 0; j < PNERF_COOP_LV; j++) reinterpret_cast<uint32_t*>(ws.feat[s])[l0 + j] = words[j];
+            };
+            gather_coop<1, PNERF_COOP_LV>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
         } else if (sm.fast_wrap) {
             uint32_t* const rows[1] = {reinterpret_cast<uint32_t*>(ws.feat[lane])};
             gather_fast<1, PNERF_GATHER_LV>(f.table_clip, sm.lp, u, v, w, in_range, rows);

@@ -29,16 +29,23 @@ class PaletteField(ctypes.Structure):
                 ("wpack", c_void_p), ("head_bias", c_void_p), ("palette", c_void_p),
                 ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
                 ("S", c_float), ("bound", c_float), ("density_scale", c_float), ("offsets_weight", c_float),
-                ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p)]
+                ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p), ("wpack_tc", c_void_p)]
 
 
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_field_forward_tc", [P, P, U, P, P, P, P, P, P, P, P])
+L.lib.pnerf_palette_tc_weight_bytes.argtypes = [U]
+L.lib.pnerf_palette_tc_weight_bytes.restype = c_uint32
 L.register("pnerf_palette_render_fused", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 ordering kernels + persistent kernel
 L.register("pnerf_palette_render_rays", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_rays"] = 2   # candidate filter + the persistent warp-per-ray kernel
 L.lib.pnerf_palette_render_rays_warps.restype = c_uint32
+L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.LAUNCHES["pnerf_palette_render_tc"] = 3     # candidate filter + thread-per-ray pre-pass (runs) + the persistent kernel
+L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
+L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
 
 
 def _frag(W, n_pad, k_pad):
@@ -132,6 +139,7 @@ class FieldCache:
             pair=torch.empty(n, 2, 2, dtype=torch.float16, device=dev),
             clip=torch.empty(n, 2, dtype=torch.float16, device=dev) if m.opt.pred_clip else None,
             wpack=torch.empty(st["n_fwd"], dtype=torch.float16, device=dev),
+            wpack_tc=torch.empty(st["tc_index"].numel(), dtype=torch.float16, device=dev), tc_index=st["tc_index"],
             bias=torch.zeros(16, dtype=torch.float32, device=dev),
             palette=torch.empty(m.num_basis, 3, dtype=torch.float32, device=dev),
             offsets=m.encoder.offsets.contiguous(), index=st["index"][:st["n_fwd"]], names=st["names"], zero=st["zero"],
@@ -143,6 +151,8 @@ class FieldCache:
         f.table_sigma = f.table_palette = f.table_sigma_palette = ptr(b["pair"])
         f.table_clip = ptr(b["clip"])
         f.offsets, f.wpack, f.head_bias, f.palette = ptr(b["offsets"]), ptr(b["wpack"]), ptr(b["bias"]), ptr(b["palette"])
+        f.wpack_tc = ptr(b["wpack_tc"])
+        assert 2 * b["wpack_tc"].numel() == L.lib.pnerf_palette_tc_weight_bytes(int(bool(m.opt.pred_clip)))
         f.L, f.H = m.encoder.num_levels, m.encoder.base_resolution
         f.pred_clip, f.clip_dim = int(bool(m.opt.pred_clip)), m.opt.clip_dim
         f.S = float(np.float32(np.log2(m.encoder.per_level_scale)))
@@ -169,6 +179,7 @@ class FieldCache:
             sd = dict(m.named_parameters())
             flat = torch.cat([sd[n].detach().reshape(-1).float() for n in b["names"]] + [b["zero"]])
             b["wpack"].copy_(flat[b["index"]])
+            b["wpack_tc"].copy_(flat[b["tc_index"]])
             b["bias"][0:13].copy_(m.offsets_radiance_net.bias.detach())
             b["palette"].copy_(m.basis_color.detach().float().clamp(0, 1))
         return f
@@ -185,10 +196,14 @@ def _cache(model):
     return c
 
 
+FIELD_KERNEL = __import__("os").environ.get("PNERF_FIELD_KERNEL", "mma")    # "mma" (mma.sync chain) | "tc" (tcgen05 / TMEM)
+
+
 @torch.no_grad()
-def field_forward(model, xyzs, dirs):
+def field_forward(model, xyzs, dirs, kernel=None):
     """fused PaletteNetwork.forward (eval): -> (sigma [M], clip [M,cd], omega [M,4], offsets_radiance [M,13],
-    view_dep [M,3], diffuse [M,3]), fp32"""
+    view_dep [M,3], diffuse [M,3]), fp32. kernel: "mma" = mma.sync register chain (csrc/fused.cu), "tc" = tcgen05 with TMEM
+    accumulators (csrc/field_tc.cu)"""
     L.require_cuda(xyzs, dirs)
     f = _cache(model).get()
     xyzs, dirs = xyzs.contiguous().float(), dirs.contiguous().float()
@@ -197,7 +212,8 @@ def field_forward(model, xyzs, dirs):
     sigma, omega, off_rad, view_dep, diffuse = e(M), e(M, NB), e(M, 13), e(M, 3), e(M, 3)
     cd = model.opt.clip_dim
     clip = e(M, cd) if model.opt.pred_clip else torch.zeros(M, cd, dtype=torch.float32, device=dev)
-    L.call("pnerf_palette_field_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(sigma),
+    entry = "pnerf_palette_field_forward_tc" if (kernel or FIELD_KERNEL) == "tc" else "pnerf_palette_field_forward"
+    L.call(entry, ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(sigma),
            ptr(clip) if model.opt.pred_clip else None, ptr(omega), ptr(off_rad), ptr(view_dep), ptr(diffuse), stream())
     return sigma, clip, omega, off_rad, view_dep, diffuse
 
@@ -205,23 +221,24 @@ def field_forward(model, xyzs, dirs):
 _T_SCRATCH = {}
 
 
-def _t_scratch(dev, max_steps):
-    """per-warp sample lists of the warp-per-ray renderer: [resident warps, max_steps] fp32, allocated once per device"""
-    key = (str(dev), int(max_steps))
+def _t_scratch(dev, max_steps, warps=None):
+    """per-warp sample lists of the warp-per-ray renderers: [resident warps, max_steps] fp32, allocated once per device"""
+    warps = int(L.lib.pnerf_palette_render_rays_warps()) if warps is None else int(warps)
+    key = (str(dev), int(max_steps), warps)
     t = _T_SCRATCH.get(key)
     if t is None:
-        t = _T_SCRATCH[key] = torch.empty(int(L.lib.pnerf_palette_render_rays_warps()) * int(max_steps), dtype=torch.float32,
-                                          device=dev)
+        t = _T_SCRATCH[key] = torch.empty(warps * int(max_steps), dtype=torch.float32, device=dev)
     return t
 
 
-RENDER_KERNEL = __import__("os").environ.get("PNERF_RENDER_KERNEL", "lanes")    # "rays" (round 2) | "lanes" (round 1, A/B)
+RENDER_KERNEL = __import__("os").environ.get("PNERF_RENDER_KERNEL", "tc")    # "rays" (round 2) | "lanes" (round 1, A/B)
 
 
 @torch.no_grad()
 def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode, kernel=None):
     """persistent fused renderer -> dict of accumulators like PaletteRenderer._infer_loop.
-    kernel: "rays" = warp-per-ray kernel (csrc/render_rays.cu, default), "lanes" = round 1's lane-per-ray kernel"""
+    kernel: "tc" = warp-per-ray kernel with the field on tcgen05 / TMEM (csrc/field_tc.cu), "rays" = warp-per-ray kernel on
+    mma.sync (csrc/render_rays.cu), "lanes" = round 1's lane-per-ray kernel"""
     f = _cache(model).get()
     N, dev = rays_o.shape[0], rays_o.device
     nb, cd = model.num_basis, model.opt.clip_dim
@@ -247,7 +264,12 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
               model.grid_size, max_steps, float(dt_gamma), float(T_thresh), ctypes.addressof(f), ptr(acc["weights_sum"]),
               ptr(acc["depth"]), ptr(acc["image"]), aux("direct_rgb"), aux("view_dep_rgb"), aux("basis_acc"), aux("basis_rgb"),
               aux("unscaled_basis_rgb"), ptr(acc["clip_feat"]) if model.opt.pred_clip else None, ptr(queue))
-    if kernel == "rays":
+    if kernel == "tc":
+        cand = torch.empty(N, dtype=torch.int32, device=dev)
+        runs = torch.empty(N * int(L.lib.pnerf_palette_render_tc_runs_bytes()), dtype=torch.uint8, device=dev)
+        L.call("pnerf_palette_render_tc", *common, ptr(cand), ptr(runs),
+               ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), stream())
+    elif kernel == "rays":
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         L.call("pnerf_palette_render_rays", *common, ptr(cand), ptr(_t_scratch(dev, max_steps)), ptr(occ), stream())
     else:

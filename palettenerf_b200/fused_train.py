@@ -74,6 +74,55 @@ def _frag_idx(Wi):
     return out.reshape(-1)
 
 
+def padded_layers(shapes, pred_clip, clip_dim):
+    """-> ({layer: int64 index matrix [n_pad, k_pad] into the flat weight vector}, zero_slot): the reference's concatenations
+    folded into zero-padded weight matrices (shared by the mma.sync fragment packing and the tcgen05 operand image)"""
+    names = WEIGHT_NAMES + (CLIP_NAMES if pred_clip else [])
+    base, off = {}, 0
+    for nme in names:
+        base[nme] = off
+        off += int(np.prod(shapes[nme]))
+    zero = off
+
+    def idx(nme):
+        return (base[nme] + torch.arange(int(np.prod(shapes[nme])))).reshape(tuple(shapes[nme]))
+
+    def pad(n_pad, k_pad):
+        return torch.full((n_pad, k_pad), zero, dtype=torch.int64)
+    m = {}
+    m["s0"], m["s1"] = idx("sigma_net.0.weight"), pad(16, 64)
+    m["s1"][:16] = idx("sigma_net.1.weight")
+    m["d0"] = pad(64, 16); m["d0"][:, 1:16] = idx("diff_net.0.weight")
+    m["d1"] = idx("diff_net.1.weight")
+    m["d2"] = pad(16, 64); m["d2"][0:3] = idx("diff_net.2.weight")
+    c0 = idx("color_net.0.weight")
+    m["v0"] = pad(64, 32); m["v0"][:, 0:16] = c0[:, 0:16]; m["v0"][:, 17:32] = c0[:, 16:31]
+    m["v1"] = idx("color_net.1.weight")
+    m["v2"] = pad(16, 64); m["v2"][0:3] = idx("color_net.2.weight")
+    m["b0"] = pad(64, 48); m["b0"][:, 0:35] = idx("basis_net.0.weight")
+    m["b1"] = pad(16, 64); m["b1"][0:15] = idx("basis_net.1.weight")
+    m["h"] = pad(32, 16)
+    m["h"][0:13, 0:15] = idx("offsets_radiance_net.weight")
+    m["h"][13:17, 0:15] = idx("omega_net.0.weight")
+    if pred_clip:
+        m["q0"] = idx("clip_net.0.weight")
+        m["q1"] = pad(16, 64); m["q1"][0:clip_dim] = idx("clip_net.1.weight")
+    return m, zero
+
+
+def tc_pack_index(shapes, pred_clip, clip_dim):
+    """index (int64) that gathers the flat weight vector into the tcgen05 B-operand image of csrc/field_tc.cuh: per layer
+    [k-chunk][n][8 halfs] (K-major, no swizzle), layers in TcLayer order"""
+    m, _ = padded_layers(shapes, pred_clip, clip_dim)
+    order = ["s0", "s1", "d0", "d1", "d2", "v0", "v1", "v2", "b0", "b1", "h"] + (["q0", "q1"] if pred_clip else [])
+    parts = []
+    for k in order:
+        W = m[k]
+        n, kk = W.shape
+        parts.append(W.reshape(n, kk // 8, 8).permute(1, 0, 2).reshape(-1))
+    return torch.cat(parts)
+
+
 def build_pack_index(shapes, pred_clip, clip_dim):
     """shapes: {name: torch.Size}. -> (index int64 [fwd halfs + bwd halfs], n_fwd_halfs, zero_slot)"""
     names = WEIGHT_NAMES + (CLIP_NAMES if pred_clip else [])
@@ -202,9 +251,10 @@ def _state(model):
         sd = dict(model.named_parameters())
         pred_clip, cd = bool(model.opt.pred_clip), int(model.opt.clip_dim)
         names = WEIGHT_NAMES + (CLIP_NAMES if pred_clip else [])
-        index, n_fwd, _ = build_pack_index({n: sd[n].shape for n in names}, pred_clip, cd)
+        shapes = {n: sd[n].shape for n in names}
+        index, n_fwd, _ = build_pack_index(shapes, pred_clip, cd)
         st = dict(device=dev, index=index.to(dev), n_fwd=n_fwd, names=names, tables=_Tables(), pred_clip=pred_clip, cd=cd,
-                  zero=torch.zeros(1, dtype=torch.float32, device=dev))
+                  zero=torch.zeros(1, dtype=torch.float32, device=dev), tc_index=tc_pack_index(shapes, pred_clip, cd).to(dev))
         assert n_fwd == 4 * L.lib.pnerf_palette_train_wfwd_units(int(pred_clip))
         assert index.numel() - n_fwd == 4 * L.lib.pnerf_palette_train_wbwd_units(int(pred_clip))
         object.__setattr__(model, "_fused_train_state", st)
