@@ -221,11 +221,16 @@ def main():
     if rank == 0:
         clocks.start()
     import ctypes
-    L.lib.pnerf_render_kernel_last_ms.restype = ctypes.c_float
-    L.lib.pnerf_render_kernel_timing(1)           # event pair around the persistent kernel itself (roofline.kernel_ms)
+    from palettenerf_b200 import fused as _fused
+    rk = _fused.RENDER_KERNEL                     # "tc" (tcgen05 warp-per-ray), "rays" (mma.sync warp-per-ray), "lanes" (round 1)
+    hook_on, hook_ms, kname = {"tc": ("pnerf_render_tc_timing", "pnerf_render_tc_last_ms", "k_render_rays_tc"),
+                               "rays": ("pnerf_render_rays_timing", "pnerf_render_rays_last_ms", "k_render_rays"),
+                               "lanes": ("pnerf_render_kernel_timing", "pnerf_render_kernel_last_ms", "k_render_fused")}[rk]
+    getattr(L.lib, hook_ms).restype = ctypes.c_float
+    getattr(L.lib, hook_on)(1)                    # event pair around the persistent kernel itself (roofline.kernel_ms)
     ms_step, launches, prof = timed(lambda: render(o_dev, d_dev), args.steps, args.warmup, profile=True)
-    k_ms_last = float(L.lib.pnerf_render_kernel_last_ms())      # the last timed launch (all launches are the same view)
-    L.lib.pnerf_render_kernel_timing(0)
+    k_ms_last = float(getattr(L.lib, hook_ms)())  # the last timed launch (all launches are the same view)
+    getattr(L.lib, hook_on)(0)
     clock_info = clocks.stop() if rank == 0 else None
     value = world * N_RAYS / (ms_step / 1e3)
 
@@ -266,21 +271,21 @@ def main():
     samples_per_step = int(q[1].item()) if q is not None else None
     tile_fill = (float(q[1].item()) / (32.0 * max(1, int(q[3].item())))) if q is not None else None
     call_ms = top[1][0] / max(1, top[1][1])
-    kernel_ms = k_ms_last if (k_ms_last > 0 and top[0] == "pnerf_palette_render_fused") else call_ms
+    is_render = top[0].startswith("pnerf_palette_render")
+    kernel_ms = k_ms_last if (k_ms_last > 0 and is_render) else call_ms
     FLOP_PER_SAMPLE = 36094                          # palette field without clip, forward
     GATHER_B_PER_SAMPLE = 2 * 16 * 8 * 4             # two fp16 F=2 tables, 16 levels, 8 corners
     roofline = {"bound": "tensor", "achieved": None, "peak": tf_peak, "unit": "TFLOP/s", "frac": None,
-                "traffic": _ncu_traffic("k_render_fused"), "traffic_source": "profiles/traffic.json (ncu --set full capture of this "
+                "traffic": _ncu_traffic(kname), "traffic_source": "profiles/traffic.json (ncu --set full capture of this "
                 "kernel, committed; not measured in this run)",
-                "kernel": top[0] + " (k_render_fused)", "kernel_ms": kernel_ms, "call_ms": call_ms,
+                "kernel": top[0] + f" ({kname})", "kernel_ms": kernel_ms, "call_ms": call_ms,
                 "peak_kind": peak_kind + " (bf16 dense, burst; fp16 assumed equal)",
                 "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {samples_per_step} samples per launch",
                 "kernel_time_share_of_own_kernels": shares}
-    if samples_per_step and top[0] == "pnerf_palette_render_fused":
+    if samples_per_step and is_render:
         ach = FLOP_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e12
         roofline.update(achieved=ach, frac=ach / tf_peak,
-                        note="the kernel is bound by the latency of its L2-resident hash-table gathers, not by the tensor pipe "
-                             "(ncu: tensor pipe 22 % active, L1/TEX pipe 81 %, issue slots 49 %, DRAM 0.07 %); see l2_gather and profiles/",
+                        note=_ncu_note(kname),
                         l2_gather={"achieved_gbs": GATHER_B_PER_SAMPLE * samples_per_step / (kernel_ms / 1e3) / 1e9,
                                    "algorithmic": f"{GATHER_B_PER_SAMPLE} B gathered per sample (2 tables x 16 levels x 8 corners x 4 B)",
                                    "hbm_peak_gbs_for_scale": hbm_peak})
@@ -325,7 +330,7 @@ def main():
                 "config": {"workload": "palette-mode inference render 800x800 lego-shaped, cuda_ray, 4 palettes "
                                        "(BASELINE config 3), one view per GPU",
                            "rays_per_step_per_gpu": N_RAYS, "gui_mode": bool(args.gui_mode),
-                           "schedule": getattr(model, "_last_schedule", "loop"),
+                           "schedule": getattr(model, "_last_schedule", "loop"), "render_kernel": rk,
                            "samples_per_step": samples_per_step, "tile_fill": tile_fill, "l2": "flushed between timed iterations (256 MB write)"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
@@ -333,6 +338,11 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ncu_note(kernel):
+    e = _ncu_entry(kernel) or {}
+    return e.get("note", "see profiles/README.md for the ncu capture of this kernel")
 
 
 def _ncu_entry(kernel):

@@ -185,8 +185,21 @@ __global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ ra
 #pragma unroll
     for (int k = 0; k < kMaxRuns; k++) { rr.t_start[k] = 0.f; rr.n[k] = 0; }
     uint32_t count = 0, n_runs = 0, run_n = 0;
-    float run_t = 0.f, x, y, z, dt;
+    float run_t = 0.f;
     bool in_run = false;
+    auto close_run = [&]() {
+        in_run = false;
+        if (n_runs < (uint32_t)kMaxRuns) {
+#pragma unroll
+            for (int k = 0; k < kMaxRuns; k++)
+                if (k == (int)n_runs) { rr.t_start[k] = run_t; rr.n[k] = run_n; }
+        }
+        n_runs++;
+    };
+    // (classifying several lattice points ahead inside a run — independent bitfield loads in flight — was measured and
+    // rejected: 80 instead of 56 registers and wasted probes cost more than the shorter dependency chains save,
+    // 0.44 -> 0.8 ms per 800x800 view)
+    float x, y, z, dt;
     while (t < far && count < max_steps) {
         if (m.probe(t, x, y, z, dt)) {
             if (!in_run) { in_run = true; run_t = t; run_n = 0; }
@@ -194,23 +207,10 @@ __global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ ra
             count++;
             t += dt;
         } else if (in_run) {          // probe() advanced t past the empty voxel: the run is closed
-            in_run = false;
-            if (n_runs < (uint32_t)kMaxRuns) {
-#pragma unroll
-                for (int k = 0; k < kMaxRuns; k++)
-                    if (k == (int)n_runs) { rr.t_start[k] = run_t; rr.n[k] = run_n; }
-            }
-            n_runs++;
+            close_run();
         }
     }
-    if (in_run) {
-        if (n_runs < (uint32_t)kMaxRuns) {
-#pragma unroll
-            for (int k = 0; k < kMaxRuns; k++)
-                if (k == (int)n_runs) { rr.t_start[k] = run_t; rr.n[k] = run_n; }
-        }
-        n_runs++;
-    }
+    if (in_run) close_run();
     rr.count = count;
     rr.n_runs = min(n_runs, (uint32_t)kMaxRuns + 1u);
     runs[i] = rr;
