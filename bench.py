@@ -132,8 +132,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
-    ap.add_argument("--sections", default="hashgrid,train,mip360,cpu",
-                    help="extra sections to run (comma list of hashgrid,train,mip360,cpu)")
+    ap.add_argument("--sections", default="hashgrid,train,mip360,strong,cpu",
+                    help="extra sections to run (comma list of hashgrid,train,mip360,strong,cpu)")
     ap.add_argument("--torch-loss", action="store_true", help="training sections: the loss as torch tensor expressions "
                     "instead of palette_loss (A/B)")
     ap.add_argument("--torch-adam", action="store_true", help="training sections: torch.optim.Adam(fused, capturable) "
@@ -301,6 +301,11 @@ def main():
                                       nccl_allreduce=args.nccl_allreduce))
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
             extras["train"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    if "strong" in sections and world > 1:
+        try:
+            extras.update(bench_strong(torch, dev, rank, world, S, model, barrier, max_over_ranks, flush, args))
+        except Exception as e:  # noqa: BLE001
+            extras["render_strong"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if "mip360" in sections:
         try:
             extras.update(bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world))
@@ -491,6 +496,43 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                                                             else "pnerf_peer_allreduce (two-shot over NVLink peer memory)"),
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
+
+
+def bench_strong(torch, dev, rank, world, S, model, barrier, max_over_ranks, flush, args):
+    """STRONG scaling of the render (north_star: "rendering is split by ray/image tile across the 8 GPUs"): ONE 800x800 view
+    (and one 1297x840 mip-360-shaped view with the semantic branch) dealt out in interleaved 256-ray tiles over the N ranks;
+    every rank's persistent kernel stores its finished rays straight into rank 0's image in symmetric (peer-mapped)
+    memory, two cross-GPU barriers bracket it. rays/s = rays of the ONE view / max-over-ranks device time."""
+    from palettenerf_b200.distributed import ShardedView
+    res = {}
+    cases = [("800x800", model, VIEW, VIEW, S.LEGO["dt_gamma"])]
+    m5 = S.build_palette_model(dev, seed=0, pred_clip=True, ground=True, scene_scale=1.5)
+    m5.min_near = 0.05
+    m5.eval()
+    cases.append(("1297x840_clip", m5, 840, 1297, 1.0 / 128))
+    for name, mdl, Hh, Ww, dtg in cases:
+        o, d = S.camera_rays(Hh, Ww, azimuth_deg=35.0)
+        o, d = o.to(dev), d.to(dev)
+        view = ShardedView(mdl, Hh * Ww, gui_mode=args.gui_mode, tile=256)
+        for _ in range(3):
+            view.render(o, d, bg_color=1, dt_gamma=dtg)
+        barrier()
+        ts = []
+        for _ in range(max(args.steps, 5)):
+            flush.fill_(1)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); view.render(o, d, bg_color=1, dt_gamma=dtg); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = max_over_ranks(sum(ts) / len(ts))
+        res[name] = {"ms_per_view": ms, "rays_per_s": Hh * Ww / (ms / 1e3), "rays": Hh * Ww,
+                     "samples_rank0": int(view.queue[1].item())}
+    res["scaling"] = "strong"
+    res["how"] = ("one view, interleaved 256-ray tiles over the ranks, retire() stores into rank 0's maps over NVLink peer memory "
+                  "(ShardedView); timed region = zero-fill of the maps on rank 0 + barrier + per-rank near/far, candidate filter, "
+                  "pre-pass, persistent kernel + barrier + per-ray epilogue on rank 0")
+    return {"render_strong": res}
 
 
 def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):

@@ -282,6 +282,8 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
  * occupied stretches (`runs`), so the persistent kernel never touches the occupancy grid.
  *   runs      [N * pnerf_palette_render_tc_runs_bytes()] bytes scratch
  *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32 scratch
+ *   out_index (optional, [N] int32): ray n writes row out_index[n] of the output maps instead of row n; the maps may live in
+ *             a peer GPU's memory (one view sharded over several GPUs, each rank storing its rays into the owner's image)
  * Needs field->wpack_tc and field->table_sigma_palette. Replaces palette/renderer.py:430-523. */
 PNERF_API uint32_t pnerf_palette_render_tc_warps(void);
 PNERF_API uint32_t pnerf_palette_render_tc_runs_bytes(void);
@@ -291,7 +293,7 @@ PNERF_API int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, 
                                       float* weights_sum, float* depth, float* image, float* direct_rgb, float* view_dep_rgb,
                                       float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb, float* clip_feat,
                                       uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
-                                      void* stream);
+                                      const int32_t* out_index, void* stream);
 PNERF_API void pnerf_render_tc_timing(int enable);
 PNERF_API float pnerf_render_tc_last_ms(void);
 /* bench hook: CUDA-event pair around the persistent kernel of the last pnerf_palette_render_rays call (off by default) */

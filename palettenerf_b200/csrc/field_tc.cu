@@ -134,6 +134,7 @@ struct RaysTcArgs {
     const int32_t* cand;                            // [N] candidate ray ids
     const RayRuns* runs;                            // [N] indexed by candidate slot
     float* t_scratch;                               // [warps, max_steps]
+    const int32_t* out_index;                       // optional [N]: row of the output maps that ray n writes (tile-sharded views)
 };
 
 enum { QT_CURSOR = 0, QT_SAMPLES = 1, QT_RAYS = 2, QT_TILES = 3, QT_CAND = 4 };
@@ -391,6 +392,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         T_run *= __shfl_sync(0xffffffffu, incl, 31);
         if (term || done >= count) {
             // ---- retire: one writer per value; lane = auxiliary channel ----
+            // (out_index: this rank renders a shard of a view whose maps live elsewhere — possibly in a peer GPU's memory,
+            // mapped over NVLink: the stores below are the gather)
+            if (a.out_index) ray = (uint32_t)a.out_index[ray];
             if (lane == 0) {
                 a.weights_sum[ray] = wsum; a.depth[ray] = dep;
                 a.image[(size_t)ray * 3] = cr; a.image[(size_t)ray * 3 + 1] = cg; a.image[(size_t)ray * 3 + 2] = cb;
@@ -431,13 +435,15 @@ uint32_t pnerf_palette_render_tc_runs_bytes(void) { return (uint32_t)sizeof(RayR
 /* Tensor-core warp-per-ray renderer (csrc/field_tc.cu): like pnerf_palette_render_rays, with the field on tcgen05 / TMEM and
  * a thread-per-ray pre-pass that records each ray's occupied stretches.
  *   queue [8] u32 zero on entry; cand [N] int32; runs [N * pnerf_palette_render_tc_runs_bytes()] bytes;
- *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32. Needs field->wpack_tc and field->table_sigma_palette. */
+ *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32. Needs field->wpack_tc and field->table_sigma_palette.
+ *   out_index (optional, [N] int32): ray n writes row out_index[n] of the output maps instead of row n — the maps may be a
+ *   peer GPU's memory (one view sharded over several GPUs: every rank stores its rays straight into the owner's image). */
 int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const float* nears, const float* fars, const float* noises,
                             const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t Hgrid, uint32_t max_steps, float dt_gamma,
                             float T_thresh, const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                             float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb,
                             float* clip_feat, uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
-                            void* stream) {
+                            const int32_t* out_index, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
     PNERF_REQUIRE(cand && runs && t_scratch);
@@ -453,7 +459,7 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
     a.weights_sum = weights_sum; a.depth = depth; a.image = image;
     a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
     a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue; a.cand = cand;
-    a.runs = (const RayRuns*)runs; a.t_scratch = t_scratch;
+    a.runs = (const RayRuns*)runs; a.t_scratch = t_scratch; a.out_index = out_index;
     cudaStream_t s = (cudaStream_t)stream;
     k_tc_candidates<<<ceil_div(N, 256u), 256, 0, s>>>(rays_o, rays_d, nears, fars, N, occ_aabb, cand, queue);
     k_tc_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, C, Hgrid, max_steps, field->bound,

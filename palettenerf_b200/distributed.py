@@ -2,8 +2,9 @@
 the box, gloo in the CPU tests). Rays are independent, so
 
   * inference shards the rays (`ray_shard`) — contiguous bands, or interleaved tiles when empty-space rays make
-    bands unbalanced — with NO data-path collective; `gather_maps` assembles per-ray outputs on every rank when a
-    caller wants the full image;
+    bands unbalanced. `ShardedView` renders ONE view on all ranks: the persistent kernel of every rank stores its finished
+    rays straight into the owner's image in symmetric (peer-mapped) memory — compute and gather in one kernel;
+    `gather_maps` is the library-collective alternative (all-gather of the per-ray maps, gloo-testable);
   * training is ray-batch data parallel: `GradBucket` packs the gradients of the tensors that actually received one
     (the sigma grid / sigma net get none in the palette stage, palette/network.py:168, palette/renderer.py:335) plus
     the GradScaler found-inf flag into ONE flat fp32 buffer and all-reduces it once per step;
@@ -37,14 +38,91 @@ def ray_shard(n_rays, world_size, rank, tile=0):
     return idx[idx < n_rays]
 
 
-def gather_maps(local, n_rays, shard, group=None):
-    """all-gather a per-ray tensor [n_local, ...] rendered for `shard` (from ray_shard) into [n_rays, ...] on every rank"""
+def gather_maps(local, n_rays, shard, group=None, tile=0):
+    """all-gather a per-ray tensor [n_local, ...] rendered for `shard` (= ray_shard(n_rays, ws, rank, tile)) into
+    [n_rays, ...] on every rank: ONE all_gather of equal-sized (padded) shards — every rank receives n_rays rows in total,
+    not world x n_rays as a sum of zero-padded images would cost"""
     ws, rank = world()
+    if ws == 1:
+        full = torch.zeros((n_rays,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        full[shard] = local
+        return full
+    sizes = []
+    for r in range(ws):
+        sh = ray_shard(n_rays, ws, r, tile)
+        sizes.append(sh.stop - sh.start if isinstance(sh, slice) else sh.numel())
+    cap = max(sizes)
+    padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(parts, padded, group=group)
     full = torch.zeros((n_rays,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    full[shard] = local
-    if ws > 1:
-        dist.all_reduce(full, group=group)   # shards are disjoint: a sum is a gather, one collective, no padding logic
+    for r in range(ws):
+        sh = ray_shard(n_rays, ws, r, tile)
+        full[sh if isinstance(sh, slice) else sh.to(local.device)] = parts[r][: sizes[r]]
     return full
+
+
+class ShardedView:
+    """ONE view rendered by all ranks of a box (north_star: "rendering is split by ray/image tile across the 8 GPUs").
+
+    The rays of the view are dealt out in interleaved tiles of `tile` consecutive pixels (empty-space rays cost nothing, so
+    contiguous bands would be unbalanced); every rank renders its shard with the persistent tensor-core renderer, whose
+    `retire` step stores each finished ray STRAIGHT INTO THE OWNER'S output maps: they live in symmetric memory (every rank
+    maps the owner's buffer, torch `_symmetric_memory`), so the stores travel over NVLink and the kernel itself is the
+    gather — no all-gather / all-reduce, no staging copy. Two cross-GPU barriers of the symmetric-memory handle bracket the
+    kernel (maps zeroed before anyone writes / every shard delivered); the per-ray epilogue (background mix, depth
+    normalisation) runs on the owner. A ray's result does not depend on which rays share its launch, so the assembled
+    image equals the single-GPU image bit for bit (tests/test_peer_gpu.py)."""
+
+    def __init__(self, model, n_rays, gui_mode=False, tile=256, owner=0, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import fused
+        group = group if group is not None else dist.group.WORLD
+        self.model, self.n_rays, self.gui_mode, self.owner = model, n_rays, gui_mode, owner
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = model.encoder.embeddings.device
+        self.layout, total = fused.accumulator_layout(n_rays, model.num_basis, model.opt.clip_dim, gui_mode)
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:   # noqa: BLE001
+            pass
+        self.buf = symm.empty(total, dtype=torch.float32, device=dev)
+        self.handle = symm.rendezvous(self.buf, group)
+        owner_buf = self.buf if self.rank == owner else self.handle.get_buffer(owner, (total,), torch.float32)
+        self.maps = {k: owner_buf[o:o + int(torch.Size(shp).numel())].view(*shp) for k, (o, shp) in self.layout.items()}
+        self.shard = ray_shard(n_rays, self.world, self.rank, tile)
+        self.shard_dev = self.shard.to(dev)
+        self.out_index = self.shard_dev.to(torch.int32).contiguous()
+
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, bg_color=1, perturb=False, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4):
+        """rays_o, rays_d: [n_rays, 3] of the WHOLE view on every rank (generated from the pose: 64 bytes of input).
+        Returns run_cuda's inference dict on the owner rank, None elsewhere."""
+        from . import fused, raymarching
+        from .nerf.renderer import render_tail
+        m = self.model
+        o, d = rays_o.view(-1, 3)[self.shard_dev].contiguous(), rays_d.view(-1, 3)[self.shard_dev].contiguous()
+        nears, fars = raymarching.near_far_from_aabb(o, d, m.aabb_infer, m.min_near)
+        if self.rank == self.owner:
+            self.buf.zero_()
+        self.handle.barrier(channel=0)                      # the owner's maps are zero before any rank stores into them
+        acc = fused.render(m, o, d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, self.gui_mode, kernel="tc",
+                           out=self.maps, out_index=self.out_index)
+        self.handle.barrier(channel=1)                      # every shard has been delivered
+        self.queue = acc["_queue"]
+        if self.rank != self.owner:
+            return None
+        nears_all, fars_all = raymarching.near_far_from_aabb(rays_o.view(-1, 3), rays_d.view(-1, 3), m.aabb_infer, m.min_near)
+        mp = self.maps
+        depth_n, image, direct = render_tail(mp["depth"], nears_all, fars_all, mp["image"], mp["weights_sum"], bg_color,
+                                             None if self.gui_mode else mp["direct_rgb"], 0)
+        out = {"depth": depth_n, "depth_origin": mp["depth"], "image": image, "weights_sum": mp["weights_sum"],
+               "clip_feat": mp["clip_feat"]}
+        if not self.gui_mode:
+            out.update(direct_rgb=direct, view_dep_rgb=mp["view_dep_rgb"], basis_rgb=mp["basis_rgb"],
+                       unscaled_basis_rgb=mp["unscaled_basis_rgb"], basis_acc=mp["basis_acc"])
+        return out
 
 
 class PeerMemory:

@@ -42,7 +42,7 @@ L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 orderi
 L.register("pnerf_palette_render_rays", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_rays"] = 2   # candidate filter + the persistent warp-per-ray kernel
 L.lib.pnerf_palette_render_rays_warps.restype = c_uint32
-L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_tc"] = 3     # candidate filter + thread-per-ray pre-pass (runs) + the persistent kernel
 L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
 L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
@@ -234,31 +234,46 @@ def _t_scratch(dev, max_steps, warps=None):
 RENDER_KERNEL = __import__("os").environ.get("PNERF_RENDER_KERNEL", "tc")    # "rays" (round 2) | "lanes" (round 1, A/B)
 
 
+def accumulator_layout(N, nb, cd, gui_mode):
+    """name -> (offset, shape) of the per-ray output maps inside ONE flat fp32 buffer, and its length in floats"""
+    shapes = {"weights_sum": (N,), "depth": (N,), "image": (N, 3), "clip_feat": (N, cd)}
+    if not gui_mode:
+        shapes.update(direct_rgb=(N, 3), view_dep_rgb=(N, 3), basis_acc=(N, nb), basis_rgb=(N, 3 * nb),
+                      unscaled_basis_rgb=(N, 3 * nb))
+    lay, off = {}, 0
+    for k, shp in shapes.items():
+        lay[k] = (off, shp)
+        off += int(np.prod(shp))
+    return lay, off
+
+
 @torch.no_grad()
-def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode, kernel=None):
+def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode, kernel=None, out=None,
+           out_index=None):
     """persistent fused renderer -> dict of accumulators like PaletteRenderer._infer_loop.
+    out / out_index (tile-sharded views, kernel "tc" only): `out` = dict of pre-zeroed output maps with as many rows as the
+    WHOLE view (they may alias a peer GPU's memory); ray n of this call writes row out_index[n].
     kernel: "tc" = warp-per-ray kernel with the field on tcgen05 / TMEM (csrc/field_tc.cu), "rays" = warp-per-ray kernel on
     mma.sync (csrc/render_rays.cu), "lanes" = round 1's lane-per-ray kernel"""
     f = _cache(model).get()
     N, dev = rays_o.shape[0], rays_o.device
     nb, cd = model.num_basis, model.opt.clip_dim
     kernel = kernel or RENDER_KERNEL
-    if kernel == "tc" and model.opt.pred_clip and "PNERF_RENDER_KERNEL" not in __import__("os").environ:
+    if kernel == "tc" and out is None and model.opt.pred_clip and "PNERF_RENDER_KERNEL" not in __import__("os").environ:
         # the semantic branch gathers a third table; until that gather is interleaved with the other two the lane-per-ray
         # kernel renders such models faster (config 5: 17.8 vs 19.6 ms per 1297x840 view)
         kernel = "lanes"
-    # every accumulator (and the queue counters) is a view of ONE zero-filled buffer: one fill launch per view instead of ten
-    shapes = {"weights_sum": (N,), "depth": (N,), "image": (N, 3), "clip_feat": (N, cd)}
-    if not gui_mode:
-        shapes.update(direct_rgb=(N, 3), view_dep_rgb=(N, 3), basis_acc=(N, nb), basis_rgb=(N, 3 * nb),
-                      unscaled_basis_rgb=(N, 3 * nb))
-    sizes = {k: int(np.prod(v)) for k, v in shapes.items()}
-    flat = torch.zeros(sum(sizes.values()) + 68, dtype=torch.float32, device=dev)
-    acc, off = {}, 0
-    for k, shp in shapes.items():
-        acc[k] = flat[off:off + sizes[k]].view(*shp)
-        off += sizes[k]
-    queue = flat[off:off + 68].view(torch.int32)             # counters (+ round 1's 32-bucket histogram and cursors)
+    if out is not None:
+        if kernel != "tc" or out_index is None:
+            raise RuntimeError("sharded output needs the tensor-core renderer (kernel='tc') and an out_index map")
+        acc = dict(out)
+        queue = torch.zeros(68, dtype=torch.int32, device=dev)
+    else:
+        # every accumulator (and the queue counters) is a view of ONE zero-filled buffer: one fill launch per view
+        lay, total = accumulator_layout(N, nb, cd, gui_mode)
+        flat = torch.zeros(total + 68, dtype=torch.float32, device=dev)
+        acc = {k: flat[o:o + int(np.prod(shp))].view(*shp) for k, (o, shp) in lay.items()}
+        queue = flat[total:total + 68].view(torch.int32)         # counters (+ round 1's 32-bucket histogram and cursors)
     noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
     aux = (lambda k: ptr(acc[k])) if not gui_mode else (lambda k: None)
     from .raymarching.raymarching import occupied_bounds
@@ -272,7 +287,7 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         runs = torch.empty(N * int(L.lib.pnerf_palette_render_tc_runs_bytes()), dtype=torch.uint8, device=dev)
         L.call("pnerf_palette_render_tc", *common, ptr(cand), ptr(runs),
-               ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), stream())
+               ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), ptr(out_index), stream())
     elif kernel == "rays":
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         L.call("pnerf_palette_render_rays", *common, ptr(cand), ptr(_t_scratch(dev, max_steps)), ptr(occ), stream())

@@ -62,7 +62,7 @@ def _worker(rank, ws, port, ret):
         truth = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3)
         for tile in (0, 64):
             sh = D.ray_shard(n, ws, rank, tile)
-            full = D.gather_maps(truth[sh].clone(), n, sh)
+            full = D.gather_maps(truth[sh].clone(), n, sh, tile=tile)
             ok &= torch.equal(full, truth)
 
         # density refresh: ranks evaluate disjoint cell ranges, merged grid identical everywhere
