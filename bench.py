@@ -413,6 +413,33 @@ def bench_hashgrid(torch, dev, L, hbm_peak, flush):
     return {"hashgrid": res}
 
 
+def _allreduce_name(bucket, nccl_allreduce):
+    if nccl_allreduce or bucket is None or bucket._pm is None:
+        return "nccl all_reduce"
+    if bucket._pm.mc_ptr:
+        return "pnerf_peer_allreduce_mc (in-switch reduction: multimem.ld_reduce / multimem.st on the multicast mapping)"
+    return "pnerf_peer_allreduce (two-shot over NVLink peer memory)"
+
+
+def _allreduce_check(torch, dist, dev, rank, world):
+    """one-shot parity check of the peer all-reduce kernel against NCCL on the same data (max abs error over 4 M floats)"""
+    from palettenerf_b200.distributed import PeerMemory
+    try:
+        n = 1 << 22
+        pm = PeerMemory(n, dev)
+        x = torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1234 + rank))
+        pm.buf[:n].copy_(x)
+        pm.all_reduce_(average=True)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        ref.div_(world)
+        err = (pm.buf[:n] - ref).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        return float(err.item())
+    except Exception as e:  # noqa: BLE001
+        return f"check failed: {type(e).__name__}: {str(e)[:120]}"
+
+
 def _adam(torch, params, torch_adam):
     if torch_adam:
         return torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True), \
@@ -492,8 +519,9 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
                       "optimizer": opt_name, "adam_alone": adam,
-                      "allreduce": None if world == 1 else ("nccl all_reduce" if nccl_allreduce or bucket._pm is None
-                                                            else "pnerf_peer_allreduce (two-shot over NVLink peer memory)"),
+                      "allreduce": None if world == 1 else _allreduce_name(bucket, nccl_allreduce),
+                      "allreduce_bucket_bytes": None if bucket is None or bucket.flat is None else 4 * bucket.flat.numel(),
+                      "allreduce_max_abs_err": None if world == 1 else _allreduce_check(torch, dist, dev, rank, world),
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
@@ -584,7 +612,11 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
 
     def loss_fn(out):
         return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1, gt_clip_feat=feat)[0]
-    step_fn = make_palette_train_step(tm, opt, scaler, to, td, loss_fn, render_kwargs=dict(dt_gamma=DTG))
+    bucket5 = None
+    if world > 1:
+        from palettenerf_b200.distributed import GradBucket
+        bucket5 = GradBucket([p for grp in opt.param_groups for p in grp["params"] if p.requires_grad], peer=True)
+    step_fn = make_palette_train_step(tm, opt, scaler, to, td, loss_fn, render_kwargs=dict(dt_gamma=DTG), bucket=bucket5)
     gs = GraphedStep(step_fn, warmup=3)
     for _ in range(3):
         gs.replay()
@@ -599,7 +631,10 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
     ms = max_over_ranks(sum(ts) / len(ts))
     res.update(train_ms=ms, train_rays_per_s=world * TRAIN_RAYS / (ms / 1e3),
                train_samples_rank0=int(tm.step_counter[(tm.local_step - 1) % 16, 0].item()),
-               train_schedule=getattr(tm, "_last_train_schedule", "torch"), train_launch="cuda_graph (per-rank, no all-reduce)")
+               train_schedule=getattr(tm, "_last_train_schedule", "torch"),
+               train_launch="cuda_graph" + ("" if world == 1 else ", data parallel: one all-reduce of the gradient bucket"),
+               train_allreduce=None if bucket5 is None else _allreduce_name(bucket5, False),
+               train_bucket_bytes=None if bucket5 is None or bucket5.flat is None else 4 * bucket5.flat.numel())
     return {"mip360": res}
 
 

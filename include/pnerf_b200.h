@@ -487,6 +487,10 @@ PNERF_API int pnerf_render_tail_backward(uint32_t N, const float* g_image, const
 #define PNERF_PEER_MAX 8
 PNERF_API int pnerf_peer_allreduce(const uint64_t* peer_ptrs, uint32_t world, uint32_t rank, uint64_t n, float scale,
                                    void* stream);
+/* The same all-reduce with the sum formed inside the NVSwitch (NVLS): mc_ptr is the MULTICAST address of the symmetric
+ * bucket; the kernel issues multimem.ld_reduce / multimem.st on slice `rank`, so only 1/world of the bucket crosses each
+ * GPU's NVLink ports per direction. Same padding contract and the same two barriers around the call. */
+PNERF_API int pnerf_peer_allreduce_mc(uint64_t mc_ptr, uint32_t world, uint32_t rank, uint64_t n, float scale, void* stream);
 
 #ifdef __cplusplus
 }

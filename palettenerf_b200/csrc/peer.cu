@@ -53,11 +53,47 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same all-reduce with the reduction done INSIDE THE NVSWITCH (NVLS): the bucket is also mapped at a multicast address;
+// multimem.ld_reduce on it returns the sum over all ranks' copies of that address (the switch reads the peers and adds),
+// multimem.st writes one value into every rank's copy. Rank r still owns slice r — one owner per element, bit-identical
+// results everywhere — but per GPU only 1/world of the bucket crosses its NVLink ports in each direction (instead of
+// (world-1)/world with peer loads and stores), and the SMs issue one load and one store per 16 bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_peer_allreduce_mc(float* __restrict__ mc, uint32_t rank, uint64_t n4_per_rank, float scale) {
+    const uint64_t base = (uint64_t)rank * n4_per_rank;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_rank; i += stride) {
+        float4* p = reinterpret_cast<float4*>(mc) + base + i;
+        float4 s;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w)
+                     : "l"(p)
+                     : "memory");
+        s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w)
+                     : "memory");
+    }
+}
+
 }  // namespace pnerf
 
 using namespace pnerf;
 
 extern "C" {
+
+/* all-reduce through the multicast mapping of the bucket (in-switch reduction, NVLS): mc_ptr = multicast address of the
+ * symmetric buffer (torch symmetric memory: handle.multicast_ptr); same contract as pnerf_peer_allreduce otherwise */
+int pnerf_peer_allreduce_mc(uint64_t mc_ptr, uint32_t world, uint32_t rank, uint64_t n, float scale, void* stream) {
+    PNERF_REQUIRE(mc_ptr != 0 && (mc_ptr & 15ull) == 0 && world >= 1 && world <= (uint32_t)kPeerMax && rank < world);
+    PNERF_REQUIRE(n % (4ull * world) == 0);
+    if (n == 0) return PNERF_OK;
+    const uint64_t n4 = n / 4 / world;
+    const uint64_t blocks = ceil_div<uint64_t>(n4, 256);
+    const uint32_t grid = (uint32_t)(blocks < 4ull * kNumSMs ? blocks : 4ull * kNumSMs);
+    k_peer_allreduce_mc<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float*>(mc_ptr), rank, n4, scale);
+    return check_launch("peer_allreduce_mc");
+}
 
 int pnerf_peer_allreduce(const uint64_t* peer_ptrs, uint32_t world, uint32_t rank, uint64_t n, float scale, void* stream) {
     PNERF_REQUIRE(peer_ptrs != nullptr && world >= 1 && world <= (uint32_t)kPeerMax && rank < world);

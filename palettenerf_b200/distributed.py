@@ -146,14 +146,24 @@ class PeerMemory:
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
         import ctypes
+        import os
         self._ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        # NVLS: the bucket's multicast mapping (0 when the fabric / driver has no multicast support) -> in-switch reduction.
+        # Used from 4 ranks up: per GPU it moves 1/world of the bucket instead of (world-1)/world; at 2 ranks the traffic
+        # is the same and the multimem round trip is slower (measured: 0.771 vs 0.721 ms per DP step, profiles/README.md).
+        want_mc = os.environ.get("PNERF_PEER_MULTICAST", "auto")
+        use_mc = want_mc == "1" or (want_mc == "auto" and self.world >= 4)
+        self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0) if use_mc else 0
 
     def all_reduce_(self, average):
         import ctypes
         from . import _lib as L
+        scale = (1.0 / self.world) if average else 1.0
         self.handle.barrier(channel=0)                      # every rank's gradients are in its bucket
-        L.call("pnerf_peer_allreduce", ctypes.addressof(self._ptrs), self.world, self.rank, self.n,
-               (1.0 / self.world) if average else 1.0, L.stream())
+        if self.mc_ptr:
+            L.call("pnerf_peer_allreduce_mc", self.mc_ptr, self.world, self.rank, self.n, scale, L.stream())
+        else:
+            L.call("pnerf_peer_allreduce", ctypes.addressof(self._ptrs), self.world, self.rank, self.n, scale, L.stream())
         self.handle.barrier(channel=1)                      # every slice has been delivered to every rank
 
 
