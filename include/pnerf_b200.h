@@ -277,6 +277,25 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
                                         float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, int32_t* cand,
                                         float* t_scratch, const float* occ_aabb, void* stream);
+/* GUI-time edit of the palette blend, evaluated per sample INSIDE the persistent renderer (ref: palette/renderer.py:121-147
+ * RegionEdit.forward, :166-183 Stylizer.forward, consulted at :474-483). All pointers are DEVICE pointers (the renderer
+ * stages them in shared memory; no host synchronisation), NULL = unset.
+ *   mode 1 (RegionEdit): every basis colour is recoloured in HSV (hue shift delta_hsv[b][0], saturation / value scales
+ *     [b][1], [b][2]), blended with weight exp(-|xyz - mean_xyz|^2 / std_xyz) * exp(-|clip_feat - mean_clip|^2 / std_clip);
+ *     weight_mode returns the weight itself as the colour.
+ *   mode 2 (Stylizer): rgb = sum_b omega_b * clamp(clamp(softplus(radiance) + dI_b, 0) * (palette_b + dP_b + offsets_b *
+ *     ddelta_b), 0, 1) + view_dep; the five debug maps are not produced (as in the reference). */
+typedef struct pnerf_palette_edit {
+    uint32_t mode, weight_mode;
+    const float* delta_hsv;     /* [4,3]   mode 1 */
+    const float* mean_xyz;      /* [3] or NULL */
+    const float* mean_clip;     /* [clip_dim] or NULL */
+    float std_xyz, std_clip;
+    const float* dI;            /* [4]     mode 2 */
+    const float* dP;            /* [4,3]   */
+    const float* ddelta;        /* [4,3,3] */
+} pnerf_palette_edit;
+
 /* The same renderer with the field on the 5th-generation tensor cores (tcgen05.mma, activations and accumulators in TMEM;
  * csrc/field_tc.cuh): a warpgroup shades 4 rays x 32 samples per tile. A thread-per-ray pre-pass records each candidate ray's
  * occupied stretches (`runs`), so the persistent kernel never touches the occupancy grid.
@@ -284,6 +303,7 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
  *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32 scratch
  *   out_index (optional, [N] int32): ray n writes row out_index[n] of the output maps instead of row n; the maps may live in
  *             a peer GPU's memory (one view sharded over several GPUs, each rank storing its rays into the owner's image)
+ *   edit      (optional): RegionEdit / Stylizer evaluated in the blend of every sample
  * Needs field->wpack_tc and field->table_sigma_palette. Replaces palette/renderer.py:430-523. */
 PNERF_API uint32_t pnerf_palette_render_tc_warps(void);
 PNERF_API uint32_t pnerf_palette_render_tc_runs_bytes(void);
@@ -293,7 +313,7 @@ PNERF_API int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, 
                                       float* weights_sum, float* depth, float* image, float* direct_rgb, float* view_dep_rgb,
                                       float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb, float* clip_feat,
                                       uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
-                                      const int32_t* out_index, void* stream);
+                                      const int32_t* out_index, const pnerf_palette_edit* edit, void* stream);
 PNERF_API void pnerf_render_tc_timing(int enable);
 PNERF_API float pnerf_render_tc_last_ms(void);
 /* bench hook: CUDA-event pair around the persistent kernel of the last pnerf_palette_render_rays call (off by default) */

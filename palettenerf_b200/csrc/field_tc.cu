@@ -1,6 +1,7 @@
 // field_tc.cu — kernels built on the tcgen05 field (field_tc.cuh): the batch field evaluation and the warp-per-ray
 // persistent renderer with a 128-sample (4 rays x 32 samples) tensor-core tile per warpgroup.
 #include "field_tc.cuh"
+#include "hsv_common.cuh"
 
 namespace pnerf {
 
@@ -135,6 +136,12 @@ struct RaysTcArgs {
     const RayRuns* runs;                            // [N] indexed by candidate slot
     float* t_scratch;                               // [warps, max_steps]
     const int32_t* out_index;                       // optional [N]: row of the output maps that ray n writes (tile-sharded views)
+    pnerf_palette_edit edit;                        // GUI-time edit of the blend (mode 0: none)
+};
+
+// edit parameters staged in shared memory (behind the group regions)
+struct EditShared {
+    float delta_hsv[kNB * 3], mean_xyz[3], mean_clip[kClipMax], dI[kNB], dP[kNB * 3], ddelta[kNB * 9];
 };
 
 enum { QT_CURSOR = 0, QT_SAMPLES = 1, QT_RAYS = 2, QT_TILES = 3, QT_CAND = 4 };
@@ -219,9 +226,10 @@ __global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ ra
 
 constexpr int kRedStride = 33;                      // floats per channel row of the reduction scratch (conflict-free both ways)
 
-__host__ __device__ constexpr size_t tc_render_smem(bool clip) { return tc_smem_bytes(clip); }
+__host__ __device__ constexpr size_t tc_render_smem(bool clip) { return tc_smem_bytes(clip) + sizeof(EditShared) + 16; }
 
-template <bool CLIP, bool AUX>
+// EDIT: 0 = plain palette blend, 1 = RegionEdit, 2 = Stylizer (csrc: pnerf_palette_edit)
+template <bool CLIP, bool AUX, int EDIT>
 __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, pnerf_palette_field f) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcShared* sm = reinterpret_cast<TcShared*>(smem_raw);
@@ -229,6 +237,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     unsigned char* groups = wts + (CLIP ? kTcWBytesClip : kTcWBytesNoClip);
     constexpr int group_bytes = CLIP ? kTcGroupBytesClip : kTcGroupBytesNoClip;
     static_assert(kAuxCh * kRedStride * 4 <= group_bytes / 4, "per-warp reduction scratch must fit a quarter of the group's regions");
+    EditShared* ed = reinterpret_cast<EditShared*>(groups + kTcGroups * group_bytes);
+    if (EDIT != 0) {
+        const int tid = threadIdx.x;
+        if (EDIT == 1) {
+            if (tid < kNB * 3) ed->delta_hsv[tid] = a.edit.delta_hsv[tid];
+            if (tid < 3) ed->mean_xyz[tid] = a.edit.mean_xyz ? a.edit.mean_xyz[tid] : 0.f;
+            if (tid < kClipMax) ed->mean_clip[tid] = (a.edit.mean_clip && tid < (int)f.clip_dim) ? a.edit.mean_clip[tid] : 0.f;
+        } else {
+            if (tid < kNB) ed->dI[tid] = a.edit.dI[tid];
+            if (tid < kNB * 3) ed->dP[tid] = a.edit.dP[tid];
+            if (tid < kNB * 9) ed->ddelta[tid] = a.edit.ddelta[tid];
+        }
+    }
     tc_prologue<kTcGroups>(f, f.wpack_tc, sm, wts, groups, group_bytes);
     TcGroup g = tc_make_group(sm, wts, groups, group_bytes);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gi = wid >> 2, wig = wid & 3;
@@ -333,18 +354,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
             const float sp = softplusf_(o.off_rad[12]);
             rgb[0] = rgb[1] = rgb[2] = 0.f;
+            if (EDIT == 2) {
+                // Stylizer.forward (ref: palette/renderer.py:166-183)
 #pragma unroll
-            for (int b = 0; b < kNB; b++) {
+                for (int b = 0; b < kNB; b++) {
+                    const float gain = fmaxf(sp + ed->dI[b], 0.f);
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float off = o.off_rad[b * 3 + c];
-                    unscaled[b * 3 + c] = sm->palette[b * 3 + c] + off;
-                    basis_rgb[b * 3 + c] = o.omega[b] * (sp * (sm->palette[b * 3 + c] + f.offsets_weight * off));
-                    rgb[c] += basis_rgb[b * 3 + c];
+                    for (int c = 0; c < 3; c++) {
+                        float off = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; i++) off += o.off_rad[b * 3 + i] * ed->ddelta[b * 9 + i * 3 + c];
+                        const float col = fminf(fmaxf(gain * (sm->palette[b * 3 + c] + ed->dP[b * 3 + c] + off), 0.f), 1.f);
+                        basis_rgb[b * 3 + c] = unscaled[b * 3 + c] = 0.f;
+                        rgb[c] += o.omega[b] * col;
+                    }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
+                for (int c = 0; c < 3; c++) rgb[c] += o.view_dep[c];
+            } else {
+                float ew = 1.f;
+                if (EDIT == 1) {
+                    // RegionEdit.forward's spatial / semantic weight (ref: palette/renderer.py:127-135)
+                    if (a.edit.mean_xyz) {
+                        const float ex = x - ed->mean_xyz[0], ey = y - ed->mean_xyz[1], ez = z - ed->mean_xyz[2];
+                        ew *= __expf(-(ex * ex + ey * ey + ez * ez) / a.edit.std_xyz);
+                    }
+                    if (a.edit.mean_clip) {
+                        float d2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kClipMax; i++) {
+                            const float e = (i < (int)f.clip_dim) ? o.clip[i] - ed->mean_clip[i] : 0.f;
+                            d2 += e * e;
+                        }
+                        ew *= __expf(-d2 / a.edit.std_clip);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < kNB; b++) {
+                    float fin[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float off = o.off_rad[b * 3 + c];
+                        unscaled[b * 3 + c] = sm->palette[b * 3 + c] + off;
+                        fin[c] = sp * (sm->palette[b * 3 + c] + f.offsets_weight * off);
+                    }
+                    if (EDIT == 1) {
+                        if (a.edit.weight_mode) {
+                            fin[0] = fin[1] = fin[2] = ew;
+                        } else {
+                            float h, sa, v, nr, ng, nb2;
+                            rgb_to_hsv_dev(fin[0], fin[1], fin[2], h, sa, v);
+                            h = fmodf(h + ed->delta_hsv[b * 3] + 360.f, 360.f);
+                            sa = fmaxf(sa * ed->delta_hsv[b * 3 + 1], 0.f);
+                            v = fmaxf(v * ed->delta_hsv[b * 3 + 2], 0.f);
+                            hsv_to_rgb_dev(h, sa, v, nr, ng, nb2);
+                            fin[0] += ew * (nr - fin[0]); fin[1] += ew * (ng - fin[1]); fin[2] += ew * (nb2 - fin[2]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        basis_rgb[b * 3 + c] = o.omega[b] * fin[c];
+                        rgb[c] += basis_rgb[b * 3 + c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
+            }
             wsum += warp_sum(wgt);
             dep += warp_sum(wgt * t_end);
             cr += warp_sum(wgt * rgb[0]); cg += warp_sum(wgt * rgb[1]); cb += warp_sum(wgt * rgb[2]);
@@ -443,7 +518,7 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
                             float T_thresh, const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                             float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb,
                             float* clip_feat, uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
-                            const int32_t* out_index, void* stream) {
+                            const int32_t* out_index, const pnerf_palette_edit* edit, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
     PNERF_REQUIRE(cand && runs && t_scratch);
@@ -460,6 +535,12 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
     a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
     a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue; a.cand = cand;
     a.runs = (const RayRuns*)runs; a.t_scratch = t_scratch; a.out_index = out_index;
+    pnerf_palette_edit none = {};
+    a.edit = edit ? *edit : none;
+    const int emode = (int)a.edit.mode;
+    PNERF_REQUIRE(emode >= 0 && emode <= 2);
+    if (emode == 1) PNERF_REQUIRE(a.edit.delta_hsv != nullptr);
+    if (emode == 2) PNERF_REQUIRE(a.edit.dI && a.edit.dP && a.edit.ddelta && !aux);   // the Stylizer produces no debug maps
     cudaStream_t s = (cudaStream_t)stream;
     k_tc_candidates<<<ceil_div(N, 256u), 256, 0, s>>>(rays_o, rays_d, nears, fars, N, occ_aabb, cand, queue);
     k_tc_prepass<<<ceil_div(N, 128u), 128, 0, s>>>(rays_o, rays_d, nears, fars, noises, bitfield, C, Hgrid, max_steps, field->bound,
@@ -467,23 +548,29 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
     const bool clip_on = field->pred_clip != 0;
     const size_t smem = tc_render_smem(clip_on);
     const uint32_t grid = (uint32_t)sm_count();
-    static bool attr_done[2][2] = {{false, false}, {false, false}};
-#define PNERF_LAUNCH_TC(CL, AX)                                                                                          \
+    static bool attr_done[2][2][3] = {};
+#define PNERF_LAUNCH_TC(CL, AX, ED)                                                                                      \
     do {                                                                                                                \
-        if (!attr_done[CL][AX]) {                                                                                       \
-            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<CL, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        if (!attr_done[CL][AX][ED]) {                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<CL, AX, ED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)tc_render_smem(CL));                                              \
             if (e != cudaSuccess) { set_last_cuda_error(e, "render_tc attr"); return PNERF_ERR_CUDA; }                  \
-            attr_done[CL][AX] = true;                                                                                   \
+            attr_done[CL][AX][ED] = true;                                                                               \
         }                                                                                                               \
-        k_render_rays_tc<CL, AX><<<grid, kTcThreads, smem, s>>>(a, *field);                                             \
+        k_render_rays_tc<CL, AX, ED><<<grid, kTcThreads, smem, s>>>(a, *field);                                         \
+    } while (0)
+#define PNERF_LAUNCH_TC_ED(CL, AX)                                                                                       \
+    do {                                                                                                                \
+        if (emode == 0) PNERF_LAUNCH_TC(CL, AX, 0); else PNERF_LAUNCH_TC(CL, AX, 1);                                    \
     } while (0)
     if (g_tc_timing) {
         if (!g_tc_ev[0]) { cudaEventCreate(&g_tc_ev[0]); cudaEventCreate(&g_tc_ev[1]); }
         cudaEventRecord(g_tc_ev[0], s);
     }
-    if (clip_on) { if (aux) PNERF_LAUNCH_TC(true, true); else PNERF_LAUNCH_TC(true, false); }
-    else { if (aux) PNERF_LAUNCH_TC(false, true); else PNERF_LAUNCH_TC(false, false); }
+    if (emode == 2) { if (clip_on) PNERF_LAUNCH_TC(true, false, 2); else PNERF_LAUNCH_TC(false, false, 2); }
+    else if (clip_on) { if (aux) PNERF_LAUNCH_TC_ED(true, true); else PNERF_LAUNCH_TC_ED(true, false); }
+    else { if (aux) PNERF_LAUNCH_TC_ED(false, true); else PNERF_LAUNCH_TC_ED(false, false); }
+#undef PNERF_LAUNCH_TC_ED
 #undef PNERF_LAUNCH_TC
     if (g_tc_timing) { cudaEventRecord(g_tc_ev[1], s); g_tc_timed = true; }
     return check_launch("palette_render_tc");

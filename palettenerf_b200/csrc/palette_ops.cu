@@ -3,48 +3,30 @@
 // H in degrees [0,360), S and V in [0,100] (the reference's convention, not OpenCV's).
 #include <cmath>
 
-#include "common.cuh"
+#include "hsv_common.cuh"
 
 namespace pnerf {
-
-__device__ __forceinline__ bool near_eq(float a, float b) { return fabsf(a - b) < 1e-9f; }
 
 __global__ void __launch_bounds__(256) k_rgb_to_hsv(uint32_t n, const float* __restrict__ input,
                                                     float* __restrict__ output) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float r = input[(size_t)i * 3], g = input[(size_t)i * 3 + 1], b = input[(size_t)i * 3 + 2];
-    const float cmax = fmaxf(fmaxf(r, g), b), cmin = fminf(fminf(r, g), b);
-    const float diff = cmax - cmin;
-    float h;
-    if (near_eq(diff, 0.f)) h = 0.f;
-    else if (near_eq(cmax, r)) h = fmodf(60 * ((g - b) / diff) + 360, 360.f);
-    else if (near_eq(cmax, g)) h = fmodf(60 * ((b - r) / diff) + 120, 360.f);
-    else h = fmodf(60 * ((r - g) / diff) + 240, 360.f);
-    const float s = near_eq(cmax, 0.f) ? 0.f : (diff / cmax) * 100;
+    float h, sat, v;
+    rgb_to_hsv_dev(input[(size_t)i * 3], input[(size_t)i * 3 + 1], input[(size_t)i * 3 + 2], h, sat, v);
     output[(size_t)i * 3] = h;
-    output[(size_t)i * 3 + 1] = s;
-    output[(size_t)i * 3 + 2] = cmax * 100;
+    output[(size_t)i * 3 + 1] = sat;
+    output[(size_t)i * 3 + 2] = v;
 }
 
 __global__ void __launch_bounds__(256) k_hsv_to_rgb(uint32_t n, const float* __restrict__ input,
                                                     float* __restrict__ output) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float h = input[(size_t)i * 3], s = input[(size_t)i * 3 + 1], v = input[(size_t)i * 3 + 2];
-    const float c = s / 100 * v / 100;
-    const float x = c * (1 - fabsf(fmodf(h / 60, 2.f) - 1));
-    const float m = v / 100 - c;
-    float r = 0, g = 0, b = 0;
-    if (h >= 0 && h < 60) { r = c; g = x; }
-    else if (h >= 60 && h < 120) { r = x; g = c; }
-    else if (h >= 120 && h < 180) { g = c; b = x; }
-    else if (h >= 180 && h < 240) { g = x; b = c; }
-    else if (h >= 240 && h < 300) { r = x; b = c; }
-    else { r = c; b = x; }
-    output[(size_t)i * 3] = r + m;
-    output[(size_t)i * 3 + 1] = g + m;
-    output[(size_t)i * 3 + 2] = b + m;
+    float r, g, b;
+    hsv_to_rgb_dev(input[(size_t)i * 3], input[(size_t)i * 3 + 1], input[(size_t)i * 3 + 2], r, g, b);
+    output[(size_t)i * 3] = r;
+    output[(size_t)i * 3 + 1] = g;
+    output[(size_t)i * 3 + 2] = b;
 }
 
 }  // namespace pnerf

@@ -32,6 +32,13 @@ class PaletteField(ctypes.Structure):
                 ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p), ("wpack_tc", c_void_p)]
 
 
+class PaletteEdit(ctypes.Structure):
+    """mirror of `struct pnerf_palette_edit` (include/pnerf_b200.h): GUI-time edit evaluated inside the persistent renderer"""
+    _fields_ = [("mode", c_uint32), ("weight_mode", c_uint32), ("delta_hsv", c_void_p), ("mean_xyz", c_void_p),
+                ("mean_clip", c_void_p), ("std_xyz", c_float), ("std_clip", c_float), ("dI", c_void_p), ("dP", c_void_p),
+                ("ddelta", c_void_p)]
+
+
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_palette_field_forward", [P, P, U, P, P, P, P, P, P, P, P])
 L.register("pnerf_palette_field_forward_tc", [P, P, U, P, P, P, P, P, P, P, P])
@@ -42,7 +49,7 @@ L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 orderi
 L.register("pnerf_palette_render_rays", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_rays"] = 2   # candidate filter + the persistent warp-per-ray kernel
 L.lib.pnerf_palette_render_rays_warps.restype = c_uint32
-L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_tc"] = 3     # candidate filter + thread-per-ray pre-pass (runs) + the persistent kernel
 L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
 L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
@@ -234,6 +241,30 @@ def _t_scratch(dev, max_steps, warps=None):
 RENDER_KERNEL = __import__("os").environ.get("PNERF_RENDER_KERNEL", "tc")    # "rays" (round 2) | "lanes" (round 1, A/B)
 
 
+def edit_struct(model, dev):
+    """-> (PaletteEdit | None, tensors to keep alive) for model.edit (RegionEdit) / model.stylizer (Stylizer); the kernel reads
+    the parameters through device pointers, so nothing is copied to the host"""
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    if getattr(model, "stylizer", None) is not None:
+        st = model.stylizer
+        keep = (f32(st.dI), f32(st.dP).reshape(-1), f32(st.ddelta).reshape(-1))
+        e = PaletteEdit()
+        e.mode = 2
+        e.dI, e.dP, e.ddelta = ptr(keep[0]), ptr(keep[1]), ptr(keep[2])
+        return e, keep
+    ed = getattr(model, "edit", None)
+    if ed is None:
+        return None, ()
+    dh = f32(ed.delta_hsv).reshape(-1)
+    mx = None if ed.mean_xyz is None else f32(ed.mean_xyz).reshape(-1)
+    mc = None if ed.mean_clip is None else f32(ed.mean_clip).reshape(-1)
+    e = PaletteEdit()
+    e.mode, e.weight_mode = 1, int(bool(ed.weight_mode))
+    e.delta_hsv, e.mean_xyz, e.mean_clip = ptr(dh), ptr(mx), ptr(mc)
+    e.std_xyz, e.std_clip = float(ed.std_xyz), float(ed.std_clip)
+    return e, (dh, mx, mc)
+
+
 def accumulator_layout(N, nb, cd, gui_mode):
     """name -> (offset, shape) of the per-ray output maps inside ONE flat fp32 buffer, and its length in floats"""
     shapes = {"weights_sum": (N,), "depth": (N,), "image": (N, 3), "clip_feat": (N, cd)}
@@ -259,7 +290,13 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     N, dev = rays_o.shape[0], rays_o.device
     nb, cd = model.num_basis, model.opt.clip_dim
     kernel = kernel or RENDER_KERNEL
-    if kernel == "tc" and out is None and model.opt.pred_clip and "PNERF_RENDER_KERNEL" not in __import__("os").environ:
+    edit, edit_keep = edit_struct(model, dev)
+    if edit is not None:
+        kernel = "tc"                    # the edit epilogue exists in the tensor-core renderer only
+        if edit.mode == 2:
+            gui_mode = True              # the Stylizer produces no debug maps (palette/renderer.py:474-475, 496-506)
+    if kernel == "tc" and out is None and edit is None and model.opt.pred_clip and \
+            "PNERF_RENDER_KERNEL" not in __import__("os").environ:
         # the semantic branch gathers a third table; until that gather is interleaved with the other two the lane-per-ray
         # kernel renders such models faster (config 5: 17.8 vs 19.6 ms per 1297x840 view)
         kernel = "lanes"
@@ -287,7 +324,9 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         runs = torch.empty(N * int(L.lib.pnerf_palette_render_tc_runs_bytes()), dtype=torch.uint8, device=dev)
         L.call("pnerf_palette_render_tc", *common, ptr(cand), ptr(runs),
-               ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), ptr(out_index), stream())
+               ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), ptr(out_index),
+               None if edit is None else ctypes.addressof(edit), stream())
+        del edit_keep
     elif kernel == "rays":
         cand = torch.empty(N, dtype=torch.int32, device=dev)
         L.call("pnerf_palette_render_rays", *common, ptr(cand), ptr(_t_scratch(dev, max_steps)), ptr(occ), stream())

@@ -374,9 +374,13 @@ class PaletteRenderer(nn.Module, OccupancyState):
     # -- fused schedule (csrc/fused.cu): one persistent kernel instead of the host loop -------------------------
     def _fused_available(self, gui_mode):
         """default policy: use the fused renderer under fp16 autocast (its MLPs run fp16 tensor-core math) whenever
-        the architecture is the one it implements and no GUI edit module is active"""
+        the architecture is the one it implements. RegionEdit / Stylizer are evaluated inside the renderer's blend (csrc/
+        field_tc.cu); a Stylizer renders without the debug maps, so it takes the fused path in gui_mode only — exactly the
+        combination the reference supports (palette/renderer.py:474-475 leaves basis_rgb undefined otherwise)."""
         from .. import fused
-        return (torch.is_autocast_enabled() and self.edit is None and self.stylizer is None and fused.supported(self))
+        if self.stylizer is not None and not gui_mode:
+            return False
+        return torch.is_autocast_enabled() and fused.supported(self)
 
     def _fused_train_available(self):
         """fused training field: same policy as inference (the smooth-loss branch included, see _smooth_channels)"""
@@ -385,8 +389,8 @@ class PaletteRenderer(nn.Module, OccupancyState):
 
     def _infer_fused(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode):
         from .. import fused
-        if self.edit is not None or self.stylizer is not None or not fused.supported(self):
-            raise RuntimeError("fused render path does not cover this model configuration (edit/stylizer/architecture)")
+        if not fused.supported(self):
+            raise RuntimeError("fused render path does not cover this model architecture")
         return fused.render(self, rays_o.float(), rays_d.float(), nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode)
 
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, test_mode=False, gui_mode=False, **kwargs):

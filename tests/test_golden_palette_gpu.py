@@ -159,6 +159,8 @@ def test_run_cuda_with_region_edit_and_stylizer(gold, case, cuda):
     finally:
         m.edit, m.stylizer, m.density_scale = None, None, 1.0
     REPORT[f"edit/{name}/schedule_under_autocast"] = {"edit": sched_edit, "stylizer": sched_style}
+    # both GUI edits are evaluated INSIDE the persistent renderer, not on a fallback schedule
+    assert sched_edit == "fused" and sched_style == "fused"
     for k in EVAL_KEYS:
         # the reference's HSV kernels are compiled with -use_fast_math (palette/setup.py): 3e-4 on recoloured maps
         _check(loop[k], gold[f"edit_{name}_fp32_{k}"], 3e-4, f"edit/{name}/{k}/fp32loop_vs_ref32")
