@@ -231,6 +231,10 @@ typedef struct pnerf_palette_field {
     /* optional (may be NULL): the MLP weights as tcgen05 B operands — per layer fp16 [k-chunk][n][8] (K-major, no swizzle),
      * pnerf_palette_tc_weight_bytes() bytes, palettenerf_b200/fused.py::tc_pack_index. Needed by the *_tc entry points. */
     const void* wpack_tc;
+    /* 0: palette model (all of the above); 1: stage-1 NeRF model (ref: nerf/network.py:95-124) — one hash grid (table_sigma),
+     * sigma net + colour net only (the same weight image with the palette layers unused); the *_tc renderer then composites
+     * the colour net's output and writes image / depth / weights_sum only */
+    uint32_t model_kind;
 } pnerf_palette_field;
 
 /* xyzs, dirs [M,3] fp32 -> sigma [M], clip [M,clip_dim] (NULL unless pred_clip), omega [M,4], off_rad [M,13],
@@ -277,6 +281,20 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
                                         float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb,
                                         float* unscaled_basis_rgb, float* clip_feat, uint32_t* queue, int32_t* cand,
                                         float* t_scratch, const float* occ_aabb, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * density-grid refresh as kernels (ref: NeRFRenderer.update_extra_state, nerf/renderer.py:467-561) — csrc/density_tc.cu
+ * ---------------------------------------------------------------------------------------------- */
+PNERF_API int pnerf_density_tc(const float* xyzs, uint32_t M, const pnerf_palette_field* field, float* sigma, void* stream);
+PNERF_API int pnerf_density_occupied_list(const float* density_grid, uint32_t C, uint32_t H, int32_t* occ_list,
+                                          uint32_t* occ_count, void* stream);
+PNERF_API int pnerf_density_grid_sweep(float* tmp_grid, uint32_t C, uint32_t H, float bound, float density_scale,
+                                       uint32_t partial, uint32_t n_random, const int32_t* occ_list, const uint32_t* occ_count,
+                                       uint64_t seed, uint32_t rank, uint32_t world, const float* jitter,
+                                       const pnerf_palette_field* field, void* stream);
+PNERF_API uint32_t pnerf_density_finalize_partials(uint64_t n_cells);
+PNERF_API int pnerf_density_grid_finalize(float* density_grid, float* tmp_grid, uint32_t C, uint32_t H, float decay,
+                                          float density_thresh, float* partials, uint8_t* bitfield, float* stats, void* stream);
+
 /* GUI-time edit of the palette blend, evaluated per sample INSIDE the persistent renderer (ref: palette/renderer.py:121-147
  * RegionEdit.forward, :166-183 Stylizer.forward, consulted at :474-483). All pointers are DEVICE pointers (the renderer
  * stages them in shared memory; no host synchronisation), NULL = unset.

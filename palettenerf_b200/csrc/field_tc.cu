@@ -40,7 +40,7 @@ k_field_forward_tc(const float* __restrict__ xyzs, const float* __restrict__ dir
             dx = dirs[(size_t)s * 3]; dy = dirs[(size_t)s * 3 + 1]; dz = dirs[(size_t)s * 3 + 2];
         }
         FieldOut o;
-        eval_field_tc<CLIP>(f, *sm, g, x, y, z, dx, dy, dz, active, lane, o);
+        eval_field_tc<CLIP ? TC_PALETTE_CLIP : TC_PALETTE>(f, *sm, g, x, y, z, dx, dy, dz, active, lane, o);
         if (active) {
             sigma[s] = o.sigma;
 #pragma unroll
@@ -228,9 +228,12 @@ constexpr int kRedStride = 33;                      // floats per channel row of
 
 __host__ __device__ constexpr size_t tc_render_smem(bool clip) { return tc_smem_bytes(clip) + sizeof(EditShared) + 16; }
 
+// MODE: TC_PALETTE / TC_PALETTE_CLIP / TC_NERF (stage-1 model: colour = the colour net's output, no palette blend)
 // EDIT: 0 = plain palette blend, 1 = RegionEdit, 2 = Stylizer (csrc: pnerf_palette_edit)
-template <bool CLIP, bool AUX, int EDIT>
+template <int MODE, bool AUX, int EDIT>
 __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, pnerf_palette_field f) {
+    constexpr bool CLIP = MODE == TC_PALETTE_CLIP;
+    static_assert(MODE != TC_NERF || (!AUX && EDIT == 0), "the stage-1 model has no palette maps and no edits");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcShared* sm = reinterpret_cast<TcShared*>(smem_raw);
     unsigned char* wts = smem_raw + kTcSharedBytes;
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         const float dt = clampf(t * a.dt_gamma, dt_min, dt_max);
         const float t_end = t + dt;
         FieldOut o;
-        eval_field_tc<CLIP>(f, *sm, g, x, y, z, active ? dx : 0.f, active ? dy : 0.f, active ? dz : 1.f, active, lane, o);
+        eval_field_tc<MODE>(f, *sm, g, x, y, z, active ? dx : 0.f, active ? dy : 0.f, active ? dz : 1.f, active, lane, o);
         if (!has_ray) continue;                         // (warp-uniform) idle warp of a busy group
         tiles++;
 
@@ -352,9 +355,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         shaded += __popc(__ballot_sync(0xffffffffu, use));
         {
             float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
-            const float sp = softplusf_(o.off_rad[12]);
+            const float sp = MODE == TC_NERF ? 0.f : softplusf_(o.off_rad[12]);
             rgb[0] = rgb[1] = rgb[2] = 0.f;
-            if (EDIT == 2) {
+            if (MODE == TC_NERF) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) rgb[c] = o.view_dep[c];
+            } else if (EDIT == 2) {
                 // Stylizer.forward (ref: palette/renderer.py:166-183)
 #pragma unroll
                 for (int b = 0; b < kNB; b++) {
@@ -522,12 +528,15 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
     PNERF_REQUIRE(cand && runs && t_scratch);
-    PNERF_REQUIRE(field->table_sigma_palette && field->offsets && field->wpack_tc && field->head_bias && field->palette);
+    const bool nerf = field->model_kind == 1;
+    PNERF_REQUIRE((nerf ? field->table_sigma : field->table_sigma_palette) && field->offsets && field->wpack_tc &&
+                  field->head_bias && field->palette);
     PNERF_REQUIRE(C >= 1 && C <= 16 && Hgrid >= 1 && max_steps >= 1);
     if (field->L != 16 || field->clip_dim > (uint32_t)kClipMax || Hgrid > 1024) return PNERF_ERR_UNSUPPORTED;
     if (field->pred_clip && !field->table_clip) return PNERF_ERR_INVALID_ARG;
     const bool aux = direct_rgb != nullptr;
     if (aux) PNERF_REQUIRE(view_dep_rgb && basis_acc && basis_rgb && unscaled_basis_rgb);
+    if (nerf) PNERF_REQUIRE(!aux && !clip_feat && !field->pred_clip && (!edit || edit->mode == 0));
     RaysTcArgs a;
     a.rays_o = rays_o; a.rays_d = rays_d; a.nears = nears; a.fars = fars; a.noises = noises; a.bitfield = bitfield; a.occ = occ_aabb;
     a.N = N; a.C = C; a.Hgrid = Hgrid; a.max_steps = max_steps; a.dt_gamma = dt_gamma; a.T_thresh = T_thresh;
@@ -552,12 +561,12 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
 #define PNERF_LAUNCH_TC(CL, AX, ED)                                                                                      \
     do {                                                                                                                \
         if (!attr_done[CL][AX][ED]) {                                                                                   \
-            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<CL, AX, ED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int)tc_render_smem(CL));                                              \
+            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<(CL) ? TC_PALETTE_CLIP : TC_PALETTE, AX, ED>,              \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_render_smem(CL)); \
             if (e != cudaSuccess) { set_last_cuda_error(e, "render_tc attr"); return PNERF_ERR_CUDA; }                  \
             attr_done[CL][AX][ED] = true;                                                                               \
         }                                                                                                               \
-        k_render_rays_tc<CL, AX, ED><<<grid, kTcThreads, smem, s>>>(a, *field);                                         \
+        k_render_rays_tc<(CL) ? TC_PALETTE_CLIP : TC_PALETTE, AX, ED><<<grid, kTcThreads, smem, s>>>(a, *field);         \
     } while (0)
 #define PNERF_LAUNCH_TC_ED(CL, AX)                                                                                       \
     do {                                                                                                                \
@@ -567,7 +576,17 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
         if (!g_tc_ev[0]) { cudaEventCreate(&g_tc_ev[0]); cudaEventCreate(&g_tc_ev[1]); }
         cudaEventRecord(g_tc_ev[0], s);
     }
-    if (emode == 2) { if (clip_on) PNERF_LAUNCH_TC(true, false, 2); else PNERF_LAUNCH_TC(false, false, 2); }
+    if (nerf) {
+        static bool nerf_attr = false;
+        if (!nerf_attr) {
+            cudaError_t e = cudaFuncSetAttribute(k_render_rays_tc<TC_NERF, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)tc_render_smem(false));
+            if (e != cudaSuccess) { set_last_cuda_error(e, "render_tc attr"); return PNERF_ERR_CUDA; }
+            nerf_attr = true;
+        }
+        k_render_rays_tc<TC_NERF, false, 0><<<grid, kTcThreads, smem, s>>>(a, *field);
+    }
+    else if (emode == 2) { if (clip_on) PNERF_LAUNCH_TC(true, false, 2); else PNERF_LAUNCH_TC(false, false, 2); }
     else if (clip_on) { if (aux) PNERF_LAUNCH_TC_ED(true, true); else PNERF_LAUNCH_TC_ED(true, false); }
     else { if (aux) PNERF_LAUNCH_TC_ED(false, true); else PNERF_LAUNCH_TC_ED(false, false); }
 #undef PNERF_LAUNCH_TC_ED

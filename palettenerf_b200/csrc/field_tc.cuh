@@ -161,10 +161,19 @@ __device__ __forceinline__ void tc_epilogue_16(const TcGroup& g, float (&out)[16
 // ------------------------------------------------------------------------------------------------
 // the field for one 128-sample tile; called by all 128 threads of a group (thread = sample)
 // ------------------------------------------------------------------------------------------------
-template <bool CLIP>
+// MODE selects the sub-network (all share one weight-image layout; unused layers are simply never issued):
+//   TC_PALETTE / TC_PALETTE_CLIP  the palette field (PaletteNetwork.forward, palette/network.py:156-280)
+//   TC_NERF     stage-1 field (NeRFNetwork.forward, nerf/network.py:95-124): sigma net + colour net (SH ++ geo), ONE hash grid;
+//               the colour lands in o.view_dep
+//   TC_DENSITY  sigma net only (NeRFNetwork.density / PaletteNetwork.density, used by the density-grid refresh)
+enum TcMode { TC_PALETTE = 0, TC_PALETTE_CLIP = 1, TC_NERF = 2, TC_DENSITY = 3 };
+
+template <int MODE>
 __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, const TcShared& sm, TcGroup& g, float x, float y,
                                               float z, float dx, float dy, float dz, bool active, int lane, FieldOut& o) {
     static_assert(PNERF_COOP_LV == 4, "one gather batch = the 4 levels of one 16-byte k-chunk");
+    constexpr bool CLIP = MODE == TC_PALETTE_CLIP;
+    constexpr bool PAL = MODE == TC_PALETTE || MODE == TC_PALETTE_CLIP;
     const float u = (x + f.bound) / (2 * f.bound), v = (y + f.bound) / (2 * f.bound), w = (z + f.bound) / (2 * f.bound);
     const bool in_range = active && !((u < 0 || u > 1) || (v < 0 || v > 1) || (w < 0 || w > 1));
     unsigned char* const RS = g.smem + kTcRS;
@@ -174,11 +183,16 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
 
     // ---- gather: both grids (one interleaved table) -> F_sigma, F_palette; SH of the view direction ----
     // (4 levels = 8 halfs = one k-chunk: a lane pair finishes a chunk per batch -> ONE conflict-free 16-byte store)
-    {
+    if (PAL) {
         auto st = [RS, RP, row0](int e, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(e == 0 ? RS : RP, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
         gather_coop<2, 4>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
+    } else {
+        auto st = [RS, row0](int, int s, int l0, const uint32_t (&wd)[4]) {
+            *tc_row_ptr(RS, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        };
+        gather_coop<1, 4>(f.table_sigma, sm.lp, u, v, w, in_range, lane, st);
     }
     if (CLIP) {
         unsigned char* const RC = g.smem + kTcRC;
@@ -187,7 +201,7 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
         };
         gather_coop<1, 4>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
     }
-    {
+    if (MODE != TC_DENSITY) {
         float sh[16];
         sh_eval<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
 #pragma unroll
@@ -208,9 +222,11 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
     }
     tc_epilogue_hidden<ACT_RELU>(g);
     tc_layer<TS1>(g, kH4);
-    tc_epilogue_16(g, t16, kTcColG, true);
+    tc_epilogue_16(g, t16, kTcColG, MODE != TC_DENSITY);
     o.sigma = fast_exp(t16[0]);
+    if (MODE == TC_DENSITY) return;
 
+    if (PAL) {
     // ---- diffuse net 15 -> 64 -> 64 -> 3 (the weight column that would see the logit is zero) ----
     {
         constexpr TcSrc a[1] = {tc_tmem(kTcColG)};
@@ -231,6 +247,7 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
         for (int i = 2; i < 8; i++) h[i] = 0u;
         tc::tmem_st8(g.tmem + kTcColX, h);                 // third k-step of the basis net: [diffuse 3 | 0 ...]
     }
+    }
 
     // ---- view-dependent colour net (SH16 ++ geo15) -> 64 -> 64 -> 3 ----
     {
@@ -248,6 +265,8 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
 #pragma unroll
         for (int i = 0; i < 3; i++) o.view_dep[i] = sigmoidf_(__uint_as_float(r[i]));
     }
+
+    if (!PAL) return;
 
     // ---- basis net (palette grid 32 ++ diffuse 3) -> 64 (ELU) -> 15, then the offsets / radiance / omega heads ----
     {

@@ -29,7 +29,7 @@ class PaletteField(ctypes.Structure):
                 ("wpack", c_void_p), ("head_bias", c_void_p), ("palette", c_void_p),
                 ("L", c_uint32), ("H", c_uint32), ("pred_clip", c_uint32), ("clip_dim", c_uint32),
                 ("S", c_float), ("bound", c_float), ("density_scale", c_float), ("offsets_weight", c_float),
-                ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p), ("wpack_tc", c_void_p)]
+                ("view_dep_weight", c_float), ("table_sigma_palette", c_void_p), ("wpack_tc", c_void_p), ("model_kind", c_uint32)]
 
 
 class PaletteEdit(ctypes.Structure):

@@ -43,7 +43,7 @@ class OccupancyState:
             self.register_buffer("density_grid", torch.zeros(self.cascade, H3))
             self.register_buffer("density_bitfield", torch.zeros(self.cascade * H3 // 8, dtype=torch.uint8))
             self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
-            self.mean_density = 0
+            self.__dict__["_mean_density"], self.__dict__["_mean_density_dev"] = 0, None
             self.iter_density = 0
             self.mean_count = 0
             self.local_step = 0
@@ -101,11 +101,41 @@ class OccupancyState:
         torch.autograd.graph.increment_version(self.density_grid)     # written through a raw pointer
         print(f"[mark untrained grid] {int(n_marked.item())} from {self.grid_size ** 3 * self.cascade}")
 
+    @property
+    def mean_density(self):
+        """mean of clamp(density_grid, 0) after the last refresh. The kernel path keeps it on the device (the threshold of
+        packbits never visits the host); reading this attribute is what synchronises."""
+        dev_val = self.__dict__.get("_mean_density_dev")
+        if dev_val is not None:
+            return float(dev_val[0].item())
+        return self.__dict__.get("_mean_density", 0)
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self.__dict__["_mean_density"] = v
+        self.__dict__["_mean_density_dev"] = None
+
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128):
-        """EMA-max refresh of the density grid + packbits + mean sample count (ref: nerf/renderer.py:467-561)"""
+    def update_extra_state(self, decay=0.95, S=128, fused=None):
+        """EMA-max refresh of the density grid + packbits + mean sample count (ref: nerf/renderer.py:467-561).
+        fused (default: whenever the model is the architecture the tensor-core field covers): three kernels — cell selection
+        + jitter + density + scatter, EMA-max + partial sums, mean / threshold / packbits — see fused_nerf.update_density_grid;
+        the only host read left is the mean sample count (it sizes the next steps' sample buffers)."""
         if not self.cuda_ray:
             return
+        from .. import fused_nerf
+        use_fused = (fused_nerf.supported(self) and self.density_grid.is_cuda) if fused is None else bool(fused)
+        if use_fused:
+            stats = fused_nerf.update_density_grid(self, decay)
+            self.__dict__["_mean_density_dev"] = stats
+            self.iter_density += 1
+            self._last_update_schedule = "fused"
+            steps = min(16, self.local_step)
+            if steps > 0:
+                self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
+            self.local_step = 0
+            return
+        self._last_update_schedule = "torch"
         dev = self.density_bitfield.device
         H = self.grid_size
         fresh = -torch.ones_like(self.density_grid)
@@ -242,6 +272,13 @@ class NeRFRenderer(nn.Module, OccupancyState):
             return self.background(sph, rays_d)
         return 1 if bg_color is None else bg_color
 
+    def _fused_infer_available(self, fused=None):
+        """default policy like the palette model's: the fused renderer under fp16 autocast for the architecture it covers"""
+        from .. import fused_nerf
+        if fused is not None:
+            return bool(fused)
+        return torch.is_autocast_enabled() and fused_nerf.supported_color(self)
+
     def run_cuda(self, rays_o, rays_d, rays_gt=None, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
                  max_steps=1024, T_thresh=1e-4, **kwargs):
         """rays_o, rays_d: [B, N, 3] (B == 1) -> dict(image [B,N,3], depth [B,N], rgb_norm, weights_sum)"""
@@ -280,7 +317,17 @@ class NeRFRenderer(nn.Module, OccupancyState):
                 depth, image, _ = render_tail(depth, nears, fars, image, weights_sum, bg_color)
                 image, depth = image.view(*prefix, 3), depth.view(*prefix)
                 rgb_norm = err_map.mean(dim=-1).view(*prefix)
+        elif self._fused_infer_available(kwargs.get("fused")):
+            # ONE persistent kernel (warp-per-ray, field on tcgen05) instead of the host loop below
+            from .. import fused_nerf
+            acc = fused_nerf.render(self, rays_o.float(), rays_d.float(), nears, fars, perturb, dt_gamma, max_steps, T_thresh)
+            self._last_schedule, self._last_queue = "fused", acc["_queue"]
+            weights_sum = acc["weights_sum"]
+            depth, image, _ = render_tail(acc["depth"], nears, fars, acc["image"], weights_sum, bg_color)
+            image, depth = image.view(*prefix, 3), depth.view(*prefix)
+            rgb_norm = torch.zeros_like(image[..., 0])
         else:
+            self._last_schedule = "loop"
             weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
             depth = torch.zeros(N, dtype=torch.float32, device=dev)
             image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
