@@ -132,8 +132,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the train-step / hash-grid / cpu-baseline sections")
-    ap.add_argument("--sections", default="hashgrid,train,mip360,strong,cpu",
-                    help="extra sections to run (comma list of hashgrid,train,mip360,strong,cpu)")
+    ap.add_argument("--sections", default="hashgrid,train,mip360,strong,nerf,cpu",
+                    help="extra sections to run (comma list of hashgrid,train,mip360,strong,nerf,cpu)")
     ap.add_argument("--torch-loss", action="store_true", help="training sections: the loss as torch tensor expressions "
                     "instead of palette_loss (A/B)")
     ap.add_argument("--torch-adam", action="store_true", help="training sections: torch.optim.Adam(fused, capturable) "
@@ -306,6 +306,11 @@ def main():
             extras.update(bench_strong(torch, dev, rank, world, S, model, barrier, max_over_ranks, flush, args))
         except Exception as e:  # noqa: BLE001
             extras["render_strong"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    if "nerf" in sections and rank == 0:
+        try:
+            extras.update(bench_nerf(torch, dev, S, flush))
+        except Exception as e:  # noqa: BLE001
+            extras["nerf_stage"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if "mip360" in sections:
         try:
             extras.update(bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world))
@@ -524,6 +529,54 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "allreduce_max_abs_err": None if world == 1 else _allreduce_check(torch, dist, dev, rank, world),
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
+
+
+def bench_nerf(torch, dev, S, flush):
+    """stage-1 model (NeRFNetwork: one hash grid, sigma + colour nets): the 800x800 render on the persistent tensor-core
+    renderer vs this repository's host-loop schedule (the reference's run_cuda loop on the new per-op kernels), and the
+    density-grid refresh (update_extra_state, full sweep and partial) as kernels vs the torch-op schedule. Rank 0 only."""
+    import torch.distributed as dist
+    import palettenerf_b200.distributed as D
+    model = S.build_nerf_model(dev, seed=0)
+    model.eval()
+    o, d = S.camera_rays(VIEW, VIEW, azimuth_deg=35.0)
+    o, d = o.to(dev)[None], d.to(dev)[None]
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sum(ts) / len(ts)
+
+    def render(fused):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model.render(o, d, staged=True, bg_color=1, perturb=False, fused=fused, dt_gamma=0.0, max_steps=1024)
+    res = {"render_fused_ms": timeit(lambda: render(None)), "render_schedule": model._last_schedule,
+           "render_loop_ms": timeit(lambda: render(False), reps=2, warm=1), "rays": N_RAYS}
+    res["render_rays_per_s"] = N_RAYS / (res["render_fused_ms"] / 1e3)
+    real_world = D.world
+    D.world = lambda: (1, 0)          # the refresh below is timed on this rank alone (no tile sharding / all-reduce)
+    try:
+        for name, it0 in (("full", 0), ("partial", 16)):
+            def upd(fused):
+                model.iter_density = it0
+                with torch.autocast("cuda", dtype=torch.float16):
+                    model.update_extra_state(fused=fused)
+            res[f"density_update_{name}_fused_ms"] = timeit(lambda: upd(None), reps=3, warm=1)
+            res[f"density_update_{name}_schedule"] = model._last_update_schedule
+            res[f"density_update_{name}_torch_ms"] = timeit(lambda: upd(False), reps=2, warm=1)
+    finally:
+        D.world = real_world
+    res["note"] = ("render: csrc/field_tc.cu (model_kind 1) vs the host loop of nerf/renderer.py:329-386 on the per-op kernels; "
+                   "density update: csrc/density_tc.cu (3-4 launches, threshold on the device) vs the torch-op schedule of "
+                   "nerf/renderer.py:467-561 (the only host read left in the fused path is mean_count)")
+    return {"nerf_stage": res}
 
 
 def bench_strong(torch, dev, rank, world, S, model, barrier, max_over_ranks, flush, args):

@@ -285,8 +285,9 @@ PNERF_API int pnerf_palette_render_rays(const float* rays_o, const float* rays_d
  * density-grid refresh as kernels (ref: NeRFRenderer.update_extra_state, nerf/renderer.py:467-561) — csrc/density_tc.cu
  * ---------------------------------------------------------------------------------------------- */
 PNERF_API int pnerf_density_tc(const float* xyzs, uint32_t M, const pnerf_palette_field* field, float* sigma, void* stream);
+PNERF_API uint32_t pnerf_density_occupied_chunks(uint32_t H);
 PNERF_API int pnerf_density_occupied_list(const float* density_grid, uint32_t C, uint32_t H, int32_t* occ_list,
-                                          uint32_t* occ_count, void* stream);
+                                          uint32_t* occ_count, uint32_t* chunk_scratch, void* stream);
 PNERF_API int pnerf_density_grid_sweep(float* tmp_grid, uint32_t C, uint32_t H, float bound, float density_scale,
                                        uint32_t partial, uint32_t n_random, const int32_t* occ_list, const uint32_t* occ_count,
                                        uint64_t seed, uint32_t rank, uint32_t world, const float* jitter,

@@ -2,8 +2,8 @@
 //
 // The reference builds the cell coordinates with meshgrid / randint / nonzero / cat, evaluates density() in chunks, scatters
 // into a temporary grid, and reads two scalars back to the host. Here:
-//   pnerf_density_occupied_list   (partial refresh only) ascending list of the cells with density > 0 per cascade — one CTA per
-//                                 cascade, deterministic (== torch.nonzero order), count left on the device;
+//   pnerf_density_occupied_list   (partial refresh only) ascending list of the cells with density > 0 per cascade (count per
+//                                 chunk, scan, ordered write: == torch.nonzero order), the count stays on the device;
 //   pnerf_density_grid_sweep      ONE kernel: cell selection (full sweep, or N uniform + N occupied cells per cascade), jitter
 //                                 from a counter-based generator, hash-grid gather + sigma net on tcgen05 (eval_field_tc<
 //                                 TC_DENSITY>), atomicMax into the temporary grid (duplicates: the reference keeps "one of
@@ -121,34 +121,84 @@ __global__ void __launch_bounds__(kDenThreads, 1) k_density_tc(const float* __re
     tc_epilogue_cta<kDenGroups>(sm);
 }
 
-// one CTA per cascade: cells with density > 0 in ascending order (torch.nonzero order), count -> occ_count[cas]
-__global__ void __launch_bounds__(1024) k_density_occupied_list(const float* __restrict__ grid, uint32_t H3,
-                                                                int32_t* __restrict__ occ_list, uint32_t* __restrict__ occ_count) {
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    const uint32_t cas = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const float* gcas = grid + (size_t)cas * H3;
-    int32_t* out = occ_list + (size_t)cas * H3;
-    if (tid == 0) carry = 0;
+// Ascending list (torch.nonzero order) of the cells with density > 0 per cascade, in three small launches: per-chunk counts,
+// an exclusive scan of the chunk counts (one CTA per cascade), ordered write. A chunk = 1024 threads x 16 consecutive cells.
+constexpr uint32_t kOccPerThread = 16, kOccChunk = 1024 * kOccPerThread;
+
+__device__ __forceinline__ uint32_t occ_thread_mask(const float* __restrict__ gcas, uint32_t first, uint32_t H3) {
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kOccPerThread; k++) {
+        const uint32_t i = first + k;
+        if (i < H3 && gcas[i] > 0.f) m |= 1u << k;
+    }
+    return m;
+}
+
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_tot, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += up;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    for (uint32_t base = 0; base < H3; base += 1024) {
-        const uint32_t i = base + tid;
-        const bool occ = i < H3 && gcas[i] > 0.f;
-        const uint32_t mask = __ballot_sync(0xffffffffu, occ);
-        if (lane == 0) warp_tot[wid] = __popc(mask);
-        __syncthreads();
-        uint32_t before = carry;
-        for (uint32_t w = 0; w < wid; w++) before += warp_tot[w];
-        if (occ) out[before + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < 32; w++) t += warp_tot[w];
-            carry += t;
+    if (wid == 0) {
+        const uint32_t w = warp_tot[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += up;
         }
+        warp_tot[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    return warp_tot[wid] + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) k_occ_count(const float* __restrict__ grid, uint32_t H3, uint32_t* __restrict__ chunk_counts) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t total;
+    const uint32_t cas = blockIdx.y, first = blockIdx.x * kOccChunk + threadIdx.x * kOccPerThread;
+    const uint32_t c = __popc(occ_thread_mask(grid + (size_t)cas * H3, first, H3));
+    block_exclusive_scan(c, warp_tot, &total);
+    if (threadIdx.x == 0) chunk_counts[cas * gridDim.x + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_occ_scan(uint32_t* __restrict__ chunk_counts, uint32_t n_chunks, uint32_t* __restrict__ occ_count) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t total;
+    const uint32_t cas = blockIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_chunks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? chunk_counts[cas * n_chunks + i] : 0u;
+        const uint32_t ex = block_exclusive_scan(v, warp_tot, &total);
+        if (i < n_chunks) chunk_counts[cas * n_chunks + i] = carry + ex;        // counts -> offsets, in place
+        carry += total;
         __syncthreads();
     }
-    if (tid == 0) occ_count[cas] = carry;
+    if (threadIdx.x == 0) occ_count[cas] = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_occ_write(const float* __restrict__ grid, uint32_t H3, const uint32_t* __restrict__ chunk_offsets,
+                                                    int32_t* __restrict__ occ_list) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t total;
+    const uint32_t cas = blockIdx.y, first = blockIdx.x * kOccChunk + threadIdx.x * kOccPerThread;
+    uint32_t m = occ_thread_mask(grid + (size_t)cas * H3, first, H3);
+    uint32_t pos = chunk_offsets[cas * gridDim.x + blockIdx.x] + block_exclusive_scan(__popc(m), warp_tot, &total);
+    int32_t* out = occ_list + (size_t)cas * H3;
+    while (m) {
+        const uint32_t k = __ffs(m) - 1;
+        out[pos++] = (int32_t)(first + k);
+        m &= m - 1;
+    }
 }
 
 constexpr int kFinThreads = 256, kFinPerThread = 16;
@@ -246,11 +296,18 @@ int pnerf_density_tc(const float* xyzs, uint32_t M, const pnerf_palette_field* f
     return check_launch("density_tc");
 }
 
-/* ascending list of the cells with density_grid > 0 of every cascade: occ_list [C, H^3] int32, occ_count [C] u32 */
+uint32_t pnerf_density_occupied_chunks(uint32_t H) { return ceil_div(H * H * H, kOccChunk); }
+
+/* ascending list of the cells with density_grid > 0 of every cascade: occ_list [C, H^3] int32, occ_count [C] u32;
+ * chunk_scratch [C * pnerf_density_occupied_chunks(H)] u32 */
 int pnerf_density_occupied_list(const float* density_grid, uint32_t C, uint32_t H, int32_t* occ_list, uint32_t* occ_count,
-                                void* stream) {
-    PNERF_REQUIRE(density_grid && occ_list && occ_count && C >= 1 && C <= 16 && H >= 2 && H <= 1024);
-    k_density_occupied_list<<<C, 1024, 0, (cudaStream_t)stream>>>(density_grid, H * H * H, occ_list, occ_count);
+                                uint32_t* chunk_scratch, void* stream) {
+    PNERF_REQUIRE(density_grid && occ_list && occ_count && chunk_scratch && C >= 1 && C <= 16 && H >= 2 && H <= 1024);
+    const uint32_t H3 = H * H * H, nb = pnerf_density_occupied_chunks(H);
+    cudaStream_t s = (cudaStream_t)stream;
+    k_occ_count<<<dim3(nb, C), 1024, 0, s>>>(density_grid, H3, chunk_scratch);
+    k_occ_scan<<<C, 1024, 0, s>>>(chunk_scratch, nb, occ_count);
+    k_occ_write<<<dim3(nb, C), 1024, 0, s>>>(density_grid, H3, chunk_scratch, occ_list);
     return check_launch("density_occupied_list");
 }
 

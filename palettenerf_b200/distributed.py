@@ -254,7 +254,10 @@ def merge_density(fresh, group=None):
 def shared_seed(seed_tensor=None, group=None):
     """broadcast rank 0's RNG seed so the stochastic cell selection of the density refresh matches on all ranks"""
     ws, rank = world()
-    t = torch.zeros(1, dtype=torch.int64) if seed_tensor is None else seed_tensor
+    dev = "cpu"
+    if ws > 1 and dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())      # NCCL moves device tensors only
+    t = torch.zeros(1, dtype=torch.int64, device=dev) if seed_tensor is None else seed_tensor
     if rank == 0 and seed_tensor is None:
         t[0] = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
     if ws > 1:

@@ -23,7 +23,10 @@ from ._lib import ptr, stream
 
 P, U, F = c_void_p, c_uint32, c_float
 L.register("pnerf_density_tc", [P, U, P, P, P])
-L.register("pnerf_density_occupied_list", [P, U, U, P, P, P])
+L.register("pnerf_density_occupied_list", [P, U, U, P, P, P, P])
+L.LAUNCHES["pnerf_density_occupied_list"] = 3
+L.lib.pnerf_density_occupied_chunks.argtypes = [U]
+L.lib.pnerf_density_occupied_chunks.restype = c_uint32
 L.register("pnerf_density_grid_sweep", [P, U, U, F, F, U, U, P, P, c_uint64, U, U, P, P, P])
 L.register("pnerf_density_grid_finalize", [P, P, U, U, F, F, P, P, P, P])
 L.LAUNCHES["pnerf_density_grid_finalize"] = 2
@@ -186,7 +189,9 @@ def update_density_grid(model, decay=0.95, jitter=None, seed=None):
     if partial:
         if st["occ_list"] is None:
             st["occ_list"] = torch.empty(C, H3, dtype=torch.int32, device=dev)
-        L.call("pnerf_density_occupied_list", ptr(model.density_grid), C, H, ptr(st["occ_list"]), ptr(st["occ_count"]), stream())
+            st["occ_chunks"] = torch.empty(C * int(L.lib.pnerf_density_occupied_chunks(H)), dtype=torch.int32, device=dev)
+        L.call("pnerf_density_occupied_list", ptr(model.density_grid), C, H, ptr(st["occ_list"]), ptr(st["occ_count"]),
+               ptr(st["occ_chunks"]), stream())
     L.call("pnerf_density_grid_sweep", ptr(st["tmp"]), C, H, float(model.bound), float(model.density_scale), int(partial), n_random,
            ptr(st["occ_list"]), ptr(st["occ_count"]), int(seed), rank, ws, ptr(jitter), ctypes.addressof(f), stream())
     if ws > 1:
