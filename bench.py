@@ -320,14 +320,16 @@ def main():
     if "hashgrid" in extras:
         hg = extras["hashgrid"]
         roofline["hashgrid_microbench"] = {
-            "bound": "hbm", "kernel": "k_grid_fwd_d3c2<half>", "achieved": hg["fwd_f16_eff_gbs"], "peak": hbm_peak, "unit": "GB/s",
-            "frac": hg["fwd_f16_eff_gbs"] / hbm_peak, "hbm_only_gbs": hg["fwd_f16_hbm_gbs"],
-            "traffic": _ncu_traffic("k_grid_fwd_d3c2_f16"),
-            "algorithmic": "588 B/point (12 xyz + 16 levels x 8 corners x 4 B gathered + 64 out) x 2^22 points; the table is "
-                           "L2-resident, compulsory HBM bytes are 76 B/point (hbm_only_gbs)",
-            "ncu": _ncu_entry("k_grid_fwd_d3c2_f16"),
-            "note": "random points: every gather instruction touches 32 different sectors, the kernel sits on the L1/TEX "
-                    "pipe (ncu l1tex throughput, see the ncu entry) with L2 close behind, not on HBM"}
+            "bound": "hbm", "kernel": "k_grid_fwd_coop_h (fp16, 2^22 points)", "achieved": hg["fwd_f16_hbm_gbs"], "peak": hbm_peak,
+            "unit": "GB/s", "frac": hg["fwd_f16_hbm_gbs"] / hbm_peak,
+            "traffic": _ncu_traffic("k_grid_fwd_coop_h"),
+            "algorithmic": "compulsory HBM bytes: 76 B/point (12 B coordinates + 64 B fp16 output) x 2^22 points; the 24 MiB table is "
+                           "L2-resident and read once",
+            "l2_gather": {"achieved_gbs": hg["fwd_f16_gather_gbs"], "peak_gbs": hg["l2_read_peak_gbs_measured"],
+                          "frac": hg["fwd_f16_gather_gbs"] / hg["l2_read_peak_gbs_measured"],
+                          "algorithmic": "512 B gathered per point (16 levels x 8 corners x 4 B) vs a measured L2 read peak"},
+            "ncu": _ncu_entry("k_grid_fwd_coop_h"),
+            "note": _ncu_note("k_grid_fwd_coop_h")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and "cpu" in sections:
@@ -377,44 +379,84 @@ def _ncu_traffic(kernel):
     return None
 
 
+def _measure_l2_read_peak(torch, dev):
+    """bandwidth of L2-resident buffers (the better of a 48 MiB reduction and a 24 -> 24 MiB copy, 20 back-to-back launches):
+    the denominator for the gather traffic of the hash grid, whose table lives in L2"""
+    best = 0.0
+    x = torch.ones(12 << 20, dtype=torch.float32, device=dev)
+    y = torch.empty(6 << 20, dtype=torch.float32, device=dev)
+    for fn, nbytes in ((lambda: x.sum(), x.numel() * 4), (lambda: y.copy_(x[:6 << 20]), 2 * y.numel() * 4)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = max(best, 20 * nbytes / (a.elapsed_time(b) / 1e3) / 1e9)
+    return best
+
+
 def bench_hashgrid(torch, dev, L, hbm_peak, flush):
-    """BASELINE config 2: 2^22 points, 16 levels, F=2, log2T=19, fwd + bwd, fp16 and fp32 tables"""
+    """BASELINE config 2 as SURVEY 8d specifies it: 2^22 points U[0,1)^3, 16 levels, F=2, log2T=19, fwd + bwd, fp16 and fp32
+    tables, per_level_scale 1.447269 (desired resolution 4096) and 1.381913 (2048), cold (L2 flushed before every launch)
+    and warm (back to back). Two units, never mixed: compulsory HBM bytes per point (12 B coordinates + 32*s B output; the table is
+    L2-resident) against the measured HBM copy peak, and gathered bytes per point (16 levels x 8 corners x F*s B) against a
+    measured L2 read peak."""
     from palettenerf_b200.gridencoder import GridEncoder
     from palettenerf_b200.gridencoder.backend import _backend as GB
     import numpy as np
     res = {}
-    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, desired_resolution=4096).to(dev)
+    l2_peak = _measure_l2_read_peak(torch, dev)
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.rand(GRID_POINTS, 3, device=dev, generator=g)
-    S_ = float(np.log2(enc.per_level_scale))
-    for name, dt in (("f16", torch.float16), ("f32", torch.float32)):
-        emb = enc.embeddings.detach().to(dt)
-        out = torch.empty(GRID_POINTS, 32, device=dev, dtype=dt)
-        grad = torch.randn(GRID_POINTS, 32, device=dev, generator=g).to(dt)
-        gemb = torch.zeros_like(emb)
+    for res_name, desired in (("", 4096), ("_res2048", 2048)):
+        enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, desired_resolution=desired).to(dev)
+        S_ = float(np.log2(enc.per_level_scale))
+        for name, dt in (("f16", torch.float16), ("f32", torch.float32)):
+            if res_name and name == "f32":
+                continue
+            emb = enc.embeddings.detach().to(dt)
+            out = torch.empty(GRID_POINTS, 32, device=dev, dtype=dt)
+            grad = torch.randn(GRID_POINTS, 32, device=dev, generator=g).to(dt)
+            gemb = torch.zeros_like(emb)
 
-        def fwd():
-            GB.grid_encode_forward_blc(x, emb, enc.offsets, out, GRID_POINTS, 3, 2, 16, S_, 16, None, 0, False)
+            def fwd():
+                GB.grid_encode_forward_blc(x, emb, enc.offsets, out, GRID_POINTS, 3, 2, 16, S_, 16, None, 0, False)
 
-        def bwd():
-            GB.grid_encode_backward_blc(grad, x, emb, enc.offsets, gemb, GRID_POINTS, 3, 2, 16, S_, 16, None, None, 0, False)
-        for fn, tag in ((fwd, "fwd"), (bwd, "bwd")):
-            for _ in range(3):
-                fn()
-            ts = []
-            for _ in range(10):
-                flush.fill_(1)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            ms = sum(ts) / len(ts)
-            s = 2 if name == "f16" else 4
-            res[f"{tag}_{name}_ms"] = ms
-            res[f"{tag}_{name}_eff_gbs"] = GRID_BYTES_PER_POINT[name] * GRID_POINTS / (ms / 1e3) / 1e9
-            res[f"{tag}_{name}_hbm_gbs"] = (12 + 32 * s) * GRID_POINTS / (ms / 1e3) / 1e9
+            def bwd():
+                GB.grid_encode_backward_blc(grad, x, emb, enc.offsets, gemb, GRID_POINTS, 3, 2, 16, S_, 16, None, None, 0, False)
+            for fn, tag in ((fwd, "fwd"), (bwd, "bwd")):
+                if res_name and tag == "bwd":
+                    continue
+                for _ in range(5):
+                    fn()
+                for temp in ("cold", "warm"):
+                    ts = []
+                    for _ in range(20):
+                        if temp == "cold":
+                            flush.fill_(1)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(); fn(); b.record()
+                        torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                    ms = sum(ts) / len(ts)
+                    s = 2 if name == "f16" else 4
+                    key = f"{tag}_{name}{res_name}" + ("" if temp == "cold" else "_warm")
+                    res[f"{key}_ms"] = ms
+                    res[f"{key}_hbm_gbs"] = (12 + 32 * s) * GRID_POINTS / (ms / 1e3) / 1e9
+                    res[f"{key}_gather_gbs"] = 16 * 8 * 2 * s * GRID_POINTS / (ms / 1e3) / 1e9
+                    if temp == "cold":     # (kept for continuity with round 1: algorithmic 588 / 1164 B per point)
+                        res[f"{key}_eff_gbs"] = GRID_BYTES_PER_POINT[name] * GRID_POINTS / (ms / 1e3) / 1e9
     res["points"] = GRID_POINTS
-    res["note"] = "eff = 588 (fp16) / 1164 (fp32) algorithmic B per point; hbm = compulsory 12 + 32*s B per point; L2 flushed"
+    res["l2_read_peak_gbs_measured"] = l2_peak
+    res["fwd_f16_frac_of_hbm_peak"] = res["fwd_f16_hbm_gbs"] / hbm_peak
+    res["fwd_f16_gather_frac_of_l2_peak"] = res["fwd_f16_gather_gbs"] / l2_peak
+    res["note"] = ("hbm_gbs = compulsory 12 + 32*s B per point vs the measured HBM copy peak; gather_gbs = 16 levels x 8 corners x F*s B "
+                   "per point vs l2_read_peak_gbs_measured (48 MiB buffer re-read by a reduction kernel); cold = L2 flushed before every "
+                   "launch (256 MB write), warm = back to back; _res2048 = per_level_scale 1.381913")
     return {"hashgrid": res}
 
 

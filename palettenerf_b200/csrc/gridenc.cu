@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "grid_common.cuh"
+#include "fused_common.cuh"   // gather_coop: lane-pair cooperative gather with FHFMA interpolation
 
 namespace pnerf {
 
@@ -458,10 +459,87 @@ __global__ void __launch_bounds__(256) k_grid_input_bwd(const T* __restrict__ gr
 // ------------------------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// fast forward for the configuration every PaletteNeRF grid uses: fp16 table, D = 3, C = 2, L = 16, hash grid, not
+// align_corners, [B, L*C] output. A warp owns 32 points; the gather is the lane-pair cooperative one of the fused kernels
+// (gather_coop: the two x-neighbour corners of a cell are adjacent table entries, so the pair of lanes that fetch them share
+// a 128-byte line — a load instruction touches ~16 lines instead of 32, which is what bounds this kernel: round 1's
+// thread-per-point version ran at 86.6 % of the L1/TEX pipe) with exact fp16 x fp16 products accumulated in fp32 (FHFMA).
+// Rows are staged in shared memory and leave as one contiguous 2 KB burst per warp.
+// Levels that cannot wrap with a mask (a hashed level whose size is not a power of two) take the per-thread path below.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoopWarps = 8;
+__global__ void __launch_bounds__(kCoopWarps * 32) k_grid_fwd_coop_h(const float* __restrict__ inputs, const __half* __restrict__ grid,
+                                                                     const int32_t* __restrict__ offsets, __half* __restrict__ outputs,
+                                                                     uint32_t B, float S, uint32_t H, bool layout_blc) {
+    __shared__ LevelParams lp[16];
+    __shared__ __align__(16) uint32_t stage[kCoopWarps][32][16 + 4];      // +4 words: rows start in different bank groups
+    __shared__ int slow_s;
+    if (threadIdx.x < 16) make_level(lp[threadIdx.x], threadIdx.x, offsets, S, H, 3, 0, false);
+    const int slow = __syncthreads_or(threadIdx.x < 16 && lp[threadIdx.x].mask == 0u);
+    if (threadIdx.x == 0) slow_s = slow;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t n_tiles = ceil_div(B, 32u);
+    for (uint32_t tile = blockIdx.x * kCoopWarps + wid; tile < n_tiles; tile += gridDim.x * kCoopWarps) {
+        const uint32_t b = tile * 32 + lane;
+        const bool active = b < B;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (active) { x = inputs[(size_t)b * 3]; y = inputs[(size_t)b * 3 + 1]; z = inputs[(size_t)b * 3 + 2]; }
+        const bool in_range = active && !((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1));
+        uint32_t (*rows)[20] = stage[wid];
+        if (!slow) {
+            auto st = [rows](int, int s, int l0, const uint32_t (&wd)[4]) {
+                *reinterpret_cast<uint4*>(&rows[s][l0]) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            };
+            gather_coop<1, 4>(grid, lp, x, y, z, in_range, lane, st);
+        } else {
+            for (int l = 0; l < 16; l++) {
+                float2 acc = make_float2(0.f, 0.f);
+                if (in_range) {
+                    uint32_t idx[8];
+                    float w[8];
+                    corner_setup(lp[l], x, y, z, idx, w, false);
+                    const __half2* g = reinterpret_cast<const __half2*>(grid) + lp[l].offset;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float2 v = __half22float2(__ldg(g + idx[c]));
+                        acc.x += w[c] * v.x; acc.y += w[c] * v.y;
+                    }
+                }
+                rows[lane][l] = pack_h2(acc.x, acc.y);
+            }
+        }
+        __syncwarp();
+        if (layout_blc) {
+            // 32 rows x 64 B = 128 uint4, contiguous in the output: lane i writes uint4 i, i + 32, i + 64, i + 96
+            uint4* out = reinterpret_cast<uint4*>(outputs + (size_t)tile * 32 * 32);
+            const uint32_t rows_here = min(32u, B - tile * 32);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int q = lane + 32 * k, r = q >> 2, c4 = q & 3;
+                if ((uint32_t)r < rows_here) out[q] = *reinterpret_cast<const uint4*>(&rows[r][c4 * 4]);
+            }
+        } else if (active) {
+            // the reference's [L, B, C] layout: per level the warp writes 32 consecutive feature pairs (128 B)
+            uint32_t* out = reinterpret_cast<uint32_t*>(outputs);
+#pragma unroll
+            for (int l = 0; l < 16; l++) out[(size_t)l * B + b] = rows[lane][l];
+        }
+        __syncwarp();
+    }
+}
+
 template <typename T>
 int grid_forward_t(const float* inputs, const T* emb, const int32_t* offsets, T* outputs, uint32_t B, uint32_t D,
                    uint32_t C, uint32_t L, float S, uint32_t H, T* dy_dx, uint32_t gridtype, bool align, bool blc,
                    cudaStream_t s) {
+    if constexpr (std::is_same<T, __half>::value) {
+        if (D == 3 && C == 2 && L == 16 && dy_dx == nullptr && gridtype == 0 && !align) {
+            const uint32_t grid = min(ceil_div(ceil_div(B, 32u), (uint32_t)kCoopWarps), 8u * (uint32_t)kNumSMs);
+            k_grid_fwd_coop_h<<<grid, kCoopWarps * 32, 0, s>>>(inputs, emb, offsets, outputs, B, S, H, blc);
+            return check_launch("grid_encode_forward");
+        }
+    }
     if (D == 3 && C == 2 && dy_dx == nullptr && sizeof(T) <= 4) {
         if constexpr (!std::is_same<T, double>::value) {
             k_grid_fwd_d3c2<T, 4><<<ceil_div(B, 256u), 256, 0, s>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype,
