@@ -438,6 +438,14 @@ PNERF_API int pnerf_grid_encode_backward_ws(const void* grad, const float* input
 PNERF_API int pnerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                              const int64_t* inds, uint64_t inds_batch_stride, uint32_t N, uint32_t B, float* rays_o,
                              float* rays_d, const float* aabb, float min_near, float* nears, float* fars, void* stream);
+/* pnerf_get_rays + the training-pixel gathers of the data loader's collate (ref: palette/provider.py:377-399) in ONE launch:
+ * images [B, H*W, c_img] fp32 -> out_images [B, N, c_img], feat_images [B, H*W, c_feat] -> out_feat [B, N, c_feat], both at
+ * the pixel indices the rays are generated for; either pair may be NULL. */
+PNERF_API int pnerf_get_rays_collate(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                                     const int64_t* inds, uint64_t inds_batch_stride, uint32_t N, uint32_t B, float* rays_o,
+                                     float* rays_d, const float* aabb, float min_near, float* nears, float* fars,
+                                     const float* images, uint32_t c_img, float* out_images, const float* feat_images,
+                                     uint32_t c_feat, float* out_feat, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * per-ray losses of the palette training step  (ref: PaletteTrainer.train_step, palette/utils.py:486-567)

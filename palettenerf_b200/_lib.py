@@ -52,6 +52,7 @@ _SIGS = {
     "pnerf_grid_encode_backward": [P, P, P, P, P, U, U, U, U, F, U, P, P, U, I, I, I, P],
     "pnerf_grid_encode_backward_ws": [P, P, P, P, P, c_uint64, U, U, F, U, U, I, I, P],
     "pnerf_get_rays": [P, F, F, F, F, U, U, P, c_uint64, U, U, P, P, P, F, P, P, P],
+    "pnerf_get_rays_collate": [P, F, F, F, F, U, U, P, c_uint64, U, U, P, P, P, F, P, P, P, U, P, P, U, P, P],
     "pnerf_peer_allreduce": [P, U, U, c_uint64, F, P],
     "pnerf_peer_allreduce_mc": [c_uint64, U, U, c_uint64, F, P],
     "pnerf_render_tail_forward": [U, P, P, P, P, P, P, U, P, U, P, P, P, P],

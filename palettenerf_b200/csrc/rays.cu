@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(kRayBlock) k_get_rays(const float* __restrict_
                                                         uint64_t inds_batch_stride, uint32_t N, uint32_t B,
                                                         float* __restrict__ rays_o, float* __restrict__ rays_d,
                                                         const float* __restrict__ aabb, float min_near,
-                                                        float* __restrict__ nears, float* __restrict__ fars) {
+                                                        float* __restrict__ nears, float* __restrict__ fars,
+                                                        const float* __restrict__ img0, uint32_t c0, float* __restrict__ out0,
+                                                        const float* __restrict__ img1, uint32_t c1, float* __restrict__ out1) {
     __shared__ __align__(16) float so[kRayBlock * 3];
     __shared__ __align__(16) float sd[kRayBlock * 3];
     const uint32_t b = blockIdx.y;
@@ -54,6 +56,18 @@ __global__ void __launch_bounds__(kRayBlock) k_get_rays(const float* __restrict_
             slab_near_far(ox, oy, oz, d[0], d[1], d[2], aabb, min_near, near, far);
             nears[(size_t)b * N + n] = near;
             fars[(size_t)b * N + n] = far;
+        }
+        // training-pixel gather of the data loader's collate (ref: palette/provider.py:387-399: torch.gather of the ground-truth
+        // image and of the semantic feature image at the sampled pixels), on the pixel index already in registers
+        if (img0) {
+            const float* src = img0 + ((size_t)b * H * W + pix) * c0;
+            float* dst = out0 + ((size_t)b * N + n) * c0;
+            for (uint32_t k = 0; k < c0; k++) dst[k] = __ldg(src + k);
+        }
+        if (img1) {
+            const float* src = img1 + ((size_t)b * H * W + pix) * c1;
+            float* dst = out1 + ((size_t)b * N + n) * c1;
+            for (uint32_t k = 0; k < c1; k++) dst[k] = __ldg(src + k);
         }
     }
     __syncthreads();
@@ -90,8 +104,31 @@ int pnerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, u
     if (B > 65535u) return PNERF_ERR_UNSUPPORTED;
     const dim3 grid(ceil_div(N, (uint32_t)kRayBlock), B, 1);
     k_get_rays<<<grid, kRayBlock, 0, (cudaStream_t)stream>>>(poses, fx, fy, cx, cy, H, W, inds, inds_batch_stride, N, B, rays_o,
-                                                            rays_d, aabb, min_near, nears, fars);
+                                                            rays_d, aabb, min_near, nears, fars, nullptr, 0, nullptr, nullptr, 0,
+                                                            nullptr);
     return check_launch("get_rays");
+}
+
+/* pnerf_get_rays + the pixel gathers of the training data loader's collate in the same launch: images [B, H*W, c_img] ->
+ * out_images [B, N, c_img] and feat_images [B, H*W, c_feat] -> out_feat [B, N, c_feat] at the same pixel indices (either pair
+ * may be NULL). Replaces get_rays + the two torch.gather calls of palette/provider.py:377-399. */
+int pnerf_get_rays_collate(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const int64_t* inds,
+                           uint64_t inds_batch_stride, uint32_t N, uint32_t B, float* rays_o, float* rays_d, const float* aabb,
+                           float min_near, float* nears, float* fars, const float* images, uint32_t c_img, float* out_images,
+                           const float* feat_images, uint32_t c_feat, float* out_feat, void* stream) {
+    if (N == 0 || B == 0) return PNERF_OK;
+    PNERF_REQUIRE(poses && rays_o && rays_d && H >= 1 && W >= 1);
+    PNERF_REQUIRE(inds || (uint64_t)N == (uint64_t)H * W);
+    PNERF_REQUIRE((nears == nullptr) == (fars == nullptr));
+    PNERF_REQUIRE(nears == nullptr || aabb != nullptr);
+    PNERF_REQUIRE((images == nullptr) == (out_images == nullptr) && (feat_images == nullptr) == (out_feat == nullptr));
+    PNERF_REQUIRE((!images || c_img >= 1) && (!feat_images || c_feat >= 1));
+    if (B > 65535u) return PNERF_ERR_UNSUPPORTED;
+    const dim3 grid(ceil_div(N, (uint32_t)kRayBlock), B, 1);
+    k_get_rays<<<grid, kRayBlock, 0, (cudaStream_t)stream>>>(poses, fx, fy, cx, cy, H, W, inds, inds_batch_stride, N, B, rays_o,
+                                                            rays_d, aabb, min_near, nears, fars, images, c_img, out_images,
+                                                            feat_images, c_feat, out_feat);
+    return check_launch("get_rays_collate");
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ import torch
 from .. import _lib as L
 from .._lib import call, ptr, require_cuda, stream
 
-__all__ = ["get_rays", "custom_meshgrid"]
+__all__ = ["get_rays", "collate", "custom_meshgrid"]
 
 
 def custom_meshgrid(*args):
@@ -80,10 +80,11 @@ def _draw_indices(B, H, W, N, error_map, patch_size, random_size, device):
 
 
 @torch.no_grad()
-def rays_from_indices(poses, intrinsics, H, W, inds=None, aabb=None, min_near=0.2):
+def rays_from_indices(poses, intrinsics, H, W, inds=None, aabb=None, min_near=0.2, images=None, feat_images=None):
     """the kernel call: poses [B,4,4], inds int64 [B,N] (any batch stride, e.g. an expanded [N]) or None = all pixels.
-    Returns rays_o, rays_d [B,N,3] (+ nears, fars [B,N] when aabb is given)."""
-    require_cuda(poses, inds, aabb)
+    Returns rays_o, rays_d [B,N,3], nears, fars [B,N] (None without aabb) and — when `images` [B,H,W,C] / `feat_images`
+    [B,H,W,Cf] are given — their rows at the same pixels ([B,N,C] / [B,N,Cf]), gathered by the same launch."""
+    require_cuda(poses, inds, aabb, images, feat_images)
     poses = poses.detach().to(torch.float32).contiguous()
     B = poses.shape[0]
     fx, fy, cx, cy = (float(v) for v in intrinsics)
@@ -105,13 +106,31 @@ def rays_from_indices(poses, intrinsics, H, W, inds=None, aabb=None, min_near=0.
         aabb = aabb.detach().to(torch.float32).contiguous()
         nears = torch.empty(B, N, dtype=torch.float32, device=dev)
         fars = torch.empty(B, N, dtype=torch.float32, device=dev)
-    call("pnerf_get_rays", ptr(poses), fx, fy, cx, cy, H, W, ptr(inds), bstride, N, B, ptr(rays_o), ptr(rays_d), ptr(aabb),
-         float(min_near), ptr(nears), ptr(fars), stream())
-    return rays_o, rays_d, nears, fars
+    if images is None and feat_images is None:
+        call("pnerf_get_rays", ptr(poses), fx, fy, cx, cy, H, W, ptr(inds), bstride, N, B, ptr(rays_o), ptr(rays_d), ptr(aabb),
+             float(min_near), ptr(nears), ptr(fars), stream())
+        return rays_o, rays_d, nears, fars
+
+    def prep(t):
+        if t is None:
+            return None, 0, None
+        if t.shape[0] != B or t.shape[1] * t.shape[2] != H * W:
+            raise RuntimeError("collate: images must be [B, H, W, C] of the view the rays are generated for")
+        t = t.detach().to(torch.float32).contiguous()
+        return t, t.shape[-1], torch.empty(B, N, t.shape[-1], dtype=torch.float32, device=dev)
+    img, c_img, out_img = prep(images)
+    feat, c_feat, out_feat = prep(feat_images)
+    call("pnerf_get_rays_collate", ptr(poses), fx, fy, cx, cy, H, W, ptr(inds), bstride, N, B, ptr(rays_o), ptr(rays_d), ptr(aabb),
+         float(min_near), ptr(nears), ptr(fars), ptr(img), c_img, ptr(out_img), ptr(feat), c_feat, ptr(out_feat), stream())
+    return rays_o, rays_d, nears, fars, out_img, out_feat
 
 
-def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, random_size=0, aabb=None, min_near=0.2):
-    """ref nerf/utils.py:52-151 (same arguments, same result dict)"""
+def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, random_size=0, aabb=None, min_near=0.2,
+             images=None, feat_images=None):
+    """ref nerf/utils.py:52-151 (same arguments, same result dict).
+    images / feat_images ([B,H,W,C] ground-truth colours / semantic features, not in the reference's signature): the result
+    also carries `images` / `feat_images` [B,N,C] gathered at the sampled pixels by the same launch — the two torch.gather
+    calls of the data loader's collate (palette/provider.py:387-399)."""
     device = poses.device
     B = poses.shape[0]
     results = {}
@@ -120,12 +139,31 @@ def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, random
         inds, extra = _draw_indices(B, H, W, N, error_map, patch_size, random_size, device)
         results.update(extra)
         results["inds"] = inds
-        rays_o, rays_d, nears, fars = rays_from_indices(poses, intrinsics, H, W, inds, aabb, min_near)
     else:
+        inds = None
         results["inds"] = torch.arange(H * W, device=device).expand([B, H * W])
-        rays_o, rays_d, nears, fars = rays_from_indices(poses, intrinsics, H, W, None, aabb, min_near)
-    results["rays_o"] = rays_o
-    results["rays_d"] = rays_d
-    if nears is not None:
-        results["nears"], results["fars"] = nears, fars
+    out = rays_from_indices(poses, intrinsics, H, W, inds, aabb, min_near, images, feat_images)
+    results["rays_o"], results["rays_d"] = out[0], out[1]
+    if out[2] is not None:
+        results["nears"], results["fars"] = out[2], out[3]
+    if images is not None:
+        results["images"] = out[4]
+    if feat_images is not None:
+        results["feat_images"] = out[5]
     return results
+
+
+def collate(poses, intrinsics, H, W, num_rays, images=None, feat_images=None, error_map=None, patch_size=1, random_size=0,
+            training=True):
+    """the ray / pixel part of NeRFDataset.collate (ref: palette/provider.py:377-403) for one batch of poses already on the
+    device: result keys H, W, rays_o, rays_d, inds [, images, feat_images, inds_coarse]. In training the ground-truth pixels
+    are gathered with the rays (one launch); in evaluation (num_rays = -1) the full images are passed through."""
+    rays = get_rays(poses, intrinsics, H, W, num_rays, error_map, patch_size, random_size,
+                    images=images if training else None, feat_images=feat_images if training else None)
+    res = {"H": H, "W": W, "rays_o": rays["rays_o"], "rays_d": rays["rays_d"], "inds": rays["inds"]}
+    for k, full in (("images", images), ("feat_images", feat_images)):
+        if full is not None:
+            res[k] = rays[k] if training else full
+    if "inds_coarse" in rays:
+        res["inds_coarse"] = rays["inds_coarse"]
+    return res

@@ -123,3 +123,30 @@ def test_index_sampling_draws_the_reference_pixels(gp, case):
     assert np.array_equal(inds.contiguous().numpy(), gp[f"rays_{case}_inds"])
     if case == "err":
         assert np.array_equal(extra["inds_coarse"].numpy(), gp["rays_err_inds_coarse"])
+
+
+@pytest.mark.gpu
+def test_collate_gathers_training_pixels_in_the_ray_kernel(cuda):
+    """f1, second half (ref: palette/provider.py:377-403): ground-truth colours and semantic features at the sampled pixels,
+    gathered by the launch that generates the rays == torch.gather of the reference's collate"""
+    import torch
+    from palettenerf_b200.nerf.utils import collate
+    B, H, W, N = 2, 37, 53, 500
+    g = torch.Generator().manual_seed(3)
+    poses = torch.eye(4).repeat(B, 1, 1)
+    poses[:, :3, 3] = torch.randn(B, 3, generator=g)
+    images = torch.rand(B, H, W, 4, generator=g).to(cuda)
+    feats = torch.randn(B, H, W, 16, generator=g).to(cuda)
+    intr = [61.7, 59.3, W / 2, H / 2]
+    torch.manual_seed(5)
+    res = collate(poses.to(cuda), intr, H, W, N, images=images, feat_images=feats)
+    inds = res["inds"]
+    assert res["images"].shape == (B, N, 4) and res["feat_images"].shape == (B, N, 16)
+    want_i = torch.gather(images.view(B, -1, 4), 1, torch.stack(4 * [inds], -1))
+    want_f = torch.gather(feats.view(B, -1, 16), 1, torch.stack(16 * [inds], -1))
+    assert torch.equal(res["images"], want_i) and torch.equal(res["feat_images"], want_f)
+    torch.manual_seed(5)
+    plain = collate(poses.to(cuda), intr, H, W, N)                     # same rays without the gathers
+    assert torch.equal(plain["rays_d"], res["rays_d"]) and torch.equal(plain["inds"], inds) and "images" not in plain
+    ev = collate(poses.to(cuda), intr, H, W, -1, images=images, training=False)
+    assert ev["images"] is images and ev["rays_o"].shape == (B, H * W, 3)
