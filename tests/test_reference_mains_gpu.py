@@ -26,10 +26,12 @@ def _run(args, cwd):
     env = dict(os.environ)
     for k in ("PNERF_RENDER_KERNEL", "PNERF_FIELD_KERNEL"):
         env.pop(k, None)
-    p = subprocess.run([sys.executable, RUNNER] + args, cwd=cwd, capture_output=True, text=True, timeout=900, env=env)
-    log = p.stdout + p.stderr
+    p = subprocess.run([sys.executable, RUNNER] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=900, env=env)
+    log = p.stdout
     assert p.returncode == 0, log[-6000:]
-    epoch_means = [float(m) for m in re.findall(r"loss=[0-9.]+ \(([0-9.]+)\), lr=[0-9.]+: : 100%", log)]
+    # one entry per epoch: the running mean tqdm prints with the 100 % bar, just before the trainer's "Finished Epoch"
+    epoch_means = [float(m) for m in re.findall(r"loss=[0-9.]+ \(([0-9.]+)\), lr=[0-9.]+: : 100%[^\n]*\n==> Finished Epoch", log)]
     sched = json.loads(re.search(r"\[run_reference_main\] schedules (\{.*\})", log).group(1))
     launches = int(re.search(r"C-ABI kernel launches: (\d+)", log).group(1))
     return epoch_means, sched, launches, log

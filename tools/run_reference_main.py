@@ -57,7 +57,7 @@ def _tally_schedules(nerf_cls, palette_cls):
     """Count which schedule every renderer call took (the renderers record it on the instance): the log line at the end is
     what tests/test_reference_mains_gpu.py asserts on."""
     def wrap(cls, name, attrs):
-        inner = cls.__dict__[name]
+        inner = getattr(cls, name)
 
         def call(self, *a, **k):
             for attr in attrs:
