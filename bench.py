@@ -495,6 +495,28 @@ def _adam(torch, params, torch_adam):
     return FusedAdam(params, betas=(0.9, 0.99), eps=1e-15), "FusedAdam(0.9,0.99,1e-15: pnerf_adam_step)+GradScaler"
 
 
+def _kernel_breakdown(torch, step, barrier, reps=3):
+    """device time per kernel name of one step (torch.profiler / CUPTI over `reps` replays, warm L2, outside every timed
+    region): says where a step's time goes — in particular what data parallelism adds (pack copy, all-reduce, barriers)"""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                step()
+            torch.cuda.synchronize()
+        barrier()
+        rows = {}
+        for e in prof.events():
+            if getattr(e, "device_type", None) is not None and "CUDA" in str(e.device_type):
+                k = e.name[:64]
+                rows[k] = rows.get(k, 0.0) + float(e.device_time if hasattr(e, "device_time") else e.cuda_time) / reps
+        top = sorted(rows.items(), key=lambda kv: -kv[1])[:24]
+        return {"total_us": round(sum(rows.values()), 1), "kernels": {k: round(v, 1) for k, v in top}}
+    except Exception as e:   # noqa: BLE001  (a diagnostic: never fails the bench)
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, flush, use_graph=True, torch_loss=False,
                 torch_adam=False, nccl_allreduce=False):
     """BASELINE config 4: palette-stage training step, 4096 rays per GPU, fwd + bwd + Adam under fp16 autocast with
@@ -547,6 +569,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     barrier()
     m = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
     ms = max_over_ranks(sum(ts) / len(ts))
+    breakdown = _kernel_breakdown(torch, step, barrier)
     # the optimizer alone (HBM stream: 16 B read + 12 B written per element with a gradient), same events / L2 flush
     adam = None
     if not torch_adam:
@@ -569,6 +592,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "allreduce": None if world == 1 else _allreduce_name(bucket, nccl_allreduce),
                       "allreduce_bucket_bytes": None if bucket is None or bucket.flat is None else 4 * bucket.flat.numel(),
                       "allreduce_max_abs_err": None if world == 1 else _allreduce_check(torch, dist, dev, rank, world),
+                      "kernel_us_per_step_rank0": breakdown,
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 

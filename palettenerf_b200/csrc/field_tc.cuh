@@ -7,8 +7,9 @@
 //            first layers: fp16 feature rows in the canonical K-major UMMA layout [k-chunk][row][8 halfs] (tc_common.cuh);
 //            SH(4) of the view direction the same way;
 //   layers   11 (13 with the semantic branch) dense layers, each ONE tcgen05.mma chain issued by one thread of the group:
-//            A = activations in shared memory, B = the layer's weights resident in shared memory (same layout), D = a 64-
-//            column fp32 accumulator in TMEM; completion arrives on the group's mbarrier (tcgen05.commit);
+//            A = the gathered inputs in shared memory (SS form) and/or the previous layer's activations in TMEM (TS form),
+//            B = the layer's weights resident in shared memory (same K-major layout), D = a 64-column fp32 accumulator in
+//            TMEM; completion arrives on the group's mbarrier (tcgen05.commit);
 //   epilogue every thread reads ITS row of the accumulator (tcgen05.ld 32x32b), applies ReLU / ELU / sigmoid, and writes the
 //            next layer's A operand back to TMEM as packed fp16 pairs (tcgen05.st; the next tcgen05.mma takes A from TMEM)
 //            — activations never touch shared memory — or keeps the value in registers when it is a result (sigma logit,
