@@ -208,14 +208,34 @@ __global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ ra
     // rejected: 80 instead of 56 registers and wasted probes cost more than the shorter dependency chains save,
     // 0.44 -> 0.8 ms per 800x800 view)
     float x, y, z, dt;
-    while (t < far && count < max_steps) {
-        if (m.probe(t, x, y, z, dt)) {
-            if (!in_run) { in_run = true; run_t = t; run_n = 0; }
-            run_n++;
-            count++;
-            t += dt;
-        } else if (in_run) {          // probe() advanced t past the empty voxel: the run is closed
-            close_run();
+    if (dt_gamma == 0.f) {
+        // constant step: an occupied point's voxel is probed ONCE; the lattice points that provably stay inside it
+        // (Marcher::probe_point<true>) cost one add and one compare each instead of a probe (~4.6 points per voxel)
+        while (t < far && count < max_steps) {
+            float tt;
+            if (m.probe_point<true>(t, x, y, z, dt, tt)) {
+                if (!in_run) { in_run = true; run_t = t; run_n = 0; }
+                const float stop = fminf(tt, far);
+                do {
+                    run_n++;
+                    count++;
+                    t += dt;
+                } while (t < stop && count < max_steps);
+            } else {
+                t = m.advance_past(t, tt);
+                if (in_run) close_run();
+            }
+        }
+    } else {
+        while (t < far && count < max_steps) {
+            if (m.probe(t, x, y, z, dt)) {
+                if (!in_run) { in_run = true; run_t = t; run_n = 0; }
+                run_n++;
+                count++;
+                t += dt;
+            } else if (in_run) {          // probe() advanced t past the empty voxel: the run is closed
+                close_run();
+            }
         }
     }
     if (in_run) close_run();
@@ -259,40 +279,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     // after the field of a tile is complete the group's input regions are dead until the next gather: a quarter of them is
     // this warp's scratch for the per-tile channel reduction
     float* const red = reinterpret_cast<float*>(g.smem + wig * (group_bytes / 4));
-    float* const t_list = a.t_scratch + (size_t)(blockIdx.x * (kTcGroups * 4) + wid) * a.max_steps;
+    // two t-lists per warp: the current ray's and the one of the ray that fills the free lanes of the current ray's last window
+    float* t_list = a.t_scratch + (size_t)(blockIdx.x * (kTcGroups * 4) + wid) * 2 * a.max_steps;
+    float* t_next = t_list + a.max_steps;
+    float* const pend = sm->pend[wid];                     // origin / direction of the ray in t_next
     const bool clip_on = CLIP && a.clip_feat != nullptr;
     const uint32_t n_cand = a.queue[QT_CAND];
     const float dt_min = 2 * 1.7320508075688772f / a.max_steps;
     const float dt_max = 2 * 1.7320508075688772f * (1u << (a.C - 1)) / a.Hgrid;
     uint32_t shaded = 0, tiles = 0, hit_rays = 0;
 
-    // per-warp ray state (warp-uniform unless noted)
+    // per-warp state of the CURRENT ray (warp-uniform unless noted)
     bool has_ray = false, exhausted = false;
     uint32_t ray = 0, count = 0, done = 0;
-    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t0 = 0.f;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
     float T_run = 1.f;
     float wsum = 0.f, dep = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;   // ray totals (warp-uniform)
     float acc_lo = 0.f, acc_hi = 0.f, acc_clip = 0.f;      // per-LANE: totals of aux channel `lane`, `lane + 32`, clip channel `lane`
 
+    // retire: one writer per value; lane = auxiliary channel
+    // (out_index: this rank renders a shard of a view whose maps live elsewhere — possibly in a peer GPU's memory, mapped over
+    // NVLink: the stores below are the gather)
+    auto retire = [&](uint32_t r, float s_w, float s_d, float s_r, float s_g, float s_b, float lo, float hi, float cl) {
+        if (a.out_index) r = (uint32_t)a.out_index[r];
+        if (lane == 0) {
+            a.weights_sum[r] = s_w; a.depth[r] = s_d;
+            a.image[(size_t)r * 3] = s_r; a.image[(size_t)r * 3 + 1] = s_g; a.image[(size_t)r * 3 + 2] = s_b;
+        }
+        if (AUX) {
+            auto dst_of = [&](int c) -> float* {           // 0-2 direct, 3-5 view_dep, 6-9 basis_acc, 10-21 basis_rgb, 22-33 unscaled
+                if (c < 3) return a.direct_rgb + (size_t)r * 3 + c;
+                if (c < 6) return a.view_dep_rgb + (size_t)r * 3 + (c - 3);
+                if (c < 6 + kNB) return a.basis_acc + (size_t)r * kNB + (c - 6);
+                if (c < 6 + kNB + kNB * 3) return a.basis_rgb + (size_t)r * kNB * 3 + (c - 6 - kNB);
+                return a.unscaled_basis_rgb + (size_t)r * kNB * 3 + (c - 6 - kNB - kNB * 3);
+            };
+            *dst_of(lane) = lo;
+            if (lane + 32 < kAuxCh) *dst_of(lane + 32) = hi;
+        }
+        if (CLIP && clip_on && lane < (int)f.clip_dim) a.clip_feat[(size_t)r * f.clip_dim + lane] = cl;
+    };
+
     for (;;) {
-        // ---- every warp makes sure it has a ray with samples left ----
-        while (!has_ray && !exhausted) {
+        // ---- this warp's window: the next samples of its ray (lanes < na); when those do not fill the window (the ray's
+        //      last one) the free lanes take the first samples of the NEXT ray from the queue (lanes na .. na + nb - 1), so
+        //      that the 128-row MMA tiles stay full: tile fill 0.90 -> 0.97 on the 800x800 view ----
+        const uint32_t na = has_ray ? min(32u, count - done) : 0u;
+        bool has_next = false;
+        uint32_t ray_n = 0, count_n = 0;
+        while (na < 32u && !has_next && !exhausted) {
             uint32_t slot = 0;
             if (lane == 0) slot = atomicAdd(a.queue + QT_CURSOR, 1u);
             slot = __shfl_sync(0xffffffffu, slot, 0);
             if (slot >= n_cand) { exhausted = true; break; }
             const RayRuns* rr = a.runs + slot;
-            count = rr->count;
-            if (count == 0) continue;
-            ray = (uint32_t)a.cand[slot];
+            count_n = rr->count;
+            if (count_n == 0) continue;
+            ray_n = (uint32_t)a.cand[slot];
             Marcher m;
-            m.init(a.rays_o + (size_t)ray * 3, a.rays_d + (size_t)ray * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid, a.bitfield);
+            m.init(a.rays_o + (size_t)ray_n * 3, a.rays_d + (size_t)ray_n * 3, f.bound, a.dt_gamma, a.max_steps, a.C, a.Hgrid, a.bitfield);
             const uint32_t n_runs = rr->n_runs;
-            t0 = rr->t0;
+            const float t0 = rr->t0;
             if (n_runs > (uint32_t)kMaxRuns) {          // too many stretches for the record: walk the ray here
-                float far = a.fars[ray];
+                float far = a.fars[ray_n];
                 if (a.occ) far = fminf(far, m.occupied_exit(a.occ));
-                count = warp_walk<false>(m, t0, far, a.max_steps, (uint32_t)lane, nullptr, nullptr, nullptr, t_list);
+                count_n = warp_walk<false>(m, t0, far, a.max_steps, (uint32_t)lane, nullptr, nullptr, nullptr, t_next);
             } else {
                 uint32_t pos = 0;
                 for (uint32_t r = 0; r < n_runs; r++) {
@@ -303,56 +354,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
                         uint32_t nvalid;
                         lattice_window(m, ts, (uint32_t)lane, t, nvalid);
                         const uint32_t nv = min(nvalid, left);
-                        if ((uint32_t)lane < nv) t_list[pos + lane] = t;
+                        if ((uint32_t)lane < nv) t_next[pos + lane] = t;
                         pos += nv;
                         left -= nv;
                         ts = __shfl_sync(0xffffffffu, t + m.step_size(t), nv - 1);
                     }
                 }
             }
+            if (lane == 0) { pend[0] = m.ox; pend[1] = m.oy; pend[2] = m.oz; pend[3] = m.dx; pend[4] = m.dy; pend[5] = m.dz; }
             __syncwarp();
-            ox = m.ox; oy = m.oy; oz = m.oz; dx = m.dx; dy = m.dy; dz = m.dz;
-            has_ray = true; done = 0; T_run = 1.f;
-            wsum = dep = cr = cg = cb = 0.f;
-            acc_lo = acc_hi = acc_clip = 0.f;
+            if (count_n == 0) continue;
+            has_next = true;
             hit_rays++;
         }
         // ---- group vote: the field is evaluated while any warp of the group has a tile ----
-        if (lane == 0) sm->flags[gi][wig] = has_ray ? 1u : 0u;
+        if (lane == 0) sm->flags[gi][wig] = (has_ray || has_next) ? 1u : 0u;
         tc::group_bar(g.bar_id, 128);
         const uint32_t any = sm->flags[gi][0] | sm->flags[gi][1] | sm->flags[gi][2] | sm->flags[gi][3];
         if (!any) break;
 
-        // ---- this warp's tile: 32 consecutive samples of its ray ----
-        const uint32_t k = done + (uint32_t)lane;
-        const bool active = has_ray && k < count;
-        const float t = active ? t_list[k] : t0;
-        const float x = clampf(ox + t * dx, -f.bound, f.bound);
-        const float y = clampf(oy + t * dy, -f.bound, f.bound);
-        const float z = clampf(oz + t * dz, -f.bound, f.bound);
+        const bool in_next = (uint32_t)lane >= na;          // lanes of the next ray (or free)
+        const uint32_t k = in_next ? (uint32_t)lane - na : done + (uint32_t)lane;
+        const bool active = in_next ? (has_next && k < count_n) : true;
+        const float lox = in_next ? pend[0] : ox, loy = in_next ? pend[1] : oy, loz = in_next ? pend[2] : oz;
+        const float ldx = in_next ? pend[3] : dx, ldy = in_next ? pend[4] : dy, ldz = in_next ? pend[5] : dz;
+        const float t = active ? (in_next ? t_next[k] : t_list[k]) : 0.f;
+        const float x = clampf(lox + t * ldx, -f.bound, f.bound);
+        const float y = clampf(loy + t * ldy, -f.bound, f.bound);
+        const float z = clampf(loz + t * ldz, -f.bound, f.bound);
         const float dt = clampf(t * a.dt_gamma, dt_min, dt_max);
         const float t_end = t + dt;
         FieldOut o;
-        eval_field_tc<MODE>(f, *sm, g, x, y, z, active ? dx : 0.f, active ? dy : 0.f, active ? dz : 1.f, active, lane, o);
-        if (!has_ray) continue;                         // (warp-uniform) idle warp of a busy group
+        eval_field_tc<MODE>(f, *sm, g, x, y, z, active ? ldx : 0.f, active ? ldy : 0.f, active ? ldz : 1.f, active, lane, o);
+        if (!has_ray && !has_next) continue;            // (warp-uniform) idle warp of a busy group
         tiles++;
 
-        // ---- front-to-back compositing of the tile (ref: raymarching.cu:1051-1110 per sample) ----
+        // ---- front-to-back compositing of the window (ref: raymarching.cu:1051-1110 per sample); the product scan of
+        //      (1 - alpha) restarts at lane na, where the next ray begins ----
         const float alpha = active ? 1.0f - fast_exp(-(f.density_scale * o.sigma) * dt) : 0.f;
         float incl = 1.0f - alpha;
+        const int seg0 = in_next ? (int)na : 0;
 #pragma unroll
         for (int ofs = 1; ofs < 32; ofs <<= 1) {
             const float up = __shfl_up_sync(0xffffffffu, incl, ofs);
-            if (lane >= ofs) incl *= up;
+            if (lane - ofs >= seg0) incl *= up;
         }
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 1.f;
-        const float T = T_run * excl;
-        const uint32_t term = __ballot_sync(0xffffffffu, active && T < a.T_thresh);
-        const int last = term ? (__ffs(term) - 1) : 31;
+        if (lane == seg0) excl = 1.f;
+        const float T = (in_next ? 1.f : T_run) * excl;
+        const uint32_t below = __ballot_sync(0xffffffffu, active && T < a.T_thresh);
+        const uint32_t mask_a = na >= 32u ? 0xffffffffu : ((1u << na) - 1u);
+        const uint32_t term = below & mask_a, term_n = below & ~mask_a;
+        const int last = in_next ? (term_n ? (__ffs(term_n) - 1) : 31) : (term ? (__ffs(term) - 1) : 31);
         const bool use = active && lane <= last;
         const float wgt = use ? alpha * T : 0.f;
         shaded += __popc(__ballot_sync(0xffffffffu, use));
+        // window totals of the next ray's lanes (the current ray's go straight into its running totals)
+        float n_w = 0.f, n_d = 0.f, n_r = 0.f, n_g = 0.f, n_b = 0.f, n_lo = 0.f, n_hi = 0.f, n_clip = 0.f;
         {
             float rgb[3], basis_rgb[kNB * 3], unscaled[kNB * 3];
             const float sp = MODE == TC_NERF ? 0.f : softplusf_(o.off_rad[12]);
@@ -426,9 +484,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
 #pragma unroll
                 for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
             }
-            wsum += warp_sum(wgt);
-            dep += warp_sum(wgt * t_end);
-            cr += warp_sum(wgt * rgb[0]); cg += warp_sum(wgt * rgb[1]); cb += warp_sum(wgt * rgb[2]);
+            if (!has_next) {
+                wsum += warp_sum(wgt);
+                dep += warp_sum(wgt * t_end);
+                cr += warp_sum(wgt * rgb[0]); cg += warp_sum(wgt * rgb[1]); cb += warp_sum(wgt * rgb[2]);
+            } else {
+                const float wa = in_next ? 0.f : wgt, wn = in_next ? wgt : 0.f;
+                wsum += warp_sum(wa); n_w = warp_sum(wn);
+                dep += warp_sum(wa * t_end); n_d = warp_sum(wn * t_end);
+                cr += warp_sum(wa * rgb[0]); n_r = warp_sum(wn * rgb[0]);
+                cg += warp_sum(wa * rgb[1]); n_g = warp_sum(wn * rgb[1]);
+                cb += warp_sum(wa * rgb[2]); n_b = warp_sum(wn * rgb[2]);
+            }
             if (AUX) {
                 // channel-major scratch red[c][lane]; the column sums below run with lane = channel
 #pragma unroll
@@ -447,14 +514,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         }
         if (AUX) {
             __syncwarp();
-            float s0 = 0.f, s1 = 0.f;
+            if (!has_next) {
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 32; q++) s0 += red[lane * kRedStride + q];
-            if (lane + 32 < kAuxCh) {
+                for (int q = 0; q < 32; q++) s0 += red[lane * kRedStride + q];
+                if (lane + 32 < kAuxCh) {
 #pragma unroll
-                for (int q = 0; q < 32; q++) s1 += red[(lane + 32) * kRedStride + q];
+                    for (int q = 0; q < 32; q++) s1 += red[(lane + 32) * kRedStride + q];
+                }
+                acc_lo += s0; acc_hi += s1;
+            } else {                                        // column sums split at lane na
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 32; q++) {
+                    const float v = red[lane * kRedStride + q];
+                    if ((uint32_t)q < na) s0 += v; else n_lo += v;
+                }
+                if (lane + 32 < kAuxCh) {
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        const float v = red[(lane + 32) * kRedStride + q];
+                        if ((uint32_t)q < na) s1 += v; else n_hi += v;
+                    }
+                }
+                acc_lo += s0; acc_hi += s1;
             }
-            acc_lo += s0; acc_hi += s1;
         }
         if (CLIP && clip_on) {
             __syncwarp();
@@ -464,35 +548,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             if (lane < kClipMax) {
                 float s = 0.f;
 #pragma unroll
-                for (int q = 0; q < 32; q++) s += red[lane * kRedStride + q];
+                for (int q = 0; q < 32; q++) {
+                    const float v = red[lane * kRedStride + q];
+                    if ((uint32_t)q < na) s += v; else n_clip += v;
+                }
                 acc_clip += s;
             }
         }
         __syncwarp();
-        done += 32;
-        T_run *= __shfl_sync(0xffffffffu, incl, 31);
-        if (term || done >= count) {
-            // ---- retire: one writer per value; lane = auxiliary channel ----
-            // (out_index: this rank renders a shard of a view whose maps live elsewhere — possibly in a peer GPU's memory,
-            // mapped over NVLink: the stores below are the gather)
-            if (a.out_index) ray = (uint32_t)a.out_index[ray];
-            if (lane == 0) {
-                a.weights_sum[ray] = wsum; a.depth[ray] = dep;
-                a.image[(size_t)ray * 3] = cr; a.image[(size_t)ray * 3 + 1] = cg; a.image[(size_t)ray * 3 + 2] = cb;
+        // ---- the current ray: finished when it ran out of samples (always the case when the window was shared) or below
+        //      the transmittance threshold ----
+        if (has_ray) {
+            done += na;
+            if (term || done >= count) {
+                retire(ray, wsum, dep, cr, cg, cb, acc_lo, acc_hi, acc_clip);
+                has_ray = false;
+            } else {
+                T_run *= __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (AUX) {
-                auto dst_of = [&](int c) -> float* {       // 0-2 direct, 3-5 view_dep, 6-9 basis_acc, 10-21 basis_rgb, 22-33 unscaled
-                    if (c < 3) return a.direct_rgb + (size_t)ray * 3 + c;
-                    if (c < 6) return a.view_dep_rgb + (size_t)ray * 3 + (c - 3);
-                    if (c < 6 + kNB) return a.basis_acc + (size_t)ray * kNB + (c - 6);
-                    if (c < 6 + kNB + kNB * 3) return a.basis_rgb + (size_t)ray * kNB * 3 + (c - 6 - kNB);
-                    return a.unscaled_basis_rgb + (size_t)ray * kNB * 3 + (c - 6 - kNB - kNB * 3);
-                };
-                *dst_of(lane) = acc_lo;
-                if (lane + 32 < kAuxCh) *dst_of(lane + 32) = acc_hi;
+        }
+        // ---- the next ray becomes the current one ----
+        if (has_next) {
+            const float T_next = __shfl_sync(0xffffffffu, incl, 31);
+            done = min(32u - na, count_n);
+            if (term_n || done >= count_n) {
+                retire(ray_n, n_w, n_d, n_r, n_g, n_b, n_lo, n_hi, n_clip);
+            } else {
+                has_ray = true;
+                ray = ray_n; count = count_n;
+                ox = pend[0]; oy = pend[1]; oz = pend[2]; dx = pend[3]; dy = pend[4]; dz = pend[5];
+                T_run = T_next;
+                wsum = n_w; dep = n_d; cr = n_r; cg = n_g; cb = n_b;
+                acc_lo = n_lo; acc_hi = n_hi; acc_clip = n_clip;
+                float* const tmp = t_list; t_list = t_next; t_next = tmp;
             }
-            if (CLIP && clip_on && lane < (int)f.clip_dim) a.clip_feat[(size_t)ray * f.clip_dim + lane] = acc_clip;
-            has_ray = false;
+            __syncwarp();                                   // pend / t_next are rewritten by the next fetch
         }
     }
     if (lane == 0 && tiles) {
@@ -510,7 +600,8 @@ static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
 
 extern "C" {
 
-uint32_t pnerf_palette_render_tc_warps(void) { return (uint32_t)sm_count() * (uint32_t)(kTcGroups * 4); }
+/* rows of max_steps floats the renderer needs in t_scratch: two per resident warp (current ray + the ray sharing its last window) */
+uint32_t pnerf_palette_render_tc_warps(void) { return 2u * (uint32_t)sm_count() * (uint32_t)(kTcGroups * 4); }
 uint32_t pnerf_palette_render_tc_runs_bytes(void) { return (uint32_t)sizeof(RayRuns); }
 
 /* Tensor-core warp-per-ray renderer (csrc/field_tc.cu): like pnerf_palette_render_rays, with the field on tcgen05 / TMEM and

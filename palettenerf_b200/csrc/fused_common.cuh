@@ -153,9 +153,10 @@ __device__ __forceinline__ float activate(float v) {
 // round-to-nearest is monotonic and sign-preserving, so max(rn(x), 0) == rn(max(x, 0)) for every finite x.
 template <int ACT>
 __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
-    if (ACT == ACT_RELU) {
-        const __half2 h = __hmax2(__floats2half2_rn(lo, hi), __float2half2_rn(0.f));
-        return *reinterpret_cast<const uint32_t*>(&h);
+    if (ACT == ACT_RELU) {   // ONE instruction (F2FP.RELU): convert, clamp at zero and pack
+        uint32_t h;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+        return h;
     }
     return pack_h2(activate<ACT>(lo), activate<ACT>(hi));
 }

@@ -106,6 +106,13 @@ struct Marcher {
         return (t_in <= t_out) ? t_out : -1.f;
     }
 
+    // STRETCH (constant step only, dt_gamma == 0): for an OCCUPIED point `tt` receives a ray parameter up to which the ray
+    // provably stays inside the point's voxel — the exit through the voxel shrunk by 1e-3 of its size on the exit sides,
+    // four orders of magnitude more than the fp32 rounding of position and index (~3e-5 voxel). Every lattice point
+    // below it lands in the same voxel at the same cascade (the cascade can only change across |x| = 2^k planes, which
+    // are voxel faces unless the cascade is capped by the bound; the step-size term is constant), so it is occupied without
+    // being probed.
+    template <bool STRETCH = false>
     __device__ __forceinline__ bool probe_point(float t, float& x, float& y, float& z, float& dt, float& tt) const {
         position(t, x, y, z, dt);
 
@@ -128,10 +135,19 @@ struct Marcher {
         // the reference forms this index in fp32 (level * H3 + morton); keep its rounding behaviour
         const uint32_t index = (uint32_t)((float)level * H3f + (float)morton_encode(nx, ny, nz));
         const bool occ = grid[index >> 3] & (1u << (index & 7u));
-        if (occ) return true;
+        if (occ && !STRETCH) return true;
 
         // distance to the exit face of this voxel along each axis
         const float sx = copysignf(1.0f, dx), sy = copysignf(1.0f, dy), sz = copysignf(1.0f, dz);
+        if (STRETCH && occ) {
+            const float ux = (((nx + 0.5f + 0.499f * sx) * rH * 2 - 1) * mip_bound - x) * rdx;
+            const float uy = (((ny + 0.5f + 0.499f * sy) * rH * 2 - 1) * mip_bound - y) * rdy;
+            const float uz = (((nz + 0.5f + 0.499f * sz) * rH * 2 - 1) * mip_bound - z) * rdz;
+            // (NaN from 0 * inf on an axis the ray does not move along is dropped by fminf. bound < 2^level: the voxel grid is
+            // scaled to the bound, the |x| = 2^k planes are no longer faces — no stretch there)
+            tt = capped ? t : t + fminf(ux, fminf(uy, uz));
+            return true;
+        }
         const float tx = (((nx + 0.5f + 0.5f * sx) * rH * 2 - 1) * mip_bound - x) * rdx;
         const float ty = (((ny + 0.5f + 0.5f * sy) * rH * 2 - 1) * mip_bound - y) * rdy;
         const float tz = (((nz + 0.5f + 0.5f * sz) * rH * 2 - 1) * mip_bound - z) * rdz;
