@@ -259,6 +259,18 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
                                          int32_t* hit_list, float* t_first, float* t_last, const float* occ_aabb,
                                          void* stream);
 
+/* The fp16 state of pnerf_palette_field rebuilt from the model's fp32 parameters (csrc/field_cache.cu; no reference
+ * counterpart: its MLPs read the fp32 parameters through autocast on every call, palette/network.py:156-280).
+ *   pnerf_field_cache_tables: table_sigma, table_palette (, table_clip or NULL) fp32 [n_entries, 2] -> pair = fp16
+ *     [n_entries][2 grids][2] (field->table_sigma_palette), clip = fp16 [n_entries, 2] (field->table_clip).
+ *   pnerf_field_cache_gather: src [n16 + n32] = device addresses of fp32 scalars (0 stands for the value 0); the first n16
+ *     are written to out16 as fp16 (the weight images wpack / wpack_tc), the other n32 to out32 as fp32, clamped to [0, 1]
+ *     from element clamp_from on (head_bias, then the palette). */
+PNERF_API int pnerf_field_cache_tables(const float* table_sigma, const float* table_palette, const float* table_clip,
+                                       uint32_t n_entries, void* pair, void* clip, void* stream);
+PNERF_API int pnerf_field_cache_gather(const uint64_t* src, uint32_t n16, uint32_t n32, uint32_t clamp_from, void* out16,
+                                       float* out32, void* stream);
+
 /* Tensor-core (tcgen05 / TMEM) version of pnerf_palette_field_forward: a warpgroup evaluates 128 samples per tile, every
  * dense layer is one tcgen05.mma chain (csrc/field_tc.cuh). Same arguments and results (fp16 operands, fp32 accumulation). */
 PNERF_API uint32_t pnerf_palette_tc_weight_bytes(uint32_t pred_clip);

@@ -53,6 +53,8 @@ L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P,
 L.LAUNCHES["pnerf_palette_render_tc"] = 3     # candidate filter + thread-per-ray pre-pass (runs) + the persistent kernel
 L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
 L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
+L.register("pnerf_field_cache_tables", [P, P, P, U, P, P, P])
+L.register("pnerf_field_cache_gather", [P, U, U, U, P, P, P])
 
 
 def _frag(W, n_pad, k_pad):
@@ -117,8 +119,8 @@ class FieldCache:
     """device-resident fp16 tables + packed weights of one model for the inference kernels.
 
     Freshness: the default (`model.fused_weights_static` unset / False) re-packs on EVERY call — three strided
-    fp32->fp16 table copies into persistent buffers (144 MB of HBM traffic, ~30 us) and one gather of the ~20 k MLP
-    weights. A version key alone is not enough: `param.data.copy_()` — what torch_ema's store / copy_to / restore do
+    fp32->fp16 table conversions into persistent buffers (pnerf_field_cache_tables: 152 MB of HBM traffic, one launch) and
+    one gather of the ~45 k MLP weight-image halfs, head bias and palette (pnerf_field_cache_gather). A version key alone is not enough: `param.data.copy_()` — what torch_ema's store / copy_to / restore do
     around every evaluate() of the reference trainer (nerf/utils.py:934-944), and what checkpoint loading or GUI edits
     may do — does not bump `Parameter._version`, so a cache keyed on it would render EMA weights after restore().
     `model.fused_weights_static = True` opts into the version key (interactive viewers that never write through .data).
@@ -142,15 +144,19 @@ class FieldCache:
         st = fused_train._state(m)
         dev = m.encoder.embeddings.device
         n = m.encoder.embeddings.shape[0]
+        n_fwd, n_tc = int(st["n_fwd"]), int(st["tc_index"].numel())
+        n_fwd_pad = (n_fwd + 7) // 8 * 8                      # keeps the tcgen05 image 16-byte aligned behind the mma image
+        w16 = torch.zeros(n_fwd_pad + n_tc, dtype=torch.float16, device=dev)
+        f32 = torch.zeros(16 + m.num_basis * 3, dtype=torch.float32, device=dev)
         self.buf = dict(
             pair=torch.empty(n, 2, 2, dtype=torch.float16, device=dev),
             clip=torch.empty(n, 2, dtype=torch.float16, device=dev) if m.opt.pred_clip else None,
-            wpack=torch.empty(st["n_fwd"], dtype=torch.float16, device=dev),
-            wpack_tc=torch.empty(st["tc_index"].numel(), dtype=torch.float16, device=dev), tc_index=st["tc_index"],
-            bias=torch.zeros(16, dtype=torch.float32, device=dev),
-            palette=torch.empty(m.num_basis, 3, dtype=torch.float32, device=dev),
+            w16=w16, f32=f32, n_fwd_pad=n_fwd_pad,
+            wpack=w16[:n_fwd], wpack_tc=w16[n_fwd_pad:], tc_index=st["tc_index"],
+            bias=f32[:16], palette=f32[16:].view(m.num_basis, 3),
             offsets=m.encoder.offsets.contiguous(), index=st["index"][:st["n_fwd"]], names=st["names"], zero=st["zero"],
             device=dev)
+        self._addr_key, self._addr = None, None
         b = self.buf
         f = PaletteField()
         # the kernels read both grids through the interleaved table; the separate-table pointers are kept non-NULL for the
@@ -178,7 +184,16 @@ class FieldCache:
             if key == self.key:
                 return f
             self.key = key
-        with torch.no_grad():
+        src = self._addresses()
+        if src is not None:
+            # two launches (csrc/field_cache.cu): the tables as one HBM stream, every small tensor through an address table
+            emb_c = m.encoder_clip.embeddings if b["clip"] is not None else None
+            L.call("pnerf_field_cache_tables", ptr(m.encoder.embeddings), ptr(m.encoder_palette.embeddings), ptr(emb_c),
+                   m.encoder.embeddings.shape[0], ptr(b["pair"]), ptr(b["clip"]), stream())
+            L.call("pnerf_field_cache_gather", ptr(src), b["w16"].numel(), b["f32"].numel(), 16, ptr(b["w16"]), ptr(b["f32"]),
+                   stream())
+            return f
+        with torch.no_grad():       # parameters that are not plain contiguous fp32 tensors: the same refresh as torch ops
             b["pair"][:, 0, :].copy_(m.encoder.embeddings.detach())
             b["pair"][:, 1, :].copy_(m.encoder_palette.embeddings.detach())
             if b["clip"] is not None:
@@ -190,6 +205,35 @@ class FieldCache:
             b["bias"][0:13].copy_(m.offsets_radiance_net.bias.detach())
             b["palette"].copy_(m.basis_color.detach().float().clamp(0, 1))
         return f
+
+    def _addresses(self):
+        """int64 device tensor: for every element of (w16 | f32) the ADDRESS of the fp32 parameter element it is made from
+        (0 = the value 0). Rebuilt only when a parameter's storage moves. None when a source is not contiguous fp32."""
+        m, b = self.model, self.buf
+        sd = dict(m.named_parameters())
+        tens = [sd[n] for n in b["names"]]
+        bias, pal = m.offsets_radiance_net.bias, m.basis_color
+        tabs = [m.encoder.embeddings, m.encoder_palette.embeddings] + ([m.encoder_clip.embeddings] if b["clip"] is not None else [])
+        if any(t.dtype != torch.float32 or not t.is_contiguous() for t in tens + [bias, pal] + tabs):
+            return None
+        key = tuple(t.data_ptr() for t in tens) + (bias.data_ptr(), pal.data_ptr())
+        if key != self._addr_key:
+            sizes = [t.numel() for t in tens]
+            flat = np.zeros(sum(sizes) + 1, dtype=np.int64)       # flat weight vector (fused_train._state) -> address; last = 0.0
+            off = 0
+            for t, k in zip(tens, sizes):
+                flat[off:off + k] = t.data_ptr() + 4 * np.arange(k, dtype=np.int64)
+                off += k
+            a16 = np.zeros(b["w16"].numel(), dtype=np.int64)
+            n_fwd = b["wpack"].numel()
+            a16[:n_fwd] = flat[b["index"].cpu().numpy()]
+            a16[b["n_fwd_pad"]:] = flat[b["tc_index"].cpu().numpy()]
+            a32 = np.zeros(b["f32"].numel(), dtype=np.int64)
+            a32[:13] = bias.data_ptr() + 4 * np.arange(13, dtype=np.int64)
+            a32[16:] = pal.data_ptr() + 4 * np.arange(pal.numel(), dtype=np.int64)
+            self._addr = torch.from_numpy(np.concatenate([a16, a32])).to(b["device"])
+            self._addr_key = key
+        return self._addr
 
     def invalidate(self):
         self.key = None
