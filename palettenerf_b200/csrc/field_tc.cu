@@ -244,8 +244,6 @@ __global__ void __launch_bounds__(128) k_tc_prepass(const float* __restrict__ ra
     runs[i] = rr;
 }
 
-constexpr int kRedStride = 33;                      // floats per channel row of the reduction scratch (conflict-free both ways)
-
 __host__ __device__ constexpr size_t tc_render_smem(bool clip) { return tc_smem_bytes(clip) + sizeof(EditShared) + 16; }
 
 // MODE: TC_PALETTE / TC_PALETTE_CLIP / TC_NERF (stage-1 model: colour = the colour net's output, no palette blend)
@@ -259,7 +257,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     unsigned char* wts = smem_raw + kTcSharedBytes;
     unsigned char* groups = wts + (CLIP ? kTcWBytesClip : kTcWBytesNoClip);
     constexpr int group_bytes = CLIP ? kTcGroupBytesClip : kTcGroupBytesNoClip;
-    static_assert(kAuxCh * kRedStride * 4 <= group_bytes / 4, "per-warp reduction scratch must fit a quarter of the group's regions");
+    static_assert(kAuxCh <= 4 * (group_bytes / kTcChunk) && kAuxCh <= 64 && kClipMax <= 4 * (group_bytes / kTcChunk),
+                  "per-warp reduction scratch: 4 channels per k-chunk of the warp's own rows");
     EditShared* ed = reinterpret_cast<EditShared*>(groups + kTcGroups * group_bytes);
     if (EDIT != 0) {
         const int tid = threadIdx.x;
@@ -276,9 +275,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     tc_prologue<kTcGroups>(f, f.wpack_tc, sm, wts, groups, group_bytes);
     TcGroup g = tc_make_group(sm, wts, groups, group_bytes);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gi = wid >> 2, wig = wid & 3;
-    // after the field of a tile is complete the group's input regions are dead until the next gather: a quarter of them is
-    // this warp's scratch for the per-tile channel reduction
-    float* const red = reinterpret_cast<float*>(g.smem + wig * (group_bytes / 4));
+    // after the field of a tile is complete the group's input regions are dead until the next gather: THIS WARP'S OWN ROWS of
+    // them (32 rows x 16 B = 512 B in each of the 10 / 14 k-chunks; nobody else ever writes there) are its scratch for the
+    // per-tile channel reduction. Channel c = 128 B in chunk c / 4; sample l of channel c sits in 16-byte segment
+    // (l / 4) ^ (c & 7), word l & 3: the row-wise writes (lane = sample) hit 32 banks, the column sums (lane = channel) read
+    // whole segments (LDS.128) whose positions differ across the 8 lanes of a quarter-warp — conflict-free both ways.
+    unsigned char* const red_base = g.smem + wig * 512;
+    auto red_row = [red_base](int c) -> unsigned char* { return red_base + (c >> 2) * kTcChunk + (c & 3) * 128; };
+    auto red = [&](int c, int l) -> float& {               // element (channel c, sample l)
+        return *reinterpret_cast<float*>(red_row(c) + (((l << 2) ^ ((c & 7) << 4))));
+    };
+    // sum over the 32 samples of channel c (c = this lane's channel); `split`: samples >= na go to `rest` instead
+    auto red_sum = [&](int c, bool split, uint32_t na_, float& rest) -> float {
+        const uint32_t y = (uint32_t)(c & 7) << 4;
+        unsigned char* const row = red_row(c);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 v = *reinterpret_cast<const float4*>(row + (((uint32_t)j << 4) ^ y));
+            if (!split) {
+                s += (v.x + v.y) + (v.z + v.w);
+            } else {
+                const uint32_t l0 = ((uint32_t)j ^ (uint32_t)(c & 7)) << 2;     // first sample of this segment
+                if (l0 + 0 < na_) s += v.x; else rest += v.x;
+                if (l0 + 1 < na_) s += v.y; else rest += v.y;
+                if (l0 + 2 < na_) s += v.z; else rest += v.z;
+                if (l0 + 3 < na_) s += v.w; else rest += v.w;
+            }
+        }
+        return s;
+    };
     // two t-lists per warp: the current ray's and the one of the ray that fills the free lanes of the current ray's last window
     float* t_list = a.t_scratch + (size_t)(blockIdx.x * (kTcGroups * 4) + wid) * 2 * a.max_steps;
     float* t_next = t_list + a.max_steps;
@@ -368,6 +394,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             hit_rays++;
         }
         // ---- group vote: the field is evaluated while any warp of the group has a tile ----
+        // (a barrier-free variant — votes read after the field, whose barriers publish them, so that an early warp starts its
+        // next gather while the others finish compositing — was measured and rejected: 5.22 vs 5.05 ms per 800x800 view;
+        // the four warps of a group run better in phase)
         if (lane == 0) sm->flags[gi][wig] = (has_ray || has_next) ? 1u : 0u;
         tc::group_bar(g.bar_id, 128);
         const uint32_t any = sm->flags[gi][0] | sm->flags[gi][1] | sm->flags[gi][2] | sm->flags[gi][3];
@@ -484,6 +513,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
 #pragma unroll
                 for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
             }
+            // (the five core sums as shuffle reductions: routing them through the scratch as five more channels was measured
+            // and is slower, 5.10 vs 5.05 ms per view)
             if (!has_next) {
                 wsum += warp_sum(wgt);
                 dep += warp_sum(wgt * t_end);
@@ -500,60 +531,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
                 // channel-major scratch red[c][lane]; the column sums below run with lane = channel
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    red[c * kRedStride + lane] = wgt * (o.diffuse[c] + o.view_dep[c]);
-                    red[(3 + c) * kRedStride + lane] = wgt * o.view_dep[c];
+                    red(c, lane) = wgt * (o.diffuse[c] + o.view_dep[c]);
+                    red(3 + c, lane) = wgt * o.view_dep[c];
                 }
 #pragma unroll
-                for (int q = 0; q < kNB; q++) red[(6 + q) * kRedStride + lane] = wgt * o.omega[q];
+                for (int q = 0; q < kNB; q++) red(6 + q, lane) = wgt * o.omega[q];
 #pragma unroll
                 for (int q = 0; q < kNB * 3; q++) {
-                    red[(6 + kNB + q) * kRedStride + lane] = wgt * basis_rgb[q];
-                    red[(6 + kNB + kNB * 3 + q) * kRedStride + lane] = wgt * unscaled[q];
+                    red(6 + kNB + q, lane) = wgt * basis_rgb[q];
+                    red(6 + kNB + kNB * 3 + q, lane) = wgt * unscaled[q];
                 }
             }
         }
         if (AUX) {
             __syncwarp();
+            float dummy = 0.f;
             if (!has_next) {
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int q = 0; q < 32; q++) s0 += red[lane * kRedStride + q];
-                if (lane + 32 < kAuxCh) {
-#pragma unroll
-                    for (int q = 0; q < 32; q++) s1 += red[(lane + 32) * kRedStride + q];
-                }
-                acc_lo += s0; acc_hi += s1;
+                acc_lo += red_sum(lane, false, 32u, dummy);
+                if (lane + 32 < kAuxCh) acc_hi += red_sum(lane + 32, false, 32u, dummy);
             } else {                                        // column sums split at lane na
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const float v = red[lane * kRedStride + q];
-                    if ((uint32_t)q < na) s0 += v; else n_lo += v;
-                }
-                if (lane + 32 < kAuxCh) {
-#pragma unroll
-                    for (int q = 0; q < 32; q++) {
-                        const float v = red[(lane + 32) * kRedStride + q];
-                        if ((uint32_t)q < na) s1 += v; else n_hi += v;
-                    }
-                }
-                acc_lo += s0; acc_hi += s1;
+                acc_lo += red_sum(lane, true, na, n_lo);
+                if (lane + 32 < kAuxCh) acc_hi += red_sum(lane + 32, true, na, n_hi);
             }
         }
         if (CLIP && clip_on) {
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < kClipMax; q++) red[q * kRedStride + lane] = wgt * o.clip[q];
+            for (int q = 0; q < kClipMax; q++) red(q, lane) = wgt * o.clip[q];
             __syncwarp();
-            if (lane < kClipMax) {
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const float v = red[lane * kRedStride + q];
-                    if ((uint32_t)q < na) s += v; else n_clip += v;
-                }
-                acc_clip += s;
-            }
+            if (lane < kClipMax) acc_clip += red_sum(lane, true, na, n_clip);
         }
         __syncwarp();
         // ---- the current ray: finished when it ran out of samples (always the case when the window was shared) or below
