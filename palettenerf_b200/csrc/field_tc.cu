@@ -137,6 +137,7 @@ struct RaysTcArgs {
     float* t_scratch;                               // [warps, max_steps]
     const int32_t* out_index;                       // optional [N]: row of the output maps that ray n writes (tile-sharded views)
     pnerf_palette_edit edit;                        // GUI-time edit of the blend (mode 0: none)
+    uint32_t share_windows;                         // 1: a ray's last window is filled with the next ray's first samples
 };
 
 // edit parameters staged in shared memory (behind the group regions)
@@ -257,7 +258,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     unsigned char* wts = smem_raw + kTcSharedBytes;
     unsigned char* groups = wts + (CLIP ? kTcWBytesClip : kTcWBytesNoClip);
     constexpr int group_bytes = CLIP ? kTcGroupBytesClip : kTcGroupBytesNoClip;
-    static_assert(kAuxCh <= 4 * (group_bytes / kTcChunk) && kAuxCh <= 64 && kClipMax <= 4 * (group_bytes / kTcChunk),
+    constexpr bool kCoreInScratch = AUX;               // the five core sums as scratch channels: 5.06 -> 4.93 ms per view
+    constexpr int kRedCh = kAuxCh + (kCoreInScratch ? 5 : 0);      // + weights_sum, depth, r, g, b
+    static_assert(kRedCh <= 4 * (group_bytes / kTcChunk) && kRedCh <= 64 && kClipMax <= 4 * (group_bytes / kTcChunk),
                   "per-warp reduction scratch: 4 channels per k-chunk of the warp's own rows");
     EditShared* ed = reinterpret_cast<EditShared*>(groups + kTcGroups * group_bytes);
     if (EDIT != 0) {
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             if (!split) {
                 s += (v.x + v.y) + (v.z + v.w);
             } else {
-                const uint32_t l0 = ((uint32_t)j ^ (uint32_t)(c & 7)) << 2;     // first sample of this segment
+                const uint32_t l0 = (uint32_t)j << 2;      // first sample of this (logical) segment
                 if (l0 + 0 < na_) s += v.x; else rest += v.x;
                 if (l0 + 1 < na_) s += v.y; else rest += v.y;
                 if (l0 + 2 < na_) s += v.z; else rest += v.z;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     const uint32_t n_cand = a.queue[QT_CAND];
     const float dt_min = 2 * 1.7320508075688772f / a.max_steps;
     const float dt_max = 2 * 1.7320508075688772f * (1u << (a.C - 1)) / a.Hgrid;
-    uint32_t shaded = 0, tiles = 0, hit_rays = 0;
+    uint32_t shaded = 0, tiles = 0, hit_rays = 0, vote = 0;
 
     // per-warp state of the CURRENT ray (warp-uniform unless noted)
     bool has_ray = false, exhausted = false;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
     // NVLink: the stores below are the gather)
     auto retire = [&](uint32_t r, float s_w, float s_d, float s_r, float s_g, float s_b, float lo, float hi, float cl) {
         if (a.out_index) r = (uint32_t)a.out_index[r];
-        if (lane == 0) {
+        if (!kCoreInScratch && lane == 0) {
             a.weights_sum[r] = s_w; a.depth[r] = s_d;
             a.image[(size_t)r * 3] = s_r; a.image[(size_t)r * 3 + 1] = s_g; a.image[(size_t)r * 3 + 2] = s_b;
         }
@@ -341,7 +344,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
                 return a.unscaled_basis_rgb + (size_t)r * kNB * 3 + (c - 6 - kNB - kNB * 3);
             };
             *dst_of(lane) = lo;
-            if (lane + 32 < kAuxCh) *dst_of(lane + 32) = hi;
+            const int c = lane + 32;                        // second channel of this lane: aux 32, 33 (then the five core sums)
+            if (c < kAuxCh) *dst_of(c) = hi;
+            else if (kCoreInScratch && c == kAuxCh) a.weights_sum[r] = hi;
+            else if (kCoreInScratch && c == kAuxCh + 1) a.depth[r] = hi;
+            else if (kCoreInScratch && c < kRedCh) a.image[(size_t)r * 3 + (c - kAuxCh - 2)] = hi;
         }
         if (CLIP && clip_on && lane < (int)f.clip_dim) a.clip_feat[(size_t)r * f.clip_dim + lane] = cl;
     };
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         const uint32_t na = has_ray ? min(32u, count - done) : 0u;
         bool has_next = false;
         uint32_t ray_n = 0, count_n = 0;
-        while (na < 32u && !has_next && !exhausted) {
+        while (na < 32u && !has_next && !exhausted && (a.share_windows || !has_ray)) {
             uint32_t slot = 0;
             if (lane == 0) slot = atomicAdd(a.queue + QT_CURSOR, 1u);
             slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -393,14 +400,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             has_next = true;
             hit_rays++;
         }
-        // ---- group vote: the field is evaluated while any warp of the group has a tile ----
-        // (a barrier-free variant — votes read after the field, whose barriers publish them, so that an early warp starts its
-        // next gather while the others finish compositing — was measured and rejected: 5.22 vs 5.05 ms per 800x800 view;
-        // the four warps of a group run better in phase)
-        if (lane == 0) sm->flags[gi][wig] = (has_ray || has_next) ? 1u : 0u;
+        // ---- group vote: the field is evaluated until no warp of the group had a tile. The warps meet here (in phase they run
+        //      better: without this barrier 5.22 instead of 5.05 ms per 800x800 view), but the votes are READ after the field:
+        //      no shared-memory load and branch between the barrier and the gather (5.22 -> 5.05 ms as well). Price: one empty
+        //      tile per group at the very end. Two sets of flags: the next vote is written while a slow warp may still be
+        //      reading this one. ----
+        if (lane == 0) sm->flags[vote][gi][wig] = (has_ray || has_next) ? 1u : 0u;
         tc::group_bar(g.bar_id, 128);
-        const uint32_t any = sm->flags[gi][0] | sm->flags[gi][1] | sm->flags[gi][2] | sm->flags[gi][3];
-        if (!any) break;
 
         const bool in_next = (uint32_t)lane >= na;          // lanes of the next ray (or free)
         const uint32_t k = in_next ? (uint32_t)lane - na : done + (uint32_t)lane;
@@ -415,6 +421,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         const float t_end = t + dt;
         FieldOut o;
         eval_field_tc<MODE>(f, *sm, g, x, y, z, active ? ldx : 0.f, active ? ldy : 0.f, active ? ldz : 1.f, active, lane, o);
+        const uint32_t any = sm->flags[vote][gi][0] | sm->flags[vote][gi][1] | sm->flags[vote][gi][2] | sm->flags[vote][gi][3];
+        vote ^= 1u;
+        if (!any) break;
         if (!has_ray && !has_next) continue;            // (warp-uniform) idle warp of a busy group
         tiles++;
 
@@ -513,9 +522,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
 #pragma unroll
                 for (int c = 0; c < 3; c++) rgb[c] += f.view_dep_weight * o.view_dep[c];
             }
-            // (the five core sums as shuffle reductions: routing them through the scratch as five more channels was measured
-            // and is slower, 5.10 vs 5.05 ms per view)
-            if (!has_next) {
+            if (kCoreInScratch) {
+                // weights_sum, depth and the colour ride in the scratch as channels kAuxCh .. kAuxCh + 4 (summed by lanes 2-6
+                // in the second column pass, which runs anyway): no shuffle reductions
+                red(kAuxCh, lane) = wgt;
+                red(kAuxCh + 1, lane) = wgt * t_end;
+#pragma unroll
+                for (int c = 0; c < 3; c++) red(kAuxCh + 2 + c, lane) = wgt * rgb[c];
+            } else if (!has_next) {
                 wsum += warp_sum(wgt);
                 dep += warp_sum(wgt * t_end);
                 cr += warp_sum(wgt * rgb[0]); cg += warp_sum(wgt * rgb[1]); cb += warp_sum(wgt * rgb[2]);
@@ -548,10 +562,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
             float dummy = 0.f;
             if (!has_next) {
                 acc_lo += red_sum(lane, false, 32u, dummy);
-                if (lane + 32 < kAuxCh) acc_hi += red_sum(lane + 32, false, 32u, dummy);
+                if (lane + 32 < kRedCh) acc_hi += red_sum(lane + 32, false, 32u, dummy);
             } else {                                        // column sums split at lane na
                 acc_lo += red_sum(lane, true, na, n_lo);
-                if (lane + 32 < kAuxCh) acc_hi += red_sum(lane + 32, true, na, n_hi);
+                if (lane + 32 < kRedCh) acc_hi += red_sum(lane + 32, true, na, n_hi);
             }
         }
         if (CLIP && clip_on) {
@@ -615,13 +629,14 @@ uint32_t pnerf_palette_render_tc_runs_bytes(void) { return (uint32_t)sizeof(RayR
  *   queue [8] u32 zero on entry; cand [N] int32; runs [N * pnerf_palette_render_tc_runs_bytes()] bytes;
  *   t_scratch [pnerf_palette_render_tc_warps() * max_steps] fp32. Needs field->wpack_tc and field->table_sigma_palette.
  *   out_index (optional, [N] int32): ray n writes row out_index[n] of the output maps instead of row n — the maps may be a
- *   peer GPU's memory (one view sharded over several GPUs: every rank stores its rays straight into the owner's image). */
+ *   peer GPU's memory (one view sharded over several GPUs: every rank stores its rays straight into the owner's image).
+ *   flags: PNERF_RENDER_REPRODUCIBLE — see include/pnerf_b200.h */
 int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const float* nears, const float* fars, const float* noises,
                             const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t Hgrid, uint32_t max_steps, float dt_gamma,
                             float T_thresh, const pnerf_palette_field* field, float* weights_sum, float* depth, float* image,
                             float* direct_rgb, float* view_dep_rgb, float* basis_acc, float* basis_rgb, float* unscaled_basis_rgb,
                             float* clip_feat, uint32_t* queue, int32_t* cand, void* runs, float* t_scratch, const float* occ_aabb,
-                            const int32_t* out_index, const pnerf_palette_edit* edit, void* stream) {
+                            const int32_t* out_index, const pnerf_palette_edit* edit, uint32_t flags, void* stream) {
     if (N == 0) return PNERF_OK;
     PNERF_REQUIRE(rays_o && rays_d && nears && fars && bitfield && field && weights_sum && depth && image && queue);
     PNERF_REQUIRE(cand && runs && t_scratch);
@@ -641,6 +656,7 @@ int pnerf_palette_render_tc(const float* rays_o, const float* rays_d, const floa
     a.direct_rgb = direct_rgb; a.view_dep_rgb = view_dep_rgb; a.basis_acc = basis_acc; a.basis_rgb = basis_rgb;
     a.unscaled_basis_rgb = unscaled_basis_rgb; a.clip_feat = clip_feat; a.queue = queue; a.cand = cand;
     a.runs = (const RayRuns*)runs; a.t_scratch = t_scratch; a.out_index = out_index;
+    a.share_windows = (flags & PNERF_RENDER_REPRODUCIBLE) ? 0u : 1u;
     pnerf_palette_edit none = {};
     a.edit = edit ? *edit : none;
     const int emode = (int)a.edit.mode;

@@ -70,7 +70,7 @@ struct TcShared {                                  // per CTA, in front of the w
     float palette[kNB * 3];
     uint64_t mbar[4];                              // one per group
     uint32_t tmem_base;
-    uint32_t flags[4][4];                          // per group: per-warp "has a tile" votes of the renderer
+    uint32_t flags[2][4][4];                       // per group: per-warp "has a tile" votes of the renderer (two alternating sets)
     float pend[16][8];                             // per warp: origin / direction of the ray that shares the current window
 };
 

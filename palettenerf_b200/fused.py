@@ -49,7 +49,7 @@ L.LAUNCHES["pnerf_palette_render_fused"] = 5  # candidates + pre-pass + 2 orderi
 L.register("pnerf_palette_render_rays", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
 L.LAUNCHES["pnerf_palette_render_rays"] = 2   # candidate filter + the persistent warp-per-ray kernel
 L.lib.pnerf_palette_render_rays_warps.restype = c_uint32
-L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+L.register("pnerf_palette_render_tc", [P, P, P, P, P, P, U, U, U, U, F, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, U, P])
 L.LAUNCHES["pnerf_palette_render_tc"] = 3     # candidate filter + thread-per-ray pre-pass (runs) + the persistent kernel
 L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
 L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
@@ -322,6 +322,16 @@ def accumulator_layout(N, nb, cd, gui_mode):
     return lay, off
 
 
+def reproducible_render(model, out=None):
+    """PNERF_RENDER_REPRODUCIBLE (include/pnerf_b200.h): bit-identical maps from run to run and from shard to shard, at ~4 %
+    of the render time. On for tile-sharded views (their contract is equality with the single-GPU image), for models with
+    `fused_reproducible = True`, and with PNERF_RENDER_REPRODUCIBLE=1 in the environment."""
+    env = __import__("os").environ.get("PNERF_RENDER_REPRODUCIBLE")
+    if env is not None:
+        return env not in ("0", "")
+    return out is not None or bool(getattr(model, "fused_reproducible", False))
+
+
 @torch.no_grad()
 def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh, gui_mode, kernel=None, out=None,
            out_index=None):
@@ -369,7 +379,7 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
         runs = torch.empty(N * int(L.lib.pnerf_palette_render_tc_runs_bytes()), dtype=torch.uint8, device=dev)
         L.call("pnerf_palette_render_tc", *common, ptr(cand), ptr(runs),
                ptr(_t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), ptr(out_index),
-               None if edit is None else ctypes.addressof(edit), stream())
+               None if edit is None else ctypes.addressof(edit), 1 if reproducible_render(model, out) else 0, stream())
         del edit_keep
     elif kernel == "rays":
         cand = torch.empty(N, dtype=torch.int32, device=dev)

@@ -160,7 +160,8 @@ def render(model, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_t
     L.call("pnerf_palette_render_tc", ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises), ptr(model.density_bitfield), N,
            model.cascade, model.grid_size, max_steps, float(dt_gamma), float(T_thresh), ctypes.addressof(f), ptr(acc["weights_sum"]),
            ptr(acc["depth"]), ptr(acc["image"]), None, None, None, None, None, None, ptr(queue), ptr(cand), ptr(runs),
-           ptr(fused._t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), None, None, stream())
+           ptr(fused._t_scratch(dev, max_steps, L.lib.pnerf_palette_render_tc_warps())), ptr(occ), None, None,
+           1 if fused.reproducible_render(model) else 0, stream())
     acc["_queue"] = queue
     return acc
 

@@ -156,3 +156,42 @@ def test_fused_render_follows_in_place_bitfield_updates(cuda):
     assert n1 > n0, "the new cells lie outside the old occupied bounds: a stale clip would not see them"
     assert (f1["image"] - l1["image"]).abs().max().item() < 2e-3
     assert (f1["weights_sum"] - l1["weights_sum"]).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("gui_mode", [False, True])
+def test_shared_windows_equal_reproducible_render(cuda, gui_mode):
+    """The tensor-core renderer fills the free lanes of a ray's last 32-sample window with the head of the next ray in the
+    queue (default) — exercised only when there are many more rays than resident warps (148 x 16), hence the 256 x 256
+    view. PNERF_RENDER_REPRODUCIBLE (model.fused_reproducible) starts every ray's windows at its own first sample. Same
+    samples, same maps up to the fp32 re-association of the per-ray sums; the reproducible render is bit-identical from
+    run to run; the shared one evaluates fewer tiles."""
+    m = S.build_palette_model(cuda, seed=3, pred_clip=False, table_scale=0.5)
+    m.eval()
+    o, d = S.camera_rays(256, 256)
+    oc, dc = o.to(cuda)[None], d.to(cuda)[None]
+
+    def render(reproducible, **kw):
+        m.fused_reproducible = reproducible
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            out = m.render(oc, dc, staged=True, bg_color=1, perturb=False, gui_mode=gui_mode, **kw)
+        assert m._last_schedule == "fused"
+        return {k: v.float().clone() for k, v in out.items()}, m._last_queue.cpu().numpy().copy()
+
+    for kw, tol, count_tol in (({}, 2e-5, 0.0), (dict(T_thresh=1e-2), 2e-4, 1e-3)):
+        if kw:
+            m.density_scale = 12.0        # some rays terminate on T < T_thresh, some of them inside a shared window
+        rep, q_rep = render(True, **kw)
+        rep2, q_rep2 = render(True, **kw)
+        sh, q_sh = render(False, **kw)
+        assert q_rep[2] > 4 * 148 * 16, "the view must give every warp several rays"
+        for k in rep:
+            assert torch.equal(rep[k], rep2[k]), f"{k}: reproducible render differs between runs"
+            scale = max(1.0, rep[k].abs().max().item())
+            err = (rep[k] - sh[k]).abs().max().item()
+            assert err <= tol * scale, f"{k}: shared vs reproducible windows {err}"
+        assert int(q_rep[1]) == int(q_rep2[1]) and int(q_rep[2]) == int(q_sh[2])
+        assert abs(int(q_rep[1]) - int(q_sh[1])) <= count_tol * int(q_rep[1])
+        fill_rep, fill_sh = q_rep[1] / (32.0 * q_rep[3]), q_sh[1] / (32.0 * q_sh[3])
+        if not kw:      # (with early termination most rays end inside their first, full window: nothing to share)
+            assert fill_sh > fill_rep + 0.03 and fill_sh > 0.9, (fill_rep, fill_sh)
+    m.fused_reproducible = False
