@@ -570,6 +570,32 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     m = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
     ms = max_over_ranks(sum(ts) / len(ts))
     breakdown = _kernel_breakdown(torch, step, barrier)
+    # config 4 WITH the smooth loss (ref: palette/renderer.py:360-381, on from epoch 30 of the reference schedule): a second
+    # fused field evaluation on jittered points + the gate arithmetic; single GPU only (same all-reduce as above otherwise)
+    smooth = None
+    if world == 1 and use_graph and not torch_loss:
+        m2 = S.build_palette_model(dev, seed=0, pred_clip=False)
+        m2.train()
+        m2.require_smooth_loss = True
+        opt2, _ = _adam(torch, m2.get_params(1e-2), torch_adam)
+        sc2 = torch.amp.GradScaler("cuda")
+
+        def loss2(out):
+            return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1, lambda_smooth=4e-3)[0]
+        g2 = GraphedStep(make_palette_train_step(m2, opt2, sc2, o, d, loss2), warmup=3)
+        for _ in range(3):
+            g2.replay()
+        t2 = []
+        for _ in range(10):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g2.replay(); b.record()
+            torch.cuda.synchronize()
+            t2.append(a.elapsed_time(b))
+        smooth = {"ms_per_step": sum(t2) / len(t2), "rays_per_s": TRAIN_RAYS / (sum(t2) / len(t2) / 1e3),
+                  "schedule": getattr(m2, "_last_train_schedule", "torch"), "lambda_smooth": 4e-3,
+                  "kernel_us_per_step": _kernel_breakdown(torch, g2.replay, barrier)}
+        del g2, m2, opt2
     # the optimizer alone (HBM stream: 16 B read + 12 B written per element with a gradient), same events / L2 flush
     adam = None
     if not torch_adam:
@@ -592,7 +618,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
                       "allreduce": None if world == 1 else _allreduce_name(bucket, nccl_allreduce),
                       "allreduce_bucket_bytes": None if bucket is None or bucket.flat is None else 4 * bucket.flat.numel(),
                       "allreduce_max_abs_err": None if world == 1 else _allreduce_check(torch, dist, dev, rank, world),
-                      "kernel_us_per_step_rank0": breakdown,
+                      "kernel_us_per_step_rank0": breakdown, "with_smooth_loss": smooth,
                       "loss": "torch expressions" if torch_loss else "palette_loss (fused: 2 launches fwd + 1 bwd)",
                       "workload": "palette-stage training step (BASELINE config 4), force_all_rays, no smooth loss"}}
 
@@ -639,6 +665,32 @@ def bench_nerf(torch, dev, S, flush):
             res[f"density_update_{name}_torch_ms"] = timeit(lambda: upd(False), reps=2, warm=1)
     finally:
         D.world = real_world
+    # stage-1 TRAINING step (ref: Trainer.train_step, nerf/utils.py:389-470 with MSE loss): 4096 rays, fwd + bwd + Adam under
+    # autocast + GradScaler. Not fused: the reference's schedule on this repository's per-op kernels (march, hash grid, SH,
+    # compositor) with the MLPs in torch, eager launches.
+    try:
+        from palettenerf_b200.optim import FusedAdam
+        tm = S.build_nerf_model(dev, seed=0)
+        tm.train()
+        opt = FusedAdam(tm.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+        scaler = torch.amp.GradScaler("cuda")
+        to, td = S.training_rays(TRAIN_RAYS, seed=0)
+        to, td = to.to(dev)[None].contiguous(), td.to(dev)[None].contiguous()
+        gt = torch.rand(1, TRAIN_RAYS, 3, device=dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = tm.render(to, td, staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0, max_steps=1024)
+                loss = ((out["image"] - gt) ** 2).mean()
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        res["train_step_ms"] = timeit(train_step, reps=10, warm=5)
+        res["train_rays_per_s"] = TRAIN_RAYS / (res["train_step_ms"] / 1e3)
+        res["train_schedule"] = "per-op kernels + torch MLPs, eager (not fused)"
+    except Exception as e:   # noqa: BLE001  (a secondary record: never fails the bench)
+        res["train_step_error"] = f"{type(e).__name__}: {e}"
     res["note"] = ("render: csrc/field_tc.cu (model_kind 1) vs the host loop of nerf/renderer.py:329-386 on the per-op kernels; "
                    "density update: csrc/density_tc.cu (3-4 launches, threshold on the device) vs the torch-op schedule of "
                    "nerf/renderer.py:467-561 (the only host read left in the fused path is mean_count)")

@@ -496,6 +496,20 @@ typedef struct pnerf_palette_loss_args {
 PNERF_API uint32_t pnerf_palette_loss_partials(uint32_t N);
 
 PNERF_API int pnerf_palette_loss(const pnerf_palette_loss_args* args, void* stream);
+/* Smooth-loss channel of the palette training field (ref: palette/renderer.py:360-381), csrc/loss.cu: from the field's channel
+ * rows and the rows of the same field at jittered positions, gate = exp(-|x - x_j|^2 / bound^2 / sigma_xyz - |diffuse -
+ * diffuse_j|^2 / sigma_color - |clip - clip_j| / sigma_clip) (a constant for the gradient), smooth = gate * (|omega_j - omega|^2
+ * + |clip_j - clip|^2), written into column 3 of `channels` IN PLACE. count (optional): device int32, number of valid rows.
+ * Backward: g_channels is updated in place (smooth column folded into the omega / clip columns, column 3 cleared),
+ * g_channels_j is written for the valid rows. */
+PNERF_API int pnerf_palette_smooth_forward(float* channels, const float* channels_j, const float* xyzs, const float* xyzs_j,
+                                           uint32_t M, const int32_t* count, uint32_t nflex, uint32_t clip_dim,
+                                           uint32_t num_basis, uint32_t pred_clip, float bound, float sigma_xyz,
+                                           float sigma_color, float sigma_clip, float* gate, void* stream);
+PNERF_API int pnerf_palette_smooth_backward(float* g_channels, float* g_channels_j, const float* channels,
+                                            const float* channels_j, const float* gate, uint32_t M, const int32_t* count,
+                                            uint32_t nflex, uint32_t clip_dim, uint32_t num_basis, uint32_t pred_clip,
+                                            void* stream);
 PNERF_API int pnerf_scale_buffers(float* b0, uint32_t n0, float* b1, uint32_t n1, float* b2, uint32_t n2, float* b3,
                                   uint32_t n3, const float* scale, void* stream);
 

@@ -38,6 +38,8 @@ L.register("pnerf_palette_train_wgrad", [U, U, P, P, P, P, P])
 F_ = c_float
 L.register("pnerf_palette_composite_train_forward", [P, P, P, P, P, U, U, U, F_, P, P, P, P, P])
 L.register("pnerf_palette_composite_train_backward", [P, P, P, P, P, U, U, U, F_, P, P, P])
+L.register("pnerf_palette_smooth_forward", [P, P, P, P, U, P, U, U, U, U, F_, F_, F_, F_, P, P])
+L.register("pnerf_palette_smooth_backward", [P, P, P, P, P, U, P, U, U, U, U, P])
 L.register("pnerf_grid_encode_backward_counted", [P, P, P, P, U, U, F_, U, U, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, F_, P])
 for _n in ("pnerf_palette_train_xbuf_bytes", "pnerf_palette_train_ybuf_bytes"):
     getattr(L.lib, _n).argtypes = [U, U]
@@ -372,6 +374,44 @@ def field(model, xyzs, dirs, palette, count=None):
         st["weights"] = [sd[n] for n in st["names"]]
     emb_clip = model.encoder_clip.embeddings if st["pred_clip"] else None
     return _TrainField.apply(model, count, xyzs, dirs, palette, model.encoder_palette.embeddings, emb_clip, *st["weights"])
+
+
+class _SmoothGate(Function):
+    """smooth-loss channel (ref: palette/renderer.py:360-381) from the field's channel rows and the rows of the same field at
+    jittered positions (csrc/loss.cu: pnerf_palette_smooth_forward / _backward): column 3 of `channels` is written IN PLACE
+    (the field's backward never reads that column), the gate is a constant of the gradient, rows beyond `count` are not
+    touched. Replaces ~30 elementwise launches over the full static capacity (3.7 ms per step) by two kernels."""
+
+    @staticmethod
+    def forward(ctx, channels, ch_j, xyzs, xyzs_j, count, dims):
+        nb, cd, pc, bound, s_xyz, s_color, s_clip = dims
+        assert channels.is_contiguous() and ch_j.is_contiguous() and channels.dtype == torch.float32 == ch_j.dtype
+        M, nflex = channels.shape
+        xyzs, xyzs_j = xyzs.contiguous().float(), xyzs_j.contiguous().float()
+        gate = ARENA.get("smooth_gate", (M,), torch.float32, channels.device).detach()
+        L.call("pnerf_palette_smooth_forward", ptr(channels), ptr(ch_j), ptr(xyzs), ptr(xyzs_j), M, ptr(count), nflex, cd, nb,
+               int(pc), float(bound), float(s_xyz), float(s_color), float(s_clip), ptr(gate), stream())
+        ctx.mark_dirty(channels)
+        ctx.save_for_backward(channels, ch_j, gate)
+        ctx.count, ctx.dims = count, (M, nflex, nb, cd, int(pc))
+        return channels
+
+    @staticmethod
+    def backward(ctx, g):
+        channels, ch_j, gate = ctx.saved_tensors
+        M, nflex, nb, cd, pc = ctx.dims
+        g = g.contiguous().float()
+        g_j = ARENA.get("g_ch_j", (M, nflex), torch.float32, g.device).detach()
+        L.call("pnerf_palette_smooth_backward", ptr(g), ptr(g_j), ptr(channels), ptr(ch_j), ptr(gate), M, ptr(ctx.count), nflex,
+               cd, nb, pc, stream())
+        return g, g_j, None, None, None, None
+
+
+def smooth_gate(model, channels, ch_j, xyzs, xyzs_j, count):
+    o = model.opt
+    dims = (model.num_basis, o.clip_dim, bool(o.pred_clip), model.bound, o.smooth_sigma_xyz, o.smooth_sigma_color,
+            o.smooth_sigma_clip if o.pred_clip else 0.0)
+    return _SmoothGate.apply(channels, ch_j, xyzs, xyzs_j, count, dims)
 
 
 class _CompositeTrain(Function):

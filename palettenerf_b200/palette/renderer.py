@@ -194,27 +194,15 @@ class PaletteRenderer(nn.Module, OccupancyState):
     def _smooth_channels(self, fused_train, xyzs, dirs, palette, valid, channels):
         """smooth-loss branch of the training field (ref: palette/renderer.py:360-381) on the fused kernels: a SECOND fused
         forward on the jittered points (its backward runs through the same hand-written kernels: the reference lets the
-        gradient of smooth_norm flow into both evaluations), the gate / norm arithmetic as a handful of per-sample tensor
-        expressions, and the result replaces column 3 of the channel buffer the one-pass compositor consumes.
+        gradient of smooth_norm flow into both evaluations), the gate / norm arithmetic as one kernel forward and one
+        backward over the valid rows (fused_train.smooth_gate), written into column 3 of the channel buffer the one-pass
+        compositor consumes.
         Rows beyond `valid` (static capacity) hold garbage on both sides and are never composited."""
         nb, cd = self.num_basis, self.opt.clip_dim
         b = self.bound
         jitter = (xyzs + torch.rand_like(xyzs) * b * 0.03).clamp(-b, b)
         _, _, ch_j = fused_train.field(self, jitter, dirs, palette, count=valid)
-        c0 = 13 + cd
-        omega, omega_j = channels[:, c0:c0 + nb], ch_j[:, c0:c0 + nb]
-        diffuse, diffuse_j = channels[:, 10:13], ch_j[:, 10:13]
-        clip, clip_j = channels[:, 13:c0], ch_j[:, 13:c0]
-        k_xyz = (xyzs - jitter).norm(dim=-1, keepdim=True) ** 2 / b ** 2 / self.opt.smooth_sigma_xyz
-        k_rgb = (diffuse - diffuse_j).norm(dim=-1, keepdim=True) ** 2 / self.opt.smooth_sigma_color
-        k_clip = 0
-        if self.opt.pred_clip and self.opt.smooth_sigma_clip > 0:
-            k_clip = (clip - clip_j).norm(dim=-1, keepdim=True) / self.opt.smooth_sigma_clip
-        gate = torch.exp(-k_xyz - k_rgb - k_clip).detach()
-        smooth = ((omega_j - omega) ** 2).sum(dim=-1, keepdim=True) * gate
-        if self.opt.pred_clip:
-            smooth = smooth + ((clip_j - clip) ** 2).sum(dim=-1, keepdim=True) * gate
-        return torch.cat([channels[:, :3], smooth, channels[:, 4:]], dim=1)
+        return fused_train.smooth_gate(self, channels, ch_j, xyzs, jitter, valid)
 
     # ------------------------------------------------------------------------------------------------
     def _train_branch(self, rays_o, rays_d, nears, fars, bg_color, prefix, dt_gamma, perturb, force_all_rays, max_steps,

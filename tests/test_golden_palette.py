@@ -226,3 +226,22 @@ def test_reference_layout_dict_round_trips_strict(gold, case):
         # initialize_palette() makes basis_color_origin an alias of basis_color's storage (palette/renderer.py:258, kept):
         # the later key of the dict wins for both, in the reference exactly as here
         assert torch.equal(v, sd["basis_color_origin" if k == "basis_color" else k]), k
+
+
+def test_render_oracle_matches_reference_on_rays_of_the_800x800_view():
+    """tests/golden/ref_view800.npz: the reference's own render of the full 800 x 800 view; the oracle renders the pinned
+    rays (every 131st; rays are independent) — a second, larger set of rays than the 32 x 32 view, same bars."""
+    import make_golden_view800 as V
+    g = np.load(os.path.join(HERE, "golden", "ref_view800.npz"))
+    stride = int(g["stride"])
+    m = PC.build_model("noclip", "cpu")
+    params = {k: v.detach() for k, v in m.state_dict().items()}
+    o, d = V.view_rays()
+    o, d = o[::stride].contiguous(), d[::stride].contiguous()
+    for ds in (40,):            # terminating rays: ~6 s on one core (ds 1 marches every ray to its end: covered on the GPU)
+        out = cpu_render.render_cuda_ray(params, o, d, m.density_bitfield, pred_clip=False, density_scale=float(ds), **PC.RENDER_KW)
+        for k in EVAL_KEYS:
+            r = g[f"ds{ds}_fp32_{k}_rows"]
+            scale = max(1.0, np.abs(r).max())
+            _close(out[k], r, 5e-5 * scale, f"view800/ds{ds}/{k} vs ref fp32")
+            _close(out[k], g[f"ds{ds}_f16_{k}_rows"], 1e-3 * scale, f"view800/ds{ds}/{k} vs ref f16")

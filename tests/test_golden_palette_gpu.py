@@ -400,3 +400,31 @@ def test_field_cache_follows_data_writes_that_do_not_bump_versions(cuda):
         p.data.copy_(s)                                         # "restore"
     c = _render(m, o, d, True)["image"]
     assert torch.equal(a, c)
+
+
+# ---- one full 800 x 800 view (BASELINE config 3's size) against the reference's own render of it ----
+VIEW800 = os.path.join(HERE, "golden", "ref_view800.npz")
+
+
+@pytest.mark.parametrize("ds", [1, 40])
+def test_full_800x800_view_against_the_reference_render(cuda, ds):
+    """tests/golden/ref_view800.npz (make_golden_view800.py: the reference's PaletteRenderer.run_cuda on its own kernels):
+    every 131st ray of the 640 000 pinned row by row, plus the mean of every map over the whole view. The fused renderer
+    runs the full view exactly as bench.py does (shared windows, 148 x 16 resident warps with ~57 rays each)."""
+    import make_golden_view800 as V
+    g = np.load(VIEW800)
+    stride = int(g["stride"])
+    m = PC.build_model("noclip", cuda)
+    m.eval()
+    m.density_scale = float(ds)
+    o, d = V.view_rays()
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    fus = _render(m, o, d, True)
+    assert m._last_queue[2].item() > 100000            # rays with samples
+    for k in EVAL_KEYS:
+        a = fus[k].detach().float().reshape(V.SIDE * V.SIDE, -1)
+        r32, r16 = g[f"ds{ds}_fp32_{k}_rows"], g[f"ds{ds}_f16_{k}_rows"]
+        _check(a[::stride], r32, TOL_F16_VS_FP32, f"view800/ds{ds}/{k}/fused_vs_ref32")
+        _check(a[::stride], r16, TOL_F16_VS_F16, f"view800/ds{ds}/{k}/fused_vs_ref16")
+        # systematic differences cannot hide in a mean over 640 000 rays: a tenth of the per-ray bar
+        _check(a.double().mean(dim=0), g[f"ds{ds}_fp32_{k}_mean"], 1e-4, f"view800/ds{ds}/{k}/mean_vs_ref32")
