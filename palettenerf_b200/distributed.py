@@ -148,6 +148,7 @@ class PeerMemory:
         import ctypes
         import os
         self._ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self._range_ptrs = {0: self._ptrs}
         # NVLS: the bucket's multicast mapping (0 when the fabric / driver has no multicast support) -> in-switch reduction.
         # Used from 4 ranks up: per GPU it moves 1/world of the bucket instead of (world-1)/world; at 2 ranks the traffic
         # is the same and the multimem round trip is slower (measured: 0.771 vs 0.721 ms per DP step, profiles/README.md).
@@ -155,42 +156,94 @@ class PeerMemory:
         use_mc = want_mc == "1" or (want_mc == "auto" and self.world >= 4)
         self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0) if use_mc else 0
 
-    def all_reduce_(self, average):
+    def all_reduce_(self, average, lo=0, hi=None, channels=(0, 1)):
+        """all-reduce of bucket[lo:hi] (both multiples of 4 * world) on the CURRENT stream. All calls of a process must be
+        stream-ordered with respect to each other (see GradBucket.early)"""
         import ctypes
         from . import _lib as L
+        hi = self.n if hi is None else hi
+        pad = 4 * self.world
+        if lo % pad or hi % pad or not (0 <= lo < hi <= self.n):
+            raise ValueError(f"peer all-reduce range [{lo}, {hi}) must be a multiple of {pad} inside the bucket")
         scale = (1.0 / self.world) if average else 1.0
-        self.handle.barrier(channel=0)                      # every rank's gradients are in its bucket
+        self.handle.barrier(channel=channels[0])            # every rank's gradients are in its bucket
         if self.mc_ptr:
-            L.call("pnerf_peer_allreduce_mc", self.mc_ptr, self.world, self.rank, self.n, scale, L.stream())
+            L.call("pnerf_peer_allreduce_mc", self.mc_ptr + 4 * lo, self.world, self.rank, hi - lo, scale, L.stream())
         else:
-            L.call("pnerf_peer_allreduce", ctypes.addressof(self._ptrs), self.world, self.rank, self.n, scale, L.stream())
-        self.handle.barrier(channel=1)                      # every slice has been delivered to every rank
+            ptrs = self._range_ptrs.get(lo)
+            if ptrs is None:
+                ptrs = self._range_ptrs[lo] = (ctypes.c_uint64 * self.world)(*[int(p) + 4 * lo for p in self.handle.buffer_ptrs])
+            L.call("pnerf_peer_allreduce", ctypes.addressof(ptrs), self.world, self.rank, hi - lo, scale, L.stream())
+        self.handle.barrier(channel=channels[1])            # every slice has been delivered to every rank
 
 
 class GradBucket:
-    """ONE flat fp32 all-reduce per step for all trainable gradients (+ the found-inf flag of the loss scaler).
-    peer=True: the bucket lives in symmetric memory and the all-reduce is `pnerf_peer_allreduce` over NVLink peer
-    memory (CUDA, one box, <= 8 ranks); otherwise (and on CPU / gloo) `dist.all_reduce`."""
+    """ONE flat fp32 bucket for all trainable gradients (+ the found-inf flag of the loss scaler), all-reduced once per step.
+    peer=True: the bucket lives in symmetric memory and the all-reduce is `pnerf_peer_allreduce[_mc]` over NVLink peer
+    memory (CUDA, one box, <= 8 ranks); otherwise (and on CPU / gloo) `dist.all_reduce`.
+
+    Layout: the LARGE tensors (>= 2^20 elements: the hash tables, 99.9 % of the bytes) first, padded to the collective's
+    granularity, then the small ones and the flag. The fused backward (palettenerf_b200/fused_train.py) asks `slot(p)` for
+    the place of a table's gradient, scatters straight into it — no pack copy — and calls `early(params)`: the large region
+    is then all-reduced on a SIDE STREAM while the main stream still computes the MLP weight gradients; `all_reduce()`
+    afterwards packs and reduces the small region and joins the side stream."""
+    BIG = 1 << 20
 
     def __init__(self, params, peer=False):
         self.params = [p for p in params if p.requires_grad]
         self.flat = None
-        self._sizes, self._views = None, []
+        self._sizes, self._views, self._off = None, [], {}
         self.peer, self._pm = bool(peer), None
+        self._big_end = 0
+        self._early_event, self._side = None, None
+        self.early_count = 0                                # times the large region went out early (tests / bench report it)
 
     def _live(self):
-        return [p for p in self.params if p.grad is not None]
+        live = [p for p in self.params if p.grad is not None]
+        return sorted(live, key=lambda p: 0 if p.numel() >= self.BIG else 1)          # stable: big tensors first
+
+    # ---- direct placement + early all-reduce of the big region (peer path only) ----
+    def slot(self, p):
+        """fresh view of the bucket where p's gradient lives (None until the first all_reduce has laid the bucket out, or
+        when p is not one of the large tensors of the peer path)"""
+        off = self._off.get(id(p))
+        if off is None or self._pm is None or off >= self._big_end:
+            return None
+        return self.flat[off:off + p.numel()].view_as(p)
+
+    def early(self, params, average=True):
+        """the gradients of `params` have been written into their slots: if they are the whole large region, all-reduce it
+        now on the side stream (returns True), else do nothing"""
+        ws, _ = world()
+        if self._pm is None or ws <= 1 or self._big_end == 0:
+            return False
+        if sum(p.numel() for p in params) != self._big_numel or any(self._off.get(id(p), self._big_end) >= self._big_end for p in params):
+            return False
+        # EVERY cross-GPU barrier of a step is issued on the side stream, in the same order on every rank (this region, then
+        # the small one in all_reduce()): two spin-waiting barriers left unordered on one rank — one per stream — can
+        # deadlock against a peer whose runtime happens to schedule them the other way round (seen under CUDA graphs)
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._pm.all_reduce_(average, 0, self._big_end)
+        self._early_event = True
+        self.early_count += 1
+        return True
 
     def all_reduce(self, found_inf=None, average=True, group=None):
         """sums (or averages) gradients across ranks; returns the global found-inf flag (max over ranks).
-        Pack = ONE multi-tensor copy into the flat bucket; after the collective every `p.grad` IS its slice of the bucket
-        (re-pointed, not copied back), so the per-step cost besides the all-reduce is one 50 MB copy and one scaling
-        kernel instead of ~40 small launches. The bucket is therefore owned by the gradients until the next backward."""
+        Pack = ONE multi-tensor copy of the gradients that are not already in place; after the collective every `p.grad` IS
+        its slice of the bucket (re-pointed, not copied back). The bucket is owned by the gradients until the next backward."""
         ws, _ = world()
         live = self._live()
         sizes = [p.grad.numel() for p in live]
-        n = sum(sizes) + 1
         dev = live[0].grad.device if live else torch.device("cpu")
+        pad = 4 * ws
+        big = sum(k for p, k in zip(live, sizes) if p.numel() >= self.BIG)
+        big_end = (big + pad - 1) // pad * pad if (self.peer and ws > 1 and dev.type == "cuda") else big
+        n = big_end + (sum(sizes) - big) + 1
         if self.flat is None or self._sizes != sizes or self.flat.device != dev:
             self._pm = None
             if self.peer and ws > 1 and dev.type == "cuda":
@@ -202,16 +255,25 @@ class GradBucket:
             if self._pm is not None:
                 self.flat = self._pm.buf[:n]
             else:
-                self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+                self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
             self._sizes = sizes
-            self._views, off = [], 0
-            for k in sizes:
+            self._views, self._off, off = [], {}, 0
+            for p, k in zip(live, sizes):
+                if off == big and big_end != big:
+                    off = big_end                                  # (padding between the large and the small region)
                 self._views.append(self.flat[off:off + k])
+                self._off[id(p)] = off
                 off += k
+            self._big_end, self._big_numel = (big_end if self._pm is not None else 0), big
+            self._early_event = None
         flat, off = self.flat, n - 1
-        srcs = [p.grad.reshape(-1) for p in live]
-        if any(s.data_ptr() != v.data_ptr() for s, v in zip(srcs, self._views)):   # (already in place: nothing to pack)
-            torch._foreach_copy_(self._views, srcs)
+        pairs = [(v, p.grad.reshape(-1)) for p, v in zip(live, self._views)]
+        todo = [(v, s) for v, s in pairs if s.data_ptr() != v.data_ptr()]          # (already in place: nothing to pack)
+        early = self._early_event is not None
+        if early and any(v.data_ptr() < flat.data_ptr() + 4 * self._big_end for v, _ in todo):
+            raise RuntimeError("GradBucket: the large region was all-reduced early but a gradient of it is not in its slot")
+        if todo:
+            torch._foreach_copy_([v for v, _ in todo], [s for _, s in todo])
         # the flag rides in the same bucket; it is summed, so any rank's inf makes it non-zero everywhere
         # (device-side writes only: a Python scalar assignment is a host->device copy, which a CUDA-graph capture rejects)
         if found_inf is None:
@@ -221,7 +283,15 @@ class GradBucket:
         else:
             flat[off:off + 1].fill_(float(found_inf))
         if ws > 1 and self._pm is not None:
-            self._pm.all_reduce_(average)              # averaging is folded into the reduction kernel
+            if early:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._pm.all_reduce_(average, self._big_end, self._pm.n)   # small region + flag (+ the bucket's tail pad)
+                main.wait_stream(self._side)
+                self._early_event = None
+            else:
+                self._pm.all_reduce_(average)              # averaging is folded into the reduction kernel
         elif ws > 1:
             dist.all_reduce(flat, group=group)
             if average:

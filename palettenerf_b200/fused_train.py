@@ -274,6 +274,8 @@ class _TrainField(Function):
     @staticmethod
     def forward(ctx, model, count, xyzs, dirs, palette, emb_palette, emb_clip, *weights):
         st = _state(model)
+        if any(ctx.needs_input_grad):
+            st["pending"] = st.get("pending", 0) + 1        # forwards whose backward has not run yet (see backward: DP slots)
         L.require_cuda(xyzs, dirs, emb_palette)
         dev = xyzs.device
         xyzs, dirs = xyzs.detach().contiguous().float(), dirs.detach().contiguous().float()
@@ -337,19 +339,33 @@ class _TrainField(Function):
         dw = torch.zeros(int(L.lib.pnerf_palette_train_dw_floats(int(pc))), dtype=torch.float32, device=dev)
         L.call("pnerf_palette_train_backward", M, ctypes.addressof(f), ptr(xbuf), ptr(ybuf), ptr(g_rgb), ptr(g_flex), ptr(flex),
                ptr(d_enc), ptr(d_enc_clip), ptr(d_pal), stream())
-        # basis_net: the reference leaves it out of get_params (palette/network.py:283-308), so nothing ever steps it and its
-        # weight gradients are dead work; they are computed only when the model asks (`fused_basis_net_grad = True`),
-        # otherwise those parameters receive NO gradient (None) on this path
-        basis = bool(getattr(model, "fused_basis_net_grad", False))
-        L.call("pnerf_palette_train_wgrad", M, int(pc) | (2 if basis else 0), ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
         # hash-grid scatter of the feature gradients (run-length kernel, fp32 accumulation, [B, L*C] layout)
         from .gridencoder.backend import _backend as GB
         enc = model.encoder_palette
         x01 = ((xyzs + model.bound) / (2 * model.bound)).contiguous() if count is None else None
         S_ = float(np.float32(np.log2(enc.per_level_scale)))
+        # data parallel (distributed.GradBucket attached to the model): the table gradients are scattered STRAIGHT INTO the
+        # bucket (no pack copy) and their all-reduce starts on a side stream before the weight-gradient kernel below runs
+        # Only when this is the step's ONLY field evaluation and nothing has been accumulated into the tables' .grad yet
+        # (a second evaluation — the smooth loss — or gradient accumulation would add to a buffer already in flight).
+        bucket = getattr(model, "_grad_bucket", None)
+        pending = st.get("pending", 1)
+        st["pending"] = max(0, pending - 1)
+        if st.get("group_left", 0) > 0:                     # a later backward of a group of several evaluations
+            st["group_left"] -= 1
+            bucket = None
+        elif pending > 1:                                   # the first backward of such a group
+            st["group_left"] = pending - 1
+            bucket = None
+        if model.encoder_palette.embeddings.grad is not None or (pc and model.encoder_clip.embeddings.grad is not None):
+            bucket = None
 
         def scatter(emb, d):
-            g = torch.zeros_like(emb, dtype=torch.float32)
+            g = bucket.slot(emb) if bucket is not None else None
+            if g is None:
+                g = torch.zeros_like(emb, dtype=torch.float32)
+            else:
+                g.zero_()
             if count is None:
                 GB.grid_encode_backward_blc(d, x01, g, offsets, g, M, 3, 2, enc.num_levels, S_, enc.base_resolution, None,
                                             None, 0, False)
@@ -360,6 +376,13 @@ class _TrainField(Function):
         emb_pal, emb_clip = model.encoder_palette.embeddings, model.encoder_clip.embeddings
         g_pal_tab = scatter(emb_pal, d_enc) if M > 0 else torch.zeros_like(emb_pal)
         g_clip_tab = (scatter(emb_clip, d_enc_clip) if M > 0 else torch.zeros_like(emb_clip)) if pc else None
+        if bucket is not None and M > 0:
+            bucket.early([emb_pal] + ([emb_clip] if pc else []))
+        # basis_net: the reference leaves it out of get_params (palette/network.py:283-308), so nothing ever steps it and its
+        # weight gradients are dead work; they are computed only when the model asks (`fused_basis_net_grad = True`),
+        # otherwise those parameters receive NO gradient (None) on this path
+        basis = bool(getattr(model, "fused_basis_net_grad", False))
+        L.call("pnerf_palette_train_wgrad", M, int(pc) | (2 if basis else 0), ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
         gw = dw_views(dw, pc, cd)
         grads = [None if (not basis and n.startswith("basis_net")) else gw.get(n) for n in st["names"]]   # sigma_net.* -> None
         return (None, None, None, None, d_pal, g_pal_tab, g_clip_tab, *grads)

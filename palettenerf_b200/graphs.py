@@ -43,6 +43,9 @@ def make_palette_train_step(model, optimizer, scaler, rays_o, rays_d, loss_fn, r
     loss_fn(out) -> scalar loss from the render dict. bucket: optional distributed.GradBucket (one all-reduce per step)."""
     kw = dict(staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0, max_steps=1024)
     kw.update(render_kwargs or {})
+    if bucket is not None:
+        # the fused backward places the hash-table gradients in the bucket itself and starts their all-reduce early
+        object.__setattr__(model, "_grad_bucket", bucket)
 
     def step_fn():
         optimizer.zero_grad(set_to_none=True)

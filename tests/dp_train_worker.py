@@ -1,0 +1,99 @@
+"""Worker of tests/test_peer_gpu.py (torchrun, one rank per GPU): the data-parallel palette training step with the peer-memory
+bucket — hash-table gradients scattered straight into the bucket, their all-reduce started on a side stream under the
+weight-gradient kernel (GradBucket.slot / early) — against the same steps with the plain NCCL bucket (pack, one all-reduce
+after backward). Same rays, same initial weights: the parameters after three steps must agree, on every rank; also with the
+smooth loss (two field evaluations per step: the early path must stand down) and inside a CUDA graph."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+from palettenerf_b200 import synthetic as S  # noqa: E402
+from palettenerf_b200.distributed import GradBucket  # noqa: E402
+from palettenerf_b200.graphs import GraphedStep, make_palette_train_step  # noqa: E402
+from palettenerf_b200.optim import FusedAdam  # noqa: E402
+from palettenerf_b200.palette.losses import palette_loss  # noqa: E402
+
+RAYS = 1024
+
+
+def build(dev, rank, peer, smooth):
+    torch.manual_seed(0)
+    model = S.build_palette_model(dev, seed=0, pred_clip=False)
+    model.train()
+    model.require_smooth_loss = smooth
+    opt = FusedAdam(model.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=10 ** 9)
+    bucket = GradBucket(params, peer=peer)
+    o, d = S.training_rays(RAYS, seed=rank)
+    o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
+    gt = torch.rand(1, RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+
+    def loss_fn(out):
+        return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1,
+                            lambda_smooth=4e-3 if smooth else 0.0)[0]
+    step = make_palette_train_step(model, opt, scaler, o, d, loss_fn, render_kwargs=dict(perturb=False), bucket=bucket)
+    return model, bucket, step
+
+
+def run_config(dev, rank, smooth, graph):
+    results = {}
+    for peer in (True, False):
+        model, bucket, step = build(dev, rank, peer, smooth)
+        if smooth:
+            torch.manual_seed(1234)             # the jitter of the smooth branch: same stream for both buckets
+        if graph:
+            g = GraphedStep(step, warmup=2)
+            g.replay()
+        else:
+            for _ in range(3):
+                step()
+        torch.cuda.synchronize()
+        if peer:
+            assert bucket._pm is not None, "the peer path must be the one that ran"
+            if smooth:
+                assert bucket.early_count == 0, "two field evaluations per step: the early all-reduce must not run"
+            else:
+                assert bucket.early_count >= 2, f"the large region was not all-reduced early ({bucket.early_count})"
+        results[peer] = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for n, a in results[True].items():
+        b = results[False][n]
+        # (not bit-equal by construction: the hash-grid scatter adds with float atomics in arbitrary order, and Adam turns
+        # a last-bit difference of a noise-level gradient into a visible fraction of lr; three steps move a weight by
+        # at most 3e-2)
+        err, mean = (a - b).abs().max().item(), (a - b).abs().mean().item()
+        assert err <= 5e-4 and mean <= 5e-6, f"smooth={smooth} graph={graph} {n}: peer vs nccl bucket {err:.3e} / {mean:.3e}"
+        ref = a.double().sum().reshape(1)
+        mine = ref.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), f"{n}: ranks hold different parameters after the peer-bucket steps"
+    moved = (results[True]["encoder_palette.embeddings"] - S.build_palette_model(dev, seed=0, pred_clip=False)
+             .encoder_palette.embeddings).abs().max().item()
+    assert moved > 1e-4, "the steps must have changed the palette table"
+
+
+def main():
+    import gc
+    import threading
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    for smooth, graph in ((False, False), (True, False), (False, True)):
+        run_config(dev, rank, smooth, graph)
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+    if rank == 0:
+        print("DP_TRAIN_OK", flush=True)
+    # the checks are done; a stalled teardown of NCCL / symmetric-memory state must not hold the GPUs
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
