@@ -406,6 +406,10 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
     }
 }
 
+// (Measured and rejected: a software-pipelined version — batches of two levels, the 8 loads of batch i + 1 issued before batch i
+// is interpolated, so that a warp always has gathers in flight instead of a burst of 16 followed by a drain — 5.12 vs 4.92 ms
+// per 800x800 view: the other three warps of the scheduler already cover the drain, the extra live batch costs scheduling
+// freedom at the 128-register cap.)
 // (Measured and rejected, profiles/README.md "gather variants": computing the corner indices once for the density and
 // palette grids — same geometry — and reading both tables with them cuts ~30 % of the gather's instructions but does not
 // speed the renderer up: the gather is bound by L1/L2 load latency, the index arithmetic hides under it, and the second
