@@ -334,6 +334,27 @@ __device__ __forceinline__ void fhfma2(float& ax, float& ay, uint32_t v, uint16_
         : "+f"(ax), "+f"(ay)
         : "r"(v), "h"(w));
 }
+// two fp32 weights -> one register of two fp16 weights with ONE conversion instruction (F2FP.F16.F32.PACK_AB), each rounded
+// to nearest exactly as cvt.rn.f16.f32 would
+__device__ __forceinline__ uint32_t f2h_pair(float lo, float hi) {
+    uint32_t p;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    return p;
+}
+// the same two FHFMA with the weight taken from the low (HI = false) or high half of a weight pair
+template <bool HI>
+__device__ __forceinline__ void fhfma2_sel(float& ax, float& ay, uint32_t v, uint32_t wpair) {
+    if (HI)
+        asm("{\n\t.reg .f16 lo, hi, wl, wh;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b32 {wl, wh}, %3;\n\tfma.rn.f32.f16 %0, lo, wh, %0;\n\t"
+            "fma.rn.f32.f16 %1, hi, wh, %1;\n\t}"
+            : "+f"(ax), "+f"(ay)
+            : "r"(v), "r"(wpair));
+    else
+        asm("{\n\t.reg .f16 lo, hi, wl, wh;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b32 {wl, wh}, %3;\n\tfma.rn.f32.f16 %0, lo, wl, %0;\n\t"
+            "fma.rn.f32.f16 %1, hi, wl, %1;\n\t}"
+            : "+f"(ax), "+f"(ay)
+            : "r"(v), "r"(wpair));
+}
 
 template <int EW, int LV, typename StoreFn>
 __device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
@@ -349,7 +370,7 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
 #pragma unroll 1
         for (int l0 = 0; l0 < 16; l0 += LV) {
             uint32_t val[LV][4][EW];
-            uint16_t wt[LV][4];
+            uint32_t wt[LV][2];                            // fp16 weight pairs {corner 0, 1}, {corner 2, 3}
 #pragma unroll
             for (int j = 0; j < LV; j++) {
                 const LevelParams& p = lp[l0 + j];
@@ -359,8 +380,8 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
                 const float rx = px - fx0, ry = py - fy0, rz = pz - fz0;
                 const float wx = xsel ? rx : 1.f - rx;
                 const float wxy0 = wx * (1.f - ry), wxy1 = wx * ry;        // (wx*wy)*wz: the reference's order
-                wt[j][0] = f2h_bits(wxy0 * (1.f - rz)); wt[j][1] = f2h_bits(wxy1 * (1.f - rz));
-                wt[j][2] = f2h_bits(wxy0 * rz);         wt[j][3] = f2h_bits(wxy1 * rz);
+                wt[j][0] = f2h_pair(wxy0 * (1.f - rz), wxy1 * (1.f - rz));
+                wt[j][1] = f2h_pair(wxy0 * rz, wxy1 * rz);
                 uint32_t idx[4];
                 const uint32_t hx = gx + xsel;
                 if (p.use_hash) {
@@ -386,7 +407,10 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
                 for (int e = 0; e < EW; e++) {
                     acc[e][0] = acc[e][1] = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) fhfma2(acc[e][0], acc[e][1], val[j][c][e], wt[j][c]);
+                    for (int c = 0; c < 4; c += 2) {
+                        fhfma2_sel<false>(acc[e][0], acc[e][1], val[j][c][e], wt[j][c >> 1]);
+                        fhfma2_sel<true>(acc[e][0], acc[e][1], val[j][c + 1][e], wt[j][c >> 1]);
+                    }
                 }
                 float rx_, ry_;
                 if (EW == 2) {
