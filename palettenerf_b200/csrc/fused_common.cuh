@@ -248,6 +248,8 @@ __device__ __forceinline__ void ldg_entry(uint64_t base, uint32_t idx, uint32_t 
     if (EW == 1) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v[0]) : "l"(addr));
     else asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[EW - 1]) : "l"(addr));
 }
+// (Tried: the entry size as a run-time register operand so that the address is one IMAD.WIDE.U32 instead of the LEA +
+// LEA.HI.X pair ptxas makes of a power-of-two immediate — ptxas then emits IMAD.WIDE + IADD3 + IMAD.X, three slots. Kept as is.)
 
 template <int EW, int LV>
 __device__ __forceinline__ void gather_fast(const void* __restrict__ table, const LevelParams* __restrict__ lp,
