@@ -111,3 +111,28 @@ def test_grad_bucket_single_process_semantics():
     ps[0].grad = torch.ones(5, 3)
     b.all_reduce()
     assert b.flat.numel() == 16 and b.signature() == [(5, 3)]
+
+
+def test_grad_bucket_puts_large_tensors_first_and_hands_out_no_slots_without_peer_memory():
+    """layout of the bucket: tensors of >= 2^20 elements (the hash tables) in front of the small ones — the region the peer
+    path all-reduces early. On the CPU / NCCL path there is no peer memory: slot() must return None and early() must do
+    nothing, so that the fused backward keeps its ordinary gradient tensors."""
+    import torch
+    from palettenerf_b200.distributed import GradBucket
+    small = torch.nn.Parameter(torch.zeros(64, 3))
+    big = torch.nn.Parameter(torch.zeros(GradBucket.BIG // 2 + 8, 2))
+    tail = torch.nn.Parameter(torch.zeros(9))
+    b = GradBucket([small, big, tail])
+    assert b.slot(big) is None                                            # nothing laid out yet
+    small.grad, big.grad, tail.grad = torch.ones(64, 3), torch.full(big.shape, 2.0), torch.arange(9.0)
+    flag = b.all_reduce(average=True)
+    assert float(flag) == 0.0
+    assert b.signature() == [tuple(big.shape), (64, 3), (9,)]
+    assert big.grad.data_ptr() == b.flat.data_ptr()                       # the large tensor leads the bucket
+    assert small.grad.data_ptr() == b.flat[big.numel():].data_ptr()
+    assert torch.equal(big.grad, torch.full(big.shape, 2.0)) and torch.equal(tail.grad, torch.arange(9.0))
+    assert b.slot(big) is None and b.early([big]) is False and b.early_count == 0
+    # a gradient that already lives in its view is not copied again
+    big.grad.mul_(3.0)
+    b.all_reduce(average=True)
+    assert torch.equal(big.grad, torch.full(big.shape, 6.0))
