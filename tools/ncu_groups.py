@@ -28,7 +28,7 @@ def load(rep, obj, kern):
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.search(r'/\*[0-9a-f]{4}\*/', ln):
+        if re.search(r'/\*[0-9a-f]{4,5}\*/', ln):
             lines.append(cur)
     return data, lines
 

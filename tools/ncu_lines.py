@@ -28,7 +28,7 @@ def main(rep, obj, kern, top=45):
     for ln in body.split("\n"):
         m = re.search(r'//## File "(.*?)", line (\d+)', ln)
         if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
-        if re.search(r'/\*[0-9a-f]{4}\*/', ln): lines.append(cur)
+        if re.search(r'/\*[0-9a-f]{4,5}\*/', ln): lines.append(cur)
     n = min(len(lines), len(data))
     print(f"sass instructions: report {len(data)}, disasm {len(lines)}")
     per_line, per_file = collections.defaultdict(lambda: [0, 0, collections.Counter()]), collections.defaultdict(lambda: [0, 0])

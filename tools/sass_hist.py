@@ -17,7 +17,7 @@ def main(obj, kern, out=None):
             name = m.group(1) if cur else name
             continue
         if cur:
-            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", ln)
+            m = re.search(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", ln)
             if m:
                 hist[m.group(1)] += 1
     total = sum(hist.values())
