@@ -665,30 +665,51 @@ def bench_nerf(torch, dev, S, flush):
             res[f"density_update_{name}_torch_ms"] = timeit(lambda: upd(False), reps=2, warm=1)
     finally:
         D.world = real_world
-    # stage-1 TRAINING step (ref: Trainer.train_step, nerf/utils.py:389-470 with MSE loss): 4096 rays, fwd + bwd + Adam under
-    # autocast + GradScaler. Not fused: the reference's schedule on this repository's per-op kernels (march, hash grid, SH,
-    # compositor) with the MLPs in torch, eager launches.
+    # stage-1 TRAINING step (ref: Trainer.train_step, nerf/utils.py:485-560 with the MSE criterion + rays_gt error channel):
+    # 4096 rays, fwd + bwd + Adam under autocast + GradScaler. Three schedules on the same model and rays: the fused step
+    # (csrc/nerf_train.cu: one field forward kernel, hand-written backward, one-pass compositor) eager and replayed from a
+    # CUDA graph, and the reference's schedule on this repository's per-op kernels with the MLPs in torch.
     try:
+        from palettenerf_b200.graphs import GraphedStep
         from palettenerf_b200.optim import FusedAdam
-        tm = S.build_nerf_model(dev, seed=0)
-        tm.train()
-        opt = FusedAdam(tm.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
-        scaler = torch.amp.GradScaler("cuda")
         to, td = S.training_rays(TRAIN_RAYS, seed=0)
         to, td = to.to(dev)[None].contiguous(), td.to(dev)[None].contiguous()
         gt = torch.rand(1, TRAIN_RAYS, 3, device=dev)
 
-        def train_step():
-            opt.zero_grad(set_to_none=True)
-            with torch.autocast("cuda", dtype=torch.float16):
-                out = tm.render(to, td, staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0, max_steps=1024)
-                loss = ((out["image"] - gt) ** 2).mean()
-            scaler.scale(loss).backward()
-            scaler.step(opt)
-            scaler.update()
-        res["train_step_ms"] = timeit(train_step, reps=10, warm=5)
+        def make(fused):
+            tm = S.build_nerf_model(dev, seed=0)
+            tm.train()
+            opt = FusedAdam(tm.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+            scaler = torch.amp.GradScaler("cuda")
+
+            def train_step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.float16):
+                    out = tm.render(to, td, rays_gt=gt, staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0,
+                                    max_steps=1024, fused=fused)
+                    loss = (((out["image"] - gt) ** 2).mean(-1) + 0.05 * out["rgb_norm"]).mean()   # lambda_sparse default, main_nerf.py:67
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                return loss.detach()
+            return tm, train_step
+        tm, step = make(None)
+        gs = GraphedStep(step, warmup=3)              # the capture stream must be the first to step this model
+        res["train_step_ms"] = timeit(gs.replay, reps=20, warm=5)
+        res["train_schedule"] = tm._last_train_schedule + " (csrc/nerf_train.cu), one CUDA graph per step"
         res["train_rays_per_s"] = TRAIN_RAYS / (res["train_step_ms"] / 1e3)
-        res["train_schedule"] = "per-op kernels + torch MLPs, eager (not fused)"
+        res["train_samples_per_step"] = int(tm.step_counter[(tm.local_step - 1) % 16, 0].item())
+        tm2, step2 = make(None)
+        res["train_step_fused_eager_ms"] = timeit(step2, reps=10, warm=5)
+        tm3, step3 = make(False)
+        res["train_step_per_op_ms"] = timeit(step3, reps=10, warm=5)
+        res["train_per_op_schedule"] = tm3._last_train_schedule + ": per-op kernels + torch MLPs, eager (round-2 record: 2.66 ms)"
+        from palettenerf_b200 import _lib as L_
+        L_.profile_start()
+        step2()
+        prof = L_.profile_stop()
+        res["train_kernel_us_fused_eager"] = {k.replace("pnerf_", ""): round(1e3 * v[0] / max(1, v[1]), 1) for k, v in
+                                              sorted(prof.items(), key=lambda kv: -kv[1][0])}
     except Exception as e:   # noqa: BLE001  (a secondary record: never fails the bench)
         res["train_step_error"] = f"{type(e).__name__}: {e}"
     res["note"] = ("render: csrc/field_tc.cu (model_kind 1) vs the host loop of nerf/renderer.py:329-386 on the per-op kernels; "

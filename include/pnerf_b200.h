@@ -412,6 +412,60 @@ PNERF_API int pnerf_palette_train_backward(uint32_t M, const pnerf_palette_train
 PNERF_API int pnerf_palette_train_wgrad(uint32_t M, uint32_t flags, const void* xbuf, const void* ybuf, float* dwbuf,
                                         const int32_t* m_dev, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Fused TRAINING field of the stage-1 model (csrc/nerf_train.cu). Replaces `sigmas, rgbs = self(xyzs, dirs)` of
+ * NeRFRenderer.run_cuda's training branch (ref: nerf/renderer.py:289-298 -> NeRFNetwork.forward, nerf/network.py:78-124:
+ * GridEncoder -> sigma_net 32-64-16 -> trunc_exp / geo_feat; SHEncoder(4) ++ geo_feat -> color_net 31-64-64-3 -> sigmoid)
+ * and its autograd graph. Architecture: the reference's defaults (L = 16, F = 2 hash grid, 64-wide bias-free MLPs).
+ *   forward : sigma [M] = density_scale * exp(h0) (the product nerf/renderer.py:299 forms), rgb [M,3]; layer inputs saved
+ *             in xbuf (pnerf_nerf_train_xbuf_bytes)
+ *   backward: (grad_sigma [M] w.r.t. the SCALED sigma, grad_rgb [M,3]) -> ybuf (per-layer pre-activation gradients) and
+ *             d_enc [M,32] fp32 = gradient of the hash-grid features (scatter it with pnerf_grid_encode_backward*);
+ *             trunc_exp's backward clamp (activation.py:14-17) is applied
+ *   wgrad   : dwbuf (pnerf_nerf_train_dw_floats, fp32, caller zero-fills) += packed weight gradients, blocks
+ *             sigma_net.0 64x32, sigma_net.1 16x64, color_net.0 64x32 (input columns [SH16 | logit(0) | geo15]),
+ *             color_net.1 64x64, color_net.2 16x64 (rows 0-2)
+ * wfwd / wbwd: fp16 mma B-fragment images built by palettenerf_b200/fused_nerf_train.py (pnerf_nerf_train_w*_units uint2).
+ * m_dev: optional device-side sample count (static-capacity step); rows >= min(M, *m_dev) are neither read nor written.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pnerf_nerf_train {
+    const void* table;          /* fp16 [n_entries,2] : encoder.embeddings */
+    const int32_t* offsets;     /* [L+1] */
+    const void* wfwd;
+    const void* wbwd;
+    const int32_t* m_dev;
+    uint32_t L, H;
+    float S, bound, density_scale;
+} pnerf_nerf_train;
+
+PNERF_API uint64_t pnerf_nerf_train_xbuf_bytes(uint32_t M);
+PNERF_API uint64_t pnerf_nerf_train_ybuf_bytes(uint32_t M);
+PNERF_API uint32_t pnerf_nerf_train_dw_floats(void);
+PNERF_API uint32_t pnerf_nerf_train_wfwd_units(void);
+PNERF_API uint32_t pnerf_nerf_train_wbwd_units(void);
+PNERF_API int pnerf_nerf_train_forward(const float* xyzs, const float* dirs, uint32_t M, const pnerf_nerf_train* p, void* xbuf,
+                                       float* sigma, float* rgb, void* stream);
+PNERF_API int pnerf_nerf_train_backward(uint32_t M, const pnerf_nerf_train* p, const void* xbuf, void* ybuf,
+                                        const float* grad_sigma, const float* grad_rgb, const float* sigma, const float* rgb,
+                                        float* d_enc, void* stream);
+PNERF_API int pnerf_nerf_train_wgrad(uint32_t M, const void* xbuf, const void* ybuf, float* dwbuf, const int32_t* m_dev,
+                                     void* stream);
+
+/* ONE-pass compositor of the stage-1 training step (ref: nerf/renderer.py:301-327 = spread_ray_to_sample + the squared
+ * error per sample + composite_rays_train twice, raymarching.cu:504-580, 681-761): rgb, depth, weights_sum and the error
+ * channel err_map[ray] = sum_i w_i |gt[ray] - rgb_i|^2 (what the reference returns as rgb_norm) in one warp-per-ray pass.
+ * gt: [N,3] target colour per ray (NULL: err_map = 0). backward: gradients w.r.t. sigmas and rgbs from (grad_weights_sum |
+ * NULL, grad_image, grad_err | NULL); every sample row of every ray that fits is written (zeros behind the terminating
+ * sample), so the gradient buffers need not be zero-initialised. */
+PNERF_API int pnerf_nerf_composite_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                                 const float* gt, uint32_t M, uint32_t N, float T_thresh, float* weights_sum,
+                                                 float* depth, float* image, float* err_map, void* stream);
+PNERF_API int pnerf_nerf_composite_train_backward(const float* grad_weights_sum, const float* grad_image, const float* grad_err,
+                                                  const float* sigmas, const float* rgbs, const float* deltas,
+                                                  const int32_t* rays, const float* gt, const float* weights_sum,
+                                                  const float* image, const float* err_map, uint32_t M, uint32_t N,
+                                                  float T_thresh, float* grad_sigmas, float* grad_rgbs, void* stream);
+
 /* ONE-pass compositor of the palette training step: composite_rays_train on (sigma, rgb) and composite_rays_flex_train
  * on the nflex auxiliary channels together (ref: raymarching.cu:504-645, palette/renderer.py:354, 387-397).
  * backward: gradients w.r.t. rgb and flex only (sigma is a constant of the palette stage); EVERY sample row of every ray

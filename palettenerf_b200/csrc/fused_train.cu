@@ -26,7 +26,7 @@
 // sigma-grid gradient; palette/network.py:168, palette/renderer.py:334-335), diffuse enters the basis net detached
 // (network.py:257) and view_dep enters rgb detached (renderer.py:351); view_dep / diffuse are trained through
 // direct_rgb and the regularisers. The smooth-loss branch (renderer.py:360-381) stays on the unfused path.
-#include "fused_common.cuh"
+#include "train_common.cuh"
 
 namespace pnerf {
 
@@ -59,77 +59,6 @@ __host__ __device__ constexpr int dw_off(int l) {
 }
 constexpr int kDwFloatsNoClip = dw_off(DW_C0);
 constexpr int kDwFloatsClip = dw_off(kNumDw);
-
-constexpr int kTrainWarps = 8;     // backward CTA: 8 warps, <= 255 registers
-constexpr int kDStride = 88;       // halfs per row of the per-warp gradient staging tile (176 B: ldmatrix rows conflict-free)
-enum DCol { DC_HEAD = 0, DC_VIEW = 32, DC_DIFF = 48, DC_CLIP = 64 };
-
-__device__ __forceinline__ void st_unit(uint32_t* __restrict__ base, int unit, const uint32_t (&a)[4], int lane) {
-    uint32_t* p = base + unit * 128 + lane;
-    p[0] = a[0]; p[32] = a[1]; p[64] = a[2]; p[96] = a[3];
-}
-__device__ __forceinline__ void ld_unit(const uint32_t* __restrict__ base, int unit, uint32_t (&a)[4], int lane) {
-    const uint32_t* p = base + unit * 128 + lane;
-    a[0] = __ldg(p); a[1] = __ldg(p + 32); a[2] = __ldg(p + 64); a[3] = __ldg(p + 96);
-}
-
-template <int STRIDE>
-__device__ __forceinline__ void ldmatrix_a_s(uint32_t (&a)[4], const __half* tile, int row0, int col0, int lane) {
-    const __half* p = tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * STRIDE + col0 + (lane >> 4) * 8;
-    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-                 : "r"(addr));
-}
-
-__device__ __forceinline__ uint32_t movmatrix_t(uint32_t v) {
-    uint32_t r;
-    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(r) : "r"(v));
-    return r;
-}
-
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
-
-// accumulators of 8 n-tiles (a 16 x 64 block of dL/d(post-activation)) times the activation derivative taken from the
-// saved post-activation fragments -> A fragments of dL/d(pre-activation), also stored as the layer's dY units
-enum Deriv { DRV_RELU, DRV_ELU };
-template <int DRV>
-__device__ __forceinline__ void deriv_pack(const float (&c)[8][4], const uint32_t* __restrict__ xbase, int xslot,
-                                           uint32_t* __restrict__ ybase, int yslot, uint32_t (&a)[4][4], int lane) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t h[4];
-        ld_unit(xbase, xslot + j, h, lane);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float2 hv = unpack_h2(h[i]);
-            const float g0 = c[2 * j + (i >> 1)][(i & 1) * 2], g1 = c[2 * j + (i >> 1)][(i & 1) * 2 + 1];
-            float d0, d1;
-            if (DRV == DRV_RELU) { d0 = hv.x > 0.f ? g0 : 0.f; d1 = hv.y > 0.f ? g1 : 0.f; }
-            else { d0 = hv.x > 0.f ? g0 : g0 * (hv.x + 1.0f); d1 = hv.y > 0.f ? g1 : g1 * (hv.y + 1.0f); }   // ELU' = elu + 1
-            a[j][i] = pack_h2(d0, d1);
-        }
-        st_unit(ybase, yslot + j, a[j], lane);
-    }
-}
-
-// 16 x 32 fp32 block of grid-feature gradients -> d_enc rows (C-fragment layout: rows g / g+8, cols nt*8 + 2q, +1)
-__device__ __forceinline__ void store_denc(float* __restrict__ d_enc, uint32_t s0, uint32_t M, const float (&c)[4][4], int lane) {
-    const uint32_t r0 = s0 + (lane >> 2), r1 = r0 + 8;
-    const int q = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-        if (r0 < M) *reinterpret_cast<float2*>(d_enc + (size_t)r0 * 32 + nt * 8 + 2 * q) = make_float2(c[nt][0], c[nt][1]);
-        if (r1 < M) *reinterpret_cast<float2*>(d_enc + (size_t)r1 * 32 + nt * 8 + 2 * q) = make_float2(c[nt][2], c[nt][3]);
-    }
-}
-
-struct TrainSmem {
-    LevelParams lp[kMaxLevels];
-    float palette[kNB * 3];
-    uint32_t fast_wrap;   // every level wraps with a mask (see FusedSmem::fast_wrap)
-    // followed by: uint2 weights[...]; per-warp scratch
-};
 
 // =====================================================================================================================
 // forward
@@ -572,13 +501,8 @@ k_field_train_bwd(uint32_t M, pnerf_palette_train f, const uint32_t* __restrict_
 // One warp owns ALL 16-row blocks of one layer for a chunk of half-tiles, so every saved fragment is read exactly once
 // (203 MB at 122 k samples instead of 371 MB when a warp owned a single 16-row block), and the loads of the next
 // half-tile are issued before the MMAs of the current one.
-struct WJob { uint16_t yslot, xslot, ny, ux, kpad, pad; uint32_t dwoff; };
-struct WJobs { WJob j[16]; uint32_t n; };
-
 __host__ inline void add_job(WJobs& J, int yslot, int ny, int xslot, int ux, int dwl) {
-    WJob& w = J.j[J.n++];
-    w.yslot = (uint16_t)yslot; w.xslot = (uint16_t)xslot; w.ny = (uint16_t)ny; w.ux = (uint16_t)ux;
-    w.kpad = (uint16_t)dw_k(dwl); w.pad = 0; w.dwoff = (uint32_t)dw_off(dwl);
+    add_job_at(J, yslot, ny, xslot, ux, dw_k(dwl), dw_off(dwl));
 }
 
 constexpr int kWgradWarps = 4;
@@ -663,6 +587,15 @@ k_field_wgrad(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ yb
             default: break;
         }
     }
+}
+
+int launch_field_wgrad(const uint32_t* xbuf, const uint32_t* ybuf, uint32_t M, const int32_t* m_dev, uint32_t UX, uint32_t UY,
+                       const WJobs& J, float* dwbuf, cudaStream_t stream, const char* what) {
+    const uint32_t n_half_cap = ceil_div(M, 32u) * 2;
+    const uint32_t grid_x = min(ceil_div(ceil_div(n_half_cap, 32u), (uint32_t)kWgradWarps), 2u * (uint32_t)kNumSMs);
+    const dim3 grid(max(grid_x, 1u), J.n, 1);
+    k_field_wgrad<<<grid, kWgradWarps * 32, 0, stream>>>(xbuf, ybuf, M, m_dev, UX, UY, J, dwbuf);
+    return check_launch(what);
 }
 
 }  // namespace pnerf
@@ -766,13 +699,8 @@ int pnerf_palette_train_wgrad(uint32_t M, uint32_t flags, const void* xbuf, cons
         add_job(J, YC0, 4, XC0, 2, DW_C0);
         add_job(J, YC1, 1, XC1, 4, DW_C1);
     }
-    const uint32_t n_half_cap = ceil_div(M, 32u) * 2;
-    const uint32_t grid_x = min(ceil_div(ceil_div(n_half_cap, 32u), (uint32_t)kWgradWarps), 2u * (uint32_t)kNumSMs);
-    const dim3 grid(max(grid_x, 1u), J.n, 1);
-    k_field_wgrad<<<grid, kWgradWarps * 32, 0, (cudaStream_t)stream>>>((const uint32_t*)xbuf, (const uint32_t*)ybuf, M, m_dev,
-                                                                       pred_clip ? kUXClip : kUXNoClip,
-                                                                       pred_clip ? kUYClip : kUYNoClip, J, dwbuf);
-    return check_launch("palette_train_wgrad");
+    return launch_field_wgrad((const uint32_t*)xbuf, (const uint32_t*)ybuf, M, m_dev, pred_clip ? kUXClip : kUXNoClip,
+                              pred_clip ? kUYClip : kUYNoClip, J, dwbuf, (cudaStream_t)stream, "palette_train_wgrad");
 }
 
 }  // extern "C"

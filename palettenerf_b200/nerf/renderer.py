@@ -279,6 +279,13 @@ class NeRFRenderer(nn.Module, OccupancyState):
             return bool(fused)
         return torch.is_autocast_enabled() and fused_nerf.supported_color(self)
 
+    def _fused_train_available(self, fused=None):
+        """default policy like the palette stage's: the fused step under fp16 autocast for the architecture it covers"""
+        from .. import fused_nerf_train
+        if fused is not None:
+            return bool(fused)
+        return torch.is_autocast_enabled() and fused_nerf_train.supported(self) and self.bg_radius <= 0
+
     def run_cuda(self, rays_o, rays_d, rays_gt=None, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
                  max_steps=1024, T_thresh=1e-4, **kwargs):
         """rays_o, rays_d: [B, N, 3] (B == 1) -> dict(image [B,N,3], depth [B,N], rgb_norm, weights_sum)"""
@@ -291,7 +298,23 @@ class NeRFRenderer(nn.Module, OccupancyState):
         bg_color = self._background(rays_o, rays_d, bg_color)
         C, H = self.cascade, self.grid_size
 
-        if self.training:
+        if self.training and self._fused_train_available(kwargs.get("fused")):
+            # Fused stage-1 step: static-capacity march (sample count stays on the device: no D2H sync), ONE forward kernel
+            # for hash grid + sigma net + SH + colour net with hand-written backward kernels, ONE compositing pass for
+            # rgb / depth / weights and the per-ray error channel (fused_nerf_train).
+            from .. import fused_nerf_train
+            self._last_train_schedule = "fused"
+            xyzs, dirs, deltas, rays, valid = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, C, H, nears, fars, self._next_counter(), self.mean_count,
+                perturb, 128, force_all_rays, dt_gamma, max_steps, True)
+            sigmas, rgbs = fused_nerf_train.field(self, xyzs, dirs, count=valid)      # density_scale applied in the kernel
+            gt = None if rays_gt is None else rays_gt.contiguous().view(-1, 3)
+            weights_sum, depth, image, err_map = fused_nerf_train.composite(sigmas, rgbs, deltas, rays, gt, T_thresh, static=True)
+            depth, image, _ = render_tail(depth, nears, fars, image, weights_sum, bg_color)
+            image, depth = image.view(*prefix, 3), depth.view(*prefix)
+            rgb_norm = err_map.view(*prefix)
+        elif self.training:
+            self._last_train_schedule = "torch"
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_bitfield, C, H, nears, fars, self._next_counter(), self.mean_count,
                 perturb, 128, force_all_rays, dt_gamma, max_steps)
