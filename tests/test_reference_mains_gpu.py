@@ -2,8 +2,8 @@
 (tools/run_reference_main.py installs them under the reference's import names; compat/ stands in for the third-party
 packages this image lacks). Stage 1 trains a NeRF for 8 epochs on a 12-view synthetic Blender-format scene, evaluates, tests
 and exports; stage 2 loads that checkpoint into the palette model and trains / evaluates it. Asserted: both mains exit 0,
-the epoch-mean loss falls, and the renderer calls took the fused schedules (density refresh, eval render, palette train
-step). The reference sources come from /root/reference here and from oracle/_ref/py (staged by build()) on the GPU box."""
+the epoch-mean loss falls, and the renderer calls took the fused schedules (density refresh, eval render, stage-1 and
+palette train steps). The reference sources come from /root/reference here and from oracle/_ref/py (staged by build()) on the GPU box."""
 import json
 import os
 import re
@@ -52,6 +52,8 @@ def test_reference_mains_run_unchanged_on_the_drop_in_packages(cuda, tmp_path):
     assert not any("update_schedule=torch" in k for k in sched), sched
     assert sched.get("NeRFRenderer.run_cuda[eval]:schedule=fused", 0) >= 6, sched      # 3 eval + 3 test views
     assert not any("schedule=loop" in k for k in sched), sched
+    assert sched.get("NeRFRenderer.run_cuda[train]:train_schedule=fused", 0) == 96, sched      # csrc/nerf_train.cu
+    assert not any("train_schedule=torch" in k for k in sched), sched
     ckpts = os.listdir(os.path.join(cwd, "results", "synth", "version_1", "checkpoints"))
     assert any(c.endswith(".pth") for c in ckpts), ckpts
 

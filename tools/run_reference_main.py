@@ -70,7 +70,7 @@ def _tally_schedules(nerf_cls, palette_cls):
             return out
         setattr(cls, name, call)
     wrap(nerf_cls, "update_extra_state", ("_last_update_schedule",))
-    wrap(nerf_cls, "run_cuda", ("_last_schedule",))
+    wrap(nerf_cls, "run_cuda", ("_last_schedule", "_last_train_schedule"))
     wrap(palette_cls, "run_cuda", ("_last_schedule", "_last_train_schedule"))
 
 
