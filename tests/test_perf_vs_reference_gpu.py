@@ -273,3 +273,74 @@ def test_end_to_end_reference_schedule_on_reference_kernels_vs_fused(cuda, flush
     _record("train_step_4096rays_palette", ref_ms, graph_ms)
     RESULTS["train_step_4096rays_palette"].update(reference_rays_per_s=4096 / ref_ms * 1e3, new_rays_per_s=4096 / graph_ms * 1e3,
                                                   new_eager_rays_per_s=4096 / eager_ms * 1e3)
+
+
+def test_stage1_reference_schedule_on_reference_kernels_vs_fused(cuda, flush):
+    """stage-1 (NeRF) model: 800x800 render and the 4096-ray training step, the reference's host schedule on the reference's own
+    kernels (oracle/_ref) against the fused paths (csrc/field_tc.cu model_kind 1, csrc/nerf_train.cu)"""
+    mods = {n: load_ref(n) for n in ("raymarching", "gridencoder", "shencoder")}
+    if any(v is None for v in mods.values()):
+        pytest.skip("oracle/_ref not built")
+    model = S.build_nerf_model(cuda, seed=0)
+    model.eval()
+    o, d = S.camera_rays(800, 800)
+    o, d = o.to(cuda), d.to(cuda)
+
+    def render(fused):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return model.render(o[None], d[None], staged=True, bg_color=1, perturb=False, fused=fused, dt_gamma=0.0, max_steps=1024,
+                                T_thresh=1e-4)
+    new_ms = _time(lambda: render(None), iters=5, flush=flush)
+    assert model._last_schedule == "fused"
+    undo = _swap_backends(mods)
+    try:
+        ref_ms = _time(lambda: render(False), iters=3, warm=1, flush=flush)
+    finally:
+        undo()
+    _record("render_800x800_nerf_stage", ref_ms, new_ms)
+    RESULTS["render_800x800_nerf_stage"].update(rays=640000, reference_rays_per_s=640000 / ref_ms * 1e3,
+                                                new_rays_per_s=640000 / new_ms * 1e3)
+
+    to, td = S.training_rays(4096, seed=0)
+    to, td = to.to(cuda)[None].contiguous(), td.to(cuda)[None].contiguous()
+    gt = torch.rand(1, 4096, 3, device=cuda, generator=torch.Generator(device=cuda).manual_seed(0))
+
+    def make(fused_adam):
+        from palettenerf_b200.optim import FusedAdam
+        m = S.build_nerf_model(cuda, seed=0)
+        m.train()
+        opt = FusedAdam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15) if fused_adam else \
+            torch.optim.Adam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
+        scaler = torch.amp.GradScaler("cuda")
+
+        def step(fused):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = m.render(to, td, rays_gt=gt, staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0,
+                               max_steps=1024, fused=fused)
+                loss = (((out["image"] - gt) ** 2).mean(-1) + 0.05 * out["rgb_norm"]).mean()      # nerf/utils.py:535-536
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+            return loss.detach()
+        return m, step
+    m2, step2 = make(False)
+    undo = _swap_backends(mods)
+    try:
+        ref_ms = _time(lambda: step2(False), iters=10, warm=5, flush=flush)
+    finally:
+        undo()
+    assert m2._last_train_schedule == "torch"
+    del m2, step2
+    m1, step1 = make(False)
+    eager_ms = _time(lambda: step1(None), iters=10, warm=5, flush=flush)
+    assert m1._last_train_schedule == "fused"
+    del m1, step1
+    from palettenerf_b200.graphs import GraphedStep
+    m3, step3 = make(True)
+    g = GraphedStep(lambda: step3(None), warmup=3)
+    graph_ms = _time(g.replay, iters=10, warm=3, flush=flush)
+    _record("train_step_4096rays_nerf_stage_eager", ref_ms, eager_ms, check=False)
+    _record("train_step_4096rays_nerf_stage", ref_ms, graph_ms)
+    RESULTS["train_step_4096rays_nerf_stage"].update(reference_rays_per_s=4096 / ref_ms * 1e3, new_rays_per_s=4096 / graph_ms * 1e3,
+                                                     new_eager_rays_per_s=4096 / eager_ms * 1e3)
