@@ -506,11 +506,18 @@ __host__ inline void add_job(WJobs& J, int yslot, int ny, int xslot, int ux, int
 }
 
 constexpr int kWgradWarps = 4;
+#ifndef PNERF_WGRAD_MIN_CHUNK
+#define PNERF_WGRAD_MIN_CHUNK 16
+#endif
 
+// One warp: split-K partial sum of one layer's dW over its chunks of half-tiles (registers), then the CTA's four partial
+// sums are added in shared memory (the warps take turns: no shared-memory atomics, fixed order) and the CTA issues ONE
+// fp32 reduction per weight — a quarter of the global reductions of a per-warp flush, which is what lets the chunks be
+// half as long (twice the warps in flight for the same latency-bound loop).
 template <int NY, int UX>
-__device__ __forceinline__ void wgrad_job(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t h0,
-                                          uint32_t h1, uint32_t UXT, uint32_t UYT, const WJob& job, float* __restrict__ dwbuf,
-                                          int lane) {
+__device__ __forceinline__ void wgrad_job(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t n_half,
+                                          uint32_t per_chunk, uint32_t chunk0, uint32_t chunk_stride, uint32_t UXT, uint32_t UYT,
+                                          const WJob& job, float* __restrict__ dwbuf, float* __restrict__ sdw, int lane, int wid) {
     float c[NY][2 * UX][4];
 #pragma unroll
     for (int m = 0; m < NY; m++)
@@ -525,74 +532,95 @@ __device__ __forceinline__ void wgrad_job(const uint32_t* __restrict__ xbuf, con
 #pragma unroll
         for (int j = 0; j < UX; j++) ld_unit(xb, job.xslot + j, q[j], lane);
     };
-    load(h0);
 #pragma unroll 1
-    for (uint32_t h = h0; h < h1; h++) {
-        // transposes of the current half-tile's fragments (registers), then prefetch the next half-tile
-        uint32_t a[NY][4], b[UX][4];
+    for (uint32_t chunk = chunk0; chunk * per_chunk < n_half; chunk += chunk_stride) {
+        const uint32_t h0 = chunk * per_chunk, h1 = min(n_half, h0 + per_chunk);
+        load(h0);
+#pragma unroll 1
+        for (uint32_t h = h0; h < h1; h++) {
+            // transposes of the current half-tile's fragments (registers), then prefetch the next half-tile
+            uint32_t a[NY][4], b[UX][4];
 #pragma unroll
-        for (int m = 0; m < NY; m++) {   // A = (dY block)^T: 8x8 transposes + swap of the off-diagonal blocks
-            a[m][0] = movmatrix_t(p[m][0]); a[m][1] = movmatrix_t(p[m][2]); a[m][2] = movmatrix_t(p[m][1]); a[m][3] = movmatrix_t(p[m][3]);
-        }
-#pragma unroll
-        for (int j = 0; j < UX; j++) {   // B (k = sample, n = k_in), .col fragment order = transposes of the stored blocks
-#pragma unroll
-            for (int i = 0; i < 4; i++) b[j][i] = movmatrix_t(q[j][i]);
-        }
-        if (h + 1 < h1) load(h + 1);
-#pragma unroll
-        for (int m = 0; m < NY; m++)
-#pragma unroll
-            for (int j = 0; j < UX; j++) {
-                mma16816(c[m][2 * j], a[m], b[j][0], b[j][1]);
-                mma16816(c[m][2 * j + 1], a[m], b[j][2], b[j][3]);
+            for (int m = 0; m < NY; m++) {   // A = (dY block)^T: 8x8 transposes + swap of the off-diagonal blocks
+                a[m][0] = movmatrix_t(p[m][0]); a[m][1] = movmatrix_t(p[m][2]); a[m][2] = movmatrix_t(p[m][1]); a[m][3] = movmatrix_t(p[m][3]);
             }
-    }
-    const int g = lane >> 2, q2 = (lane & 3) * 2;
 #pragma unroll
-    for (int m = 0; m < NY; m++) {
-        float* dw = dwbuf + job.dwoff + m * 16 * job.kpad;
+            for (int j = 0; j < UX; j++) {   // B (k = sample, n = k_in), .col fragment order = transposes of the stored blocks
 #pragma unroll
-        for (int nt = 0; nt < 2 * UX; nt++) {
-            const int col = nt * 8 + q2;
-            atomicAdd(dw + g * job.kpad + col, c[m][nt][0]);
-            atomicAdd(dw + g * job.kpad + col + 1, c[m][nt][1]);
-            atomicAdd(dw + (g + 8) * job.kpad + col, c[m][nt][2]);
-            atomicAdd(dw + (g + 8) * job.kpad + col + 1, c[m][nt][3]);
+                for (int i = 0; i < 4; i++) b[j][i] = movmatrix_t(q[j][i]);
+            }
+            if (h + 1 < h1) load(h + 1);
+#pragma unroll
+            for (int m = 0; m < NY; m++)
+#pragma unroll
+                for (int j = 0; j < UX; j++) {
+                    mma16816(c[m][2 * j], a[m], b[j][0], b[j][1]);
+                    mma16816(c[m][2 * j + 1], a[m], b[j][2], b[j][3]);
+                }
         }
+    }
+    // CTA-level sum: rows m * 16 + g (+8), compact row stride 16 * UX
+    constexpr int KP = 16 * UX;
+    const int g = lane >> 2, q2 = (lane & 3) * 2;
+#pragma unroll 1
+    for (int w = 0; w < kWgradWarps; w++) {
+        if (wid == w) {
+#pragma unroll
+            for (int m = 0; m < NY; m++) {
+                float* r0 = sdw + (m * 16 + g) * KP + q2;
+                float* r1 = r0 + 8 * KP;
+#pragma unroll
+                for (int nt = 0; nt < 2 * UX; nt++) {
+                    float2 v0 = make_float2(c[m][nt][0], c[m][nt][1]), v1 = make_float2(c[m][nt][2], c[m][nt][3]);
+                    if (w != 0) {
+                        const float2 o0 = *reinterpret_cast<const float2*>(r0 + nt * 8), o1 = *reinterpret_cast<const float2*>(r1 + nt * 8);
+                        v0.x += o0.x; v0.y += o0.y; v1.x += o1.x; v1.y += o1.y;
+                    }
+                    *reinterpret_cast<float2*>(r0 + nt * 8) = v0;
+                    *reinterpret_cast<float2*>(r1 + nt * 8) = v1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* dw = dwbuf + job.dwoff;
+    for (int i = threadIdx.x; i < NY * 16 * KP; i += kWgradWarps * 32) {
+        const int r = i / KP, col = i - r * KP;
+        const float v = sdw[i];
+        if (v != 0.f) atomicAdd(dw + r * job.kpad + col, v);
     }
 }
 
 __global__ void __launch_bounds__(kWgradWarps * 32)
 k_field_wgrad(const uint32_t* __restrict__ xbuf, const uint32_t* __restrict__ ybuf, uint32_t M, const int32_t* __restrict__ m_dev,
               uint32_t UX, uint32_t UY, const __grid_constant__ WJobs jobs, float* __restrict__ dwbuf) {
+    __shared__ __align__(16) float sdw[64 * 64];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const WJob job = jobs.j[blockIdx.y];
     if (m_dev) M = min(M, (uint32_t)__ldg(m_dev));
     const uint32_t n_half = ceil_div(M, 32u) * 2;
-    // every warp of this job gets one chunk of half-tiles when there is enough work, but never fewer than 32 half-tiles
-    // (512 samples) so that the closing atomics (one per weight per chunk) stay negligible; long inputs loop.
+    // every warp of this job gets one chunk of half-tiles when there is enough work, but never fewer than
+    // PNERF_WGRAD_MIN_CHUNK half-tiles so that the closing reductions (one per weight per CTA) stay negligible; long inputs loop.
     const uint32_t n_warps = gridDim.x * kWgradWarps;
-    const uint32_t per_chunk = min(128u, max(32u, ceil_div(n_half, n_warps)));
-    const int shape = job.ny * 8 + job.ux;   // uniform per blockIdx.y
-    for (uint32_t chunk = blockIdx.x * kWgradWarps + wid; chunk * per_chunk < n_half; chunk += n_warps) {
-        const uint32_t h0 = chunk * per_chunk, h1 = min(n_half, h0 + per_chunk);
-        switch (shape) {
-            case 4 * 8 + 1: wgrad_job<4, 1>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            case 4 * 8 + 2: wgrad_job<4, 2>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            case 4 * 8 + 3: wgrad_job<4, 3>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            case 4 * 8 + 4: wgrad_job<4, 4>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            case 1 * 8 + 4: wgrad_job<1, 4>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            case 2 * 8 + 1: wgrad_job<2, 1>(xbuf, ybuf, h0, h1, UX, UY, job, dwbuf, lane); break;
-            default: break;
-        }
+    const uint32_t per_chunk = min(128u, max((uint32_t)PNERF_WGRAD_MIN_CHUNK, ceil_div(n_half, n_warps)));
+    const uint32_t chunk0 = blockIdx.x * kWgradWarps;
+    if (chunk0 * per_chunk >= n_half) return;                 // no warp of this CTA has work (CTA-uniform)
+    const int shape = job.ny * 8 + job.ux;                    // uniform per blockIdx.y
+    switch (shape) {
+        case 4 * 8 + 1: wgrad_job<4, 1>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        case 4 * 8 + 2: wgrad_job<4, 2>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        case 4 * 8 + 3: wgrad_job<4, 3>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        case 4 * 8 + 4: wgrad_job<4, 4>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        case 1 * 8 + 4: wgrad_job<1, 4>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        case 2 * 8 + 1: wgrad_job<2, 1>(xbuf, ybuf, n_half, per_chunk, chunk0 + wid, n_warps, UX, UY, job, dwbuf, sdw, lane, wid); break;
+        default: break;
     }
 }
 
 int launch_field_wgrad(const uint32_t* xbuf, const uint32_t* ybuf, uint32_t M, const int32_t* m_dev, uint32_t UX, uint32_t UY,
                        const WJobs& J, float* dwbuf, cudaStream_t stream, const char* what) {
     const uint32_t n_half_cap = ceil_div(M, 32u) * 2;
-    const uint32_t grid_x = min(ceil_div(ceil_div(n_half_cap, 32u), (uint32_t)kWgradWarps), 2u * (uint32_t)kNumSMs);
+    const uint32_t grid_x = min(ceil_div(ceil_div(n_half_cap, (uint32_t)PNERF_WGRAD_MIN_CHUNK), (uint32_t)kWgradWarps), 4u * (uint32_t)kNumSMs);
     const dim3 grid(max(grid_x, 1u), J.n, 1);
     k_field_wgrad<<<grid, kWgradWarps * 32, 0, stream>>>(xbuf, ybuf, M, m_dev, UX, UY, J, dwbuf);
     return check_launch(what);
