@@ -292,6 +292,17 @@ def main():
 
     extras = {}
     sections = set() if args.no_extras else set(args.sections.split(","))
+    if not args.no_extras:
+        # config 3's second variant: the same view without / with the five debug maps (reference gui_mode)
+        other = not args.gui_mode
+
+        def render_other():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                return model.render(o_dev[None], d_dev[None], staged=True, bg_color=1, perturb=False, gui_mode=other, fused=fused,
+                                    dt_gamma=S.LEGO["dt_gamma"], max_steps=S.LEGO["max_steps"], T_thresh=1e-4)
+        ms_other, _, _ = timed(render_other, max(3, min(args.steps, 10)), 3)
+        extras["render_gui_mode_variant"] = {"gui_mode": other, "ms_per_step": ms_other, "rays_per_s": world * N_RAYS / (ms_other / 1e3),
+                                             "note": "gui_mode=True skips direct / view-dependent / basis maps (palette/renderer.py:436-443)"}
     if "hashgrid" in sections:
         extras.update(bench_hashgrid(torch, dev, L, hbm_peak, flush))
     if "train" in sections:
