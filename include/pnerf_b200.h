@@ -265,11 +265,18 @@ PNERF_API int pnerf_palette_render_fused(const float* rays_o, const float* rays_
  *     [n_entries][2 grids][2] (field->table_sigma_palette), clip = fp16 [n_entries, 2] (field->table_clip).
  *   pnerf_field_cache_gather: src [n16 + n32] = device addresses of fp32 scalars (0 stands for the value 0); the first n16
  *     are written to out16 as fp16 (the weight images wpack / wpack_tc), the other n32 to out32 as fp32, clamped to [0, 1]
- *     from element clamp_from on (head_bias, then the palette). */
+ *     from element clamp_from on (head_bias, then the palette).
+ *   pnerf_field_cache_merge: the two product layers of the tcgen05 weight image (csrc/field_tc.cuh layer table), from the
+ *     fp32 parameters sigma_net.1.weight [16,64], diff_net.0.weight [64,15], basis_net.1.weight [15,64],
+ *     offsets_radiance_net.weight [13,15], omega_net.0.weight [4,15]: TD0 = diff_net.0 x sigma_net.1[1:16] and
+ *     TB1 = [offsets_radiance_net ; omega_net.0] x basis_net.1 (the reference applies no activation between these layers,
+ *     nerf/network.py:101-107, palette/network.py:262-268), written into wimage_tc (field->wpack_tc) after the gather. */
 PNERF_API int pnerf_field_cache_tables(const float* table_sigma, const float* table_palette, const float* table_clip,
                                        uint32_t n_entries, void* pair, void* clip, void* stream);
 PNERF_API int pnerf_field_cache_gather(const uint64_t* src, uint32_t n16, uint32_t n32, uint32_t clamp_from, void* out16,
                                        float* out32, void* stream);
+PNERF_API int pnerf_field_cache_merge(const float* sigma1_w, const float* diff0_w, const float* basis1_w, const float* offrad_w,
+                                      const float* omega_w, void* wimage_tc, void* stream);
 
 /* Tensor-core (tcgen05 / TMEM) version of pnerf_palette_field_forward: a warpgroup evaluates 128 samples per tile, every
  * dense layer is one tcgen05.mma chain (csrc/field_tc.cuh). Same arguments and results (fp16 operands, fp32 accumulation). */

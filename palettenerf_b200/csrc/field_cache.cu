@@ -5,11 +5,15 @@
 //   pnerf_field_cache_gather  every small tensor (MLP weight images in mma.sync and tcgen05 order, head bias, palette):
 //                             out[i] = *src[i] through a table of source ADDRESSES built once by the host (the parameters are
 //                             ~15 separate tensors; the address table is rebuilt only when one of them moves).
+//   pnerf_field_cache_merge   the two layers of the tcgen05 weight image that are products of reference layers without an
+//                             activation between them (field_tc.cuh layer table): fp32 products of the fp32 parameters, rounded
+//                             to fp16 once, written in the image's [k-chunk][n][8 halfs] order. 78 k MACs, one small launch.
 // Before: 3 strided torch copies + cat + 2 index + ~6 small copies = ~12 launches, 93 us per view; the reference has no
 // counterpart (its MLPs read the fp32 parameters through autocast on every call, palette/network.py:156-280).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "field_tc.cuh"
 
 namespace pnerf {
 
@@ -44,6 +48,29 @@ __global__ void __launch_bounds__(256) k_cache_gather(const unsigned long long* 
     }
 }
 
+// one thread per element of TD0 (64 x 64) and TB1 (32 x 64) of the tcgen05 weight image
+__global__ void __launch_bounds__(256) k_cache_merge(const float* __restrict__ s1 /*[16,64]*/, const float* __restrict__ d0 /*[64,15]*/,
+                                                     const float* __restrict__ b1 /*[15,64]*/, const float* __restrict__ orw /*[13,15]*/,
+                                                     const float* __restrict__ omw /*[4,15]*/, __half* __restrict__ image) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64 * 64) {
+        const int n = i >> 6, k = i & 63;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 15; j++) acc = fmaf(__ldg(d0 + n * 15 + j), __ldg(s1 + (1 + j) * 64 + k), acc);
+        image[tc_woff(TD0) / 2 + ((k >> 3) * 64 + n) * 8 + (k & 7)] = __float2half_rn(acc);
+    } else if (i < 64 * 64 + 32 * 64) {
+        const int e = i - 64 * 64, n = e >> 6, k = e & 63;
+        float acc = 0.f;
+        if (n < 17) {
+            const float* w = n < 13 ? orw + n * 15 : omw + (n - 13) * 15;
+#pragma unroll
+            for (int j = 0; j < 15; j++) acc = fmaf(__ldg(w + j), __ldg(b1 + j * 64 + k), acc);
+        }
+        image[tc_woff(TB1) / 2 + ((k >> 3) * 32 + n) * 8 + (k & 7)] = __float2half_rn(acc);
+    }
+}
+
 }  // namespace pnerf
 
 using namespace pnerf;
@@ -67,6 +94,14 @@ int pnerf_field_cache_gather(const uint64_t* src, uint32_t n16, uint32_t n32, ui
     k_cache_gather<<<ceil_div(n16 + n32, 256u), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)src, n16, n32,
                                                                                  clamp_from, (__half*)out16, out32);
     return check_launch("pnerf_field_cache_gather");
+}
+
+int pnerf_field_cache_merge(const float* sigma1_w, const float* diff0_w, const float* basis1_w, const float* offrad_w,
+                            const float* omega_w, void* wimage_tc, void* stream) {
+    if (!sigma1_w || !diff0_w || !basis1_w || !offrad_w || !omega_w || !wimage_tc) return PNERF_ERR_INVALID_ARG;
+    k_cache_merge<<<(64 * 64 + 32 * 64) / 256, 256, 0, (cudaStream_t)stream>>>(sigma1_w, diff0_w, basis1_w, offrad_w, omega_w,
+                                                                              (__half*)wimage_tc);
+    return check_launch("pnerf_field_cache_merge");
 }
 
 }  // extern "C"

@@ -28,14 +28,22 @@
 
 namespace pnerf {
 
-// ---- weights: per layer [k-chunk][n][8 halfs], layers in this order (palettenerf_b200/fused.py::tc_pack_index) ----
+// ---- weights: per layer [k-chunk][n][8 halfs], layers in this order (palettenerf_b200/fused_train.py::tc_pack_index) ----
+// Two layers of the image are PRODUCTS of reference layers that have no activation between them (csrc/field_cache.cu::
+// k_cache_merge computes them in fp32 whenever the weight cache is refreshed):
+//   TD0 = diff_net.0 [64 x 15] x sigma_net.1[1:16] [15 x 64]: the geo features are a linear function of the sigma net's hidden
+//         activations (nerf/network.py:101-107: no activation on the last sigma layer), so the first diffuse layer reads those
+//         activations directly and runs in the SAME round as sigma_net.1 instead of waiting for it;
+//   TB1 = [offsets_radiance_net ; omega_net.0] [17 x 15] x basis_net.1 [15 x 64] (palette/network.py:262-268: the heads are
+//         applied to the basis net's raw output): one layer instead of two.
+// 9 MMA rounds per tile instead of 11. (TH is kept in the table as 512 unused bytes so that offsets stay a pure function.)
 enum TcLayer { TS0, TS1, TD0, TD1, TD2, TV0, TV1, TV2, TB0, TB1, TH, TC0, TC1, kTcLayers };
 __host__ __device__ constexpr int tc_n(int l) {   // padded output width (multiple of 16: M = 128 needs N % 16 == 0)
     return l == TS0 ? 64 : l == TS1 ? 16 : l == TD0 ? 64 : l == TD1 ? 64 : l == TD2 ? 16 : l == TV0 ? 64 : l == TV1 ? 64
-         : l == TV2 ? 16 : l == TB0 ? 64 : l == TB1 ? 16 : l == TH ? 32 : l == TC0 ? 64 : 16;
+         : l == TV2 ? 16 : l == TB0 ? 64 : l == TB1 ? 32 : l == TH ? 16 : l == TC0 ? 64 : 16;
 }
 __host__ __device__ constexpr int tc_k(int l) {   // padded input width (multiple of 16)
-    return l == TS0 ? 32 : l == TS1 ? 64 : l == TD0 ? 16 : l == TD1 ? 64 : l == TD2 ? 64 : l == TV0 ? 32 : l == TV1 ? 64
+    return l == TS0 ? 32 : l == TS1 ? 64 : l == TD0 ? 64 : l == TD1 ? 64 : l == TD2 ? 64 : l == TV0 ? 32 : l == TV1 ? 64
          : l == TV2 ? 64 : l == TB0 ? 48 : l == TB1 ? 64 : l == TH ? 16 : l == TC0 ? 32 : 64;
 }
 __host__ __device__ constexpr int tc_woff(int l) {   // byte offset of layer l in the weight image
@@ -61,7 +69,7 @@ constexpr uint32_t kTcColD = 0;                    // fp32 accumulator, up to 64
 constexpr uint32_t kTcColH = 64;                   // hidden activations, 64 halfs = 32 columns
 constexpr uint32_t kTcColG = 96;                   // [sigma logit | geo 15]: 8 columns
 constexpr uint32_t kTcColX = 104;                  // [diffuse 3 | 0 ...]: 8 columns
-constexpr uint32_t kTcColZ = 112;                  // basis-net output (15 + pad): 8 columns
+constexpr uint32_t kTcColS = 112;                  // second fp32 accumulator (16 columns): sigma_net.1 next to the first diffuse layer
 constexpr uint32_t kTcColsPerGroup = 128;
 
 struct TcShared {                                  // per CTA, in front of the weights
@@ -127,6 +135,33 @@ __device__ __forceinline__ void tc_layer(TcGroup& g, const TcSrc (&src)[NS], boo
     tc::tc_fence_after();
 }
 
+// two layers that read the SAME hidden activations (H columns) in one round: layer LA accumulates at column kTcColS (16 wide),
+// layer LB at kTcColD; one commit, one wait
+template <int LA, int LB>
+__device__ __forceinline__ void tc_layer_pair_from_hidden(TcGroup& g) {
+    static_assert(tc_k(LA) == 64 && tc_k(LB) == 64 && tc_n(LA) == 16, "both layers take the 64 hidden activations");
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    tc::group_bar(g.bar_id, 128);
+    if (g.leader) {
+        tc::tc_fence_after();
+        constexpr uint32_t ia = tc::make_idesc_f16(128, tc_n(LA)), ib = tc::make_idesc_f16(128, tc_n(LB));
+        const uint32_t wa = g.w_addr + tc_woff(LA), wb = g.w_addr + tc_woff(LB);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+            tc::umma_f16_ts(g.tmem0 + kTcColS, g.tmem0 + kTcColH + 8 * ks, tc::make_smem_desc(wa + ks * 2 * (tc_n(LA) * 16), tc_n(LA) * 16, 128),
+                            ia, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+            tc::umma_f16_ts(g.tmem0 + kTcColD, g.tmem0 + kTcColH + 8 * ks, tc::make_smem_desc(wb + ks * 2 * (tc_n(LB) * 16), tc_n(LB) * 16, 128),
+                            ib, ks > 0);
+        tc::umma_commit(g.mbar);
+    }
+    tc::mbar_wait(g.mbar, g.phase);
+    g.phase ^= 1u;
+    tc::tc_fence_after();
+}
+
 // epilogue of a 64-wide hidden layer: activation, fp16 pairs, into the H columns of this thread's TMEM lane
 template <int ACT>
 __device__ __forceinline__ void tc_epilogue_hidden(const TcGroup& g) {
@@ -146,9 +181,10 @@ __device__ __forceinline__ void tc_epilogue_hidden(const TcGroup& g) {
 }
 
 // epilogue of a 16-wide layer: the 16 accumulators of this row (fp32) -> out, and as fp16 pairs into 8 TMEM columns
-__device__ __forceinline__ void tc_epilogue_16(const TcGroup& g, float (&out)[16], uint32_t dst_col, bool store) {
+__device__ __forceinline__ void tc_epilogue_16(const TcGroup& g, float (&out)[16], uint32_t dst_col, bool store,
+                                               uint32_t src_col = kTcColD) {
     uint32_t r[16];
-    tc::tmem_ld16(g.tmem + kTcColD, r);
+    tc::tmem_ld16(g.tmem + src_col, r);
     tc::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; i++) out[i] = __uint_as_float(r[i]);
@@ -189,19 +225,19 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
         auto st = [RS, RP, row0](int e, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(e == 0 ? RS : RP, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<2, 4>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<2, 4, PNERF_GATHER_HACC != 0>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
     } else {
         auto st = [RS, row0](int, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(RS, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<1, 4>(f.table_sigma, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<1, 4, PNERF_GATHER_HACC != 0>(f.table_sigma, sm.lp, u, v, w, in_range, lane, st);
     }
     if (CLIP) {
         unsigned char* const RC = g.smem + kTcRC;
         auto st = [RC, row0](int, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(RC, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<1, 4>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<1, 4, PNERF_GATHER_HACC != 0>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
     }
     if (MODE != TC_DENSITY) {
         float sh[16];
@@ -223,32 +259,32 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
         tc_layer<TS0>(g, a, true);
     }
     tc_epilogue_hidden<ACT_RELU>(g);
-    tc_layer<TS1>(g, kH4);
-    tc_epilogue_16(g, t16, kTcColG, MODE != TC_DENSITY);
-    o.sigma = fast_exp(t16[0]);
-    if (MODE == TC_DENSITY) return;
-
     if (PAL) {
-    // ---- diffuse net 15 -> 64 -> 64 -> 3 (the weight column that would see the logit is zero) ----
-    {
-        constexpr TcSrc a[1] = {tc_tmem(kTcColG)};
-        tc_layer<TD0>(g, a);
-    }
-    tc_epilogue_hidden<ACT_RELU>(g);
-    tc_layer<TD1>(g, kH4);
-    tc_epilogue_hidden<ACT_RELU>(g);
-    tc_layer<TD2>(g, kH4);
-    {
-        uint32_t r[8], h[8];
-        tc::tmem_ld8(g.tmem + kTcColD, r);
-        tc::tmem_ld_wait();
+        // sigma_net.1 and the first diffuse layer (folded through sigma_net.1, see the layer table) in ONE round
+        tc_layer_pair_from_hidden<TS1, TD0>(g);
+        tc_epilogue_16(g, t16, kTcColG, true, kTcColS);
+        o.sigma = fast_exp(t16[0]);
+        // ---- diffuse net (15 ->) 64 -> 64 -> 3 ----
+        tc_epilogue_hidden<ACT_RELU>(g);
+        tc_layer<TD1>(g, kH4);
+        tc_epilogue_hidden<ACT_RELU>(g);
+        tc_layer<TD2>(g, kH4);
+        {
+            uint32_t r[8], h[8];
+            tc::tmem_ld8(g.tmem + kTcColD, r);
+            tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 3; i++) o.diffuse[i] = sigmoidf_(__uint_as_float(r[i]));
-        h[0] = pack_h2(o.diffuse[0], o.diffuse[1]); h[1] = pack_h2(o.diffuse[2], 0.f);
+            for (int i = 0; i < 3; i++) o.diffuse[i] = sigmoidf_(__uint_as_float(r[i]));
+            h[0] = pack_h2(o.diffuse[0], o.diffuse[1]); h[1] = pack_h2(o.diffuse[2], 0.f);
 #pragma unroll
-        for (int i = 2; i < 8; i++) h[i] = 0u;
-        tc::tmem_st8(g.tmem + kTcColX, h);                 // third k-step of the basis net: [diffuse 3 | 0 ...]
-    }
+            for (int i = 2; i < 8; i++) h[i] = 0u;
+            tc::tmem_st8(g.tmem + kTcColX, h);                 // third k-step of the basis net: [diffuse 3 | 0 ...]
+        }
+    } else {
+        tc_layer<TS1>(g, kH4);
+        tc_epilogue_16(g, t16, kTcColG, MODE != TC_DENSITY);
+        o.sigma = fast_exp(t16[0]);
+        if (MODE == TC_DENSITY) return;
     }
 
     // ---- view-dependent colour net (SH16 ++ geo15) -> 64 -> 64 -> 3 ----
@@ -270,18 +306,13 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
 
     if (!PAL) return;
 
-    // ---- basis net (palette grid 32 ++ diffuse 3) -> 64 (ELU) -> 15, then the offsets / radiance / omega heads ----
+    // ---- basis net (palette grid 32 ++ diffuse 3) -> 64 (ELU) -> [15 ->] offsets / radiance / omega heads ----
     {
         constexpr TcSrc a[3] = {tc_smem(kTcRP), tc_smem(kTcRP + 2 * kTcChunk), tc_tmem(kTcColX)};
         tc_layer<TB0>(g, a);
     }
     tc_epilogue_hidden<ACT_ELU>(g);
-    tc_layer<TB1>(g, kH4);
-    tc_epilogue_16(g, t16, kTcColZ, true);
-    {
-        constexpr TcSrc a[1] = {tc_tmem(kTcColZ)};
-        tc_layer<TH>(g, a);
-    }
+    tc_layer<TB1>(g, kH4);                                  // basis_net.1 and the heads as one layer (see the layer table)
     {
         uint32_t r0[16], r1[8];
         tc::tmem_ld16(g.tmem + kTcColD, r0);

@@ -11,6 +11,9 @@
 
 namespace pnerf {
 
+#ifndef PNERF_GATHER_HACC
+#define PNERF_GATHER_HACC 1   // packed-half interpolation in the INFERENCE renderers' gathers (gather_coop / gather_fast <.., HACC>)
+#endif
 #ifndef PNERF_COOP_LV
 #define PNERF_COOP_LV 4       // levels per iteration of the lane-pair gather (x 4 corners x 8 B loads in flight per lane)
 #endif
@@ -251,7 +254,7 @@ __device__ __forceinline__ void ldg_entry(uint64_t base, uint32_t idx, uint32_t 
 // (Tried: the entry size as a run-time register operand so that the address is one IMAD.WIDE.U32 instead of the LEA +
 // LEA.HI.X pair ptxas makes of a power-of-two immediate — ptxas then emits IMAD.WIDE + IADD3 + IMAD.X, three slots. Kept as is.)
 
-template <int EW, int LV>
+template <int EW, int LV, bool HACC = false>
 __device__ __forceinline__ void gather_fast(const void* __restrict__ table, const LevelParams* __restrict__ lp,
                                             float u, float v, float w, bool in_range, uint32_t* const (&rows)[EW]) {
     static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
@@ -291,6 +294,23 @@ __device__ __forceinline__ void gather_fast(const void* __restrict__ table, cons
         }
 #pragma unroll
         for (int j = 0; j < LV; j++) {
+            if (HACC) {
+                // packed-half accumulation: one HMUL2 / HFMA2 per corner and table with the weight broadcast to both halves
+                // (one fp16 rounding per corner = the reference kernel's arithmetic, gridencoder.cu:142-165) instead of two
+                // conversions + two FFMA
+                uint32_t w2[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) asm("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(w2[c]) : "f"(wt[j][c]));
+#pragma unroll
+                for (int e = 0; e < EW; e++) {
+                    uint32_t a2;
+                    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a2) : "r"(val[j][0][e]), "r"(w2[0]));
+#pragma unroll
+                    for (int c = 1; c < 8; c++) asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(a2) : "r"(val[j][c][e]), "r"(w2[c]));
+                    rows[e][l0 + j] = in_range ? a2 : 0u;
+                }
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < EW; e++) {
                 float ax = 0.f, ay = 0.f;
@@ -358,7 +378,7 @@ __device__ __forceinline__ void fhfma2_sel(float& ax, float& ay, uint32_t v, uin
             : "r"(v), "r"(wpair));
 }
 
-template <int EW, int LV, typename StoreFn>
+template <int EW, int LV, bool HACC = false, typename StoreFn>
 __device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
                                             float w, bool in_range, int lane, StoreFn st) {
     static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
@@ -372,7 +392,7 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
 #pragma unroll 1
         for (int l0 = 0; l0 < 16; l0 += LV) {
             uint32_t val[LV][4][EW];
-            uint32_t wt[LV][2];                            // fp16 weight pairs {corner 0, 1}, {corner 2, 3}
+            uint32_t wt[LV][HACC ? 4 : 2];                 // fp16 weight pairs {corner 0, 1}, {corner 2, 3}; HACC: {w_c, w_c} per corner
 #pragma unroll
             for (int j = 0; j < LV; j++) {
                 const LevelParams& p = lp[l0 + j];
@@ -382,8 +402,14 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
                 const float rx = px - fx0, ry = py - fy0, rz = pz - fz0;
                 const float wx = xsel ? rx : 1.f - rx;
                 const float wxy0 = wx * (1.f - ry), wxy1 = wx * ry;        // (wx*wy)*wz: the reference's order
-                wt[j][0] = f2h_pair(wxy0 * (1.f - rz), wxy1 * (1.f - rz));
-                wt[j][1] = f2h_pair(wxy0 * rz, wxy1 * rz);
+                if (HACC) {
+                    const float w0 = wxy0 * (1.f - rz), w1 = wxy1 * (1.f - rz), w2 = wxy0 * rz, w3 = wxy1 * rz;
+                    wt[j][0] = f2h_pair(w0, w0); wt[j][1] = f2h_pair(w1, w1);
+                    wt[j][HACC ? 2 : 0] = f2h_pair(w2, w2); wt[j][HACC ? 3 : 1] = f2h_pair(w3, w3);
+                } else {
+                    wt[j][0] = f2h_pair(wxy0 * (1.f - rz), wxy1 * (1.f - rz));
+                    wt[j][1] = f2h_pair(wxy0 * rz, wxy1 * rz);
+                }
                 uint32_t idx[4];
                 const uint32_t hx = gx + xsel;
                 if (p.use_hash) {
@@ -404,6 +430,27 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
             uint32_t words[LV];
 #pragma unroll
             for (int j = 0; j < LV; j++) {
+                if (HACC) {
+                    // packed-half accumulation (HMUL2 + 3 HFMA2 per table instead of 8 FHFMA; the partner's half arrives as ONE
+                    // packed word): one fp16 rounding per corner, which is the reference kernel's own arithmetic
+                    // (gridencoder.cu:142-165 accumulates in scalar_t = half)
+                    uint32_t a2[EW];
+#pragma unroll
+                    for (int e = 0; e < EW; e++) {
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a2[e]) : "r"(val[j][0][e]), "r"(wt[j][0]));
+#pragma unroll
+                        for (int c = 1; c < 4; c++)
+                            asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(a2[e]) : "r"(val[j][c][e]), "r"(wt[j][HACC ? c : 0]));
+                    }
+                    uint32_t mine, send;
+                    if (EW == 2) { mine = xsel ? a2[EW - 1] : a2[0]; send = xsel ? a2[0] : a2[EW - 1]; }
+                    else { mine = a2[0]; send = a2[0]; }
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
+                    uint32_t sum;
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(sum) : "r"(mine), "r"(got));
+                    words[j] = inr ? sum : 0u;
+                    continue;
+                }
                 float acc[EW][2];
 #pragma unroll
                 for (int e = 0; e < EW; e++) {

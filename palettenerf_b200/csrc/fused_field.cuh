@@ -44,10 +44,10 @@ __device__ __forceinline__ void eval_field(const pnerf_palette_field& f, const F
 #pragma unroll
             for (int j = 0; j < PNERF_COOP_LV; j++) dst[l0 + j] = words[j];
         };
-        gather_coop<2, PNERF_COOP_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<2, PNERF_COOP_LV, PNERF_GATHER_HACC != 0>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
     } else if (paired) {
         uint32_t* const rows[2] = {reinterpret_cast<uint32_t*>(ws.feat[lane]), park};
-        gather_fast<2, PNERF_GATHER_LV>(f.table_sigma_palette, sm.lp, u, v, w, in_range, rows);
+        gather_fast<2, PNERF_GATHER_LV, PNERF_GATHER_HACC != 0>(f.table_sigma_palette, sm.lp, u, v, w, in_range, rows);
     } else {
         gather_features((const __half*)f.table_sigma, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
     }
@@ -152,10 +152,10 @@ PNERF_TILE_LOOP
 #pragma unroll
                 for (int j = 0; j < PNERF_COOP_LV; j++) reinterpret_cast<uint32_t*>(ws.feat[s])[l0 + j] = words[j];
             };
-            gather_coop<1, PNERF_COOP_LV>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
+            gather_coop<1, PNERF_COOP_LV, PNERF_GATHER_HACC != 0>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
         } else if (sm.fast_wrap) {
             uint32_t* const rows[1] = {reinterpret_cast<uint32_t*>(ws.feat[lane])};
-            gather_fast<1, PNERF_GATHER_LV>(f.table_clip, sm.lp, u, v, w, in_range, rows);
+            gather_fast<1, PNERF_GATHER_LV, PNERF_GATHER_HACC != 0>(f.table_clip, sm.lp, u, v, w, in_range, rows);
         } else {
             gather_features((const __half*)f.table_clip, sm.lp, f.L, u, v, w, in_range, ws.feat[lane]);
         }

@@ -55,6 +55,7 @@ L.lib.pnerf_palette_render_tc_warps.restype = c_uint32
 L.lib.pnerf_palette_render_tc_runs_bytes.restype = c_uint32
 L.register("pnerf_field_cache_tables", [P, P, P, U, P, P, P])
 L.register("pnerf_field_cache_gather", [P, U, U, U, P, P, P])
+L.register("pnerf_field_cache_merge", [P, P, P, P, P, P, P])
 
 
 def _frag(W, n_pad, k_pad):
@@ -192,6 +193,9 @@ class FieldCache:
                    m.encoder.embeddings.shape[0], ptr(b["pair"]), ptr(b["clip"]), stream())
             L.call("pnerf_field_cache_gather", ptr(src), b["w16"].numel(), b["f32"].numel(), 16, ptr(b["w16"]), ptr(b["f32"]),
                    stream())
+            # the two product layers of the tcgen05 image (field_tc.cuh layer table), after the gather has zeroed them
+            L.call("pnerf_field_cache_merge", ptr(m.sigma_net[1].weight), ptr(m.diff_net[0].weight), ptr(m.basis_net[1].weight),
+                   ptr(m.offsets_radiance_net.weight), ptr(m.omega_net[0].weight), ptr(b["wpack_tc"]), stream())
             return f
         with torch.no_grad():       # parameters that are not plain contiguous fp32 tensors: the same refresh as torch ops
             b["pair"][:, 0, :].copy_(m.encoder.embeddings.detach())
@@ -202,6 +206,8 @@ class FieldCache:
             flat = torch.cat([sd[n].detach().reshape(-1).float() for n in b["names"]] + [b["zero"]])
             b["wpack"].copy_(flat[b["index"]])
             b["wpack_tc"].copy_(flat[b["tc_index"]])
+            from . import fused_train
+            fused_train.tc_merge_layers(m, b["wpack_tc"])
             b["bias"][0:13].copy_(m.offsets_radiance_net.bias.detach())
             b["palette"].copy_(m.basis_color.detach().float().clamp(0, 1))
         return f

@@ -35,8 +35,8 @@ L.lib.pnerf_density_finalize_partials.restype = c_uint32
 
 # (layer, parameter, n_pad, k_pad, row range, source columns -> destination columns) of the stage-1 / density sub-network
 _LAYERS = ["s0", "s1", "d0", "d1", "d2", "v0", "v1", "v2", "b0", "b1", "h"]
-_SHAPE = {"s0": (64, 32), "s1": (16, 64), "d0": (64, 16), "d1": (64, 64), "d2": (16, 64), "v0": (64, 32), "v1": (64, 64),
-          "v2": (16, 64), "b0": (64, 48), "b1": (16, 64), "h": (32, 16)}
+_SHAPE = {"s0": (64, 32), "s1": (16, 64), "d0": (64, 64), "d1": (64, 64), "d2": (16, 64), "v0": (64, 32), "v1": (64, 64),
+          "v2": (16, 64), "b0": (64, 48), "b1": (32, 64), "h": (16, 16)}      # = csrc/field_tc.cuh::tc_n / tc_k
 
 
 def _index(model, with_color):

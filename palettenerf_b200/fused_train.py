@@ -114,8 +114,12 @@ def padded_layers(shapes, pred_clip, clip_dim):
 
 def tc_pack_index(shapes, pred_clip, clip_dim):
     """index (int64) that gathers the flat weight vector into the tcgen05 B-operand image of csrc/field_tc.cuh: per layer
-    [k-chunk][n][8 halfs] (K-major, no swizzle), layers in TcLayer order"""
-    m, _ = padded_layers(shapes, pred_clip, clip_dim)
+    [k-chunk][n][8 halfs] (K-major, no swizzle), layers in TcLayer order. The layers d0 (64 x 64), b1 (32 x 64) are PRODUCTS of
+    reference layers (field_tc.cuh layer table): the gather leaves them zero and `tc_merge_layers` / pnerf_field_cache_merge
+    fills them; h (16 x 16) is unused padding."""
+    m, zero = padded_layers(shapes, pred_clip, clip_dim)
+    for k, shp in TC_MERGED_SHAPES.items():
+        m[k] = torch.full(shp, zero, dtype=torch.int64)
     order = ["s0", "s1", "d0", "d1", "d2", "v0", "v1", "v2", "b0", "b1", "h"] + (["q0", "q1"] if pred_clip else [])
     parts = []
     for k in order:
@@ -123,6 +127,36 @@ def tc_pack_index(shapes, pred_clip, clip_dim):
         n, kk = W.shape
         parts.append(W.reshape(n, kk // 8, 8).permute(1, 0, 2).reshape(-1))
     return torch.cat(parts)
+
+
+TC_MERGED_SHAPES = {"d0": (64, 64), "b1": (32, 64), "h": (16, 16)}
+_TC_ORDER_SHAPES = [("s0", 64, 32), ("s1", 16, 64), ("d0", 64, 64), ("d1", 64, 64), ("d2", 16, 64), ("v0", 64, 32), ("v1", 64, 64),
+                    ("v2", 16, 64), ("b0", 64, 48), ("b1", 32, 64), ("h", 16, 16)]
+
+
+def tc_layer_offset(name):
+    """offset (in halfs) of a layer in the tcgen05 weight image"""
+    off = 0
+    for k, n, kk in _TC_ORDER_SHAPES:
+        if k == name:
+            return off
+        off += n * kk
+    raise KeyError(name)
+
+
+def tc_merge_layers(model, wimage):
+    """torch restatement of pnerf_field_cache_merge (used when a parameter is not a plain contiguous fp32 tensor): writes the
+    product layers d0 = diff_net.0 x sigma_net.1[1:16] and b1 = [offsets_radiance_net ; omega_net.0] x basis_net.1 into the image"""
+    sd = dict(model.named_parameters())
+    f = lambda n: sd[n].detach().float()  # noqa: E731
+    d0 = f("diff_net.0.weight") @ f("sigma_net.1.weight")[1:16]
+    b1 = torch.zeros(32, 64, dtype=torch.float32, device=d0.device)
+    b1[0:13] = f("offsets_radiance_net.weight") @ f("basis_net.1.weight")
+    b1[13:17] = f("omega_net.0.weight") @ f("basis_net.1.weight")
+    for name, W in (("d0", d0), ("b1", b1)):
+        n, kk = W.shape
+        off = tc_layer_offset(name)
+        wimage[off:off + n * kk].copy_(W.reshape(n, kk // 8, 8).permute(1, 0, 2).reshape(-1))
 
 
 def build_pack_index(shapes, pred_clip, clip_dim):
