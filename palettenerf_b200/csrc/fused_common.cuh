@@ -14,6 +14,9 @@ namespace pnerf {
 #ifndef PNERF_GATHER_HACC
 #define PNERF_GATHER_HACC 1   // packed-half interpolation in the INFERENCE renderers' gathers (gather_coop / gather_fast <.., HACC>)
 #endif
+#ifndef PNERF_GATHER_PACKED_W
+#define PNERF_GATHER_PACKED_W 0
+#endif
 #ifndef PNERF_COOP_LV
 #define PNERF_COOP_LV 4       // levels per iteration of the lane-pair gather (x 4 corners x 8 B loads in flight per lane)
 #endif
@@ -244,6 +247,17 @@ static __device__ __noinline__ void gather_features(const __half* __restrict__ t
 //   EW: 32-bit words per table entry (1: one F=2 fp16 table, 2: two interleaved tables); rows[e] receives table e.
 //   LV: levels per iteration (LV x 8 loads in flight per lane).
 // ------------------------------------------------------------------------------------------------
+// floor of a coordinate 0 <= p < 2^22 WITHOUT the conversion pipe: t = p + 2^23 rounded toward -inf is 2^23 + floor(p)
+// exactly (FADD.RM, fma pipe, 4 cycles), its low 23 bits are the integer and t - 2^23 is the floor as a float (exact) — the
+// same bits floorf() and the float -> int conversion deliver (FRND + F2I: quarter-rate XU pipe, tracked by the short
+// scoreboard, in the middle of the address chain of every gather). `raw` keeps the exponent bits (0x4B000000 + floor).
+__device__ __forceinline__ void floor_split(float p, float& fl, uint32_t& raw) {
+    const float t = __fadd_rd(p, 8388608.0f);
+    raw = __float_as_uint(t);
+    fl = t - 8388608.0f;
+}
+constexpr uint32_t kFloorRawMask = 0x007fffffu;   // raw & mask = floor(p) as an integer
+
 template <int EW>
 __device__ __forceinline__ void ldg_entry(uint64_t base, uint32_t idx, uint32_t (&v)[EW]) {
     uint64_t addr;
@@ -267,21 +281,25 @@ __device__ __forceinline__ void gather_fast(const void* __restrict__ table, cons
         for (int j = 0; j < LV; j++) {
             const LevelParams& p = lp[l0 + j];
             const float px = fmaf(u, p.scale, 0.5f), py = fmaf(v, p.scale, 0.5f), pz = fmaf(w, p.scale, 0.5f);
-            const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-            const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
-            const float rx = px - (float)gx, ry = py - (float)gy, rz = pz - (float)gz;
+            float fx0, fy0, fz0;
+            uint32_t gx, gy, gz;                       // raw words (see floor_split): stripped in the dense branch only
+            floor_split(px, fx0, gx); floor_split(py, fy0, gy); floor_split(pz, fz0, gz);
+            const float rx = px - fx0, ry = py - fy0, rz = pz - fz0;
             const float wx[2] = {1 - rx, rx}, wy[2] = {1 - ry, ry}, wz[2] = {1 - rz, rz};
             const float wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};   // (wx*wy)*wz: the reference's order
 #pragma unroll
             for (int c = 0; c < 8; c++) wt[j][c] = wxy[c & 3] * wz[c >> 2];
             uint32_t idx[8];
             if (p.use_hash) {
+                // hashed level, table of <= 2^24 entries (make_level): the exponent bits of the raw words reach index bits >= 24
+                // only (x: as they are; y, z: 0x4B000000 * prime has no bit below 24), which the mask drops
                 const uint32_t hx1 = gx + 1, hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
                 const uint32_t hy1 = hy0 + 2654435761u, hz1 = hz0 + 805459861u;
                 const uint32_t yz[4] = {hy0 ^ hz0, hy1 ^ hz0, hy0 ^ hz1, hy1 ^ hz1};
 #pragma unroll
                 for (int c = 0; c < 8; c++) idx[c] = (((c & 1) ? hx1 : gx) ^ yz[c >> 1]) & p.mask;
             } else {
+                gx &= kFloorRawMask; gy &= kFloorRawMask; gz &= kFloorRawMask;
                 const uint32_t ix0 = gx * p.stride[0], iy0 = gy * p.stride[1], iz0 = gz * p.stride[2];
                 const uint32_t yz[4] = {iy0 + iz0, iy0 + p.stride[1] + iz0, iy0 + iz0 + p.stride[2],
                                         iy0 + p.stride[1] + iz0 + p.stride[2]};
@@ -378,6 +396,24 @@ __device__ __forceinline__ void fhfma2_sel(float& ax, float& ay, uint32_t v, uin
             : "r"(v), "r"(wpair));
 }
 
+// acc (half2) += v (half2) * w, w = the low (HI = false) / high half of a packed weight pair, broadcast to both halves:
+// ptxas folds the broadcast into the operand selector of ONE HFMA2 (R.H0_H0 / R.H1_H1)
+template <bool HI>
+__device__ __forceinline__ void hfma2_bcast(uint32_t& acc, uint32_t v, uint32_t wpair) {
+    if (HI)
+        asm("{\n\t.reg .f16 lo, hi;\n\t.reg .b32 w;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b32 w, {hi, hi};\n\tfma.rn.f16x2 %0, %1, w, %0;\n\t}"
+            : "+r"(acc) : "r"(v), "r"(wpair));
+    else
+        asm("{\n\t.reg .f16 lo, hi;\n\t.reg .b32 w;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b32 w, {lo, lo};\n\tfma.rn.f16x2 %0, %1, w, %0;\n\t}"
+            : "+r"(acc) : "r"(v), "r"(wpair));
+}
+__device__ __forceinline__ uint32_t hmul2_bcast_lo(uint32_t v, uint32_t wpair) {
+    uint32_t r;
+    asm("{\n\t.reg .f16 lo, hi;\n\t.reg .b32 w;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b32 w, {lo, lo};\n\tmul.rn.f16x2 %0, %1, w;\n\t}"
+        : "=r"(r) : "r"(v), "r"(wpair));
+    return r;
+}
+
 template <int EW, int LV, bool HACC = false, typename StoreFn>
 __device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
                                             float w, bool in_range, int lane, StoreFn st) {
@@ -392,32 +428,40 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
 #pragma unroll 1
         for (int l0 = 0; l0 < 16; l0 += LV) {
             uint32_t val[LV][4][EW];
-            uint32_t wt[LV][HACC ? 4 : 2];                 // fp16 weight pairs {corner 0, 1}, {corner 2, 3}; HACC: {w_c, w_c} per corner
+            uint32_t wt[LV][2];                            // fp16 weight pairs {corner 0, 1}, {corner 2, 3}
 #pragma unroll
             for (int j = 0; j < LV; j++) {
                 const LevelParams& p = lp[l0 + j];
                 const float px = fmaf(us, p.scale, 0.5f), py = fmaf(vs, p.scale, 0.5f), pz = fmaf(wsm, p.scale, 0.5f);
-                const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-                const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+                float fx0, fy0, fz0;
+                uint32_t gx, gy, gz;                   // raw words (see floor_split): stripped in the dense branch only
+                floor_split(px, fx0, gx); floor_split(py, fy0, gy); floor_split(pz, fz0, gz);
                 const float rx = px - fx0, ry = py - fy0, rz = pz - fz0;
                 const float wx = xsel ? rx : 1.f - rx;
                 const float wxy0 = wx * (1.f - ry), wxy1 = wx * ry;        // (wx*wy)*wz: the reference's order
-                if (HACC) {
-                    const float w0 = wxy0 * (1.f - rz), w1 = wxy1 * (1.f - rz), w2 = wxy0 * rz, w3 = wxy1 * rz;
-                    wt[j][0] = f2h_pair(w0, w0); wt[j][1] = f2h_pair(w1, w1);
-                    wt[j][HACC ? 2 : 0] = f2h_pair(w2, w2); wt[j][HACC ? 3 : 1] = f2h_pair(w3, w3);
-                } else {
+#if PNERF_GATHER_PACKED_W
+                if (HACC) {   // {w0, w1} = {wxy0, wxy1} * (1 - rz), {w2, w3} = {wxy0, wxy1} * rz as two packed multiplies
+                    const uint32_t wxy = f2h_pair(wxy0, wxy1), wz = f2h_pair(1.f - rz, rz);
+                    wt[j][0] = hmul2_bcast_lo(wxy, wz);
+                    uint32_t zero = 0u;
+                    hfma2_bcast<true>(zero, wxy, wz);
+                    wt[j][1] = zero;
+                } else
+#endif
+                {
                     wt[j][0] = f2h_pair(wxy0 * (1.f - rz), wxy1 * (1.f - rz));
                     wt[j][1] = f2h_pair(wxy0 * rz, wxy1 * rz);
                 }
                 uint32_t idx[4];
-                const uint32_t hx = gx + xsel;
-                if (p.use_hash) {
+                if (p.use_hash) {   // raw words: see gather_fast
+                    const uint32_t hx = gx + xsel;
                     const uint32_t hy0 = gy * 2654435761u, hz0 = gz * 805459861u;
                     const uint32_t hy1 = hy0 + 2654435761u, hz1 = hz0 + 805459861u;
                     idx[0] = (hx ^ hy0 ^ hz0) & p.mask; idx[1] = (hx ^ hy1 ^ hz0) & p.mask;
                     idx[2] = (hx ^ hy0 ^ hz1) & p.mask; idx[3] = (hx ^ hy1 ^ hz1) & p.mask;
                 } else {
+                    const uint32_t hx = (gx & kFloorRawMask) + xsel;
+                    gy &= kFloorRawMask; gz &= kFloorRawMask;
                     const uint32_t ix = hx * p.stride[0], iy0 = gy * p.stride[1], iz0 = gz * p.stride[2];
                     const uint32_t iy1 = iy0 + p.stride[1], iz1 = iz0 + p.stride[2];
                     idx[0] = (ix + iy0 + iz0) & p.mask; idx[1] = (ix + iy1 + iz0) & p.mask;
@@ -431,16 +475,17 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
 #pragma unroll
             for (int j = 0; j < LV; j++) {
                 if (HACC) {
-                    // packed-half accumulation (HMUL2 + 3 HFMA2 per table instead of 8 FHFMA; the partner's half arrives as ONE
+                    // packed-half accumulation (HMUL2 + 3 HFMA2 per table instead of 8 FHFMA, the weight broadcast by the operand
+                    // selector of the instruction; the partner's half arrives as ONE
                     // packed word): one fp16 rounding per corner, which is the reference kernel's own arithmetic
                     // (gridencoder.cu:142-165 accumulates in scalar_t = half)
                     uint32_t a2[EW];
 #pragma unroll
                     for (int e = 0; e < EW; e++) {
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a2[e]) : "r"(val[j][0][e]), "r"(wt[j][0]));
-#pragma unroll
-                        for (int c = 1; c < 4; c++)
-                            asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(a2[e]) : "r"(val[j][c][e]), "r"(wt[j][HACC ? c : 0]));
+                        a2[e] = hmul2_bcast_lo(val[j][0][e], wt[j][0]);
+                        hfma2_bcast<true>(a2[e], val[j][1][e], wt[j][0]);
+                        hfma2_bcast<false>(a2[e], val[j][2][e], wt[j][1]);
+                        hfma2_bcast<true>(a2[e], val[j][3][e], wt[j][1]);
                     }
                     uint32_t mine, send;
                     if (EW == 2) { mine = xsel ? a2[EW - 1] : a2[0]; send = xsel ? a2[0] : a2[EW - 1]; }

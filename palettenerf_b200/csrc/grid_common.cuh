@@ -34,6 +34,9 @@ __device__ __forceinline__ void make_level(LevelParams& p, uint32_t level, const
     }
     p.use_hash = (gridtype == 0 && stride > p.size) ? 1u : 0u;
     p.mask = ((p.size & (p.size - 1)) == 0) ? (p.size - 1) : 0u;
+    // the mask-wrapping fast paths (fused_common.cuh::gather_fast / gather_coop) form hashed indices from raw float words whose
+    // exponent bits sit at bit 24 and above: tables of more than 2^24 entries per level take the generic (modulo) path
+    if (p.use_hash && p.mask > 0x00ffffffu) p.mask = 0u;
     // dense level whose full (res+1)^D lattice fits the table: every index is < stride <= size, so the reference's
     // `index % hashmap_size` (gridencoder.cu:71) is the identity and the integer division can be dropped.
     // NOT with align_corners: the stride multiplier is `resolution` there while an input of exactly 1.0 on an integer

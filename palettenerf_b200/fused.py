@@ -111,6 +111,7 @@ def supported(model):
                 and model.geo_feat_dim == 15 and model.num_layers_color == 3 and enc.num_levels == 16 and enc.level_dim == 2
                 and enc.input_dim == 3 and enc.gridtype == "hash" and not enc.align_corners
                 and getattr(model.encoder_dir, "degree", 0) == 4 and model.bg_radius <= 0
+                and getattr(enc, "log2_hashmap_size", 19) <= 24        # raw-word hashing of the fast gathers (grid_common.cuh)
                 and model.encoder.embeddings.is_cuda)
     except AttributeError:
         return False

@@ -75,7 +75,7 @@ def supported(model):
         enc = model.encoder
         ok = (enc.num_levels == 16 and enc.level_dim == 2 and enc.input_dim == 3 and enc.gridtype == "hash"
               and not enc.align_corners and model.hidden_dim == 64 and model.geo_feat_dim == 15 and model.num_layers == 2
-              and enc.embeddings.is_cuda and model.bg_radius <= 0)
+              and enc.embeddings.is_cuda and model.bg_radius <= 0 and getattr(enc, "log2_hashmap_size", 19) <= 24)
         return bool(ok)
     except AttributeError:
         return False
