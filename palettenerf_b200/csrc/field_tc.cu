@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_render_rays_tc(RaysTcArgs a, 
         const float dt = clampf(t * a.dt_gamma, dt_min, dt_max);
         const float t_end = t + dt;
         FieldOut o;
-        eval_field_tc<MODE>(f, *sm, g, x, y, z, active ? ldx : 0.f, active ? ldy : 0.f, active ? ldz : 1.f, active, lane, o);
+        eval_field_tc<MODE, true>(f, *sm, g, x, y, z, active ? ldx : 0.f, active ? ldy : 0.f, active ? ldz : 1.f, active, lane, o);   // x, y, z clamped above
         const uint32_t any = sm->flags[vote][gi][0] | sm->flags[vote][gi][1] | sm->flags[vote][gi][2] | sm->flags[vote][gi][3];
         vote ^= 1u;
         if (!any) break;

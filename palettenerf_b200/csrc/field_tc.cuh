@@ -206,7 +206,9 @@ __device__ __forceinline__ void tc_epilogue_16(const TcGroup& g, float (&out)[16
 //   TC_DENSITY  sigma net only (NeRFNetwork.density / PaletteNetwork.density, used by the density-grid refresh)
 enum TcMode { TC_PALETTE = 0, TC_PALETTE_CLIP = 1, TC_NERF = 2, TC_DENSITY = 3 };
 
-template <int MODE>
+// CLAMPED: the caller guarantees -bound <= x, y, z <= bound for every lane (the renderer clamps its samples): the gather then
+// skips the out-of-range zeroing of the features (gridencoder.cu:118-130), one select per level
+template <int MODE, bool CLAMPED = false>
 __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, const TcShared& sm, TcGroup& g, float x, float y,
                                               float z, float dx, float dy, float dz, bool active, int lane, FieldOut& o) {
     static_assert(PNERF_COOP_LV == 4, "one gather batch = the 4 levels of one 16-byte k-chunk");
@@ -225,19 +227,19 @@ __device__ __forceinline__ void eval_field_tc(const pnerf_palette_field& f, cons
         auto st = [RS, RP, row0](int e, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(e == 0 ? RS : RP, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<2, 4, PNERF_GATHER_HACC != 0>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<2, 4, PNERF_GATHER_HACC != 0, !CLAMPED>(f.table_sigma_palette, sm.lp, u, v, w, in_range, lane, st);
     } else {
         auto st = [RS, row0](int, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(RS, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<1, 4, PNERF_GATHER_HACC != 0>(f.table_sigma, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<1, 4, PNERF_GATHER_HACC != 0, !CLAMPED>(f.table_sigma, sm.lp, u, v, w, in_range, lane, st);
     }
     if (CLIP) {
         unsigned char* const RC = g.smem + kTcRC;
         auto st = [RC, row0](int, int s, int l0, const uint32_t (&wd)[4]) {
             *tc_row_ptr(RC, l0 >> 2, row0 + s) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         };
-        gather_coop<1, 4, PNERF_GATHER_HACC != 0>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
+        gather_coop<1, 4, PNERF_GATHER_HACC != 0, !CLAMPED>(f.table_clip, sm.lp, u, v, w, in_range, lane, st);
     }
     if (MODE != TC_DENSITY) {
         float sh[16];

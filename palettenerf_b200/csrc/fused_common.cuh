@@ -414,7 +414,7 @@ __device__ __forceinline__ uint32_t hmul2_bcast_lo(uint32_t v, uint32_t wpair) {
     return r;
 }
 
-template <int EW, int LV, bool HACC = false, typename StoreFn>
+template <int EW, int LV, bool HACC = false, bool ZERO_OOR = true, typename StoreFn>
 __device__ __forceinline__ void gather_coop(const void* __restrict__ table, const LevelParams* __restrict__ lp, float u, float v,
                                             float w, bool in_range, int lane, StoreFn st) {
     static_assert(EW == 1 || EW == 2, "one table or two interleaved tables");
@@ -493,7 +493,7 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
                     const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
                     uint32_t sum;
                     asm("add.rn.f16x2 %0, %1, %2;" : "=r"(sum) : "r"(mine), "r"(got));
-                    words[j] = inr ? sum : 0u;
+                    words[j] = (!ZERO_OOR || inr) ? sum : 0u;   // ZERO_OOR = false: the caller clamps every sample into the grid
                     continue;
                 }
                 float acc[EW][2];
@@ -524,6 +524,9 @@ __device__ __forceinline__ void gather_coop(const void* __restrict__ table, cons
     }
 }
 
+// (Measured and rejected: batches whose four levels are all hashed as straight-line code — no branch per level, ptxas then
+// interleaves the four address chains and clusters the 16 loads behind them — 4.90 vs 4.62 ms per view: the loads of a level are no longer issued while the next level's addresses are computed (they reach the first use later), more values live at the 128-register
+// cap, more spills; the per-level branch is a useful fence.)
 // (Measured and rejected: a software-pipelined version — batches of two levels, the 8 loads of batch i + 1 issued before batch i
 // is interpolated, so that a warp always has gathers in flight instead of a burst of 16 followed by a drain — 5.12 vs 4.92 ms
 // per 800x800 view: the other three warps of the scheduler already cover the drain, the extra live batch costs scheduling
