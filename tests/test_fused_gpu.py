@@ -195,3 +195,33 @@ def test_shared_windows_equal_reproducible_render(cuda, gui_mode):
         if not kw:      # (with early termination most rays end inside their first, full window: nothing to share)
             assert fill_sh > fill_rep + 0.03 and fill_sh > 0.9, (fill_rep, fill_sh)
     m.fused_reproducible = False
+
+
+def test_weight_image_product_layers_kernel_equals_torch_restatement(cuda, model):
+    """the two product layers of the tcgen05 weight image (field_tc.cuh layer table): pnerf_field_cache_merge (the kernel the
+    cache refresh runs) against fused_train.tc_merge_layers (torch matmuls, the path for non-contiguous parameters) and against
+    the products formed in fp64; everything else in the image is a pure gather"""
+    from palettenerf_b200 import fused, fused_train as FT
+    cache = fused._cache(model)
+    cache.invalidate()
+    cache.get()
+    img = cache.buf["wpack_tc"].clone()
+    alt = torch.zeros_like(img)
+    FT.tc_merge_layers(model, alt)
+    sd = {k: v.detach().double() for k, v in model.named_parameters()}
+    d0 = sd["diff_net.0.weight"] @ sd["sigma_net.1.weight"][1:16]
+    b1 = torch.zeros(32, 64, dtype=torch.float64, device=cuda)
+    b1[0:13] = sd["offsets_radiance_net.weight"] @ sd["basis_net.1.weight"]
+    b1[13:17] = sd["omega_net.0.weight"] @ sd["basis_net.1.weight"]
+    for name, W in (("d0", d0), ("b1", b1)):
+        n, k = W.shape
+        off = FT.tc_layer_offset(name)
+        want = W.reshape(n, k // 8, 8).permute(1, 0, 2).reshape(-1)
+        got, got_alt = img[off:off + n * k].double(), alt[off:off + n * k].double()
+        tol = 2.0 ** -10 * want.abs().clamp(min=1e-4)                    # fp16 rounding of an fp32 product sum
+        assert ((got - want).abs() <= tol).all(), name
+        assert ((got_alt - want).abs() <= tol).all(), name
+        assert want.abs().max() > 1e-3
+    # the unused pad layer stays zero
+    off = FT.tc_layer_offset("h")
+    assert img[off:off + 256].abs().max().item() == 0.0
