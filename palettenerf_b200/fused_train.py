@@ -347,7 +347,10 @@ class _TrainField(Function):
         sigma, rgb, flex = new("sigma", M), new("rgb", M, 3), new("flex", M, nflex)
         L.call("pnerf_palette_train_forward", ptr(xyzs), ptr(dirs), M, ctypes.addressof(f), ptr(xbuf), ptr(sigma), ptr(rgb),
                ptr(flex), stream())
-        ctx.keep = (f, blob, (t_sigma, t_pair), t_pal, t_clip, pal, offsets, xbuf, flex, xyzs, count)
+        # `flex` is an OUTPUT: holding the returned object itself would tie ctx and its output into a reference cycle that only
+        # the cyclic GC breaks — until then the arena sees the step's buffers (GBs at full capacity) as busy and allocates new
+        # ones every eager step. A detached alias shares the storage without the cycle.
+        ctx.keep = (f, blob, (t_sigma, t_pair), t_pal, t_clip, pal, offsets, xbuf, flex.detach(), xyzs, count)
         ctx.model, ctx.M, ctx.n_weights = model, M, len(weights)
         ctx.need_palette = palette.requires_grad
         ctx.mark_non_differentiable(sigma)

@@ -261,3 +261,41 @@ def test_fused_adam_mirror_trains_like_torch_adam_with_table_refresh(cuda):
     for (n1, p1), (_, p2) in zip(m_new.named_parameters(), m_ref.named_parameters()):
         if p1.requires_grad and p1.numel() < 100000:
             assert torch.allclose(p1, p2, rtol=5e-2, atol=5e-3), n1
+
+
+@pytest.mark.parametrize("stage", ["palette", "nerf"])
+def test_eager_steps_reuse_the_arena_without_the_cyclic_gc(cuda, stage):
+    """the static-capacity step takes its large buffers from the arena, which hands a buffer out again as soon as nothing
+    references it. An autograd ctx that holds one of its own OUTPUTS forms a reference cycle only the cyclic GC breaks: with the
+    collector off (what a long eager training loop looks like between two gen-2 collections) the arena must still stay at the
+    working set of ONE step"""
+    import gc
+    from palettenerf_b200.arena import ARENA
+    if stage == "palette":
+        m = S.build_palette_model(cuda, seed=0, pred_clip=False)
+    else:
+        m = S.build_nerf_model(cuda, seed=0)
+    m.train()
+    o, d = S.training_rays(512, H=200, W=200, seed=0, n_views=2)
+    o, d = o.to(cuda)[None], d.to(cuda)[None]
+    gt = torch.rand(1, 512, 3, device=cuda)
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = m.render(o, d, staged=False, bg_color=1, perturb=True, force_all_rays=True, max_steps=256)
+            loss = ((out["image"] - gt) ** 2).mean()
+        loss.backward()
+    ARENA.clear()
+    gc.collect()
+    gc.disable()
+    try:
+        step(); step()
+        base = ARENA.bytes()
+        for _ in range(5):
+            step()
+        assert ARENA.bytes() == base, (ARENA.bytes(), base)
+    finally:
+        gc.enable()
+    assert m._last_train_schedule == "fused" and base > 0
