@@ -5,7 +5,10 @@
 
 namespace pnerf {
 
-constexpr int kTcGroups = 4;                       // warpgroups per CTA (one CTA per SM): 16 warps, <= 128 registers/thread
+#ifndef PNERF_TC_GROUPS
+#define PNERF_TC_GROUPS 4
+#endif
+constexpr int kTcGroups = PNERF_TC_GROUPS;                       // warpgroups per CTA (one CTA per SM): 16 warps, <= 128 registers/thread
 constexpr int kTcThreads = kTcGroups * 128;
 constexpr int kTcSharedBytes = (sizeof(TcShared) + 1023) & ~1023;
 
