@@ -622,7 +622,36 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
         ams = sum(tt) / len(tt)
         adam = {"ms": ams, "elements": n_el, "gbs": 28.0 * n_el / (ams / 1e3) / 1e9,
                 "algorithmic": "28 B/element (p, g, m, v read; p, m, v written), all tensors of the step in one launch"}
-    return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS,
+    # the stage-1 (NeRF) step data parallel: same bucket machinery, the density table's gradient all-reduced early
+    stage1 = None
+    if world > 1 and use_graph and not torch_adam:
+        try:
+            from palettenerf_b200.graphs import make_nerf_train_step
+            m1 = S.build_nerf_model(dev, seed=0)
+            m1.train()
+            opt1, _ = _adam(torch, m1.get_params(1e-2), False)
+            p1 = [p for grp in opt1.param_groups for p in grp["params"] if p.requires_grad]
+            b1 = GradBucket(p1, peer=not nccl_allreduce)
+            g1 = GraphedStep(make_nerf_train_step(m1, opt1, torch.amp.GradScaler("cuda"), o, d, gt, bucket=b1), warmup=3)
+            for _ in range(3):
+                g1.replay()
+            barrier()
+            t1 = []
+            for _ in range(10):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); g1.replay(); b.record()
+                torch.cuda.synchronize()
+                t1.append(a.elapsed_time(b))
+            barrier()
+            ms1 = max_over_ranks(sum(t1) / len(t1))
+            stage1 = {"ms_per_step": ms1, "rays_per_s": world * TRAIN_RAYS / (ms1 / 1e3), "schedule": m1._last_train_schedule,
+                      "allreduce_bucket_bytes": None if b1.flat is None else 4 * b1.flat.numel(), "early_allreduces": b1.early_count,
+                      "workload": "stage-1 (NeRF) training step, 4096 rays per GPU, MSE + rgb_norm loss, one CUDA graph per step"}
+            del g1, m1, opt1, b1
+        except Exception as e:   # noqa: BLE001  (a secondary record)
+            stage1 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    return {"train": {"rays_per_s": world * TRAIN_RAYS / (ms / 1e3), "ms_per_step": ms, "rays_per_gpu": TRAIN_RAYS, "stage1_dp": stage1,
                       "samples_per_step_rank0": m, "schedule": getattr(model, "_last_train_schedule", "torch"),
                       "launch": mode, "own_kernel_launches_per_step": own_launches,
                       "optimizer": opt_name, "adam_alone": adam,

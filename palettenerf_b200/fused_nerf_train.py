@@ -156,8 +156,20 @@ class _NerfTrainField(Function):
                ptr(rgb), ptr(d_enc), stream())
         enc = model.encoder
         g_tab = None
+        # data parallel (distributed.GradBucket attached to the model): the density table's gradient — 99.9 % of the stage-1
+        # bucket — is scattered STRAIGHT INTO the bucket (no pack copy) and its all-reduce starts on a side stream before the
+        # weight-gradient kernel below runs; not when gradients are being accumulated into an existing .grad
+        bucket = getattr(model, "_grad_bucket", None)
+        if enc.embeddings.grad is not None or M == 0:
+            bucket = None
+        early = False
         if ctx.needs_input_grad[4]:
-            g_tab = torch.zeros_like(enc.embeddings, dtype=torch.float32)
+            g_tab = bucket.slot(enc.embeddings) if bucket is not None else None
+            if g_tab is None:
+                g_tab = torch.zeros_like(enc.embeddings, dtype=torch.float32)
+            else:
+                g_tab.zero_()
+                early = True
             if M > 0:
                 S_ = float(np.float32(np.log2(enc.per_level_scale)))
                 if count is None:
@@ -168,6 +180,8 @@ class _NerfTrainField(Function):
                 else:   # number of rows taken from device memory
                     L.call("pnerf_grid_encode_backward_counted", ptr(d_enc), ptr(xyzs), ptr(offsets), ptr(g_tab), M, enc.num_levels,
                            S_, enc.base_resolution, 0, 0, L.F32, L.LAYOUT_BLC, ptr(count), float(model.bound), stream())
+        if early:
+            bucket.early([enc.embeddings])
         L.call("pnerf_nerf_train_wgrad", M, ptr(xbuf), ptr(ybuf), ptr(dw), ptr(count), stream())
         gw = dw_views(dw)
         return (None, None, None, None, g_tab, *[gw[n] for n in WEIGHT_NAMES])

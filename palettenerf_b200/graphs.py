@@ -59,3 +59,26 @@ def make_palette_train_step(model, optimizer, scaler, rays_o, rays_d, loss_fn, r
         scaler.update()
         return loss.detach()
     return step_fn
+
+
+def make_nerf_train_step(model, optimizer, scaler, rays_o, rays_d, gt_rgb, lambda_sparse=0.05, render_kwargs=None, bucket=None):
+    """-> step_fn for GraphedStep: stage-1 step (ref: Trainer.train_step, nerf/utils.py:485-560 with the MSE criterion) on the
+    static tensors rays_o / rays_d / gt_rgb ([1, N, 3]). bucket: optional distributed.GradBucket (one all-reduce per step; the
+    fused backward places the density table's gradient in it and starts that region's all-reduce early)."""
+    kw = dict(staged=False, bg_color=1, perturb=True, force_all_rays=True, dt_gamma=0.0, max_steps=1024)
+    kw.update(render_kwargs or {})
+    if bucket is not None:
+        object.__setattr__(model, "_grad_bucket", bucket)
+
+    def step_fn():
+        optimizer.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.render(rays_o, rays_d, rays_gt=gt_rgb, **kw)
+            loss = (((out["image"] - gt_rgb) ** 2).mean(-1) + lambda_sparse * out["rgb_norm"]).mean()
+        scaler.scale(loss).backward()
+        if bucket is not None:
+            bucket.all_reduce(average=True)
+        scaler.step(optimizer)
+        scaler.update()
+        return loss.detach()
+    return step_fn

@@ -11,18 +11,27 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 from palettenerf_b200 import synthetic as S  # noqa: E402
 from palettenerf_b200.distributed import GradBucket  # noqa: E402
-from palettenerf_b200.graphs import GraphedStep, make_palette_train_step  # noqa: E402
+from palettenerf_b200.graphs import GraphedStep, make_nerf_train_step, make_palette_train_step  # noqa: E402
 from palettenerf_b200.optim import FusedAdam  # noqa: E402
 from palettenerf_b200.palette.losses import palette_loss  # noqa: E402
 
 RAYS = 1024
+STAGE = "nerf" if "--stage-nerf" in sys.argv else "palette"       # --stage-nerf: the stage-1 model and its fused step
+TABLE = "encoder.embeddings" if STAGE == "nerf" else "encoder_palette.embeddings"
+
+
+def fresh_model(dev):
+    if STAGE == "nerf":
+        return S.build_nerf_model(dev, seed=0)
+    return S.build_palette_model(dev, seed=0, pred_clip=False)
 
 
 def build(dev, rank, peer, smooth):
     torch.manual_seed(0)
-    model = S.build_palette_model(dev, seed=0, pred_clip=False)
+    model = fresh_model(dev)
     model.train()
-    model.require_smooth_loss = smooth
+    if STAGE == "palette":
+        model.require_smooth_loss = smooth
     opt = FusedAdam(model.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
     scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=10 ** 9)
@@ -30,6 +39,10 @@ def build(dev, rank, peer, smooth):
     o, d = S.training_rays(RAYS, seed=rank)
     o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
     gt = torch.rand(1, RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+
+    if STAGE == "nerf":
+        step = make_nerf_train_step(model, opt, scaler, o, d, gt, render_kwargs=dict(perturb=False), bucket=bucket)
+        return model, bucket, step
 
     def loss_fn(out):
         return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1,
@@ -63,15 +76,20 @@ def run_config(dev, rank, smooth, graph):
         # (not bit-equal by construction: the hash-grid scatter adds with float atomics in arbitrary order, and Adam turns
         # a last-bit difference of a noise-level gradient into a visible fraction of lr; three steps move a weight by
         # at most 3e-2)
-        err, mean = (a - b).abs().max().item(), (a - b).abs().mean().item()
-        assert err <= 5e-4 and mean <= 5e-6, f"smooth={smooth} graph={graph} {n}: peer vs nccl bucket {err:.3e} / {mean:.3e}"
+        diff = (a - b).abs()
+        err, mean = diff.max().item(), diff.mean().item()
+        # (stage 1: entries of the density table whose gradient is at noise level — Adam with eps = 1e-15 turns the sign of a
+        # 1e-12 gradient into a full +-lr step — may differ by up to 2 lr per step between two summation orders; they must stay
+        # a handful out of 12.6 M, and the mean must not move)
+        outliers = int((diff > 5e-4).sum().item())
+        ok = (err <= 5e-4 or (STAGE == "nerf" and outliers <= 1e-5 * diff.numel() and err <= 0.1)) and mean <= 5e-6
+        assert ok, f"smooth={smooth} graph={graph} {n}: peer vs nccl bucket {err:.3e} / {mean:.3e} ({outliers} outliers)"
         ref = a.double().sum().reshape(1)
         mine = ref.clone()
         dist.broadcast(ref, src=0)
         assert torch.equal(mine, ref), f"{n}: ranks hold different parameters after the peer-bucket steps"
-    moved = (results[True]["encoder_palette.embeddings"] - S.build_palette_model(dev, seed=0, pred_clip=False)
-             .encoder_palette.embeddings).abs().max().item()
-    assert moved > 1e-4, "the steps must have changed the palette table"
+    moved = (results[True][TABLE] - dict(fresh_model(dev).named_parameters())[TABLE]).abs().max().item()
+    assert moved > 1e-4, "the steps must have changed the trained hash table"
 
 
 def main():
@@ -81,7 +99,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    for smooth, graph in ((False, False), (True, False), (False, True)):
+    for smooth, graph in (((False, False), (False, True)) if STAGE == "nerf" else ((False, False), (True, False), (False, True))):
         run_config(dev, rank, smooth, graph)
         gc.collect()
         torch.cuda.synchronize()

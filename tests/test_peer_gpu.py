@@ -60,3 +60,16 @@ def test_data_parallel_train_step_with_early_table_allreduce_world2(cuda):
            "--master-port", "29563", os.path.join(ROOT, "tests", "dp_train_worker.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "DP_TRAIN_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_data_parallel_stage1_train_step_with_early_table_allreduce_world2(cuda):
+    """the same for the stage-1 (NeRF) model: its fused backward scatters the density table's gradient into the bucket and
+    starts that region's all-reduce under the weight-gradient kernel (csrc/nerf_train.cu, fused_nerf_train.py)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29564", os.path.join(ROOT, "tests", "dp_train_worker.py"), "--stage-nerf"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "DP_TRAIN_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
