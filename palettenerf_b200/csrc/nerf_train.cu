@@ -58,7 +58,6 @@ struct NerfFwdScratch {
     float out[32][12];          // [0] logit, [1..3] rgb, [4..11] carried geo fragments (uint32)
 };
 
-template <int DUMMY>
 __global__ void __launch_bounds__(kNerfFwdWarps * 32, 2)
 k_nerf_train_fwd(const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M, pnerf_nerf_train f,
                  uint32_t* __restrict__ xbuf, float* __restrict__ sigma, float* __restrict__ rgb) {
@@ -408,11 +407,11 @@ int pnerf_nerf_train_forward(const float* xyzs, const float* dirs, uint32_t M, c
     const uint32_t grid = min(ceil_div(ceil_div(M, 32u), (uint32_t)kNerfFwdWarps), 2u * (uint32_t)kNumSMs);
     static bool attr_done = false;   // once per process (keeps cudaFuncSetAttribute out of graph capture)
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_nerf_train_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_nerf_train_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_cuda_error(e, "nerf_train_forward attr"); return PNERF_ERR_CUDA; }
         attr_done = true;
     }
-    k_nerf_train_fwd<0><<<grid, kNerfFwdWarps * 32, smem, (cudaStream_t)stream>>>(xyzs, dirs, M, *p, (uint32_t*)xbuf, sigma, rgb);
+    k_nerf_train_fwd<<<grid, kNerfFwdWarps * 32, smem, (cudaStream_t)stream>>>(xyzs, dirs, M, *p, (uint32_t*)xbuf, sigma, rgb);
     return check_launch("nerf_train_forward");
 }
 
