@@ -309,6 +309,59 @@ def train_forward_cuda_ray(params, rays_o, rays_d, bitfield, bound=2.0, C=2, H=1
                 weights_sum=ws, maps=maps, n_samples=int(counter[0]))
 
 
+def nerf_train_step_cuda_ray(params, rays_o, rays_d, rays_gt, bitfield, bound=2.0, C=2, H=128, min_near=0.2,
+                             per_level_scale=2 ** (8 / 15), dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, bg_color=1.0,
+                             density_scale=1.0, noises=None, loss_fn=None):
+    """stage-1 training branch of NeRFRenderer.run_cuda (nerf/renderer.py:282-330) on the oracle kernels, and — with `loss_fn`
+    (maps dict -> scalar torch loss) — the gradients of the step by the oracle's composite backward + torch autograd of the
+    field. `params`: state dict; tensors that should receive gradients must have requires_grad. Returns (maps, grads | None);
+    maps = image / depth / weights_sum / rgb_norm as the reference returns them."""
+    rays_o = np.ascontiguousarray(_t(rays_o).float().reshape(-1, 3).numpy())
+    rays_d = np.ascontiguousarray(_t(rays_d).float().reshape(-1, 3).numpy())
+    gt = np.ascontiguousarray(_t(rays_gt).float().reshape(-1, 3).numpy())
+    N = rays_o.shape[0]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o, rays_d, aabb, min_near)
+    noises = np.zeros(N, np.float32) if noises is None else noises
+    xyzs, dirs, deltas, rays, counter = O.march_rays_train(rays_o, rays_d, _t(bitfield).numpy(), bound, dt_gamma, max_steps, C,
+                                                           H, N * max_steps if N * max_steps < (1 << 24) else (1 << 24),
+                                                           nears, fars, noises)
+    m = int(counter[0])
+    m += 128 - m % 128
+    xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+    sigma_t, rgb_t = nerf_forward(params, xyzs, dirs, bound, per_level_scale)
+    sig_t = density_scale * sigma_t                                                                  # :299
+    sig, rgbs = sig_t.detach().numpy(), rgb_t.detach().numpy()
+    gt_s = O.spread_ray_to_sample(gt, rays, m)                                                       # :303
+    err_t = ((torch.from_numpy(gt_s) - rgb_t) ** 2).sum(-1, keepdim=True).repeat(1, 3)              # :304
+    err = err_t.detach().numpy()
+    ws, depth, image = O.composite_rays_train_forward(sig, rgbs, deltas, rays, T_thresh)            # :325
+    _, _, err_img = O.composite_rays_train_forward(sig, err, deltas, rays, T_thresh)                # :326
+    maps = dict(image=image + (1 - ws)[:, None] * bg_color, depth=np.clip(depth - nears, 0, None) / (fars - nears),
+                weights_sum=ws, rgb_norm=err_img.mean(-1), n_samples=int(counter[0]))
+    if loss_fn is None:
+        return maps, None
+    # per-ray gradients of the loss by autograd on the maps, through the compositor by the oracle's backward kernels, through
+    # the field by autograd again
+    leaf = {k: torch.from_numpy(np.ascontiguousarray(maps[k])).requires_grad_() for k in ("image", "weights_sum", "rgb_norm")}
+    loss = loss_fn(leaf)
+    loss.backward()
+    z = lambda t, shape: np.zeros(shape, np.float32) if t.grad is None else t.grad.numpy()     # noqa: E731
+    g_img, g_ws_direct, g_err = z(leaf["image"], (N, 3)), z(leaf["weights_sum"], (N,)), z(leaf["rgb_norm"], (N,))
+    # image = composite + (1 - ws) * bg: d/d ws picks up -bg . g_img
+    g_ws = g_ws_direct - (g_img * bg_color).sum(-1)
+    gs1, gr1 = O.composite_rays_train_backward(g_ws, g_img, sig, rgbs, deltas, rays, ws, image, T_thresh)
+    g_err3 = np.repeat(g_err[:, None] / 3.0, 3, axis=1).astype(np.float32)                           # mean over 3 equal channels
+    gs2, ge2 = O.composite_rays_train_backward(np.zeros(N, np.float32), g_err3, sig, err, deltas, rays,
+                                               np.zeros(N, np.float32) + O.composite_rays_train_forward(sig, err, deltas, rays, T_thresh)[0],
+                                               err_img, T_thresh)
+    grads_in = [torch.from_numpy(gs1 + gs2), torch.from_numpy(gr1), torch.from_numpy(ge2)]
+    leaves = [v for v in params.values() if torch.is_tensor(v) and v.requires_grad]
+    g = torch.autograd.grad([sig_t, rgb_t, err_t], leaves, grads_in, allow_unused=True)
+    names = [k for k, v in params.items() if torch.is_tensor(v) and v.requires_grad]
+    return maps, {k: gi for k, gi in zip(names, g) if gi is not None}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # per-ray losses of the palette training step (TEST INFRASTRUCTURE; restates palette/utils.py:486-567 in torch)
 # ---------------------------------------------------------------------------------------------------------------

@@ -179,6 +179,46 @@ def test_nerf_oracle_matches_reference_forward(gold):
     _close(rgb.numpy(), gold["nerf_fwd_f16_color"], 1e-3, "nerf colour vs ref f16")
 
 
+def test_nerf_train_oracle_matches_reference_step_outputs_and_gradients(gold):
+    """stage-1 training branch (nerf/renderer.py:282-330): the oracle's maps and — through the oracle's composite backward and
+    torch autograd of the restated field — the gradients of the reference's own step (`nerf_train_fp32_*`)"""
+    from palettenerf_b200 import synthetic as S
+    m = S.build_nerf_model("cpu", seed=4, table_scale=0.5)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    names = [n for n, _ in m.named_parameters()]
+    for n in names:
+        params[n].requires_grad_()
+    o, d = PC.train_rays()
+    gt, _ = PC.train_targets(False)
+    with PC.FixedRandom():
+        noises = torch.rand(PC.TRAIN_RAYS).numpy()
+    gt_flat = gt.reshape(-1, 3)
+    maps, grads = cpu_render.nerf_train_step_cuda_ray(
+        params, o, d, gt, m.density_bitfield, per_level_scale=m.encoder.per_level_scale, noises=noises,
+        loss_fn=lambda r: ((r["image"] - gt_flat) ** 2).mean(), **PC.RENDER_KW)
+    for k in ("image", "depth", "weights_sum", "rgb_norm"):
+        r = gold[f"nerf_train_fp32_{k}"].reshape(maps[k].shape)
+        _close(maps[k], r, 5e-5, f"nerf train {k} vs ref fp32")
+        _close(maps[k], gold[f"nerf_train_f16_{k}"].reshape(maps[k].shape), 1e-3, f"nerf train {k} vs ref f16")
+    checked = 0
+    for n in names:
+        g = grads[n].double().numpy()
+        if f"nerf_train_fp32_grad_{n}" in gold.files:
+            a, r = g.reshape(-1), gold[f"nerf_train_fp32_grad_{n}"].astype(np.float64).reshape(-1)
+        else:
+            idx = PC.table_grad_indices(g.shape[0]).numpy()
+            a, r = g[idx].reshape(-1), gold[f"nerf_train_fp32_gradrows_{n}"].astype(np.float64).reshape(-1)
+            assert abs(np.linalg.norm(g) - gold[f"nerf_train_fp32_gradnorm_{n}"][0]) <= 1e-3 * gold[f"nerf_train_fp32_gradnorm_{n}"][0]
+        rel = np.linalg.norm(a - r) / np.linalg.norm(r)
+        # the sigma gradient of the compositor is a difference of nearly equal sums (T c_i - remaining colour): the 1e-6 the
+        # CPU matmuls differ from the GPU's by comes out as ~1e-3 on everything upstream of sigma (measured: table 1.0e-3,
+        # sigma_net.0 3.8e-4; the colour net, which sees no cancellation, 7e-5 and below). The CUDA fp32 path, which shares the
+        # reference's GEMM kernels, is held to 2e-4 in test_golden_palette_gpu.py.
+        assert rel <= (3e-3 if n.startswith(("encoder", "sigma_net")) else 3e-4), (n, rel)
+        checked += 1
+    assert checked == 6
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # checkpoint layout (SURVEY Appendix B; a20 / f4): key set + shapes == the reference's, and a reference-layout dict loads
 # ------------------------------------------------------------------------------------------------------------------
