@@ -503,7 +503,16 @@ def _adam(torch, params, torch_adam):
         return torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True), \
             "torch Adam(0.9,0.99,1e-15,fused,capturable)+GradScaler"
     from palettenerf_b200.optim import FusedAdam
-    return FusedAdam(params, betas=(0.9, 0.99), eps=1e-15), "FusedAdam(0.9,0.99,1e-15: pnerf_adam_step)+GradScaler"
+    return FusedAdam(params, betas=(0.9, 0.99), eps=1e-15), \
+        "FusedAdam(0.9,0.99,1e-15: pnerf_adam_step)+GradScaler(non-finite check: pnerf_found_inf)"
+
+
+def _scaler(torch, torch_adam):
+    """torch's GradScaler; with FusedAdam its non-finite check in front of the step is one pass of pnerf_found_inf"""
+    if torch_adam:
+        return torch.amp.GradScaler("cuda")
+    from palettenerf_b200.optim import GradScaler
+    return GradScaler("cuda")
 
 
 def _kernel_breakdown(torch, step, barrier, reps=3):
@@ -540,7 +549,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
     model.train()
     opt, opt_name = _adam(torch, model.get_params(1e-2), torch_adam)
     params = [p for grp in opt.param_groups for p in grp["params"] if p.requires_grad]
-    scaler = torch.amp.GradScaler("cuda")
+    scaler = _scaler(torch, torch_adam)
     bucket = GradBucket(params, peer=not nccl_allreduce) if world > 1 else None
     o, d = S.training_rays(TRAIN_RAYS, seed=rank)
     o, d = o.to(dev)[None].contiguous(), d.to(dev)[None].contiguous()
@@ -589,7 +598,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
         m2.train()
         m2.require_smooth_loss = True
         opt2, _ = _adam(torch, m2.get_params(1e-2), torch_adam)
-        sc2 = torch.amp.GradScaler("cuda")
+        sc2 = _scaler(torch, torch_adam)
 
         def loss2(out):
             return palette_loss(out, gt, lambda_sparsity=2e-4, lambda_offsets=0.03, lambda_view_dep=0.1, lambda_smooth=4e-3)[0]
@@ -632,7 +641,7 @@ def bench_train(torch, dist, dev, world, rank, S, L, barrier, max_over_ranks, fl
             opt1, _ = _adam(torch, m1.get_params(1e-2), False)
             p1 = [p for grp in opt1.param_groups for p in grp["params"] if p.requires_grad]
             b1 = GradBucket(p1, peer=not nccl_allreduce)
-            g1 = GraphedStep(make_nerf_train_step(m1, opt1, torch.amp.GradScaler("cuda"), o, d, gt, bucket=b1), warmup=3)
+            g1 = GraphedStep(make_nerf_train_step(m1, opt1, _scaler(torch, False), o, d, gt, bucket=b1), warmup=3)
             for _ in range(3):
                 g1.replay()
             barrier()
@@ -720,7 +729,7 @@ def bench_nerf(torch, dev, S, flush):
             tm = S.build_nerf_model(dev, seed=0)
             tm.train()
             opt = FusedAdam(tm.get_params(1e-2), lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
-            scaler = torch.amp.GradScaler("cuda")
+            scaler = _scaler(torch, False)
 
             def train_step():
                 opt.zero_grad(set_to_none=True)
@@ -833,7 +842,7 @@ def bench_mip360(torch, dev, rank, S, L, barrier, max_over_ranks, flush, world):
     tm.min_near = 0.05
     tm.train()
     opt, _ = _adam(torch, tm.get_params(1e-2), False)
-    scaler = torch.amp.GradScaler("cuda")
+    scaler = _scaler(torch, False)
     to, td = S.training_rays(TRAIN_RAYS, H=Hm, W=Wm, seed=rank)
     to, td = to.to(dev)[None].contiguous(), td.to(dev)[None].contiguous()
     g = torch.Generator(device=dev).manual_seed(rank)

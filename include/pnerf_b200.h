@@ -600,6 +600,12 @@ PNERF_API int pnerf_adam_step(const pnerf_adam_tensor* tensors, uint32_t count, 
                               float beta2, float eps, float weight_decay, const float* grad_scale, const float* found_inf,
                               void* stream);
 
+/* GradScaler's check in front of the step (ref: scaler.step(optimizer), palette/utils.py:719-724 -> torch's
+ * _amp_foreach_non_finite_check_and_unscale_ with a unit scale for an optimizer that unscales on the fly): *found_inf = 1
+ * if any element of the tensors' gradients (`g`, `n` of each entry; the other fields are ignored) is not finite. The caller
+ * zeroes found_inf. One streaming pass; at most PNERF_ADAM_MAX_TENSORS tensors per call. */
+PNERF_API int pnerf_found_inf(const pnerf_adam_tensor* tensors, uint32_t count, float* found_inf, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * per-ray epilogue of run_cuda  (ref: palette/renderer.py:399-429, 525-551; nerf/renderer.py:335-343)
  *   depth_n = clamp(depth - near, 0) / (far - near) (depth_n NULL: skipped); image_out = image + (1 - weights_sum) bg;

@@ -29,6 +29,7 @@ MAX_TENSORS = 32
 L.register("pnerf_adam_step", [c_void_p, c_uint32, c_float, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                                c_void_p])
 L.LAUNCHES["pnerf_adam_step"] = 2
+L.register("pnerf_found_inf", [c_void_p, c_uint32, c_void_p, c_void_p])
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -109,3 +110,31 @@ class FusedAdam(torch.optim.Optimizer):
                 for p in mirrored:        # the mirror holds fp16(p) for exactly this version of p
                     p._pnerf_mirror_version = p._version
         return loss
+
+
+class GradScaler(torch.amp.GradScaler):
+    """torch.amp.GradScaler whose non-finite check in front of a `FusedAdam` step is ONE streaming pass of `pnerf_found_inf`
+    over the gradients instead of torch's multi-tensor check-and-unscale kernel with a unit scale (22 us -> ~10 us for the
+    50 MB of a hash table's gradient). Everything else — scale growth / backoff, `unscale_()`, other optimizers — is torch's."""
+
+    def __init__(self, device="cuda", **kw):
+        super().__init__(device, **kw)
+
+    def _check_inf_per_device(self, optimizer):
+        if not isinstance(optimizer, FusedAdam):
+            return super()._check_inf_per_device(optimizer)
+        _scale, _ = self._check_scale_growth_tracker("_check_inf_per_device")
+        found_inf = torch.full((), 0.0, dtype=torch.float32, device=_scale.device)
+        grads = [p.grad for group in optimizer.param_groups for p in group["params"] if p.grad is not None]
+        if any(g.is_sparse or g.dtype != torch.float32 or not g.is_cuda or g.device != _scale.device for g in grads):
+            return super()._check_inf_per_device(optimizer)
+        grads = [g.contiguous() for g in grads]
+        for i in range(0, len(grads), MAX_TENSORS):
+            chunk = grads[i:i + MAX_TENSORS]
+            arr = (_AdamTensor * len(chunk))()
+            for k, g in enumerate(chunk):
+                arr[k].g, arr[k].n = ptr(g), g.numel()
+            L.call("pnerf_found_inf", ctypes.addressof(arr), len(chunk), ptr(found_inf), stream())
+        state = self._per_optimizer_states[id(optimizer)]
+        state["found_inf_per_device"] = {_scale.device: found_inf}
+        return state["found_inf_per_device"]

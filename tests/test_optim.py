@@ -136,3 +136,39 @@ def test_fused_adam_bumps_tensor_versions(cuda):
     v0 = p._version
     opt.step()
     assert p._version > v0
+
+
+@pytest.mark.gpu
+def test_grad_scaler_with_fused_found_inf_check_behaves_like_torch(cuda):
+    """optim.GradScaler: the non-finite check in front of a FusedAdam step is pnerf_found_inf (one streaming pass) instead of
+    torch's multi-tensor check-and-unscale; same skips, same scale schedule, same parameters as torch's scaler"""
+    from palettenerf_b200.optim import FusedAdam, GradScaler
+    g = torch.Generator().manual_seed(11)
+    shapes = [(1 << 20) + 3, 1, 7, 64 * 64, 1023] + [5 + i for i in range(36)]       # odd sizes, > 32 tensors, one large
+    base = [torch.randn(s, generator=g).to(cuda) for s in shapes]
+    base[4] = torch.randn(1024, generator=g).to(cuda)[1:]                               # a 4-byte-aligned (not 16) gradient
+    pa = [torch.nn.Parameter(t.clone()) for t in base]
+    pb = [torch.nn.Parameter(t.clone()) for t in base]
+    kw = dict(lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+    opt, ref = FusedAdam(pa, **kw), FusedAdam(pb, **kw)
+    sa, sb = GradScaler("cuda", init_scale=256.0, growth_interval=3), torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=3)
+    poison = {1: (0, 12345, float("inf")), 3: (40, 2, float("nan")), 5: (4, 1022, float("-inf")), 6: (0, (1 << 20) + 2, float("nan"))}
+    for it in range(9):
+        for k, (a, b) in enumerate(zip(pa, pb)):
+            gr = torch.randn(a.shape, generator=g).to(cuda)
+            if gr.data_ptr() % 16 == 0 and k == 4:
+                gr = torch.randn(a.numel() + 1, generator=g).to(cuda)[1:]
+            if it in poison and poison[it][0] == k:
+                gr.view(-1)[poison[it][1]] = poison[it][2]
+            a.grad, b.grad = gr.clone() if k != 4 else gr, gr.clone()
+        before = [a.detach().clone() for a in pa]
+        sa.scale(torch.ones((), device=cuda)); sb.scale(torch.ones((), device=cuda))
+        sa.step(opt); sa.update()
+        sb.step(ref); sb.update()
+        if it in poison:
+            assert all(torch.equal(x, y) for x, y in zip(before, pa)), it
+        else:
+            assert not torch.equal(before[0], pa[0])
+        assert sa.get_scale() == sb.get_scale(), (it, sa.get_scale(), sb.get_scale())
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
