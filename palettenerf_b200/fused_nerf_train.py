@@ -166,9 +166,9 @@ class _NerfTrainField(Function):
         if ctx.needs_input_grad[4]:
             g_tab = bucket.slot(enc.embeddings) if bucket is not None else None
             if g_tab is None:
-                g_tab = torch.zeros_like(enc.embeddings, dtype=torch.float32)
+                g_tab = L.zeros_like_fast(enc.embeddings, torch.float32)     # (a memset node instead of torch's fill kernel)
             else:
-                g_tab.zero_()
+                L.zero_(g_tab)
                 early = True
             if M > 0:
                 S_ = float(np.float32(np.log2(enc.per_level_scale)))

@@ -400,9 +400,9 @@ class _TrainField(Function):
         def scatter(emb, d):
             g = bucket.slot(emb) if bucket is not None else None
             if g is None:
-                g = torch.zeros_like(emb, dtype=torch.float32)
+                g = L.zeros_like_fast(emb, torch.float32)        # (a memset node: 21 -> 8 us for the 50 MB of a table)
             else:
-                g.zero_()
+                L.zero_(g)
             if count is None:
                 GB.grid_encode_backward_blc(d, x01, g, offsets, g, M, 3, 2, enc.num_levels, S_, enc.base_resolution, None,
                                             None, 0, False)
