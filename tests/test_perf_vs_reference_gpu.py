@@ -254,7 +254,8 @@ def test_end_to_end_reference_schedule_on_reference_kernels_vs_fused(cuda, flush
     m3 = S.build_palette_model(cuda, seed=0, pred_clip=False)
     m3.train()
     o3 = FusedAdam(m3.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
-    s3 = torch.amp.GradScaler("cuda")
+    from palettenerf_b200.optim import GradScaler
+    s3 = GradScaler("cuda")                      # torch.amp.GradScaler with the non-finite check as one pass (pnerf_found_inf)
 
     def step3():
         o3.zero_grad(set_to_none=True)
@@ -311,7 +312,8 @@ def test_stage1_reference_schedule_on_reference_kernels_vs_fused(cuda, flush):
         m.train()
         opt = FusedAdam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15) if fused_adam else \
             torch.optim.Adam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15, fused=True)
-        scaler = torch.amp.GradScaler("cuda")
+        from palettenerf_b200.optim import GradScaler
+        scaler = GradScaler("cuda") if fused_adam else torch.amp.GradScaler("cuda")
 
         def step(fused):
             opt.zero_grad(set_to_none=True)
