@@ -1,8 +1,9 @@
+"""cProfile of eager training steps of both stages (torch.optim.Adam as the reference's trainers build it): where the host time of an
+eager step goes. usage (under gpurun): python tools/profile_eager_steps.py"""
 import cProfile, pstats, sys, os, io
 sys.path.insert(0, os.getcwd())
 import torch
 from palettenerf_b200 import synthetic as S
-from palettenerf_b200.optim import FusedAdam
 dev = torch.device("cuda:0")
 def make(kind):
     if kind == "nerf":
