@@ -172,3 +172,21 @@ def test_grad_scaler_with_fused_found_inf_check_behaves_like_torch(cuda):
         assert sa.get_scale() == sb.get_scale(), (it, sa.get_scale(), sb.get_scale())
     for a, b in zip(pa, pb):
         assert torch.equal(a, b)
+
+
+def test_grad_scaler_subclass_falls_back_to_torch_for_other_optimizers():
+    """optim.GradScaler only replaces the non-finite check in front of a FusedAdam step; any other optimizer (here on the CPU)
+    goes through torch's own path unchanged"""
+    from palettenerf_b200.optim import GradScaler
+    p = torch.nn.Parameter(torch.ones(5))
+    opt = torch.optim.SGD([p], lr=0.1)
+    sc = GradScaler("cpu", init_scale=4.0, growth_interval=2)
+    for it, bad in enumerate((False, True, False, False)):
+        opt.zero_grad()
+        loss = (p * (float("inf") if bad else 1.0)).sum()
+        sc.scale(loss).backward()
+        before = p.detach().clone()
+        sc.step(opt)
+        sc.update()
+        assert torch.equal(before, p.detach()) == bad, it
+    assert sc.get_scale() == 4.0          # halved by the skipped step, doubled again after two good ones
